@@ -1,0 +1,457 @@
+/*
+ * fur_reader.cpp -- loads a reference-built Fulgor index (.fur / .mfur, unchanged on-disk format)
+ * and flattens it into the device image described in image.h. Host-only C++; no CUDA here.
+ *
+ * File format: the `essentials` visitor serialisation (reference
+ * external/sshash/external/pthash/external/bits/external/essentials/include/essentials.hpp:287-306):
+ * PODs are raw little-endian bytes, std::vector<POD> is u64 n + n elements, everything else is the
+ * concatenation of its members in `visit` order. Field order per type: SURVEY.md Appendix A, cited
+ * at each reader below ("bits/" = external/sshash/external/pthash/external/bits/include/,
+ * "pthash/" = external/sshash/external/pthash/include/, "sshash/" = external/sshash/include/).
+ */
+#include "fur_reader.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace fgb {
+namespace {
+
+typedef unsigned __int128 u128;
+
+struct byte_reader {
+    const uint8_t* p;
+    const uint8_t* end;
+    const uint8_t* take(uint64_t n) {
+        if (uint64_t(end - p) < n) throw std::runtime_error("index file truncated");
+        const uint8_t* q = p;
+        p += n;
+        return q;
+    }
+    template <typename T>
+    T pod() {
+        T v;
+        std::memcpy(&v, take(sizeof(T)), sizeof(T));
+        return v;
+    }
+    /* std::vector<POD> */
+    template <typename T>
+    std::vector<T> vec() {
+        uint64_t n = pod<uint64_t>();
+        if (n > uint64_t(end - p) / sizeof(T)) throw std::runtime_error("index file truncated (vector)");
+        std::vector<T> v(n);
+        if (n) std::memcpy(v.data(), take(n * sizeof(T)), n * sizeof(T));
+        return v;
+    }
+};
+
+/* bits/bit_vector.hpp:343-351 */
+struct bit_vector {
+    uint64_t num_bits = 0;
+    std::vector<uint64_t> words;
+    void read(byte_reader& r) {
+        num_bits = r.pod<uint64_t>();
+        words = r.vec<uint64_t>();
+    }
+};
+
+/* bits/compact_vector.hpp:290-301; value i sits at bit i*width, LSB first */
+struct compact_vector {
+    uint64_t size = 0, width = 0, mask = 0;
+    std::vector<uint64_t> words;
+    void read(byte_reader& r) {
+        size = r.pod<uint64_t>();
+        width = r.pod<uint64_t>();
+        mask = r.pod<uint64_t>();
+        words = r.vec<uint64_t>();
+    }
+    uint64_t operator[](uint64_t i) const {
+        if (width == 0) return 0;
+        const uint64_t pos = i * width, w = pos >> 6, s = pos & 63;
+        uint64_t v = words[w] >> s;
+        if (s + width > 64) v |= words[w + 1] << (64 - s);
+        return v & mask;
+    }
+};
+
+/* bits/darray.hpp:146-158 -- a select index; the flattener enumerates sequentially and never needs it */
+void skip_darray(byte_reader& r) {
+    r.pod<uint64_t>();
+    r.vec<int64_t>();
+    r.vec<uint16_t>();
+    r.vec<uint64_t>();
+}
+
+/* bits/elias_fano.hpp:303-317; access(i) = ((select1(high, i) - i) << l) | low[i] (:159-163) */
+struct elias_fano {
+    uint64_t back = 0;
+    bit_vector high;
+    compact_vector low;
+    void read(byte_reader& r) {
+        back = r.pod<uint64_t>();
+        high.read(r);
+        skip_darray(r);
+        skip_darray(r);
+        low.read(r);
+    }
+    uint64_t size() const { return low.size; }
+    /* all values, by one pass over the ones of the high-bits vector */
+    std::vector<uint64_t> decode() const {
+        std::vector<uint64_t> out(size());
+        uint64_t i = 0;
+        const uint64_t l = low.width;
+        for (uint64_t w = 0; w < high.words.size() && i < out.size(); ++w) {
+            uint64_t x = high.words[w];
+            while (x && i < out.size()) {
+                const uint64_t pos = (w << 6) + uint64_t(__builtin_ctzll(x));
+                out[i] = ((pos - i) << l) | low[i];
+                ++i;
+                x &= x - 1;
+            }
+        }
+        if (i != out.size()) throw std::runtime_error("malformed Elias-Fano sequence");
+        return out;
+    }
+};
+
+/* pthash/utils/hasher.hpp:53-117 for an 8-byte key */
+inline uint64_t murmur2_64(uint64_t key, uint64_t seed) {
+    const uint64_t m = 0xc6a4a7935bd1e995ULL;
+    uint64_t h = seed ^ (8 * m);
+    uint64_t k = key * m;
+    k ^= k >> 47;
+    k *= m;
+    h ^= k;
+    h *= m;
+    h ^= h >> 47;
+    h *= m;
+    h ^= h >> 47;
+    return h;
+}
+
+/* growing image with aligned sections */
+struct image_writer {
+    std::vector<uint8_t> bytes;
+    uint64_t begin_section() {
+        bytes.resize((bytes.size() + FGI_ALIGN - 1) / FGI_ALIGN * FGI_ALIGN, 0);
+        return bytes.size();
+    }
+    template <typename T>
+    uint64_t section(std::vector<T> const& v, uint64_t pad_elems = 0) {
+        uint64_t off = begin_section();
+        bytes.resize(off + (v.size() + pad_elems) * sizeof(T), 0);
+        if (!v.empty()) std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+        return off;
+    }
+};
+
+struct flattener {
+    fgi_header H{};
+    std::vector<fgi_phf> phfs;
+    std::vector<fgi_phf_part> parts;
+    std::vector<uint64_t> hashed_pilots;
+    std::vector<uint32_t> free_slots;
+    std::vector<uint32_t> skew_positions;
+    std::vector<fgi_hybrid> hybrids;
+    std::vector<uint64_t> set_bit_off;
+    std::vector<uint64_t> color_words;
+
+    static void split(u128 v, uint64_t& lo, uint64_t& hi) {
+        lo = uint64_t(v);
+        hi = uint64_t(v >> 64);
+    }
+
+    /* pthash/single_phf.hpp:140-150; pilots pthash/utils/encoders.hpp:207-215,406-414 */
+    void read_single_phf(byte_reader& r, uint64_t partition_offset) {
+        fgi_phf_part P{};
+        P.seed = r.pod<uint64_t>();
+        P.num_keys = r.pod<uint64_t>();
+        P.table_size = r.pod<uint64_t>();
+        uint64_t lo = r.pod<uint64_t>(), hi = r.pod<uint64_t>();
+        P.M_table_lo = lo, P.M_table_hi = hi;
+        r.pod<uint64_t>(); /* M_64, only used by non-minimal/other search types */
+        P.num_dense = r.pod<uint64_t>();
+        P.num_sparse = r.pod<uint64_t>();
+        P.M_dense_lo = r.pod<uint64_t>(), P.M_dense_hi = r.pod<uint64_t>();
+        P.M_sparse_lo = r.pod<uint64_t>(), P.M_sparse_hi = r.pod<uint64_t>();
+        compact_vector front_ranks, front_dict, back_ranks, back_dict;
+        front_ranks.read(r);
+        front_dict.read(r);
+        back_ranks.read(r);
+        back_dict.read(r);
+        elias_fano fs;
+        fs.read(r);
+        P.offset = partition_offset;
+        P.pilot_base = hashed_pilots.size();
+        P.free_base = free_slots.size();
+        /* dual<dictionary,dictionary>::access (encoders.hpp:391-394,192-195), with the pilot hash of
+           single_phf::position (single_phf.hpp:84-87) applied once here */
+        for (uint64_t i = 0; i < front_ranks.size; ++i)
+            hashed_pilots.push_back(murmur2_64(front_dict[front_ranks[i]], P.seed));
+        for (uint64_t i = 0; i < back_ranks.size; ++i)
+            hashed_pilots.push_back(murmur2_64(back_dict[back_ranks[i]], P.seed));
+        if (P.num_keys >= (1ULL << 32)) throw std::runtime_error("MPHF partition with >= 2^32 keys is not supported");
+        for (uint64_t v : fs.decode()) free_slots.push_back(uint32_t(v));
+        parts.push_back(P);
+    }
+
+    /* pthash/partitioned_phf.hpp:203-210,23-43; range_bucketer utils/bucketers.hpp:244-248 */
+    uint32_t read_partitioned_phf(byte_reader& r) {
+        fgi_phf F{};
+        F.seed = r.pod<uint64_t>();
+        F.num_keys = r.pod<uint64_t>();
+        r.pod<uint64_t>(); /* table_size */
+        F.num_partitions = r.pod<uint64_t>();
+        r.pod<uint64_t>();
+        r.pod<uint64_t>(); /* range_bucketer M (unused) */
+        const uint64_t n = r.pod<uint64_t>();
+        if (n > uint64_t(r.end - r.p)) throw std::runtime_error("index file truncated (partitions)");
+        F.first_part = parts.size();
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t off = r.pod<uint64_t>();
+            read_single_phf(r, off);
+        }
+        if (n == 0) {
+            /* a never-built (empty) skew partition: seed/num_keys/table_size are uninitialised words
+               in the file (partitioned_phf.hpp:213-215 has no default initialisers) */
+            F.num_partitions = 0;
+            F.num_keys = 0;
+        } else if (n != F.num_partitions) {
+            throw std::runtime_error("partitioned MPHF: bucketer/partition count mismatch");
+        }
+        phfs.push_back(F);
+        return uint32_t(phfs.size() - 1);
+    }
+
+    /* include/color_sets/hybrid.hpp:339-345 */
+    void read_hybrid(byte_reader& r) {
+        fgi_hybrid h{};
+        h.num_colors = r.pod<uint32_t>();
+        h.sparse_thr = r.pod<uint32_t>();
+        h.very_dense_thr = r.pod<uint32_t>();
+        elias_fano offs;
+        offs.read(r);
+        bit_vector bits;
+        bits.read(r);
+        if (offs.size() == 0) throw std::runtime_error("hybrid color sets: empty offsets");
+        h.num_sets = offs.size() - 1;
+        h.set_off_base = set_bit_off.size();
+        h.word_base = color_words.size();
+        for (uint64_t v : offs.decode()) set_bit_off.push_back(v);
+        color_words.insert(color_words.end(), bits.words.begin(), bits.words.end());
+        color_words.push_back(0); /* the decoders read 128-bit windows */
+        color_words.push_back(0);
+        hybrids.push_back(h);
+    }
+};
+
+bool ends_with(std::string const& s, const char* suf) {
+    const size_t n = std::strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+}  // namespace
+
+std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
+    byte_reader r{file, file + size};
+    flattener F;
+    fgi_header& H = F.H;
+    H.magic = FGI_MAGIC;
+    H.type = uint32_t(type);
+
+    /* include/index.hpp:94-102 begins with the version (include/util.hpp:31-35,91-95) */
+    const uint8_t major = r.pod<uint8_t>();
+    r.pod<uint8_t>();
+    r.pod<uint8_t>();
+    if (major != 4) throw std::runtime_error("MAJOR index version mismatch: Fulgor index must be rebuilt with the current library version");
+    /* sshash::dictionary (sshash/dictionary.hpp:141-154); version check sshash/util.hpp:149-153 */
+    const uint8_t smajor = r.pod<uint8_t>();
+    r.pod<uint8_t>();
+    r.pod<uint8_t>();
+    if (smajor != 4) throw std::runtime_error("MAJOR index version mismatch: SSHash index must be rebuilt with the current library version");
+    H.num_kmers = r.pod<uint64_t>();
+    H.k = r.pod<uint16_t>();
+    H.m = r.pod<uint16_t>();
+    const uint8_t canonical = r.pod<uint8_t>();
+    if (!canonical) throw std::runtime_error("only canonical SSHash dictionaries are supported (Fulgor always builds canonical ones)");
+    if (H.k == 0 || H.k > 31 || H.m == 0 || H.m > H.k) throw std::runtime_error("unsupported k/m (k must be <= 31)");
+    H.hash_magic = r.pod<uint64_t>();
+    {
+        static const float a = 0.6f; /* pthash/utils/util.hpp:26: a FLOAT constant */
+        H.bucketer_T = uint64_t(a * double(UINT64_MAX));
+    }
+    F.read_partitioned_phf(r); /* phfs[0]: minimizers (sshash/minimizers.hpp) */
+
+    /* buckets (sshash/buckets.hpp:330-336) */
+    elias_fano pieces_ef, nskb_ef;
+    pieces_ef.read(r);
+    nskb_ef.read(r);
+    compact_vector offsets;
+    offsets.read(r);
+    bit_vector strings;
+    strings.read(r);
+
+    /* skew index (sshash/skew_index.hpp:84-91) */
+    H.skew_min_log2 = r.pod<uint16_t>();
+    H.skew_max_log2 = r.pod<uint16_t>();
+    H.skew_log2_max_bucket = r.pod<uint32_t>();
+    const uint64_t n_skew = r.pod<uint64_t>();
+    if (n_skew > FGI_MAX_SKEW) throw std::runtime_error("too many skew-index partitions");
+    H.num_skew = uint32_t(n_skew);
+    for (uint64_t i = 0; i < n_skew; ++i) H.skew_phf[i] = F.read_partitioned_phf(r);
+    if (r.pod<uint64_t>() != n_skew) throw std::runtime_error("skew index: mphfs/positions size mismatch");
+    for (uint64_t i = 0; i < n_skew; ++i) {
+        compact_vector pos;
+        pos.read(r);
+        H.skew_pos_base[i] = F.skew_positions.size();
+        for (uint64_t j = 0; j < pos.size; ++j) F.skew_positions.push_back(uint32_t(pos[j]));
+    }
+    { /* weights (sshash/weights.hpp:183-187): empty in Fulgor indexes */
+        compact_vector a, c;
+        elias_fano b;
+        a.read(r);
+        b.read(r);
+        c.read(r);
+    }
+
+    /* u2c + rank9 (include/index.hpp:94-102); the rank index is rebuilt implicitly below */
+    bit_vector u2c;
+    u2c.read(r);
+    r.vec<uint64_t>();
+
+    if (type == 0) {
+        F.read_hybrid(r);
+        H.num_colors = F.hybrids[0].num_colors;
+        H.num_color_sets = F.hybrids[0].num_sets;
+        H.num_partitions = 1;
+    }
+    std::vector<uint64_t> meta_off;
+    std::vector<uint32_t> meta_vals, part_min_color, part_sets_before;
+    if (type == 1) { /* include/color_sets/meta.hpp:275-281 */
+        H.num_colors = r.pod<uint32_t>();
+        compact_vector meta_sets;
+        meta_sets.read(r);
+        elias_fano moff;
+        moff.read(r);
+        const uint64_t np = r.pod<uint64_t>();
+        if (np > uint64_t(r.end - r.p)) throw std::runtime_error("index file truncated (partial color sets)");
+        for (uint64_t i = 0; i < np; ++i) F.read_hybrid(r);
+        struct endpoint { uint32_t min_color, num_color_sets_before; }; /* meta.hpp:9-17 */
+        std::vector<endpoint> eps = r.vec<endpoint>();
+        if (eps.size() != np + 1) throw std::runtime_error("meta color sets: endpoints/partitions size mismatch");
+        meta_off = moff.decode();
+        if (meta_off.empty()) throw std::runtime_error("meta color sets: empty offsets");
+        H.num_color_sets = meta_off.size() - 1;
+        H.num_partitions = uint32_t(np);
+        meta_vals.resize(meta_sets.size);
+        for (uint64_t i = 0; i < meta_sets.size; ++i) meta_vals[i] = uint32_t(meta_sets[i]);
+        for (auto const& e : eps) {
+            part_min_color.push_back(e.min_color);
+            part_sets_before.push_back(e.num_color_sets_before);
+        }
+    }
+    /* filenames (include/filenames.hpp:37-41) are not needed on the device */
+    r.vec<uint32_t>();
+    r.vec<char>();
+    if (r.p != r.end) throw std::runtime_error("index file has trailing bytes (wrong index type for this suffix?)");
+
+    /* ---- derived arrays ---- */
+    const std::vector<uint64_t> pieces = pieces_ef.decode();
+    const std::vector<uint64_t> nskb = nskb_ef.decode();
+    if (pieces.size() < 2 || nskb.empty()) throw std::runtime_error("empty dictionary");
+    H.num_unitigs = pieces.size() - 1;
+    H.num_minimizers = nskb.size() - 1;
+    H.num_super_kmers = offsets.size;
+    if (u2c.num_bits != H.num_unitigs) throw std::runtime_error("u2c size does not match the number of unitigs");
+    if (H.num_super_kmers >= (1ULL << 32) || pieces.back() >= (1ULL << 32))
+        throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / string offsets");
+    if (H.num_color_sets > FGI_SK_CID_MASK) throw std::runtime_error("too many color sets for the packed super-k-mer record");
+    if (H.k - H.m + 1 > 31) throw std::runtime_error("k - m + 1 > 31 is not supported");
+
+    /* buckets::locate_bucket (sshash/buckets.hpp:62-67): begin(b) = EF[b] + b */
+    std::vector<uint32_t> bucket_begin(nskb.size());
+    for (uint64_t b = 0; b < nskb.size(); ++b) bucket_begin[b] = uint32_t(nskb[b] + b);
+    if (bucket_begin.back() != H.num_super_kmers) throw std::runtime_error("bucket sizes do not add up to the number of super-k-mers");
+
+    /* index::u2c (include/index.hpp:37): color-set id of unitig u = number of ones in u2c[0, u) */
+    std::vector<uint32_t> unitig_cid(H.num_unitigs);
+    {
+        uint32_t rank = 0;
+        for (uint64_t u = 0; u < H.num_unitigs; ++u) {
+            unitig_cid[u] = rank;
+            rank += uint32_t((u2c.words[u >> 6] >> (u & 63)) & 1);
+        }
+    }
+    /* per super-k-mer: offset, window = min(k-m+1, contig_end - offset - k + 1) (buckets.hpp:133-160),
+       and the color-set id of the unitig that contains it (buckets.hpp:13-40 + u2c) */
+    std::vector<uint64_t> sk_records(H.num_super_kmers);
+    const uint64_t max_window = H.k - H.m + 1;
+    for (uint64_t s = 0; s < H.num_super_kmers; ++s) {
+        const uint64_t off = offsets[s];
+        const uint64_t u = uint64_t(std::upper_bound(pieces.begin(), pieces.end(), off) - pieces.begin()) - 1;
+        if (u >= H.num_unitigs) throw std::runtime_error("super-k-mer offset outside the strings");
+        const uint64_t contig_end = pieces[u + 1];
+        uint64_t window = 0;
+        if (contig_end >= off + H.k) window = std::min<uint64_t>(max_window, contig_end - off - H.k + 1);
+        const uint32_t meta = (uint32_t(window) << FGI_SK_CID_BITS) | unitig_cid[u];
+        sk_records[s] = uint64_t(uint32_t(off)) | (uint64_t(meta) << 32);
+    }
+
+    H.num_string_words = strings.words.size();
+    H.num_phfs = uint32_t(F.phfs.size());
+    H.num_phf_parts = uint32_t(F.parts.size());
+
+    /* ---- emit ---- */
+    image_writer W;
+    W.bytes.resize(sizeof(fgi_header), 0);
+    H.off_phfs = W.section(F.phfs);
+    H.off_phf_parts = W.section(F.parts);
+    H.off_hashed_pilots = W.section(F.hashed_pilots);
+    H.off_free_slots = W.section(F.free_slots, 1);
+    H.off_bucket_begin = W.section(bucket_begin);
+    H.off_sk_records = W.section(sk_records);
+    H.off_strings = W.section(strings.words, 2);
+    H.off_skew_positions = W.section(F.skew_positions, 1);
+    H.off_hybrids = W.section(F.hybrids);
+    H.off_set_bit_off = W.section(F.set_bit_off);
+    H.off_color_words = W.section(F.color_words);
+    H.off_meta_off = W.section(meta_off, 1);
+    H.off_meta_vals = W.section(meta_vals, 1);
+    H.off_part_min_color = W.section(part_min_color, 1);
+    H.off_part_sets_before = W.section(part_sets_before, 1);
+    W.begin_section();
+    H.total_bytes = W.bytes.size();
+    std::memcpy(W.bytes.data(), &H, sizeof(H));
+    return std::move(W.bytes);
+}
+
+int index_type_from_path(const char* path) {
+    /* the reference infers the index type from the file suffix only (tools/util.cpp:5-19) */
+    std::string p(path);
+    if (ends_with(p, ".mdfur")) return -2;
+    if (ends_with(p, ".dfur")) return -2;
+    if (ends_with(p, ".mfur")) return 1;
+    if (ends_with(p, ".fur")) return 0;
+    return -1;
+}
+
+std::vector<uint8_t> build_image_from_file(const char* path) {
+    const int type = index_type_from_path(path);
+    if (type == -2) throw std::runtime_error(std::string("differential indexes (.dfur/.mdfur) are not supported yet: ") + path);
+    if (type < 0) throw std::runtime_error(std::string("Wrong index filename supplied: ") + path);
+    FILE* f = std::fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("error in opening binary file: ") + path);
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(sz > 0 ? size_t(sz) : 0);
+    const size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
+    std::fclose(f);
+    if (got != buf.size()) throw std::runtime_error(std::string("short read on ") + path);
+    return build_image(buf.data(), buf.size(), type);
+}
+
+}  // namespace fgb

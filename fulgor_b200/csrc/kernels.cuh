@@ -1,0 +1,415 @@
+/*
+ * kernels.cuh -- sm_100a device code of the pseudoalignment hot path.
+ *
+ * Mapping: ONE WARP PER READ. Lanes own consecutive k-mer start positions (tiles of 32 k-mers);
+ * every lane resolves its own k-mer independently -- canonical minimizer -> minimizer MPHF ->
+ * bucket range -> super-k-mer record -> 2-bit string window compare. A lookup answer is a pure
+ * function of the k-mer (the reference asserts this itself: external/sshash/include/
+ * streaming_query.hpp:107 compares every streamed answer with a from-scratch lookup), so the
+ * reference's sequential seed-and-extend state machine is NOT reproduced: neighbouring lanes that
+ * share a minimizer issue identical addresses, which the LSU coalesces into one sector request,
+ * and that is the device analogue of "extension".
+ *
+ * Citations: "sshash/" = reference external/sshash/include/, "pthash/" =
+ * external/sshash/external/pthash/include/, "bits/" = .../pthash/external/bits/include/.
+ */
+#ifndef FULGOR_B200_KERNELS_CUH
+#define FULGOR_B200_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "image.h"
+
+/* The per-lane functions (hashing, MPHF, string compare, color-set decode) are FG_HD so that
+   tests/host_emul.cu can run the SAME source on the host against the oracle when no GPU is around.
+   That harness is test infrastructure; the library itself has no CPU path. */
+#define FG_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define FG_LDG(p) __ldg(p)
+#else
+#define FG_LDG(p) (*(p))
+#endif
+
+namespace fgb {
+
+FG_HD uint64_t fg_mulhi64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return uint64_t((unsigned __int128)a * b >> 64);
+#endif
+}
+FG_HD uint64_t fg_brev64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    return __builtin_bswap64(x);
+#endif
+}
+FG_HD uint32_t fg_ffs64(uint64_t x) { /* 1-based index of the lowest set bit, 0 if none */
+#ifdef __CUDA_ARCH__
+    return uint32_t(__ffsll((long long)x));
+#else
+    return uint32_t(__builtin_ffsll((long long)x));
+#endif
+}
+FG_HD uint32_t fg_clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return uint32_t(__clz(int(x)));
+#else
+    return x ? uint32_t(__builtin_clz(x)) : 32u;
+#endif
+}
+
+#define FG_FULL 0xffffffffu
+#define FG_NOT_FOUND 0xffffffffu
+#define FG_MAX_ENTRIES 32 /* distinct color sets per read held in registers (one per lane) */
+
+/* device view of the image: absolute pointers + the scalars the kernels need */
+struct dev_index {
+    const fgi_phf* phfs;
+    const fgi_phf_part* parts;
+    const uint64_t* hashed_pilots;
+    const uint32_t* free_slots;
+    const uint32_t* bucket_begin;
+    const uint2* sk_records;
+    const uint64_t* strings;
+    const uint32_t* skew_positions;
+    const fgi_hybrid* hybrids;
+    const uint64_t* set_bit_off;
+    const uint64_t* color_words;
+    const uint64_t* meta_off;
+    const uint32_t* meta_vals;
+    const uint32_t* part_min_color;
+    const uint32_t* part_sets_before;
+    uint64_t hash_magic, bucketer_T;
+    uint32_t k, m;
+    uint32_t skew_min_log2, skew_max_log2, skew_log2_max_bucket, num_skew;
+    uint32_t skew_phf[FGI_MAX_SKEW];
+    uint64_t skew_pos_base[FGI_MAX_SKEW];
+    uint32_t type, num_colors, num_partitions, pad;
+};
+
+/* ------------------------------------------------------------------ hashing */
+
+/* MurmurHash2_64 of an 8-byte key (pthash/utils/hasher.hpp:53-117) */
+FG_HD uint64_t murmur2_64(uint64_t key, uint64_t seed) {
+    const uint64_t m = 0xc6a4a7935bd1e995ULL;
+    uint64_t h = seed ^ (8 * m);
+    uint64_t k = key * m;
+    k ^= k >> 47;
+    k *= m;
+    h ^= k;
+    h *= m;
+    h ^= h >> 47;
+    h *= m;
+    h ^= h >> 47;
+    return h;
+}
+
+/* a mod d with the precomputed M = floor(2^128 / d) + 1 (pthash/external/fastmod/fastmod.h:159-162):
+   lowbits = M * a (mod 2^128); result = (lowbits * d) >> 128 */
+FG_HD uint64_t fastmod_u64(uint64_t a, uint64_t M_lo, uint64_t M_hi, uint64_t d) {
+    const uint64_t lo = M_lo * a;
+    const uint64_t hi = fg_mulhi64(M_lo, a) + M_hi * a;
+    const uint64_t bottom = fg_mulhi64(lo, d);
+    const uint64_t top_lo = hi * d;
+    const uint64_t top_hi = fg_mulhi64(hi, d);
+    const uint64_t sum = bottom + top_lo;
+    return top_hi + (sum < bottom ? 1 : 0);
+}
+
+/* partitioned_phf::operator() (pthash/partitioned_phf.hpp:150-159) -> single_phf::position
+   (pthash/single_phf.hpp:79-101) with murmurhash2_128 (utils/hasher.hpp:203-207), skew_bucketer
+   (utils/bucketers.hpp:163-168), xor displacement, minimal (free slots) */
+FG_HD uint64_t phf_lookup(const dev_index& I, uint32_t phf_id, uint64_t key) {
+    const fgi_phf* F = I.phfs + phf_id;
+    const uint64_t seed = FG_LDG(&F->seed);
+    const uint64_t nparts = FG_LDG(&F->num_partitions);
+    const uint64_t first = murmur2_64(key, seed);
+    const uint64_t second = murmur2_64(key, ~seed);
+    uint64_t p = 0;
+    if (nparts > 1) p = (((first ^ second) >> 32) * nparts) >> 32; /* range_bucketer, bucketers.hpp:216-218 */
+    const fgi_phf_part* P = I.parts + FG_LDG(&F->first_part) + p;
+    const uint64_t num_dense = FG_LDG(&P->num_dense);
+    uint64_t bucket;
+    if (first < I.bucketer_T) {
+        bucket = fastmod_u64(first, FG_LDG(&P->M_dense_lo), FG_LDG(&P->M_dense_hi), num_dense);
+    } else {
+        bucket = num_dense + fastmod_u64(first, FG_LDG(&P->M_sparse_lo), FG_LDG(&P->M_sparse_hi), FG_LDG(&P->num_sparse));
+    }
+    const uint64_t hashed_pilot = FG_LDG(I.hashed_pilots + FG_LDG(&P->pilot_base) + bucket);
+    uint64_t pos = fastmod_u64(second ^ hashed_pilot, FG_LDG(&P->M_table_lo), FG_LDG(&P->M_table_hi), FG_LDG(&P->table_size));
+    const uint64_t num_keys = FG_LDG(&P->num_keys);
+    if (pos >= num_keys) pos = FG_LDG(I.free_slots + FG_LDG(&P->free_base) + (pos - num_keys));
+    return FG_LDG(&P->offset) + pos;
+}
+
+/* ------------------------------------------------------------------ k-mers */
+
+/* reverse complement of a 2-bit packed k-mer (sshash/kmer.hpp:146-170; A=0 C=1 T=2 G=3 so the
+   complement is XOR 10b per base) */
+FG_HD uint64_t revcomp(uint64_t x, uint32_t k) {
+    uint64_t y = fg_brev64(x ^ 0xAAAAAAAAAAAAAAAAULL);
+    y = ((y & 0x5555555555555555ULL) << 1) | ((y >> 1) & 0x5555555555555555ULL);
+    return y >> (64 - 2 * k);
+}
+
+/* util::compute_minimizer (sshash/util.hpp:220-239) with mixer_64 (sshash/hash_util.hpp:97) */
+template <int W /* k - m + 1, 0 = runtime */>
+FG_HD uint64_t kmer_minimizer(uint64_t x, uint32_t window, uint64_t mmer_mask, uint64_t magic) {
+    uint64_t best_h = UINT64_MAX, best = UINT64_MAX;
+    const int n = W ? W : int(window);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const uint64_t y = x & mmer_mask;
+        const uint64_t h = (y * 0x517cc1b727220a95ULL) ^ magic;
+        if (h < best_h) {
+            best_h = h;
+            best = y;
+        }
+        x >>= 2;
+    }
+    return best;
+}
+
+FG_HD uint32_t ceil_log2_u32(uint32_t v) { /* bits/util.hpp ceil_log2_uint32 */
+    return v <= 1 ? 0u : 32u - fg_clz32(v - 1);
+}
+
+/* lookup_canonical_in_super_kmer (sshash/buckets.hpp:133-160) on the flattened record: compare the
+   k-mer and its reverse complement with the `window` consecutive k-mers that start at `offset` in the
+   2-bit strings. Returns the color-set id of the enclosing unitig, or FG_NOT_FOUND. */
+FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t rc, uint64_t kmask) {
+    const uint2 rec = FG_LDG(I.sk_records + sk);
+    const uint32_t window = rec.y >> FGI_SK_CID_BITS;
+    const uint64_t bit = 2 * uint64_t(rec.x);
+    const uint64_t* w = I.strings + (bit >> 6);
+    const uint32_t sh = uint32_t(bit & 63);
+    const uint64_t w0 = FG_LDG(w), w1 = FG_LDG(w + 1), w2 = FG_LDG(w + 2);
+    uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+    bool hit = false;
+    for (uint32_t t = 0; t < window; ++t) {
+        const uint64_t cand = lo & kmask;
+        hit |= (cand == fwd) | (cand == rc);
+        lo = (lo >> 2) | (hi << 62);
+        hi >>= 2;
+    }
+    return hit ? (rec.y & FGI_SK_CID_MASK) : FG_NOT_FOUND;
+}
+
+/* dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:47-77) + buckets::lookup_canonical
+   (sshash/buckets.hpp:162-209) + index::u2c. The "minimizer of the bucket's first k-mer must equal
+   the target" test (buckets.hpp:168-180) is an early-out only: equal k-mers have equal minimizers,
+   so a k-mer whose minimizer is absent cannot match any stored k-mer. */
+FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, uint64_t minimizer, uint64_t kmask) {
+    const uint64_t b = phf_lookup(I, 0, minimizer);
+    const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
+    const uint32_t n = end - begin;
+    if (I.num_skew != 0) {
+        const uint32_t log2n = ceil_log2_u32(n);
+        if (log2n > I.skew_min_log2) { /* skew_index::lookup (sshash/skew_index.hpp:40-52) */
+            uint32_t pid = log2n - (I.skew_min_log2 + 1);
+            if (log2n == I.skew_log2_max_bucket || log2n > I.skew_max_log2) pid = I.num_skew - 1;
+            const uint32_t f = I.skew_phf[pid];
+            if (FG_LDG(&I.phfs[f].num_partitions) == 0) return FG_NOT_FOUND;
+            const uint64_t h = phf_lookup(I, f, fwd < rc ? fwd : rc);
+            const uint32_t pos = FG_LDG(I.skew_positions + I.skew_pos_base[pid] + h);
+            if (pos < n) return scan_super_kmer(I, begin + pos, fwd, rc, kmask);
+            return FG_NOT_FOUND;
+        }
+    }
+    for (uint32_t s = begin; s < end; ++s) {
+        const uint32_t cid = scan_super_kmer(I, s, fwd, rc, kmask);
+        if (cid != FG_NOT_FOUND) return cid;
+    }
+    return FG_NOT_FOUND;
+}
+
+/* ------------------------------------------------------------------ stage 1 for one read, one warp */
+
+struct read_hits {
+    uint32_t cid;       /* lane j < n holds the j-th distinct color-set id (ascending after sort) */
+    uint32_t cnt;       /* ... and the number of positive k-mers that map to it */
+    uint32_t n;         /* number of distinct color sets (warp-uniform) */
+    uint32_t npos;      /* number of positive k-mers (warp-uniform) */
+    bool overflow;      /* more than FG_MAX_ENTRIES distinct color sets */
+};
+
+/* valid characters are exactly ACGTacgt (sshash/kmer.hpp:214-224,258-260); code = (c >> 1) & 3 (kmer.hpp:199) */
+FG_HD bool base_valid(uint32_t c) {
+    const uint32_t u = c & 0xDFu; /* fold case */
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+
+/* 32 characters (one per lane) -> one 64-bit word of 2-bit codes (char j at bits [2j, 2j+1]) + validity mask */
+__device__ __forceinline__ void pack_chars(uint32_t c, bool in_range, uint32_t lane, uint64_t& word, uint32_t& valid) {
+    const uint32_t code = (c >> 1) & 3u;
+    const uint32_t sh = (lane & 15u) * 2u;
+    const uint32_t lo = __reduce_or_sync(FG_FULL, lane < 16 ? code << sh : 0u);
+    const uint32_t hi = __reduce_or_sync(FG_FULL, lane >= 16 ? code << sh : 0u);
+    word = uint64_t(lo) | (uint64_t(hi) << 32);
+    valid = __ballot_sync(FG_FULL, in_range && base_valid(c));
+}
+
+/* index::fetch_color_set_ids (src/ps_full_intersection.cpp:335-374) and the counting half of
+   index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read.
+   The two sort+unique passes of the reference become: warp match on the color-set id inside a tile,
+   a 32-entry register table (one entry per lane) across tiles, one bitonic sort at the end. */
+template <int W>
+__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, uint32_t lane) {
+    read_hits R;
+    R.cid = FG_NOT_FOUND;
+    R.cnt = 0;
+    R.n = 0;
+    R.npos = 0;
+    R.overflow = false;
+    const uint32_t k = I.k;
+    if (len < k) return R; /* src/ps_full_intersection.cpp:337 */
+    const uint32_t nk = len - k + 1;
+    const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint64_t mmer_mask = (1ULL << (2 * I.m)) - 1;
+    const uint32_t window = k - I.m + 1;
+    const uint32_t kbits = (k == 32) ? ~0u : ((1u << k) - 1u);
+
+    uint64_t w0, w1;
+    uint32_t v0, v1;
+    {
+        const uint32_t c = lane < len ? seq[lane] : 0u;
+        pack_chars(c, lane < len, lane, w0, v0);
+    }
+    for (uint32_t t0 = 0; t0 < nk; t0 += 32) {
+        {
+            const uint32_t p = t0 + 32 + lane;
+            const uint32_t c = p < len ? seq[p] : 0u;
+            pack_chars(c, p < len, lane, w1, v1);
+        }
+        const uint32_t i = t0 + lane;
+        const bool valid = i < nk && ((__funnelshift_r(v0, v1, lane) & kbits) == kbits);
+        uint32_t cid = FG_NOT_FOUND;
+        if (valid) {
+            const uint32_t sh = 2 * lane;
+            const uint64_t fwd = (sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0) & kmask;
+            const uint64_t rc = revcomp(fwd, k);
+            const uint64_t a = kmer_minimizer<W>(fwd, window, mmer_mask, I.hash_magic);
+            const uint64_t b = kmer_minimizer<W>(rc, window, mmer_mask, I.hash_magic);
+            cid = lookup_color_set(I, fwd, rc, a < b ? a : b, kmask);
+        }
+        __syncwarp();
+        const bool found = cid != FG_NOT_FOUND;
+        const uint32_t found_mask = __ballot_sync(FG_FULL, found);
+        R.npos += __popc(found_mask);
+        if (found_mask) {
+            const uint32_t grp = __match_any_sync(FG_FULL, cid);
+            const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
+            const uint32_t gcnt = __popc(grp);
+            uint32_t leaders = __ballot_sync(FG_FULL, leader);
+            while (leaders) {
+                const int src = __ffs(int(leaders)) - 1;
+                leaders &= leaders - 1;
+                const uint32_t kk = __shfl_sync(FG_FULL, cid, src);
+                const uint32_t cc = __shfl_sync(FG_FULL, gcnt, src);
+                const uint32_t hit = __ballot_sync(FG_FULL, R.cid == kk);
+                if (hit) {
+                    if (R.cid == kk) R.cnt += cc;
+                } else if (R.n < FG_MAX_ENTRIES) {
+                    if (lane == R.n) {
+                        R.cid = kk;
+                        R.cnt = cc;
+                    }
+                    R.n += 1;
+                } else {
+                    R.overflow = true;
+                }
+            }
+        }
+        w0 = w1;
+        v0 = v1;
+    }
+    if (R.n > 1) { /* bitonic sort by color-set id; unused lanes hold FG_NOT_FOUND and sink to the end */
+#pragma unroll
+        for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                const uint32_t ok = __shfl_xor_sync(FG_FULL, R.cid, j);
+                const uint32_t oc = __shfl_xor_sync(FG_FULL, R.cnt, j);
+                const bool up = (lane & kk) == 0;
+                const bool lower = (lane & j) == 0;
+                const bool take = (up == lower) ? (ok < R.cid) : (ok > R.cid);
+                if (take) {
+                    R.cid = ok;
+                    R.cnt = oc;
+                }
+            }
+        }
+    }
+    return R;
+}
+
+/* ------------------------------------------------------------------ color-set decoding */
+
+/* 64 bits of an LSB-first bit stream starting at bit `pos` (bits/bit_vector.hpp:185-192) */
+FG_HD uint64_t bits_at(const uint64_t* __restrict__ words, uint64_t pos) {
+    const uint64_t* w = words + (pos >> 6);
+    const uint32_t sh = uint32_t(pos & 63);
+    const uint64_t a = FG_LDG(w);
+    if (sh == 0) return a;
+    return (a >> sh) | (FG_LDG(w + 1) << (64 - sh));
+}
+
+/* Elias delta (bits/integer_codes.hpp:54-71 over bit_vector::iterator, bit_vector.hpp:234-294):
+   gamma(b) then b payload bits; values here are < 2^32 so one 64-bit window always holds a code */
+FG_HD uint32_t read_delta(const uint64_t* __restrict__ words, uint64_t& pos) {
+    const uint64_t w = bits_at(words, pos);
+    const uint32_t u = fg_ffs64(w) - 1u;                /* unary: u zeros, then a one */
+    const uint32_t b = uint32_t(((w >> (u + 1)) & ((1ULL << u) - 1)) | (1ULL << u)) - 1u; /* gamma */
+    const uint64_t payload = (w >> (2 * u + 1)) & ((1ULL << b) - 1);
+    pos += 2 * u + 1 + b;
+    return uint32_t((payload | (1ULL << b)) - 1);
+}
+
+/* One hybrid color set (include/color_sets/hybrid.hpp:162-188 rewind, :37-95 layout) of a container
+   with at most 32 colors, as a bit mask. */
+FG_HD uint32_t hybrid_set_mask(const dev_index& I, uint32_t container, uint64_t local_id) {
+    const fgi_hybrid* h = I.hybrids + container;
+    const uint32_t C = FG_LDG(&h->num_colors);
+    const uint32_t cmask = C >= 32 ? ~0u : ((1u << C) - 1u);
+    const uint64_t* words = I.color_words + FG_LDG(&h->word_base);
+    uint64_t pos = FG_LDG(I.set_bit_off + FG_LDG(&h->set_off_base) + local_id);
+    const uint32_t size = read_delta(words, pos);
+    if (size >= FG_LDG(&h->sparse_thr) && size < FG_LDG(&h->very_dense_thr)) { /* raw bitmap, unaligned */
+        return uint32_t(bits_at(words, pos)) & cmask;
+    }
+    const bool complement = size >= FG_LDG(&h->very_dense_thr);
+    const uint32_t n = complement ? C - size : size;
+    uint32_t mask = 0, v = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t d = read_delta(words, pos);
+        v = i ? v + d + 1 : d;
+        mask |= 1u << (v & 31);
+    }
+    return complement ? (~mask & cmask) : mask;
+}
+
+/* color set `cid` of the index as a mask (num_colors <= 32). Meta (include/color_sets/meta.hpp:93-236):
+   the set is the concatenation of its partial sets, each shifted by its partition's min_color. */
+FG_HD uint32_t color_set_mask(const dev_index& I, uint32_t cid) {
+    if (I.type == 0) return hybrid_set_mask(I, 0, cid);
+    const uint64_t b = FG_LDG(I.meta_off + cid);
+    const uint32_t n = FG_LDG(I.meta_vals + b);
+    uint32_t mask = 0, p = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t mc = FG_LDG(I.meta_vals + b + 1 + i);
+        while (p + 1 < I.num_partitions && mc >= FG_LDG(I.part_sets_before + p + 1)) ++p; /* meta.hpp:227-235 */
+        mask |= hybrid_set_mask(I, p, mc - FG_LDG(I.part_sets_before + p)) << FG_LDG(I.part_min_color + p);
+    }
+    return mask;
+}
+
+}  // namespace fgb
+#endif

@@ -1,0 +1,122 @@
+/*
+ * fulgor_gpu.h -- C ABI of libfulgor_gpu.so: the B200 (sm_100a) implementation of Fulgor's
+ * pseudoalignment hot path, as a drop-in for the three `index<ColorSets>` member functions the
+ * reference's `pseudoalign` tool calls (reference include/index.hpp:39-46):
+ *
+ *     fetch_color_set_ids            src/ps_full_intersection.cpp:335-374   (called src/ps_utils.cpp:278)
+ *     pseudoalign_full_intersection  src/ps_full_intersection.cpp:377-400   (called tools/pseudoalign.cpp:29)
+ *     pseudoalign_threshold_union    src/ps_threshold_union.cpp:321-402     (called tools/pseudoalign.cpp:32)
+ *
+ * The reference processes one read per call; a GPU needs batches, so the boundary sits one level
+ * up, at the body of `pseudoalign_worker` (tools/pseudoalign.cpp:22-52): a chunk of reads in,
+ * per-read color lists out, in CSR form.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary; no torch / C++ types in signatures.
+ *   - return 0 on success, a negative errno-style code otherwise (FULGOR_GPU_E*); the message is
+ *     available from fulgor_gpu_last_error() on the calling thread.
+ *   - the caller owns every buffer. Host buffers may be pageable; pinned memory
+ *     (fulgor_gpu_host_alloc) is recommended and is what the end-to-end numbers are measured with.
+ *   - results of read i are values[off[i] .. off[i+1]), ascending: exactly the vector the reference
+ *     hands to formatter.format(query_id, colors) (src/ps_utils.cpp:55,127,168).
+ *   - when `cap` is too small the call returns FULGOR_GPU_E2BIG and off[n_reads] holds the required
+ *     capacity (offsets are complete, values are not), so the caller can retry.
+ *   - one in-flight call per handle; a handle is bound to one CUDA device.
+ *   - there is NO CPU fallback: every entry point that computes fails with FULGOR_GPU_ENODEV when
+ *     no CUDA device is usable.
+ */
+#ifndef FULGOR_GPU_H
+#define FULGOR_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FULGOR_GPU_EIO (-5)      /* CUDA failure, unreadable file */
+#define FULGOR_GPU_E2BIG (-7)    /* output capacity too small; off[n] = required */
+#define FULGOR_GPU_ENOMEM (-12)
+#define FULGOR_GPU_ENODEV (-19)  /* no usable CUDA device */
+#define FULGOR_GPU_EINVAL (-22)
+
+#define FULGOR_GPU_FULL_INTERSECTION 0 /* reference: pseudoalignment_algorithm::FULL_INTERSECTION */
+#define FULGOR_GPU_THRESHOLD_UNION 1   /* reference: pseudoalignment_algorithm::THRESHOLD_UNION */
+
+typedef struct fulgor_gpu_index fulgor_gpu_index; /* opaque: device image + per-call scratch */
+
+/* what index<ColorSets>::{k, num_colors, num_unitigs, num_color_sets} and sshash::dictionary::{m, size}
+   report (include/index.hpp:56-66) */
+typedef struct fulgor_gpu_info {
+    uint32_t k, m;
+    uint64_t num_kmers, num_unitigs, num_color_sets;
+    uint32_t num_colors;
+    uint32_t type;        /* 0 = hybrid (.fur), 1 = meta (.mfur) */
+    uint64_t image_bytes; /* size of the flattened device image */
+    int32_t device;       /* CUDA device ordinal the handle is bound to; -1 for a host-only image */
+    uint32_t pad;
+} fulgor_gpu_info;
+
+/* ---- index image: host side, no GPU needed -------------------------------------------------- */
+
+/* Replaces essentials::load(index, path) (reference tools/pseudoalign.cpp:340): parses a
+   reference-built .fur / .mfur (type by file suffix, tools/util.cpp:5-19) and flattens it into one
+   position-independent byte image. *image is malloc'ed by the library; release it with
+   fulgor_gpu_image_free. Load errors mirror the reference's std::runtime_error texts. */
+int fulgor_gpu_image_build(const char* index_path, uint8_t** image, uint64_t* image_bytes);
+void fulgor_gpu_image_free(uint8_t* image);
+/* header fields of an image (host pointer) */
+int fulgor_gpu_image_info(const uint8_t* image, uint64_t image_bytes, fulgor_gpu_info* out);
+
+/* ---- handles ----------------------------------------------------------------------------- */
+
+/* build the image from the file and upload it to CUDA device `device` */
+int fulgor_gpu_index_open(const char* index_path, int device, fulgor_gpu_index** out);
+/* upload a host image (e.g. one received from another process) to `device` */
+int fulgor_gpu_index_open_image(const uint8_t* image, uint64_t image_bytes, int device, fulgor_gpu_index** out);
+/* adopt an image that is ALREADY in device memory of `device` (e.g. the receive buffer of an NCCL
+   broadcast: multi-GPU replication needs one broadcast of the bytes and no other collective). The
+   memory stays owned by the caller and must outlive the handle. */
+int fulgor_gpu_index_adopt_device_image(const void* device_image, uint64_t image_bytes, int device, fulgor_gpu_index** out);
+void fulgor_gpu_index_close(fulgor_gpu_index*);
+int fulgor_gpu_index_info(const fulgor_gpu_index*, fulgor_gpu_info* out);
+
+/* ---- the hot path, host buffers in / host buffers out (H2D and D2H inside the call) -------- */
+
+/* Stage 1. Replaces index::fetch_color_set_ids for a batch: per read, the ascending distinct
+   color-set ids of its positive k-mers; num_positive[i] (nullable) = number of positive k-mers
+   (what pseudoalign_threshold_union counts, src/ps_threshold_union.cpp:327-347).
+   bases: concatenated read characters; read i = bases[read_off[i] .. read_off[i+1]). */
+int fulgor_gpu_fetch_color_set_ids(fulgor_gpu_index*, const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                                   uint64_t* cid_off /* n_reads+1 */, uint32_t* cids, uint64_t cids_cap,
+                                   uint32_t* num_positive /* n_reads, nullable */);
+
+/* Whole path. algo = FULGOR_GPU_FULL_INTERSECTION: fetch_color_set_ids + pseudoalign_full_intersection;
+   algo = FULGOR_GPU_THRESHOLD_UNION: pseudoalign_threshold_union(sequence, colors, threshold), threshold in (0,1]. */
+int fulgor_gpu_pseudoalign(fulgor_gpu_index*, int algo, double threshold,
+                           const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                           uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
+
+/* ---- the same path on DEVICE-resident inputs (kernel-only timing, pipelines that keep reads on
+        the GPU). All pointers are device pointers on the handle's device; offsets are CSR like above.
+        *total_out (host) receives off[n_reads]. Runs on the handle's stream and synchronises it. */
+int fulgor_gpu_pseudoalign_device(fulgor_gpu_index*, int algo, double threshold,
+                                  const char* d_bases, const uint64_t* d_read_off, uint32_t n_reads, uint64_t read_off_base,
+                                  uint64_t* d_color_off, uint32_t* d_colors, uint64_t colors_cap, uint64_t* total_out);
+
+/* device time (ms, CUDA events on the handle's stream) of the kernels of the last *_device call:
+   [0] k-mer lookup (+ fused small-color-count intersect/union), [1] color-set kernel (0 when fused),
+   [2] offsets scan + emit. Returns the number of kernel launches of that call. */
+int fulgor_gpu_last_kernel_times(const fulgor_gpu_index*, float ms[3]);
+
+/* ---- utilities ----------------------------------------------------------------------------- */
+int fulgor_gpu_device_count(void);
+void* fulgor_gpu_host_alloc(uint64_t bytes); /* pinned host memory (cudaHostAlloc); NULL on failure */
+void fulgor_gpu_host_free(void*);
+const char* fulgor_gpu_last_error(void);     /* thread-local */
+const char* fulgor_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

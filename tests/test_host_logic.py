@@ -1,0 +1,139 @@
+"""CPU tier: the index loader / flattener (host C++ inside libfulgor_gpu.so) and the per-lane device arithmetic
+compiled for the host (tests/host_emul.cu), both against the oracle; and the C ABI surface."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _checkers as ck
+
+ROOT = ck.ROOT
+EMUL_SO = os.path.join(ROOT, "build", "libfg_host_emul.so")
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur"]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul.cu")
+    deps = [src, os.path.join(ROOT, "fulgor_b200", "csrc", "kernels.cuh"), os.path.join(ROOT, "fulgor_b200", "csrc", "image.h")]
+    if not os.path.exists(EMUL_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_SO) for d in deps):
+        os.makedirs(os.path.dirname(EMUL_SO), exist_ok=True)
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-Xcompiler", "-fPIC,-w", "-shared", "-o", EMUL_SO, src])
+    E = C.CDLL(EMUL_SO)
+    E.emul_lookup_read.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p]
+    E.emul_color_set_mask.restype = C.c_uint32
+    E.emul_color_set_mask.argtypes = [C.c_void_p, C.c_uint32]
+    return E
+
+
+@pytest.fixture(scope="module", params=INDEXES)
+def loaded(request, built_lib):
+    import fulgor_b200 as fg
+
+    path = ck.index_path(request.param)
+    img = fg.build_image(path)
+    o = ck.Oracle(path)
+    yield fg, img, o
+    o.close()
+
+
+def test_image_header_matches_index(loaded):
+    fg, img, o = loaded
+    i = fg.image_info(img)
+    assert (i.k, i.m, i.num_kmers, i.num_unitigs, i.num_colors, i.num_color_sets, i.type) == (
+        o.k, o.m, o.num_kmers, o.num_unitigs, o.num_colors, o.num_color_sets, o.type)
+    assert i.image_bytes == img.size and i.device == -1
+    assert img.size % 256 == 0
+
+
+def test_image_build_is_deterministic(loaded):
+    fg, img, o = loaded
+    path = ck.index_path("salmonella_10.fur" if o.type == 0 else "salmonella_10.mfur")
+    assert np.array_equal(fg.build_image(path), img)
+
+
+def test_every_color_set_decodes_like_the_oracle(loaded, emul):
+    fg, img, o = loaded
+    for cid in range(o.num_color_sets):
+        mask = emul.emul_color_set_mask(img.ctypes.data, cid)
+        exp = 0
+        for c in o.color_set(cid):
+            exp |= 1 << int(c)
+        assert mask == exp, cid
+
+
+def test_per_kmer_lookup_like_the_oracle(loaded, emul):
+    """every k-mer looked up independently (what one GPU lane does) == the reference's streaming answer"""
+    fg, img, o = loaded
+    bases, off = ck.gen_reads(1500, 75, 300, seed=7)
+    for i in range(1500):
+        seq = bases[int(off[i]):int(off[i + 1])].tobytes()
+        if i % 50 == 0:
+            seq = seq[:40] + b"N" + seq[41:]
+        if i % 50 == 1:
+            seq = seq.lower()
+        contigs = o.lookup_read(seq)
+        exp = np.array([0xFFFFFFFF if c == 0xFFFFFFFFFFFFFFFF else o.u2c(int(c)) for c in contigs], dtype=np.uint32)
+        got = np.full(len(exp), 0xFFFFFFFF, dtype=np.uint32)
+        emul.emul_lookup_read(img.ctypes.data, seq, len(seq), got.ctypes.data)
+        assert np.array_equal(got, exp), i
+
+
+def test_loader_rejects_bad_input(built_lib, tmp_path):
+    import fulgor_b200 as fg
+
+    with pytest.raises(fg.FulgorGpuError) as e:
+        fg.build_image(str(tmp_path / "missing.fur"))
+    assert "opening" in str(e.value)
+    with pytest.raises(fg.FulgorGpuError):
+        fg.build_image(str(tmp_path / "index.txt"))  # wrong suffix (reference: "Wrong index filename supplied.")
+    raw = open(ck.index_path("salmonella_10.fur"), "rb").read()
+    trunc = tmp_path / "trunc.fur"
+    trunc.write_bytes(raw[: len(raw) // 2])
+    with pytest.raises(fg.FulgorGpuError):
+        fg.build_image(str(trunc))
+    badver = tmp_path / "badver.fur"
+    badver.write_bytes(b"\x03" + raw[1:])
+    with pytest.raises(fg.FulgorGpuError) as e:
+        fg.build_image(str(badver))
+    assert "version mismatch" in str(e.value)
+    wrong = tmp_path / "wrong.mfur"  # a hybrid file under the meta suffix must not load silently
+    wrong.write_bytes(raw)
+    with pytest.raises(fg.FulgorGpuError):
+        fg.build_image(str(wrong))
+
+
+def test_c_abi_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "fulgor_gpu.h")).read()
+    names = sorted(set(re.findall(r"\b(fulgor_gpu_[a-z_]+)\s*\(", header)))
+    assert len(names) >= 15
+    L = C.CDLL(built_lib)
+    for n in names:
+        assert hasattr(L, n), n
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built_lib], text=True)
+    exported = set(re.findall(r" T (fulgor_gpu_[a-z_]+)", out))
+    assert set(names) <= exported
+
+
+def test_no_cpu_fallback_without_a_gpu(built_lib):
+    """on a box without a GPU the compute entry points must fail loudly (ENODEV), never compute on the CPU"""
+    import fulgor_b200 as fg
+
+    if fg.lib().fulgor_gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fg.FulgorGpuError) as e:
+        fg.Index.open(ck.index_path("salmonella_10.fur"), 0)
+    assert e.value.code == fg.index.ENODEV
+
+
+def test_product_does_not_reference_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py may touch oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fulgor_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "fulgor_oracle" not in text and "oracle/" not in text and "_checkers" not in text, os.path.join(dirpath, f)

@@ -1,0 +1,77 @@
+"""Pins the plain-C oracle (oracle/fulgor_oracle.c) against the UNMODIFIED reference compiled from /root/reference
+(oracle/_ref/libfulgor_ref.so, built by `make -C oracle ref`). Skipped where that library was not built."""
+import numpy as np
+import pytest
+
+import _checkers as ck
+
+pytestmark = pytest.mark.skipif(not ck.reference_available(), reason="oracle/_ref/libfulgor_ref.so not built (needs /root/reference)")
+
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur"]
+
+
+@pytest.fixture(scope="module", params=INDEXES)
+def pair(request):
+    path = ck.index_path(request.param)
+    o, r = ck.Oracle(path), ck.Reference(path)
+    yield o, r
+    o.close()
+    r.close()
+
+
+def _same(a, b):
+    return np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_info(pair):
+    o, r = pair
+    assert (o.k, o.m, o.num_kmers, o.num_unitigs, o.num_colors, o.num_color_sets, o.type) == (
+        r.k, r.m, r.num_kmers, r.num_unitigs, r.num_colors, r.num_color_sets, r.type)
+
+
+def test_every_color_set(pair):
+    o, r = pair
+    for i in range(o.num_color_sets):
+        assert np.array_equal(o.color_set(i), r.color_set(i)), i
+
+
+def test_u2c_sample(pair):
+    o, r = pair
+    rng = np.random.default_rng(1)
+    for u in list(rng.integers(0, o.num_unitigs, 2000)) + [0, o.num_unitigs - 1]:
+        assert o.u2c(int(u)) == r.u2c(int(u))
+
+
+def test_streaming_lookup_per_kmer(pair):
+    o, r = pair
+    bases, off = ck.gen_reads(400, 75, 300, seed=11)
+    for i in range(400):
+        seq = bases[int(off[i]):int(off[i + 1])].tobytes()
+        if i % 7 == 0:
+            seq = seq[:50] + b"N" + seq[51:]
+        assert np.array_equal(o.lookup_read(seq), r.lookup_read(seq)), i
+
+
+@pytest.mark.parametrize("lens", [(150, 150), (75, 300)])
+def test_fetch_color_set_ids(pair, lens):
+    o, r = pair
+    reads = ck.gen_reads(6000, lens[0], lens[1], seed=42)
+    assert _same(o.fetch_color_set_ids(reads), r.fetch_color_set_ids(reads, threads=4))
+
+
+@pytest.mark.parametrize("algo,thr", [(0, 1.0), (1, 0.8), (1, 1.0), (1, 0.05)])
+def test_pseudoalign(pair, algo, thr):
+    o, r = pair
+    reads = ck.gen_reads(6000, 75, 300, seed=1234)
+    assert _same(o.pseudoalign(reads, algo, thr), r.pseudoalign(reads, algo, thr, threads=4))
+
+
+def test_edge_reads(pair):
+    o, r = pair
+    g = ck.gen_reads(8, seed=99)
+    s = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(8)]
+    reads = ck.reads_from_list([b"", b"A", s[0][:30], s[0][:31], s[1].lower(), b"N" * 150, s[2][:75] + b"N" + s[2][76:], b"A" * 200,
+                                s[3] + s[4], s[5][:149] + b"X"])
+    for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.001)):
+        assert _same(o.pseudoalign(reads, algo, thr), r.pseudoalign(reads, algo, thr))
+    assert _same(o.fetch_color_set_ids(reads), r.fetch_color_set_ids(reads))
