@@ -14,7 +14,8 @@
  * (not necessarily maximal) monochromatic unitigs: exactly what `load` requires. Color sets are
  * numbered in order of first appearance after sorting by bitmask; unitigs are sorted by color set.
  *
- *   mkdump [-k 31] BASE genome1.fa[.gz] genome2.fa[.gz] ...          (up to 64 genomes)
+ *   mkdump [-k 31] BASE genome1.fa[.gz] genome2.fa[.gz] ...          (up to 65535 genomes)
+ *   mkdump [-k 31] BASE @list.txt                                    (one path per line)
  */
 #include <zlib.h>
 #include <algorithm>
@@ -23,7 +24,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <unordered_map>
+#include <fstream>
+#include <map>
 #include <vector>
 
 struct contig_t {
@@ -97,54 +99,70 @@ int main(int argc, char** argv) {
         return 1;
     }
     std::string base = argv[a++];
-    const int num_genomes = argc - a;
-    if (num_genomes > 64 || k > 31 || k < 3) {
-        fprintf(stderr, "mkdump: at most 64 genomes, 3 <= k <= 31\n");
+    std::vector<std::string> filenames;
+    for (int i = a; i < argc; ++i) {
+        if (argv[i][0] == '@') {
+            std::ifstream in(argv[i] + 1);
+            std::string line;
+            while (std::getline(in, line))
+                if (!line.empty()) filenames.push_back(line);
+        } else {
+            filenames.push_back(argv[i]);
+        }
+    }
+    const int num_genomes = (int)filenames.size();
+    if (num_genomes > 65535 || num_genomes < 1 || k > 31 || k < 3) {
+        fprintf(stderr, "mkdump: 1..65535 genomes, 3 <= k <= 31\n");
         return 1;
     }
     std::vector<contig_t> contigs;
-    std::vector<std::string> filenames;
     for (int g = 0; g < num_genomes; ++g) {
-        if (!read_fasta(argv[a + g], g, contigs)) {
-            fprintf(stderr, "mkdump: cannot open %s\n", argv[a + g]);
+        if (!read_fasta(filenames[g].c_str(), g, contigs)) {
+            fprintf(stderr, "mkdump: cannot open %s\n", filenames[g].c_str());
             return 1;
         }
-        filenames.push_back(argv[a + g]);
     }
     uint64_t total_bases = 0;
     for (auto const& c : contigs) total_bases += c.seq.size();
     fprintf(stderr, "mkdump: %d genomes, %zu contigs, %lu bases\n", num_genomes, contigs.size(),
             (unsigned long)total_bases);
 
-    /* pass 1: canonical k-mer -> color bitmask */
-    std::vector<std::pair<uint64_t, uint64_t>> occ;
+    /* pass 1: canonical k-mer -> ascending list of genomes, interned as a color-set id */
+    std::vector<std::pair<uint64_t, uint16_t>> occ;
     occ.reserve(total_bases);
     for (auto const& c : contigs) {
         kmer_walker w(k);
         for (char ch : c.seq)
-            if (w.push(ch)) occ.push_back({w.canon(), 1ULL << c.genome});
+            if (w.push(ch)) occ.push_back({w.canon(), (uint16_t)c.genome});
     }
     std::sort(occ.begin(), occ.end());
-    std::vector<uint64_t> kmers, masks;
+    std::vector<uint64_t> kmers;
+    std::vector<uint32_t> masks; /* provisional color-set id per k-mer */
+    std::map<std::vector<uint16_t>, uint32_t> interned;
     for (size_t i = 0; i < occ.size();) {
         size_t j = i;
-        uint64_t m = 0;
-        while (j < occ.size() && occ[j].first == occ[i].first) m |= occ[j++].second;
+        std::vector<uint16_t> cs;
+        while (j < occ.size() && occ[j].first == occ[i].first) {
+            if (cs.empty() || cs.back() != occ[j].second) cs.push_back(occ[j].second);
+            ++j;
+        }
         kmers.push_back(occ[i].first);
-        masks.push_back(m);
+        auto it = interned.emplace(std::move(cs), (uint32_t)interned.size()).first;
+        masks.push_back(it->second);
         i = j;
     }
-    std::vector<std::pair<uint64_t, uint64_t>>().swap(occ);
+    std::vector<std::pair<uint64_t, uint16_t>>().swap(occ);
     const uint64_t num_kmers = kmers.size();
     fprintf(stderr, "mkdump: %lu distinct canonical %lu-mers\n", (unsigned long)num_kmers,
             (unsigned long)k);
 
-    /* color sets = distinct masks, numbered by ascending (popcount-agnostic) mask value */
-    std::vector<uint64_t> distinct(masks);
-    std::sort(distinct.begin(), distinct.end());
-    distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
-    std::unordered_map<uint64_t, uint32_t> mask_to_id;
-    for (size_t i = 0; i < distinct.size(); ++i) mask_to_id[distinct[i]] = (uint32_t)i;
+    /* final color-set ids: lexicographic order of the genome lists (deterministic) */
+    std::vector<std::vector<uint16_t> const*> distinct;
+    std::vector<uint32_t> mask_to_id(interned.size());
+    for (auto const& kv : interned) {
+        mask_to_id[kv.second] = (uint32_t)distinct.size();
+        distinct.push_back(&kv.first);
+    }
 
     /* pass 2: cut genomes into monochromatic paths using every k-mer once */
     std::vector<uint8_t> visited(num_kmers, 0);
@@ -155,7 +173,7 @@ int main(int argc, char** argv) {
     for (auto const& c : contigs) {
         kmer_walker w(k);
         std::string cur;
-        uint64_t cur_mask = 0;
+        uint32_t cur_mask = 0;
         auto close = [&]() {
             if (!cur.empty()) unitigs.push_back({mask_to_id[cur_mask], cur});
             cur.clear();
@@ -204,10 +222,9 @@ int main(int argc, char** argv) {
     }
     fclose(f);
     f = open(".color_sets.txt");
-    for (uint64_t m : distinct) {
-        fprintf(f, "size=%d", __builtin_popcountll(m));
-        for (int g = 0; g < num_genomes; ++g)
-            if (m >> g & 1) fprintf(f, " %d", g);
+    for (auto const* cs : distinct) {
+        fprintf(f, "size=%zu", cs->size());
+        for (uint16_t g : *cs) fprintf(f, " %u", (unsigned)g);
         fprintf(f, "\n");
     }
     fclose(f);
