@@ -30,41 +30,57 @@ namespace fgb {
 #define FG_BLOCK (FG_WARPS_PER_BLOCK * 32)
 #define FG_STAGE_STRIDE FG_MAX_ENTRIES
 
-/* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask.
+/* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask,
+   accumulated tile by tile (no per-read table: AND is idempotent and scores are sums over k-mers).
    Full intersection (src/ps_full_intersection.cpp:377-400 -> intersect :33-127): AND of the hit sets.
    Threshold union (src/ps_threshold_union.cpp:389 + merge :17-40 / merge_meta :43-120): color c is
-   reported iff sum of multiplicities of the hit sets containing c >= uint64(double(npos) * threshold). */
+   reported iff sum over positive k-mers of [c in set(k-mer)] >= uint64(double(npos) * threshold). */
 template <int W>
 __global__ void __launch_bounds__(FG_BLOCK) k_pseudoalign_small(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
                                                                const uint64_t* __restrict__ read_off, uint64_t read_off_base,
                                                                uint32_t n_reads, int algo, double threshold,
-                                                               uint32_t* __restrict__ masks, uint32_t* __restrict__ overflow_count) {
+                                                               uint32_t* __restrict__ masks) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        const read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane);
-        if (R.overflow) {
-            if (lane == 0) {
-                atomicAdd(overflow_count, 1u);
-                masks[r] = 0;
-            }
-            continue;
-        }
-        uint32_t res = 0;
-        if (R.n) {
-            const uint32_t my = lane < R.n ? color_set_mask(I, R.cid) : 0u;
+        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane);
+        uint32_t acc = ~0u, score = 0, npos = 0;
+        uint32_t cache_cid = FG_NOT_FOUND, cache_mask = 0;
+        while (!tiles.done()) {
+            const uint32_t cid = tiles.next();
+            const bool found = cid != FG_NOT_FOUND;
+            const uint32_t found_mask = __ballot_sync(FG_FULL, found);
+            if (!found_mask) continue;
+            npos += __popc(found_mask);
+            /* decode; the set of the previous tile's first hit is cached (reads mostly stay inside one color set) */
+            uint32_t mask = cache_mask;
+            if (found && cid != cache_cid) mask = color_set_mask(I, cid);
             __syncwarp();
+            const int first = __ffs(int(found_mask)) - 1;
+            cache_cid = __shfl_sync(FG_FULL, cid, first);
+            cache_mask = __shfl_sync(FG_FULL, mask, first);
             if (algo == FULGOR_GPU_FULL_INTERSECTION) {
-                res = __reduce_and_sync(FG_FULL, lane < R.n ? my : ~0u);
+                acc &= __reduce_and_sync(FG_FULL, found ? mask : ~0u);
             } else {
-                uint32_t score = 0;
-                for (uint32_t j = 0; j < R.n; ++j) {
-                    const uint32_t mj = __shfl_sync(FG_FULL, my, j);
-                    const uint32_t wj = __shfl_sync(FG_FULL, R.cnt, j);
+                const uint32_t grp = __match_any_sync(FG_FULL, cid);
+                const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
+                uint32_t leaders = __ballot_sync(FG_FULL, leader);
+                while (leaders) {
+                    const int src = __ffs(int(leaders)) - 1;
+                    leaders &= leaders - 1;
+                    const uint32_t mj = __shfl_sync(FG_FULL, mask, src);
+                    const uint32_t wj = __shfl_sync(FG_FULL, uint32_t(__popc(grp)), src);
                     score += ((mj >> lane) & 1u) ? wj : 0u;
                 }
-                const uint64_t min_score = uint64_t(double(R.npos) * threshold);
+            }
+        }
+        uint32_t res = 0;
+        if (npos) {
+            if (algo == FULGOR_GPU_FULL_INTERSECTION) {
+                res = acc;
+            } else {
+                const uint64_t min_score = uint64_t(double(npos) * threshold);
                 res = __ballot_sync(FG_FULL, lane < I.num_colors && uint64_t(score) >= min_score);
             }
         }
@@ -72,28 +88,133 @@ __global__ void __launch_bounds__(FG_BLOCK) k_pseudoalign_small(const __grid_con
     }
 }
 
-/* K1 alone: per read, ascending distinct color-set ids (+ multiplicities) into a fixed-stride stage */
+#define FG_SCRATCH_ENTRIES 256 /* per-warp shared-memory list for reads with more than 32 distinct color sets */
+
+/* where the sorted {color-set id, multiplicity} list of read r lives: counts[r] <= 32 -> stage[r*32 ..];
+   otherwise in the pool at the 64-bit entry offset stored in stage[r*32] */
+__device__ __forceinline__ const uint2* entries_of(uint32_t r, uint32_t n, const uint2* __restrict__ stage, const uint2* __restrict__ pool) {
+    const uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
+    if (n <= FG_STAGE_STRIDE) return s;
+    const uint2 o = s[0];
+    return pool + (uint64_t(o.x) | (uint64_t(o.y) << 32));
+}
+
+/* K1 alone: per read, ascending distinct color-set ids with multiplicities */
 template <int W>
 __global__ void __launch_bounds__(FG_BLOCK) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
                                                               const uint64_t* __restrict__ read_off, uint64_t read_off_base,
-                                                              uint32_t n_reads, uint32_t* __restrict__ stage_cid,
-                                                              uint32_t* __restrict__ stage_cnt /* nullable */,
-                                                              uint32_t* __restrict__ counts, uint32_t* __restrict__ num_positive /* nullable */,
-                                                              uint32_t* __restrict__ overflow_count) {
-    const uint32_t lane = threadIdx.x & 31;
+                                                              uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
+                                                              uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool) {
+    __shared__ uint2 scratch[FG_WARPS_PER_BLOCK][FG_SCRATCH_ENTRIES];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
-    for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
+    for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        const read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane);
-        if (R.overflow && lane == 0) atomicAdd(overflow_count, 1u);
-        if (lane < R.n) {
-            stage_cid[uint64_t(r) * FG_STAGE_STRIDE + lane] = R.cid;
-            if (stage_cnt) stage_cnt[uint64_t(r) * FG_STAGE_STRIDE + lane] = R.cnt;
+        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, scratch[wib], FG_SCRATCH_ENTRIES, pool);
+        uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
+        if (R.tab == nullptr) {
+            if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);
+        } else if (!R.failed) {
+            unsigned long long off;
+            if (R.tab == scratch[wib]) { /* the list must outlive this warp's shared memory */
+                if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)R.n);
+                off = __shfl_sync(FG_FULL, off, 0);
+                if (off + R.n > pool.cap) {
+                    if (lane == 0) *pool.exhausted = 1;
+                    R.failed = true;
+                } else {
+                    for (uint32_t i = lane; i < R.n; i += 32) pool.base[off + i] = R.tab[i];
+                }
+            } else {
+                off = (unsigned long long)(R.tab - pool.base);
+            }
+            if (lane == 0) s[0] = make_uint2(uint32_t(off), uint32_t(off >> 32));
         }
         if (lane == 0) {
-            counts[r] = R.overflow ? 0u : R.n;
+            counts[r] = R.failed ? 0u : R.n;
             if (num_positive) num_positive[r] = R.npos;
         }
+        __syncwarp();
+    }
+}
+
+/* K2 for indexes with more than 32 colors: one warp per read, per-color int32 scores in shared memory.
+   Full intersection = colors present in all n hit sets (weight 1 each, min_score = n) -- the same set as
+   the reference's intersect / meta_intersect (src/ps_full_intersection.cpp:33-127, 243-332);
+   threshold union = colors with score >= uint64(double(npos) * threshold) (src/ps_threshold_union.cpp:389,
+   merge :17-40, merge_meta :43-120). The result is a bitmap of num_colors bits per read + its popcount. */
+__global__ void __launch_bounds__(FG_BLOCK) k_color_sets_general(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
+                                                                const uint2* __restrict__ stage, const uint2* __restrict__ pool,
+                                                                const uint32_t* __restrict__ num_positive, uint32_t n_reads, int algo,
+                                                                double threshold, uint32_t words_per_read, uint32_t smem_ints_per_warp,
+                                                                uint32_t* __restrict__ res_bits, uint32_t* __restrict__ res_counts) {
+    extern __shared__ int smem[];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    int* scores = smem + size_t(wib) * smem_ints_per_warp;
+    int* base = scores + I.num_colors;
+    const uint32_t C = I.num_colors, P = I.num_partitions;
+    const uint32_t warps = gridDim.x * wpb;
+    for (uint32_t r = blockIdx.x * wpb + wib; r < n_reads; r += warps) {
+        const uint32_t n = __ldg(counts + r);
+        uint32_t* out = res_bits + uint64_t(r) * words_per_read;
+        if (n == 0) { /* no positive k-mer: empty result (src/ps_full_intersection.cpp:385, ps_threshold_union.cpp:355) */
+            for (uint32_t w = lane; w < words_per_read; w += 32) out[w] = 0;
+            if (lane == 0) res_counts[r] = 0;
+            continue;
+        }
+        const uint2* ents = entries_of(r, n, stage, pool);
+        for (uint32_t c = lane; c < C + P; c += 32) scores[c] = 0;
+        __syncwarp();
+        const bool fi = algo == FULGOR_GPU_FULL_INTERSECTION;
+        const uint64_t min_score = fi ? uint64_t(n) : uint64_t(double(__ldg(num_positive + r)) * threshold);
+        if (I.type == 0) {
+            for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                set_item it;
+                it.enc = FG_ENC_NONE;
+                if (j < n) {
+                    const uint2 e = ents[j];
+                    it = open_set(I, 0, e.x, 0, fi ? 1u : e.y);
+                }
+                apply_sets(I, j < n, it, scores, base, lane);
+            }
+        } else { /* meta: a color set is the list of its partial sets (include/color_sets/meta.hpp:93-236) */
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e = ents[j];
+                const uint64_t b = __ldg(I.meta_off + e.x);
+                const uint32_t nm = __ldg(I.meta_vals + b);
+                for (uint32_t i0 = 0; i0 < nm; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    set_item it;
+                    it.enc = FG_ENC_NONE;
+                    if (i < nm) {
+                        const uint32_t mc = __ldg(I.meta_vals + b + 1 + i);
+                        uint32_t lo = 0, hi = P; /* largest p with sets_before[p] <= mc (meta.hpp:227-235) */
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (__ldg(I.part_sets_before + mid) <= mc) lo = mid; else hi = mid;
+                        }
+                        it = open_set(I, lo, mc - __ldg(I.part_sets_before + lo), __ldg(I.part_min_color + lo), fi ? 1u : e.y);
+                    }
+                    apply_sets(I, i < nm, it, scores, base, lane);
+                }
+            }
+        }
+        uint32_t total = 0, p = 0;
+        for (uint32_t w = 0; w < words_per_read; ++w) {
+            const uint32_t c = w * 32 + lane;
+            bool pass = false;
+            if (c < C) {
+                while (p + 1 < P && c >= __ldg(I.part_min_color + p + 1)) ++p;
+                const int sc = scores[c] + base[p];
+                pass = uint64_t(uint32_t(sc)) >= min_score;
+            }
+            const uint32_t word = __ballot_sync(FG_FULL, pass);
+            if (lane == 0) out[w] = word;
+            total += __popc(word);
+        }
+        if (lane == 0) res_counts[r] = total;
+        __syncwarp();
     }
 }
 
@@ -212,16 +333,39 @@ __global__ void __launch_bounds__(256) k_emit_masks(const uint32_t* __restrict__
     }
 }
 
-/* staged fixed-stride lists -> CSR */
-__global__ void __launch_bounds__(256) k_emit_stage(const uint32_t* __restrict__ stage, const uint32_t* __restrict__ counts,
-                                                   const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
-                                                   uint32_t* __restrict__ out, uint64_t out_cap) {
+/* per-read {color-set id, multiplicity} lists (stage or pool) -> CSR of color-set ids */
+__global__ void __launch_bounds__(256) k_emit_entries(const uint2* __restrict__ stage, const uint2* __restrict__ pool, const uint32_t* __restrict__ counts,
+                                                     const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
+                                                     uint32_t* __restrict__ out, uint64_t out_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
     const uint32_t c = __ldg(counts + r);
+    if (c == 0) return;
     const uint64_t o = __ldg(off + r) - chunk_info[0];
-    if (lane < c && o + lane < out_cap) out[o + lane] = __ldg(stage + uint64_t(r) * FG_STAGE_STRIDE + lane);
+    const uint2* e = entries_of(r, c, stage, pool);
+    for (uint32_t i = lane; i < c; i += 32)
+        if (o + i < out_cap) out[o + i] = e[i].x;
+}
+
+/* per-read color bitmaps -> ascending color lists at their CSR positions */
+__global__ void __launch_bounds__(256) k_emit_bits(const uint32_t* __restrict__ res_bits, uint32_t words_per_read, const uint32_t* __restrict__ counts,
+                                                  const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
+                                                  uint32_t* __restrict__ out, uint64_t out_cap) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    if (__ldg(counts + r) == 0) return;
+    uint64_t o = __ldg(off + r) - chunk_info[0];
+    const uint32_t* bits = res_bits + uint64_t(r) * words_per_read;
+    for (uint32_t w = 0; w < words_per_read; ++w) {
+        const uint32_t word = __ldg(bits + w);
+        if ((word >> lane) & 1u) {
+            const uint64_t at = o + __popc(word & ((1u << lane) - 1u));
+            if (at < out_cap) out[at] = w * 32 + lane;
+        }
+        o += __popc(word);
+    }
 }
 
 /* ================================================================== host side */
@@ -262,10 +406,11 @@ struct dev_buffer {
 struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
-    dev_buffer bases, read_off, per_read /* masks or counts */, stage_cid, stage_cnt, npos, tile_sums, tile_off, off, out;
-    uint64_t* chunk_info = nullptr;   /* device: {base, total} */
-    uint64_t* h_info = nullptr;       /* pinned host: {base, total, overflow_count} */
-    uint32_t* overflow = nullptr;     /* device counter */
+    dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out;
+    uint64_t* chunk_info = nullptr;        /* device: {base, total} */
+    uint64_t* h_info = nullptr;            /* pinned host: {base, total, pool exhausted} */
+    uint32_t* exhausted = nullptr;         /* device flag: the entry pool was too small */
+    unsigned long long* pool_used = nullptr; /* device: entries handed out */
     bool busy = false;
 };
 
@@ -282,6 +427,7 @@ struct fulgor_gpu_index {
     slot slots[2];
     uint64_t* d_carry = nullptr;
     int sm_count = 0;
+    uint64_t pool_per_read = 8; /* entry-pool size per read of a chunk; grows (x4) when a launch exhausts it */
     /* timing of the last *_device call */
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[3] = {0, 0, 0};
@@ -369,7 +515,8 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
             FG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             FG_CUDA(cudaEventCreateWithFlags(&s.info_ready, cudaEventDisableTiming));
             FG_CUDA(cudaMalloc(&s.chunk_info, 16));
-            FG_CUDA(cudaMalloc(&s.overflow, 4));
+            FG_CUDA(cudaMalloc(&s.exhausted, 4));
+            FG_CUDA(cudaMalloc(&s.pool_used, 8));
             FG_CUDA(cudaHostAlloc(&s.h_info, 32, cudaHostAllocDefault));
             std::memset(s.h_info, 0, 32);
         }
@@ -419,93 +566,151 @@ static int enqueue_scan(fulgor_gpu_index* x, slot& s, const uint32_t* d_counts, 
     return 3;
 }
 
-/* full path on device-resident chunk; writes CSR offsets to d_off (n+1) and colors to d_out (chunk-local) */
-static int enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_args& a, int algo, double threshold, uint64_t* d_off,
-                               uint32_t* d_out, uint64_t out_cap, cudaEvent_t after_k1, cudaEvent_t after_k2) {
-    int launches = 0;
-    if (x->H.num_colors > 32) throw std::runtime_error("indexes with more than 32 colors: color-set kernel not built yet");
-    s.per_read.reserve(size_t(a.n) * 4);
-    FG_CUDA(cudaMemsetAsync(s.overflow, 0, 4, s.stream));
-    const uint32_t grid = read_grid(x, a.n);
-    dispatch_window(x->H, [&](auto w) {
-        k_pseudoalign_small<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, algo,
-                                                                                   threshold, s.per_read.as<uint32_t>(), s.overflow);
-    });
-    ++launches;
-    if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
-    if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
-    launches += enqueue_scan<true>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
-    k_emit_masks<<<(a.n + 255) / 256, 256, 0, s.stream>>>(s.per_read.as<uint32_t>(), d_off, s.chunk_info, a.n, d_out, out_cap);
-    ++launches;
+/* how a chunk's per-read results become CSR values; kept so that the emit can be repeated into a larger buffer */
+struct emit_plan {
+    enum kind_t { MASKS, ENTRIES, BITS } kind = MASKS;
+    uint32_t n = 0, words_per_read = 0;
+};
+
+static void enqueue_emit(slot& s, const emit_plan& e, const uint64_t* d_off, uint32_t* d_out, uint64_t out_cap) {
+    if (e.n == 0) return;
+    switch (e.kind) {
+        case emit_plan::MASKS:
+            k_emit_masks<<<(e.n + 255) / 256, 256, 0, s.stream>>>(s.per_read.as<uint32_t>(), d_off, s.chunk_info, e.n, d_out, out_cap);
+            break;
+        case emit_plan::ENTRIES:
+            k_emit_entries<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.stage.as<uint2>(), s.pool.as<uint2>(), s.per_read.as<uint32_t>(),
+                                                                                          d_off, s.chunk_info, e.n, d_out, out_cap);
+            break;
+        case emit_plan::BITS:
+            k_emit_bits<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(),
+                                                                                       d_off, s.chunk_info, e.n, d_out, out_cap);
+            break;
+    }
     FG_CUDA(cudaGetLastError());
-    return launches;
 }
 
-static int enqueue_fetch(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool want_npos, uint64_t* d_off, uint32_t* d_out, uint64_t out_cap) {
-    int launches = 0;
+/* K1 alone into stage/pool + counts (+ npos) */
+static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool want_npos) {
     s.per_read.reserve(size_t(a.n) * 4);
-    s.stage_cid.reserve(size_t(a.n) * FG_STAGE_STRIDE * 4);
+    s.stage.reserve(size_t(a.n) * FG_STAGE_STRIDE * sizeof(uint2));
     if (want_npos) s.npos.reserve(size_t(a.n) * 4);
-    FG_CUDA(cudaMemsetAsync(s.overflow, 0, 4, s.stream));
+    const uint64_t pool_entries = std::max<uint64_t>(1u << 16, uint64_t(a.n) * x->pool_per_read);
+    s.pool.reserve(size_t(pool_entries) * sizeof(uint2));
+    FG_CUDA(cudaMemsetAsync(s.exhausted, 0, 4, s.stream));
+    FG_CUDA(cudaMemsetAsync(s.pool_used, 0, 8, s.stream));
+    entry_pool pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted};
     const uint32_t grid = read_grid(x, a.n);
     dispatch_window(x->H, [&](auto w) {
-        k_fetch_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n,
-                                                                                  s.stage_cid.as<uint32_t>(), nullptr, s.per_read.as<uint32_t>(),
-                                                                                  want_npos ? s.npos.as<uint32_t>() : nullptr, s.overflow);
+        k_fetch_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, s.stage.as<uint2>(),
+                                                                                  s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr, pool);
     });
-    ++launches;
-    launches += enqueue_scan<false>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
-    k_emit_stage<<<(uint64_t(a.n) * 32 + 255) / 256, 256, 0, s.stream>>>(s.stage_cid.as<uint32_t>(), s.per_read.as<uint32_t>(), d_off, s.chunk_info,
-                                                                       a.n, d_out, out_cap);
-    ++launches;
     FG_CUDA(cudaGetLastError());
-    return launches;
+    return 1;
+}
+
+/* whole path for a device-resident chunk, up to the CSR offsets (d_off, n+1 entries); returns how to emit the values */
+static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_args& a, int algo, double threshold, uint64_t* d_off,
+                                     cudaEvent_t after_k1, cudaEvent_t after_k2, int* launches) {
+    emit_plan e;
+    e.n = a.n;
+    FG_CUDA(cudaMemsetAsync(s.exhausted, 0, 4, s.stream));
+    if (x->H.num_colors <= 32) { /* fused: lookup + intersect/union, one 32-bit mask per read */
+        s.per_read.reserve(size_t(a.n) * 4);
+        const uint32_t grid = read_grid(x, a.n);
+        dispatch_window(x->H, [&](auto w) {
+            k_pseudoalign_small<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, algo, threshold,
+                                                                                       s.per_read.as<uint32_t>());
+        });
+        FG_CUDA(cudaGetLastError());
+        *launches += 1;
+        if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
+        if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
+        *launches += enqueue_scan<true>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
+        e.kind = emit_plan::MASKS;
+        return e;
+    }
+    *launches += enqueue_k1(x, s, a, true);
+    if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
+    const uint32_t C = x->H.num_colors, P = x->H.num_partitions;
+    const uint32_t ints = (C + P + 1) & ~1u;
+    if (size_t(ints) * 4 > 200 * 1024) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
+    uint32_t wpb = uint32_t(std::min<size_t>(FG_WARPS_PER_BLOCK, std::max<size_t>(1, (96 * 1024) / (size_t(ints) * 4))));
+    const size_t smem = size_t(wpb) * ints * 4;
+    FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
+    e.words_per_read = (C + 31) / 32;
+    s.res_bits.reserve(size_t(a.n) * e.words_per_read * 4);
+    s.res_counts.reserve(size_t(a.n) * 4);
+    const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
+    const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
+    k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
+                                                           a.n, algo, threshold, e.words_per_read, ints, s.res_bits.as<uint32_t>(),
+                                                           s.res_counts.as<uint32_t>());
+    FG_CUDA(cudaGetLastError());
+    *launches += 1;
+    if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
+    *launches += enqueue_scan<false>(x, s, s.res_counts.as<uint32_t>(), a.n, d_off);
+    e.kind = emit_plan::BITS;
+    return e;
+}
+
+static emit_plan enqueue_fetch(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool want_npos, uint64_t* d_off, int* launches) {
+    emit_plan e;
+    e.n = a.n;
+    e.kind = emit_plan::ENTRIES;
+    *launches += enqueue_k1(x, s, a, want_npos);
+    *launches += enqueue_scan<false>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
+    return e;
 }
 
 /* ---- the chunked host pipeline ---- */
 
 static const uint64_t CHUNK_MAX_READS = 1u << 20;
 static const uint64_t CHUNK_MAX_BASES = 256ull << 20;
+static const uint64_t CHUNK_MAX_RESULT_BITS_BYTES = 256ull << 20;
+static const int RC_RETRY_LARGER_POOL = 1;
 
 enum class op_kind { FETCH, PSEUDOALIGN };
 
-static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
-                          uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
-    FG_CUDA(cudaSetDevice(x->device));
-    out_off[0] = 0;
-    if (n_reads == 0) return 0;
-    for (uint32_t i = 0; i < n_reads; ++i) {
-        if (read_off[i + 1] < read_off[i]) throw std::invalid_argument("read_off must be non-decreasing");
-        if (read_off[i + 1] - read_off[i] >= (1ull << 31)) throw std::invalid_argument("reads of 2^31 characters or more are not supported");
-    }
+static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
+                               uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
     FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, x->slots[0].stream));
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
-    const uint32_t max_vals_per_read = op == op_kind::FETCH ? FG_MAX_ENTRIES : x->H.num_colors;
-    struct pending { uint32_t first, n; int slot; };
+    const bool small = x->H.num_colors <= 32;
+    uint64_t max_reads = CHUNK_MAX_READS;
+    if (op == op_kind::PSEUDOALIGN && !small)
+        max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (((x->H.num_colors + 31) / 32) * 4)));
+    struct pending { uint32_t first, n; int slot; emit_plan plan; };
     std::vector<pending> chunks;
     for (uint32_t first = 0; first < n_reads;) {
         uint32_t n = 1;
-        while (first + n < n_reads && n < CHUNK_MAX_READS && read_off[first + n + 1] - read_off[first] <= CHUNK_MAX_BASES) ++n;
-        chunks.push_back({first, n, int(chunks.size() & 1)});
+        while (first + n < n_reads && n < max_reads && read_off[first + n + 1] - read_off[first] <= CHUNK_MAX_BASES) ++n;
+        chunks.push_back({first, n, int(chunks.size() & 1), emit_plan()});
         first += n;
     }
-    bool too_big = false;
-    uint64_t overflow_reads = 0;
+    bool too_big = false, exhausted = false;
     cudaEvent_t prev_scanned = nullptr;
 
     auto finalize = [&](const pending& c) {
         slot& s = x->slots[c.slot];
         FG_CUDA(cudaEventSynchronize(s.info_ready));
         const uint64_t base = s.h_info[0], total = s.h_info[1];
-        overflow_reads += s.h_info[2];
+        if (uint32_t(s.h_info[2])) exhausted = true;
         if (base + total > cap) too_big = true;
-        if (!too_big && total) FG_CUDA(cudaMemcpyAsync(out_vals + base, s.out.p, total * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (!too_big && !exhausted && total) {
+            if (total * 4 > s.out.cap) { /* the first emit ran into the end of the buffer: grow and repeat it */
+                FG_CUDA(cudaStreamSynchronize(s.stream));
+                s.out.reserve(size_t(total) * 4);
+                enqueue_emit(s, c.plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
+            }
+            FG_CUDA(cudaMemcpyAsync(out_vals + base, s.out.p, total * 4, cudaMemcpyDeviceToHost, s.stream));
+        }
         FG_CUDA(cudaEventRecord(s.done, s.stream));
     };
 
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
-        const pending& c = chunks[ci];
+        pending& c = chunks[ci];
         slot& s = x->slots[c.slot];
         if (s.busy) FG_CUDA(cudaEventSynchronize(s.done));
         s.busy = true;
@@ -513,23 +718,26 @@ static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double thre
         s.bases.reserve(size_t(b1 - b0) + 64);
         s.read_off.reserve(size_t(c.n + 1) * 8);
         s.off.reserve(size_t(c.n + 1) * 8);
-        s.out.reserve(size_t(c.n) * max_vals_per_read * 4);
+        /* values buffer: exact upper bound when it is small, otherwise a guess that finalize() corrects */
+        const uint64_t per_read_guess = (op == op_kind::PSEUDOALIGN && small) ? x->H.num_colors : 64;
+        s.out.reserve(size_t(c.n) * per_read_guess * 4);
         if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
         FG_CUDA(cudaMemcpyAsync(s.read_off.p, read_off + c.first, size_t(c.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
         if (prev_scanned) FG_CUDA(cudaStreamWaitEvent(s.stream, prev_scanned, 0));
         chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, c.n};
-        const uint64_t out_cap = uint64_t(c.n) * max_vals_per_read;
+        int launches = 0;
         if (op == op_kind::FETCH) {
-            enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), s.out.as<uint32_t>(), out_cap);
+            c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), &launches);
         } else {
-            enqueue_pseudoalign(x, s, a, algo, threshold, s.off.as<uint64_t>(), s.out.as<uint32_t>(), out_cap, nullptr, nullptr);
+            c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, s.off.as<uint64_t>(), nullptr, nullptr, &launches);
         }
         FG_CUDA(cudaEventRecord(s.scanned, s.stream));
         prev_scanned = s.scanned;
+        enqueue_emit(s, c.plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
         FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
-        FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.overflow, 4, cudaMemcpyDeviceToHost, s.stream));
+        FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
         FG_CUDA(cudaEventRecord(s.info_ready, s.stream));
-        /* offsets of reads [first, first+n) and the running total at [first+n] (overwritten by the next chunk's first entry with the same value) */
+        /* offsets of reads [first, first+n) and the running total at [first+n] (the next chunk rewrites that entry with the same value) */
         FG_CUDA(cudaMemcpyAsync(out_off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
         if (op == op_kind::FETCH && num_positive)
             FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.npos.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -540,10 +748,25 @@ static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double thre
         FG_CUDA(cudaStreamSynchronize(s.stream));
         s.busy = false;
     }
-    if (overflow_reads)
-        throw std::runtime_error(std::to_string(overflow_reads) + " read(s) hit more than " + std::to_string(FG_MAX_ENTRIES) +
-                                 " distinct color sets: not supported yet");
+    if (exhausted) return RC_RETRY_LARGER_POOL;
     return too_big ? FULGOR_GPU_E2BIG : 0;
+}
+
+static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
+                          uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
+    FG_CUDA(cudaSetDevice(x->device));
+    out_off[0] = 0;
+    if (n_reads == 0) return 0;
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        if (read_off[i + 1] < read_off[i]) throw std::invalid_argument("read_off must be non-decreasing");
+        if (read_off[i + 1] - read_off[i] >= (1ull << 31)) throw std::invalid_argument("reads of 2^31 characters or more are not supported");
+    }
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        const int rc = run_host_batch_once(x, op, algo, threshold, bases, read_off, n_reads, out_off, out_vals, cap, num_positive);
+        if (rc != RC_RETRY_LARGER_POOL) return rc;
+        x->pool_per_read *= 4; /* reads with many distinct color sets: rerun with a larger entry pool (kept for later calls) */
+    }
+    throw std::runtime_error("entry pool kept overflowing");
 }
 
 template <typename F>
@@ -679,10 +902,12 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
     cudaSetDevice(x->device);
     for (auto& s : x->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (dev_buffer* b : {&s.bases, &s.read_off, &s.per_read, &s.stage_cid, &s.stage_cnt, &s.npos, &s.tile_sums, &s.tile_off, &s.off, &s.out})
+        for (dev_buffer* b : {&s.bases, &s.read_off, &s.per_read, &s.stage, &s.pool, &s.npos, &s.res_bits, &s.res_counts, &s.tile_sums, &s.tile_off,
+                              &s.off, &s.out})
             b->release();
         if (s.chunk_info) cudaFree(s.chunk_info);
-        if (s.overflow) cudaFree(s.overflow);
+        if (s.exhausted) cudaFree(s.exhausted);
+        if (s.pool_used) cudaFree(s.pool_used);
         if (s.h_info) cudaFreeHost(s.h_info);
         if (s.scanned) cudaEventDestroy(s.scanned);
         if (s.done) cudaEventDestroy(s.done);
@@ -747,17 +972,23 @@ int fulgor_gpu_pseudoalign_device(fulgor_gpu_index* x, int algo, double threshol
             return 0;
         }
         chunk_args a{reinterpret_cast<const uint8_t*>(d_bases), d_read_off, read_off_base, n_reads};
-        FG_CUDA(cudaEventRecord(x->ev[0], s.stream));
-        x->last_launches = enqueue_pseudoalign(x, s, a, algo, threshold, d_color_off, d_colors, colors_cap, x->ev[1], x->ev[2]);
-        FG_CUDA(cudaEventRecord(x->ev[3], s.stream));
-        FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
-        FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.overflow, 4, cudaMemcpyDeviceToHost, s.stream));
-        FG_CUDA(cudaStreamSynchronize(s.stream));
+        for (int attempt = 0;; ++attempt) {
+            FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
+            FG_CUDA(cudaEventRecord(x->ev[0], s.stream));
+            x->last_launches = 0;
+            const emit_plan plan = enqueue_pseudoalign(x, s, a, algo, threshold, d_color_off, x->ev[1], x->ev[2], &x->last_launches);
+            enqueue_emit(s, plan, d_color_off, d_colors, colors_cap);
+            x->last_launches += 1;
+            FG_CUDA(cudaEventRecord(x->ev[3], s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            if (!uint32_t(s.h_info[2])) break;
+            if (attempt >= 12) throw std::runtime_error("entry pool kept overflowing");
+            x->pool_per_read *= 4;
+        }
         for (int i = 0; i < 3; ++i) FG_CUDA(cudaEventElapsedTime(&x->last_ms[i], x->ev[i], x->ev[i + 1]));
         *total_out = s.h_info[1];
-        if (uint32_t(s.h_info[2]))
-            throw std::runtime_error(std::to_string(uint32_t(s.h_info[2])) + " read(s) hit more than " + std::to_string(FG_MAX_ENTRIES) +
-                                     " distinct color sets: not supported yet");
         if (s.h_info[1] > colors_cap) return fail(FULGOR_GPU_E2BIG, "colors_cap too small; *total_out holds the required capacity");
         return 0;
     });

@@ -233,14 +233,6 @@ FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, u
 
 /* ------------------------------------------------------------------ stage 1 for one read, one warp */
 
-struct read_hits {
-    uint32_t cid;       /* lane j < n holds the j-th distinct color-set id (ascending after sort) */
-    uint32_t cnt;       /* ... and the number of positive k-mers that map to it */
-    uint32_t n;         /* number of distinct color sets (warp-uniform) */
-    uint32_t npos;      /* number of positive k-mers (warp-uniform) */
-    bool overflow;      /* more than FG_MAX_ENTRIES distinct color sets */
-};
-
 /* valid characters are exactly ACGTacgt (sshash/kmer.hpp:214-224,258-260); code = (c >> 1) & 3 (kmer.hpp:199) */
 FG_HD bool base_valid(uint32_t c) {
     const uint32_t u = c & 0xDFu; /* fold case */
@@ -257,33 +249,40 @@ __device__ __forceinline__ void pack_chars(uint32_t c, bool in_range, uint32_t l
     valid = __ballot_sync(FG_FULL, in_range && base_valid(c));
 }
 
-/* index::fetch_color_set_ids (src/ps_full_intersection.cpp:335-374) and the counting half of
-   index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read.
-   The two sort+unique passes of the reference become: warp match on the color-set id inside a tile,
-   a 32-entry register table (one entry per lane) across tiles, one bitonic sort at the end. */
+/* Walks one read in tiles of 32 consecutive k-mers: after next(), lane l holds the color-set id of the
+   k-mer that starts at position t0 + l (FG_NOT_FOUND when negative, invalid or past the end).
+   Replaces the per-k-mer loop around streaming_query::lookup_advanced (sshash/streaming_query.hpp:50-109,
+   driven from src/ps_full_intersection.cpp:344-353): validity test (:53-59), 2-bit packing and reverse
+   complement (:62-74), canonical minimizer (:76-83), dictionary lookup (:144-190). */
 template <int W>
-__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, uint32_t lane) {
-    read_hits R;
-    R.cid = FG_NOT_FOUND;
-    R.cnt = 0;
-    R.n = 0;
-    R.npos = 0;
-    R.overflow = false;
-    const uint32_t k = I.k;
-    if (len < k) return R; /* src/ps_full_intersection.cpp:337 */
-    const uint32_t nk = len - k + 1;
-    const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
-    const uint64_t mmer_mask = (1ULL << (2 * I.m)) - 1;
-    const uint32_t window = k - I.m + 1;
-    const uint32_t kbits = (k == 32) ? ~0u : ((1u << k) - 1u);
+struct kmer_tiles {
+    const dev_index& I;
+    const uint8_t* __restrict__ seq;
+    uint32_t len, lane, nk, t0;
+    uint64_t kmask, mmer_mask, w0, w1;
+    uint32_t window, kbits, v0, v1;
 
-    uint64_t w0, w1;
-    uint32_t v0, v1;
-    {
-        const uint32_t c = lane < len ? seq[lane] : 0u;
-        pack_chars(c, lane < len, lane, w0, v0);
+    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, uint32_t lane_)
+        : I(I_), seq(seq_), len(len_), lane(lane_) {
+        const uint32_t k = I.k;
+        nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
+        t0 = 0;
+        kmask = (1ULL << (2 * k)) - 1;
+        mmer_mask = (1ULL << (2 * I.m)) - 1;
+        window = k - I.m + 1;
+        kbits = (1u << k) - 1u;
+        w1 = 0;
+        v1 = 0;
+        if (nk) {
+            const uint32_t c = lane < len ? seq[lane] : 0u;
+            pack_chars(c, lane < len, lane, w0, v0);
+        } else {
+            w0 = 0;
+            v0 = 0;
+        }
     }
-    for (uint32_t t0 = 0; t0 < nk; t0 += 32) {
+    __device__ __forceinline__ bool done() const { return t0 >= nk; }
+    __device__ __forceinline__ uint32_t next() {
         {
             const uint32_t p = t0 + 32 + lane;
             const uint32_t c = p < len ? seq[p] : 0u;
@@ -295,43 +294,150 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
         if (valid) {
             const uint32_t sh = 2 * lane;
             const uint64_t fwd = (sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0) & kmask;
-            const uint64_t rc = revcomp(fwd, k);
+            const uint64_t rc = revcomp(fwd, I.k);
             const uint64_t a = kmer_minimizer<W>(fwd, window, mmer_mask, I.hash_magic);
             const uint64_t b = kmer_minimizer<W>(rc, window, mmer_mask, I.hash_magic);
             cid = lookup_color_set(I, fwd, rc, a < b ? a : b, kmask);
         }
         __syncwarp();
+        w0 = w1;
+        v0 = v1;
+        t0 += 32;
+        return cid;
+    }
+};
+
+/* a growable list of {color-set id, multiplicity} in global memory, bump-allocated from one pool per launch */
+struct entry_pool {
+    uint2* base;
+    unsigned long long* used; /* entries handed out so far */
+    uint64_t cap;             /* entries available */
+    uint32_t* exhausted;      /* set when an allocation failed: the host grows the pool and reruns */
+};
+
+struct read_hits {
+    uint32_t cid;   /* n <= 32: lane j < n holds the j-th distinct color-set id (ascending) ... */
+    uint32_t cnt;   /*          ... and the number of positive k-mers that map to it */
+    uint32_t n;     /* number of distinct color sets (warp-uniform) */
+    uint32_t npos;  /* number of positive k-mers (warp-uniform) */
+    uint2* tab;     /* n > 32: the sorted list lives here (shared or pool memory); nullptr otherwise */
+    uint32_t cap;   /* capacity of tab (a power of two) */
+    bool failed;    /* the pool was exhausted: this read's result is incomplete */
+};
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __clz(int(v - 1))); }
+
+/* slow path of the per-read table: more than 32 distinct color sets. Lanes stride over the list. */
+__device__ __noinline__ void table_insert(read_hits& R, uint32_t kk, uint32_t cc, uint32_t nk, const entry_pool& pool, uint32_t lane) {
+    uint32_t found = 0;
+    for (uint32_t i0 = 0; i0 < R.n && !found; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool eq = i < R.n && R.tab[i].x == kk;
+        found = __ballot_sync(FG_FULL, eq);
+        if (eq) R.tab[i].y += cc;
+    }
+    if (!found) {
+        if (R.n == R.cap) { /* grow into the pool: nk bounds the number of distinct color sets of this read */
+            const uint32_t want = next_pow2(nk);
+            unsigned long long off = 0;
+            if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)want);
+            off = __shfl_sync(FG_FULL, off, 0);
+            if (want <= R.cap || off + want > pool.cap) {
+                if (lane == 0) *pool.exhausted = 1;
+                R.failed = true;
+                return;
+            }
+            uint2* nt = pool.base + off;
+            for (uint32_t i = lane; i < R.n; i += 32) nt[i] = R.tab[i];
+            R.tab = nt;
+            R.cap = want;
+        }
+        if (lane == 0) R.tab[R.n] = make_uint2(kk, cc);
+        R.n += 1;
+    }
+    __syncwarp();
+}
+
+/* ascending sort by color-set id of tab[0, n): bitonic network over the next power of two */
+__device__ __noinline__ void table_sort(uint2* tab, uint32_t n, uint32_t lane) {
+    const uint32_t P = next_pow2(n);
+    for (uint32_t i = n + lane; i < P; i += 32) tab[i] = make_uint2(FG_NOT_FOUND, 0);
+    __syncwarp();
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < P / 2; t += 32) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); /* index with bit j clear */
+                const uint32_t l = i | j;
+                const uint2 a = tab[i], b = tab[l];
+                const bool up = (i & kk) == 0;
+                if ((a.x > b.x) == up) {
+                    tab[i] = b;
+                    tab[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+/* index::fetch_color_set_ids (src/ps_full_intersection.cpp:335-374) and the counting half of
+   index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read.
+   The reference's two sort+unique passes become: warp match on the color-set id inside a tile, a
+   32-entry register table (one entry per lane) across tiles -- spilling to `scratch` (shared memory,
+   scratch_cap entries, a power of two) and then to the pool for reads with more distinct color sets --
+   and one bitonic sort at the end. */
+template <int W>
+__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, uint32_t lane,
+                                                           uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
+    read_hits R;
+    R.cid = FG_NOT_FOUND;
+    R.cnt = 0;
+    R.n = 0;
+    R.npos = 0;
+    R.tab = nullptr;
+    R.cap = 0;
+    R.failed = false;
+    kmer_tiles<W> tiles(I, seq, len, lane);
+    while (!tiles.done()) {
+        const uint32_t cid = tiles.next();
         const bool found = cid != FG_NOT_FOUND;
         const uint32_t found_mask = __ballot_sync(FG_FULL, found);
         R.npos += __popc(found_mask);
-        if (found_mask) {
-            const uint32_t grp = __match_any_sync(FG_FULL, cid);
-            const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
-            const uint32_t gcnt = __popc(grp);
-            uint32_t leaders = __ballot_sync(FG_FULL, leader);
-            while (leaders) {
-                const int src = __ffs(int(leaders)) - 1;
-                leaders &= leaders - 1;
-                const uint32_t kk = __shfl_sync(FG_FULL, cid, src);
-                const uint32_t cc = __shfl_sync(FG_FULL, gcnt, src);
+        if (!found_mask) continue;
+        const uint32_t grp = __match_any_sync(FG_FULL, cid);
+        const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
+        const uint32_t gcnt = __popc(grp);
+        uint32_t leaders = __ballot_sync(FG_FULL, leader);
+        while (leaders) {
+            const int src = __ffs(int(leaders)) - 1;
+            leaders &= leaders - 1;
+            const uint32_t kk = __shfl_sync(FG_FULL, cid, src);
+            const uint32_t cc = __shfl_sync(FG_FULL, gcnt, src);
+            if (R.tab == nullptr) {
                 const uint32_t hit = __ballot_sync(FG_FULL, R.cid == kk);
                 if (hit) {
                     if (R.cid == kk) R.cnt += cc;
-                } else if (R.n < FG_MAX_ENTRIES) {
+                    continue;
+                }
+                if (R.n < FG_MAX_ENTRIES) {
                     if (lane == R.n) {
                         R.cid = kk;
                         R.cnt = cc;
                     }
                     R.n += 1;
-                } else {
-                    R.overflow = true;
+                    continue;
                 }
+                scratch[lane] = make_uint2(R.cid, R.cnt); /* registers are full: move to the list */
+                R.tab = scratch;
+                R.cap = scratch_cap;
+                __syncwarp();
             }
+            if (!R.failed) table_insert(R, kk, cc, tiles.nk, pool, lane);
         }
-        w0 = w1;
-        v0 = v1;
     }
-    if (R.n > 1) { /* bitonic sort by color-set id; unused lanes hold FG_NOT_FOUND and sink to the end */
+    if (R.tab != nullptr) {
+        if (!R.failed) table_sort(R.tab, R.n, lane);
+    } else if (R.n > 1) { /* bitonic sort across lanes; unused lanes hold FG_NOT_FOUND and sink to the end */
 #pragma unroll
         for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
@@ -409,6 +515,89 @@ FG_HD uint32_t color_set_mask(const dev_index& I, uint32_t cid) {
         mask |= hybrid_set_mask(I, p, mc - FG_LDG(I.part_sets_before + p)) << FG_LDG(I.part_min_color + p);
     }
     return mask;
+}
+
+
+/* ------------------------------------------------------------------ color sets of any width */
+
+enum { FG_ENC_DELTA = 0, FG_ENC_BITMAP = 1, FG_ENC_COMPLEMENT = 2, FG_ENC_NONE = 3 };
+
+/* one partial color set to be applied to the per-read score array */
+struct set_item {
+    uint64_t pos;        /* bit position right after the size header */
+    uint32_t container;  /* hybrid container (partition) */
+    uint32_t color_base; /* first global color of the container */
+    uint32_t num_colors; /* colors in the container */
+    uint32_t nvals;      /* delta-coded values that follow (the set, or its complement) */
+    uint32_t weight;
+    uint32_t enc;
+};
+
+/* hybrid::forward_iterator::rewind (include/color_sets/hybrid.hpp:162-188): size header -> encoding */
+__device__ __forceinline__ set_item open_set(const dev_index& I, uint32_t container, uint64_t local_id, uint32_t color_base, uint32_t weight) {
+    set_item it;
+    const fgi_hybrid* h = I.hybrids + container;
+    it.container = container;
+    it.color_base = color_base;
+    it.num_colors = FG_LDG(&h->num_colors);
+    it.weight = weight;
+    const uint64_t* words = I.color_words + FG_LDG(&h->word_base);
+    it.pos = FG_LDG(I.set_bit_off + FG_LDG(&h->set_off_base) + local_id);
+    const uint32_t size = read_delta(words, it.pos);
+    if (size < FG_LDG(&h->sparse_thr)) {
+        it.enc = FG_ENC_DELTA;
+        it.nvals = size;
+    } else if (size < FG_LDG(&h->very_dense_thr)) {
+        it.enc = FG_ENC_BITMAP;
+        it.nvals = 0;
+    } else {
+        it.enc = FG_ENC_COMPLEMENT;
+        it.nvals = it.num_colors - size;
+    }
+    return it;
+}
+
+/* Adds one round of up to 32 partial sets (one per lane, `valid` lanes only) to the warp's score array:
+     scores[c] += weight for every color of a delta-coded or bitmap set,
+     base[container] += weight and scores[c] -= weight for every MISSING color of a complement-coded set
+   (the same trick as the reference's merge, src/ps_threshold_union.cpp:23-29, so the cost of a set is
+   proportional to its encoded length). Bitmap sets are expanded by the whole warp (one 32-bit chunk
+   per lane, no conflicts); delta-coded sets are decoded lane-parallel with shared-memory atomics. */
+__device__ __forceinline__ void apply_sets(const dev_index& I, bool valid, const set_item& it, int* scores, int* base, uint32_t lane) {
+    uint32_t bm = __ballot_sync(FG_FULL, valid && it.enc == FG_ENC_BITMAP);
+    while (bm) {
+        const int src = __ffs(int(bm)) - 1;
+        bm &= bm - 1;
+        const uint64_t pos = __shfl_sync(FG_FULL, it.pos, src);
+        const uint32_t container = __shfl_sync(FG_FULL, it.container, src);
+        const uint32_t cb = __shfl_sync(FG_FULL, it.color_base, src);
+        const uint32_t nc = __shfl_sync(FG_FULL, it.num_colors, src);
+        const int w = int(__shfl_sync(FG_FULL, it.weight, src));
+        const uint64_t* words = I.color_words + FG_LDG(&I.hybrids[container].word_base);
+        for (uint32_t c0 = lane * 32; c0 < nc; c0 += 32 * 32) {
+            uint32_t bits = uint32_t(bits_at(words, pos + c0));
+            if (nc - c0 < 32) bits &= (1u << (nc - c0)) - 1u;
+            while (bits) {
+                const uint32_t b = uint32_t(__ffs(int(bits))) - 1u;
+                bits &= bits - 1;
+                scores[cb + c0 + b] += w;
+            }
+        }
+        __syncwarp();
+    }
+    if (valid && it.enc != FG_ENC_BITMAP) {
+        const uint64_t* words = I.color_words + FG_LDG(&I.hybrids[it.container].word_base);
+        const int w = it.enc == FG_ENC_COMPLEMENT ? -int(it.weight) : int(it.weight);
+        if (it.enc == FG_ENC_COMPLEMENT) atomicAdd(base + it.container, int(it.weight));
+        uint64_t pos = it.pos;
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < it.nvals; ++i) {
+            const uint32_t d = read_delta(words, pos);
+            v = i ? v + d + 1 : d;
+            atomicAdd(scores + it.color_base + v, w);
+        }
+    }
+    __syncwarp();
 }
 
 }  // namespace fgb

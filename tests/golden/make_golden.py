@@ -20,6 +20,8 @@ CASES = [  # name, index, n, min_len, max_len, seed
     ("s10_fur_mixed", "salmonella_10.fur", 4000, 75, 300, 43),
     ("s10_mfur_150", "salmonella_10.mfur", 4000, 150, 150, 42),
     ("s10_mfur_mixed", "salmonella_10.mfur", 4000, 75, 300, 43),
+    ("synth200_fur_mixed", "synth_200.fur", 3000, 75, 300, 44),
+    ("synth200_mfur_mixed", "synth_200.mfur", 3000, 75, 300, 44),
 ]
 THRESHOLDS = [0.8, 1.0, 0.3]
 
@@ -28,7 +30,7 @@ def main():
     assert ck.reference_available(), "build the reference first: make -C oracle ref"
     for name, index, n, lo, hi, seed in CASES:
         ref = ck.Reference(ck.index_path(index))
-        reads = ck.gen_reads(n, lo, hi, seed=seed)
+        reads = ck.gen_reads(n, lo, hi, seed=seed, genomes=index.split(".")[0])
         out = {"index": index, "n": n, "min_len": lo, "max_len": hi, "seed": seed, "thresholds": np.array(THRESHOLDS),
                "reads_checksum": np.uint64(int(reads[0].astype(np.uint64).sum()))}
         out["cid_off"], out["cids"] = ref.fetch_color_set_ids(reads)

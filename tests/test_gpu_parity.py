@@ -7,7 +7,7 @@ import _checkers as ck
 
 pytestmark = pytest.mark.gpu
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]  # 10 colors (fused kernel) and 200 colors (general kernels)
 
 
 @pytest.fixture(scope="module", params=INDEXES)
@@ -17,6 +17,7 @@ def pair(request, built_lib):
     path = ck.index_path(request.param)
     gpu = fg.Index.open(path, 0)
     oracle = ck.Oracle(path)
+    gpu.genomes = oracle.genomes = request.param.split(".")[0]
     yield gpu, oracle
     gpu.close()
     oracle.close()
@@ -26,9 +27,9 @@ def _same(a, b):
     return a[0].shape == b[0].shape and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
-def edge_reads(k=31):
+def edge_reads(genomes, k=31):
     rng = np.random.default_rng(5)
-    g = ck.gen_reads(64, 150, 150, seed=99)
+    g = ck.gen_reads(64, 150, 150, seed=99, genomes=genomes)
     seqs = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(64)]
     out = [b"", b"A", b"ACGT" * 7 + b"AC", seqs[0][:31], seqs[1][:32], seqs[2].lower(), seqs[3][:75] + b"N" + seqs[3][76:],
            b"N" * 150, seqs[4][:30] + b"n" + seqs[4][31:], b"A" * 200, b"ACGT" * 50, seqs[5] + seqs[6] + seqs[7],
@@ -45,7 +46,7 @@ def test_info(pair):
 @pytest.mark.parametrize("lens", [(150, 150), (75, 300)])
 def test_fetch_color_set_ids(pair, lens):
     gpu, o = pair
-    reads = ck.gen_reads(20000, lens[0], lens[1], seed=42)
+    reads = ck.gen_reads(20000, lens[0], lens[1], seed=42, genomes=gpu.genomes)
     got = gpu.fetch_color_set_ids(reads, want_positive=True)
     exp = o.fetch_color_set_ids(reads, want_positive=True)
     assert _same(got, exp)
@@ -56,14 +57,14 @@ def test_fetch_color_set_ids(pair, lens):
 @pytest.mark.parametrize("lens", [(150, 150), (75, 300)])
 def test_pseudoalign(pair, algo, thr, lens):
     gpu, o = pair
-    reads = ck.gen_reads(20000, lens[0], lens[1], seed=1234)
+    reads = ck.gen_reads(20000, lens[0], lens[1], seed=1234, genomes=gpu.genomes)
     assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
 
 
 @pytest.mark.parametrize("algo,thr", [(0, 1.0), (1, 0.8), (1, 0.001)])
 def test_edge_cases(pair, algo, thr):
     gpu, o = pair
-    reads = edge_reads()
+    reads = edge_reads(gpu.genomes)
     assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
     assert _same(gpu.fetch_color_set_ids(reads), o.fetch_color_set_ids(reads))
 
@@ -79,7 +80,7 @@ def test_e2big_reports_required_capacity(pair):
     import fulgor_b200 as fg
 
     gpu, o = pair
-    reads = ck.gen_reads(5000, seed=3)
+    reads = ck.gen_reads(5000, seed=3, genomes=gpu.genomes)
     exp = o.pseudoalign(reads, 0)
     bases, off = reads
     color_off = np.zeros(len(off), dtype=np.uint64)
@@ -94,8 +95,8 @@ def test_multi_chunk_large_batch(pair):
     """more reads than one pipeline chunk (2^20): exercises the cross-chunk CSR carry; checked against the oracle on
     a sample and through size-independent properties on the whole batch"""
     gpu, o = pair
-    n = (1 << 20) + 70000
-    reads = ck.gen_reads(n, seed=77)
+    n = (1 << 20) + 70000 if gpu.num_colors <= 32 else 300000
+    reads = ck.gen_reads(n, seed=77, genomes=gpu.genomes)
     off, vals = gpu.pseudoalign(reads, 0)
     assert off.size == n + 1 and off[0] == 0 and int(off[-1]) == vals.size
     assert np.all(np.diff(off.astype(np.int64)) >= 0)
@@ -104,10 +105,22 @@ def test_multi_chunk_large_batch(pair):
     drops = np.nonzero(np.diff(vals.astype(np.int64)) <= 0)[0] + 1
     assert np.all(np.isin(drops, off))
     # idempotence + the batch split does not matter: the tail, recomputed alone, equals the slice of the whole
-    lo = n - 50000
+    lo = n - 20000
     bases, roff = reads
     sub = (bases[int(roff[lo]):], roff[lo:] - roff[lo])
     soff, svals = gpu.pseudoalign(sub, 0)
     assert np.array_equal(soff, off[lo:] - off[lo]) and np.array_equal(svals, vals[int(off[lo]):])
     eoff, evals = o.pseudoalign(sub, 0)
     assert np.array_equal(soff, eoff) and np.array_equal(svals, evals)
+
+
+def test_long_reads_many_color_sets(pair):
+    """reads of 2-5 kbp hit far more than 32 (and more than 256) distinct color sets on the fragmented synthetic index:
+    exercises the register -> shared-memory -> pool spill of the per-read table and its retry-with-a-larger-pool path"""
+    gpu, o = pair
+    reads = ck.gen_reads(600, 2000, 5000, seed=8, genomes=gpu.genomes)
+    got = gpu.fetch_color_set_ids(reads, want_positive=True)
+    exp = o.fetch_color_set_ids(reads, want_positive=True)
+    assert _same(got, exp) and np.array_equal(got[2], exp[2])
+    for algo, thr in ((0, 1.0), (1, 0.7)):
+        assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))

@@ -13,7 +13,7 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)
 
 def load_case(path):
     g = np.load(path)
-    reads = ck.gen_reads(int(g["n"]), int(g["min_len"]), int(g["max_len"]), seed=int(g["seed"]))
+    reads = ck.gen_reads(int(g["n"]), int(g["min_len"]), int(g["max_len"]), seed=int(g["seed"]), genomes=str(g["index"]).split(".")[0])
     assert int(reads[0].astype(np.uint64).sum()) == int(g["reads_checksum"]), "read generator drifted from the golden inputs"
     return g, reads
 

@@ -7,13 +7,14 @@ import _checkers as ck
 
 pytestmark = pytest.mark.skipif(not ck.reference_available(), reason="oracle/_ref/libfulgor_ref.so not built (needs /root/reference)")
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]
 
 
 @pytest.fixture(scope="module", params=INDEXES)
 def pair(request):
     path = ck.index_path(request.param)
     o, r = ck.Oracle(path), ck.Reference(path)
+    o.genomes = request.param.split(".")[0]
     yield o, r
     o.close()
     r.close()
@@ -31,7 +32,7 @@ def test_info(pair):
 
 def test_every_color_set(pair):
     o, r = pair
-    for i in range(o.num_color_sets):
+    for i in range(0, o.num_color_sets, 1 if o.num_color_sets < 1000 else 5):
         assert np.array_equal(o.color_set(i), r.color_set(i)), i
 
 
@@ -44,7 +45,7 @@ def test_u2c_sample(pair):
 
 def test_streaming_lookup_per_kmer(pair):
     o, r = pair
-    bases, off = ck.gen_reads(400, 75, 300, seed=11)
+    bases, off = ck.gen_reads(400, 75, 300, seed=11, genomes=o.genomes)
     for i in range(400):
         seq = bases[int(off[i]):int(off[i + 1])].tobytes()
         if i % 7 == 0:
@@ -55,20 +56,20 @@ def test_streaming_lookup_per_kmer(pair):
 @pytest.mark.parametrize("lens", [(150, 150), (75, 300)])
 def test_fetch_color_set_ids(pair, lens):
     o, r = pair
-    reads = ck.gen_reads(6000, lens[0], lens[1], seed=42)
+    reads = ck.gen_reads(6000, lens[0], lens[1], seed=42, genomes=o.genomes)
     assert _same(o.fetch_color_set_ids(reads), r.fetch_color_set_ids(reads, threads=4))
 
 
 @pytest.mark.parametrize("algo,thr", [(0, 1.0), (1, 0.8), (1, 1.0), (1, 0.05)])
 def test_pseudoalign(pair, algo, thr):
     o, r = pair
-    reads = ck.gen_reads(6000, 75, 300, seed=1234)
+    reads = ck.gen_reads(6000, 75, 300, seed=1234, genomes=o.genomes)
     assert _same(o.pseudoalign(reads, algo, thr), r.pseudoalign(reads, algo, thr, threads=4))
 
 
 def test_edge_reads(pair):
     o, r = pair
-    g = ck.gen_reads(8, seed=99)
+    g = ck.gen_reads(8, seed=99, genomes=o.genomes)
     s = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(8)]
     reads = ck.reads_from_list([b"", b"A", s[0][:30], s[0][:31], s[1].lower(), b"N" * 150, s[2][:75] + b"N" + s[2][76:], b"A" * 200,
                                 s[3] + s[4], s[5][:149] + b"X"])
