@@ -1,0 +1,177 @@
+"""The `fulgor_b200_pseudoalign` CLI (fulgor_b200/csrc/pseudoalign_cli.cpp) against the oracle and, where its binary was
+built (oracle/_ref/fulgor_ref, compiled from the unmodified reference sources), against the reference's own
+`fulgor pseudoalign` run on the same files: same records, compared after sorting by read id (the reference's record
+order depends on thread scheduling, reference README.md:220)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _checkers as ck
+
+CLI = os.path.join(ck.ROOT, "fulgor_b200", "fulgor_b200_pseudoalign")
+
+
+def write_fastq(path, reads, gz=False, fasta=False):
+    bases, off = reads
+    op = gzip.open if gz else open
+    with op(path, "wb") as f:
+        for i in range(len(off) - 1):
+            s = bases[int(off[i]):int(off[i + 1])].tobytes()
+            if fasta:
+                f.write(b">r%d\n%s\n" % (i, s))
+            else:
+                f.write(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+
+
+def ascii_records(path):
+    recs = {}
+    for line in open(path, "rb").read().split(b"\n"):
+        if not line:
+            continue
+        f = line.split(b"\t")
+        rid, n = int(f[0]), int(f[1])
+        assert len(f) == 2 + n
+        recs[rid] = [int(x) for x in f[2:]]
+    return recs
+
+
+def binary_records(path):
+    a = np.fromfile(path, dtype=np.uint32)
+    recs, p = {}, 0
+    while p < a.size:
+        rid, n = int(a[p]), int(a[p + 1])
+        recs[rid] = a[p + 2: p + 2 + n].tolist()
+        p += 2 + n
+    return recs
+
+
+class BitReader:
+    def __init__(self, words, nbits):
+        self.w, self.n, self.p = words, nbits, 0
+
+    def take(self, l):
+        v = 0
+        for i in range(l):
+            v |= ((int(self.w[(self.p + i) >> 6]) >> ((self.p + i) & 63)) & 1) << i
+        self.p += l
+        return v
+
+    def unary(self):
+        z = 0
+        while self.take(1) == 0:
+            z += 1
+        return z
+
+    def gamma(self):
+        b = self.unary()
+        return (self.take(b) | (1 << b)) - 1
+
+    def delta(self):
+        b = self.gamma()
+        return (self.take(b) | (1 << b)) - 1
+
+
+def compressed_records(path):
+    """decoder for psa_compressed_formatter's output (reference src/ps_utils.cpp:149-243)"""
+    raw = open(path, "rb").read()
+    C = int.from_bytes(raw[:8], "little")
+    sparse, dense = int(0.25 * C), int(0.75 * C)
+    recs, p = {}, 8
+    while p < len(raw):
+        nbits = int.from_bytes(raw[p:p + 8], "little")
+        nwords = (nbits + 63) // 64
+        words = np.frombuffer(raw, dtype="<u8", count=nwords, offset=p + 8)
+        p += 8 + 8 * nwords
+        r = BitReader(words, nbits)
+        while r.p < nbits:
+            rid, size = r.delta(), r.delta()
+            if size == 0:
+                vals = []
+            elif size < sparse:
+                vals = [r.delta()]
+                for _ in range(size - 1):
+                    vals.append(vals[-1] + r.delta() + 1)
+            elif size < dense:
+                bits = r.take(C)
+                vals = [c for c in range(C) if (bits >> c) & 1]
+            else:
+                missing = []
+                for i in range(C - size):
+                    missing.append(r.delta() if i == 0 else missing[-1] + r.delta() + 1)
+                ms = set(missing)
+                vals = [c for c in range(C) if c not in ms]
+            recs[rid] = vals
+    return C, recs
+
+
+def csr_records(csr):
+    off, vals = csr
+    return {i: vals[int(off[i]):int(off[i + 1])].tolist() for i in range(len(off) - 1)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("index,algo_args", [("salmonella_10.fur", []), ("salmonella_10.fur", ["-r", "0.8"]), ("salmonella_10.mfur", []),
+                                             ("synth_200.fur", []), ("synth_200.mfur", ["-r", "0.6"])])
+def test_cli_matches_oracle_and_reference(index, algo_args, built_lib, tmp_path):
+    genomes = index.split(".")[0]
+    reads = ck.gen_reads(3000, 75, 300, seed=31, genomes=genomes)
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path(index)
+    o = ck.Oracle(path)
+    thr = float(algo_args[1]) if algo_args else 1.0
+    exp = csr_records(o.pseudoalign(reads, 1 if algo_args else 0, thr))
+    outs = {}
+    for fmt in ("ascii", "binary", "compressed"):
+        out = str(tmp_path / f"out.{fmt}")
+        subprocess.check_call([CLI, "-i", path, "-q", fq, "-o", out, "--format", fmt, "--batch-reads", "1000"] + algo_args)
+        outs[fmt] = out
+    assert ascii_records(outs["ascii"]) == exp
+    assert binary_records(outs["binary"]) == exp
+    C, recs = compressed_records(outs["compressed"])
+    assert C == o.num_colors and recs == exp
+    # exact text of the ascii format: "id \t n [\t c]* \n" in read order
+    want = b"".join(b"\t".join([b"%d" % i, b"%d" % len(exp[i])] + [b"%d" % c for c in exp[i]]) + b"\n" for i in range(len(exp)))
+    assert open(outs["ascii"], "rb").read() == want
+    if os.path.exists(ck.REF_CLI):
+        for fmt, parse in (("ascii", ascii_records), ("binary", binary_records)):
+            ref_out = str(tmp_path / f"ref.{fmt}")
+            subprocess.check_call([ck.REF_CLI, "pseudoalign", "-i", path, "-q", fq, "-o", ref_out, "-t", "4", "--format", fmt] + algo_args,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert parse(ref_out) == parse(outs[fmt])
+        ref_out = str(tmp_path / "ref.compressed")
+        subprocess.check_call([ck.REF_CLI, "pseudoalign", "-i", path, "-q", fq, "-o", ref_out, "-t", "2", "--format", "compressed"] + algo_args,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert compressed_records(ref_out) == (C, recs)
+
+
+@pytest.mark.gpu
+def test_cli_gz_fasta_and_verbose_summary(built_lib, tmp_path):
+    reads = ck.gen_reads(2000, seed=5)
+    fa = str(tmp_path / "reads.fa.gz")
+    write_fastq(fa, reads, gz=True, fasta=True)
+    path = ck.index_path("salmonella_10.fur")
+    out = str(tmp_path / "out.txt")
+    p = subprocess.run([CLI, "-i", path, "-q", fa, "-o", out, "--verbose"], capture_output=True, text=True, check=True)
+    exp = csr_records(ck.Oracle(path).pseudoalign(reads, 0))
+    assert ascii_records(out) == exp
+    mapped = sum(1 for v in exp.values() if v)
+    assert "processed 2000 reads" in p.stdout and "musec/read" in p.stdout
+    assert f"num_mapped_reads {mapped}/2000" in p.stdout
+
+
+def test_cli_flag_errors(built_lib, tmp_path):
+    """flag validation mirrors tools/pseudoalign.cpp:272-321 and needs no GPU"""
+    if not os.path.exists(CLI):
+        pytest.skip("CLI not built")
+    r = subprocess.run([CLI, "-i", "x.fur", "-q", "q.fq", "-o", "o", "-r", "1.5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "threshold must be a float in (0.0,1.0]" in r.stderr
+    r = subprocess.run([CLI, "-i", "x.txt", "-q", "q.fq", "-o", "o"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Wrong index filename supplied." in r.stderr
+    r = subprocess.run([CLI, "-i", "x.fur", "-q", "q.fq", "-o", "o", "--format", "xml"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown output format" in r.stdout
+    r = subprocess.run([CLI, "-q", "q.fq", "-o", "o"], capture_output=True, text=True)
+    assert r.returncode == 1
