@@ -172,19 +172,11 @@ def main():
 
     # ---- index: rank 0 parses + flattens the .fur; one NCCL broadcast replicates the image; no other collective on the data path
     algo = fg.FULL_INTERSECTION if args.algo == "fi" else fg.THRESHOLD_UNION
+    from fulgor_b200 import replicate
+
     if world > 1:
-        size = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            image = fg.build_image(ck.index_path(args.index))
-            size[0] = image.size
-        dist.broadcast(size, 0)
-        d_image = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            d_image.copy_(torch.from_numpy(image))
-        dist.broadcast(d_image, 0)
-        torch.cuda.synchronize()
-        idx = fg.Index.adopt_device_image(d_image.data_ptr(), d_image.numel(), local_rank, keepalive=d_image)
-        image = d_image.cpu().numpy() if rank != 0 else image
+        idx, d_image = replicate.open_replica(ck.index_path(args.index), local_rank)
+        image = d_image.cpu().numpy()
     else:
         image = fg.build_image(ck.index_path(args.index))
         idx = fg.Index.from_image(image, local_rank)

@@ -10,7 +10,7 @@ import _checkers as ck
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 name = sys.argv[2] if len(sys.argv) > 2 else "salmonella_10.fur"
 idx = fg.Index.open(ck.index_path(name), 0)
-t = time.time(); bases, off = ck.gen_reads(n, seed=42, threads=32); print("gen", time.time() - t)
+t = time.time(); bases, off = ck.gen_reads(n, seed=42, threads=32, genomes=name.split(".")[0]); print("gen", time.time() - t)
 db = torch.from_numpy(bases).cuda(); do = torch.from_numpy(off.view(np.int64)).cuda()
 dco = torch.zeros(n + 1, dtype=torch.int64, device="cuda"); dc = torch.zeros(n * idx.num_colors, dtype=torch.int32, device="cuda")
 for algo, thr in ((0, 1.0), (1, 0.8)):
