@@ -40,11 +40,12 @@ __global__ void __launch_bounds__(FG_BLOCK) k_pseudoalign_small(const __grid_con
                                                                const uint64_t* __restrict__ read_off, uint64_t read_off_base,
                                                                uint32_t n_reads, int algo, double threshold,
                                                                uint32_t* __restrict__ masks) {
+    __shared__ warp_stage stage[FG_WARPS_PER_BLOCK];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane);
+        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, stage[threadIdx.x >> 5]);
         uint32_t acc = ~0u, score = 0, npos = 0;
         uint32_t cache_cid = FG_NOT_FOUND, cache_mask = 0;
         while (!tiles.done()) {
@@ -106,11 +107,12 @@ __global__ void __launch_bounds__(FG_BLOCK) k_fetch_color_sets(const __grid_cons
                                                               uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
                                                               uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool) {
     __shared__ uint2 scratch[FG_WARPS_PER_BLOCK][FG_SCRATCH_ENTRIES];
+    __shared__ warp_stage wstage[FG_WARPS_PER_BLOCK];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, scratch[wib], FG_SCRATCH_ENTRIES, pool);
+        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, wstage[wib], scratch[wib], FG_SCRATCH_ENTRIES, pool);
         uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
         if (R.tab == nullptr) {
             if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);
@@ -462,6 +464,7 @@ static dev_index make_view(const fgi_header& H, const uint8_t* base) {
     I.free_slots = reinterpret_cast<const uint32_t*>(base + H.off_free_slots);
     I.bucket_begin = reinterpret_cast<const uint32_t*>(base + H.off_bucket_begin);
     I.sk_records = reinterpret_cast<const uint2*>(base + H.off_sk_records);
+    I.sk_cid = H.off_sk_cid ? reinterpret_cast<const uint32_t*>(base + H.off_sk_cid) : nullptr;
     I.strings = reinterpret_cast<const uint64_t*>(base + H.off_strings);
     I.skew_positions = reinterpret_cast<const uint32_t*>(base + H.off_skew_positions);
     I.hybrids = reinterpret_cast<const fgi_hybrid*>(base + H.off_hybrids);

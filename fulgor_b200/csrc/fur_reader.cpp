@@ -16,6 +16,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace fgb {
 namespace {
@@ -132,6 +133,43 @@ inline uint64_t murmur2_64(uint64_t key, uint64_t seed) {
     return h;
 }
 
+/* canonical minimizer of a k-mer WITH its position, the same arithmetic as kernels.cuh (util::compute_minimizer,
+   sshash/util.hpp:220-239; mixer_64, sshash/hash_util.hpp:97). Returns false when both strands give the same value
+   (position ambiguous). pos = base offset of the minimizer inside the k-mer, in forward (string) coordinates. */
+inline uint64_t revcomp_bits(uint64_t x, uint32_t n) {
+    uint64_t c = x ^ 0xAAAAAAAAAAAAAAAAULL, y = 0;
+    for (uint32_t i = 0; i < 32; ++i) {
+        y = (y << 2) | (c & 3);
+        c >>= 2;
+    }
+    return y >> (64 - 2 * n);
+}
+inline void strand_minimizer(uint64_t x, uint32_t window, uint64_t mmer_mask, uint64_t magic, uint64_t& value, uint32_t& pos) {
+    uint64_t best_h = UINT64_MAX;
+    value = UINT64_MAX;
+    pos = 0;
+    for (uint32_t i = 0; i < window; ++i) {
+        const uint64_t y = x & mmer_mask;
+        const uint64_t h = (y * 0x517cc1b727220a95ULL) ^ magic;
+        if (h < best_h) {
+            best_h = h;
+            value = y;
+            pos = i;
+        }
+        x >>= 2;
+    }
+}
+inline bool canonical_minimizer_pos(uint64_t fwd, uint32_t k, uint32_t m, uint64_t magic, uint64_t& value, uint32_t& pos) {
+    const uint64_t mmer_mask = (1ULL << (2 * m)) - 1;
+    uint64_t vf, vr;
+    uint32_t jf, jr;
+    strand_minimizer(fwd, k - m + 1, mmer_mask, magic, vf, jf);
+    strand_minimizer(revcomp_bits(fwd, k), k - m + 1, mmer_mask, magic, vr, jr);
+    value = vf < vr ? vf : vr;
+    pos = vf < vr ? jf : (k - m) - jr;
+    return vf != vr;
+}
+
 /* growing image with aligned sections */
 struct image_writer {
     std::vector<uint8_t> bytes;
@@ -170,13 +208,23 @@ struct flattener {
         P.seed = r.pod<uint64_t>();
         P.num_keys = r.pod<uint64_t>();
         P.table_size = r.pod<uint64_t>();
-        uint64_t lo = r.pod<uint64_t>(), hi = r.pod<uint64_t>();
-        P.M_table_lo = lo, P.M_table_hi = hi;
-        r.pod<uint64_t>(); /* M_64, only used by non-minimal/other search types */
+        r.pod<uint64_t>(); /* M_128 (fastmod constant of table_size): recomputed below in 64-bit form */
+        r.pod<uint64_t>();
+        r.pod<uint64_t>(); /* M_64 */
         P.num_dense = r.pod<uint64_t>();
         P.num_sparse = r.pod<uint64_t>();
-        P.M_dense_lo = r.pod<uint64_t>(), P.M_dense_hi = r.pod<uint64_t>();
-        P.M_sparse_lo = r.pod<uint64_t>(), P.M_sparse_hi = r.pod<uint64_t>();
+        r.pod<uint64_t>(); /* M_dense, M_sparse */
+        r.pod<uint64_t>();
+        r.pod<uint64_t>();
+        r.pod<uint64_t>();
+        auto inverse = [](uint64_t d) -> uint64_t {
+            if (d >= (1ULL << 32)) throw std::runtime_error("MPHF partition with a modulus >= 2^32 is not supported");
+            if (d <= 1) return UINT64_MAX;
+            return uint64_t((u128(1) << 64) / d);
+        };
+        P.inv_table = inverse(P.table_size);
+        P.inv_dense = inverse(P.num_dense);
+        P.inv_sparse = inverse(P.num_sparse);
         compact_vector front_ranks, front_dict, back_ranks, back_dict;
         front_ranks.read(r);
         front_dict.read(r);
@@ -368,7 +416,6 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
     if (u2c.num_bits != H.num_unitigs) throw std::runtime_error("u2c size does not match the number of unitigs");
     if (H.num_super_kmers >= (1ULL << 32) || pieces.back() >= (1ULL << 32))
         throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / string offsets");
-    if (H.num_color_sets > FGI_SK_CID_MASK) throw std::runtime_error("too many color sets for the packed super-k-mer record");
     if (H.k - H.m + 1 > 31) throw std::runtime_error("k - m + 1 > 31 is not supported");
 
     /* buckets::locate_bucket (sshash/buckets.hpp:62-67): begin(b) = EF[b] + b */
@@ -385,20 +432,71 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
             rank += uint32_t((u2c.words[u >> 6] >> (u & 63)) & 1);
         }
     }
-    /* per super-k-mer: offset, window = min(k-m+1, contig_end - offset - k + 1) (buckets.hpp:133-160),
-       and the color-set id of the unitig that contains it (buckets.hpp:13-40 + u2c) */
+    /* per super-k-mer: offset, window = min(k-m+1, contig_end - offset - k + 1) (buckets.hpp:133-160), the color-set id
+       of the unitig that contains it (buckets.hpp:13-40 + u2c), and the position of the canonical minimizer */
     std::vector<uint64_t> sk_records(H.num_super_kmers);
+    std::vector<uint32_t> sk_cid;
+    const bool wide_cids = H.num_color_sets > (uint64_t(FGI_SK_CID_MASK) + 1);
+    if (wide_cids) sk_cid.resize(H.num_super_kmers);
     const uint64_t max_window = H.k - H.m + 1;
-    for (uint64_t s = 0; s < H.num_super_kmers; ++s) {
-        const uint64_t off = offsets[s];
-        const uint64_t u = uint64_t(std::upper_bound(pieces.begin(), pieces.end(), off) - pieces.begin()) - 1;
-        if (u >= H.num_unitigs) throw std::runtime_error("super-k-mer offset outside the strings");
-        const uint64_t contig_end = pieces[u + 1];
-        uint64_t window = 0;
-        if (contig_end >= off + H.k) window = std::min<uint64_t>(max_window, contig_end - off - H.k + 1);
-        const uint32_t meta = (uint32_t(window) << FGI_SK_CID_BITS) | unitig_cid[u];
-        sk_records[s] = uint64_t(uint32_t(off)) | (uint64_t(meta) << 32);
+    const uint64_t kmask = (1ULL << (2 * H.k)) - 1;
+    std::vector<uint64_t> strings_padded(strings.words);
+    strings_padded.push_back(0);
+    strings_padded.push_back(0);
+    const unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> unpinned(nthreads, 0);
+    std::vector<std::string> errors(nthreads);
+    auto work = [&](unsigned tid) {
+        const uint64_t lo = H.num_super_kmers * tid / nthreads, hi = H.num_super_kmers * (tid + 1) / nthreads;
+        for (uint64_t s = lo; s < hi; ++s) {
+            const uint64_t off = offsets[s];
+            const uint64_t u = uint64_t(std::upper_bound(pieces.begin(), pieces.end(), off) - pieces.begin()) - 1;
+            if (u >= H.num_unitigs) {
+                errors[tid] = "super-k-mer offset outside the strings";
+                return;
+            }
+            const uint64_t contig_end = pieces[u + 1];
+            uint64_t window = 0;
+            if (contig_end >= off + H.k) window = std::min<uint64_t>(max_window, contig_end - off - H.k + 1);
+            /* The reference scans up to k-m+1 k-mers from the offset (buckets.hpp:133-160), which can run past the end of
+               the super-k-mer into k-mers of OTHER buckets. Only k-mers whose canonical minimizer equals the one of the
+               first k-mer (the bucket's key) can ever match a query routed to this bucket, so the window stops there. */
+            bool pinned = window > 0;
+            uint32_t pm = 0;
+            uint64_t v0 = 0;
+            for (uint64_t t = 0; t < window; ++t) {
+                const uint64_t bit = 2 * (off + t), w = bit >> 6, sh = bit & 63;
+                const uint64_t x = (sh ? (strings_padded[w] >> sh) | (strings_padded[w + 1] << (64 - sh)) : strings_padded[w]) & kmask;
+                uint64_t value;
+                uint32_t pos;
+                const bool unique = canonical_minimizer_pos(x, H.k, H.m, H.hash_magic, value, pos);
+                if (t == 0) {
+                    v0 = value;
+                    pm = pos;
+                } else if (value != v0) {
+                    window = t;
+                    break;
+                }
+                if (!unique || uint32_t(t) + pos != pm) pinned = false;
+            }
+            if (!pinned) {
+                pm = 0;
+                ++unpinned[tid];
+            }
+            uint32_t hi32 = (uint32_t(window) << FGI_SK_WINDOW_SHIFT) | (pm << FGI_SK_PM_SHIFT) | (uint32_t(pinned) << FGI_SK_PINNED_SHIFT);
+            if (wide_cids) sk_cid[s] = unitig_cid[u];
+            else hi32 |= unitig_cid[u];
+            sk_records[s] = uint64_t(uint32_t(off)) | (uint64_t(hi32) << 32);
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+        for (auto& t : pool) t.join();
     }
+    for (auto const& e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+    for (uint64_t v : unpinned) H.num_unpinned += v;
 
     H.num_string_words = strings.words.size();
     H.num_phfs = uint32_t(F.phfs.size());
@@ -413,6 +511,7 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
     H.off_free_slots = W.section(F.free_slots, 1);
     H.off_bucket_begin = W.section(bucket_begin);
     H.off_sk_records = W.section(sk_records);
+    H.off_sk_cid = wide_cids ? W.section(sk_cid) : 0;
     H.off_strings = W.section(strings.words, 2);
     H.off_skew_positions = W.section(F.skew_positions, 1);
     H.off_hybrids = W.section(F.hybrids);

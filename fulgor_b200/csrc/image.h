@@ -10,10 +10,13 @@
  *     (single_phf.hpp:84-87 hashes the pilot at every query): 1 gather instead of 2 + a hash.
  *   - Elias-Fano sequences that are only ever `access`ed (free slots, bucket sizes, color-set bit
  *     offsets, meta offsets; bits/include/elias_fano.hpp:159-163) become plain arrays.
- *   - each super-k-mer gets an 8-byte record {string offset, window length, color-set id} which folds
- *     buckets::offset_to_id (sshash/include/buckets.hpp:13-40, an Elias-Fano locate over `pieces`),
- *     the window clamp of lookup_canonical_in_super_kmer (buckets.hpp:133-160) and index::u2c
- *     (include/index.hpp:37, rank9) into the one gather that fetches the offset.
+ *   - each super-k-mer gets an 8-byte record {string offset, window length, color-set id, minimizer
+ *     position} which folds buckets::offset_to_id (sshash/include/buckets.hpp:13-40, an Elias-Fano
+ *     locate over `pieces`), the window clamp of lookup_canonical_in_super_kmer (buckets.hpp:133-160)
+ *     and index::u2c (include/index.hpp:37, rank9) into the one gather that fetches the offset. The
+ *     minimizer position (where, relative to the super-k-mer's first base, the canonical minimizer of
+ *     ALL its k-mers starts; computed at load with the same arithmetic the kernels use) lets a query
+ *     compare at most two window positions instead of all k-m+1 (see scan_super_kmer).
  *   - the 2-bit `strings` and the compressed color-set bit streams stay VERBATIM (bit-identical
  *     words); the kernels decode them in place.
  */
@@ -25,19 +28,19 @@
 #define FGI_MAGIC 0x3130474D49475546ULL /* "FUGIMG01" */
 #define FGI_ALIGN 256
 
-/* one single_phf partition (pthash/include/single_phf.hpp:140-150) */
+/* one single_phf partition (pthash/include/single_phf.hpp:140-150). The three moduli (table size, dense / sparse bucket
+   counts) are < 2^32, so `a mod d` is evaluated as a - mulhi64(a, inv) * d with one conditional correction, where
+   inv = floor(2^64 / d): the exact remainder, like the reference's 128-bit fastmod (external/fastmod/fastmod.h:159-162). */
 struct fgi_phf_part {
     uint64_t seed;
     uint64_t num_keys;
-    uint64_t table_size;
-    uint64_t M_table_lo, M_table_hi; /* fastmod constant for table_size */
-    uint64_t num_dense, num_sparse;  /* skew_bucketer (utils/bucketers.hpp:197-206) */
-    uint64_t M_dense_lo, M_dense_hi;
-    uint64_t M_sparse_lo, M_sparse_hi;
+    uint64_t table_size, inv_table;
+    uint64_t num_dense, inv_dense;   /* skew_bucketer (utils/bucketers.hpp:197-206) */
+    uint64_t num_sparse, inv_sparse;
     uint64_t offset;      /* partitioned_phf partition offset (partitioned_phf.hpp:23-43) */
     uint64_t pilot_base;  /* first entry of this partition in hashed_pilots[] */
     uint64_t free_base;   /* first entry of this partition in free_slots[] */
-    uint64_t pad[2];
+    uint64_t pad[5];
 };
 
 /* one partitioned_phf (pthash/include/partitioned_phf.hpp:203-210) */
@@ -86,7 +89,7 @@ struct fgi_header {
     uint64_t off_hashed_pilots;  /* u64[] */
     uint64_t off_free_slots;     /* u32[] */
     uint64_t off_bucket_begin;   /* u32[num_minimizers + 1]: first super-k-mer id of bucket b (buckets.hpp:62-67) */
-    uint64_t off_sk_records;     /* uint2[num_super_kmers]: {offset, window << 27 | color_set_id} */
+    uint64_t off_sk_records;     /* uint2[num_super_kmers]: {offset, FGI_SK_* fields} */
     uint64_t off_strings;        /* u64[num_string_words + 2 pad] verbatim */
     uint64_t off_skew_positions; /* u32[] */
     uint64_t off_hybrids;        /* fgi_hybrid[num_partitions] */
@@ -96,10 +99,16 @@ struct fgi_header {
     uint64_t off_meta_vals;      /* u32[]: records [n, meta_color_1..n] */
     uint64_t off_part_min_color; /* u32[num_partitions + 1] */
     uint64_t off_part_sets_before; /* u32[num_partitions + 1] */
-    uint64_t reserved[8];
+    uint64_t off_sk_cid;         /* u32[num_super_kmers], only when num_color_sets > 2^21 (else 0): color-set ids that do not fit the record */
+    uint64_t num_unpinned;       /* super-k-mers whose k-mers disagree on the minimizer position (full window scan) */
+    uint64_t reserved[6];
 };
 
-#define FGI_SK_CID_BITS 27
+/* high word of a super-k-mer record */
+#define FGI_SK_CID_BITS 21
 #define FGI_SK_CID_MASK ((1u << FGI_SK_CID_BITS) - 1u)
+#define FGI_SK_WINDOW_SHIFT 21 /* 5 bits: number of k-mers of the super-k-mer */
+#define FGI_SK_PM_SHIFT 26     /* 5 bits: base offset of the canonical minimizer from the super-k-mer start */
+#define FGI_SK_PINNED_SHIFT 31 /* 1 bit: the minimizer position is the same for all k-mers of the super-k-mer */
 
 #endif

@@ -77,6 +77,7 @@ struct dev_index {
     const uint32_t* free_slots;
     const uint32_t* bucket_begin;
     const uint2* sk_records;
+    const uint32_t* sk_cid; /* nullptr unless the color-set ids do not fit the records */
     const uint64_t* strings;
     const uint32_t* skew_positions;
     const fgi_hybrid* hybrids;
@@ -111,16 +112,14 @@ FG_HD uint64_t murmur2_64(uint64_t key, uint64_t seed) {
     return h;
 }
 
-/* a mod d with the precomputed M = floor(2^128 / d) + 1 (pthash/external/fastmod/fastmod.h:159-162):
-   lowbits = M * a (mod 2^128); result = (lowbits * d) >> 128 */
-FG_HD uint64_t fastmod_u64(uint64_t a, uint64_t M_lo, uint64_t M_hi, uint64_t d) {
-    const uint64_t lo = M_lo * a;
-    const uint64_t hi = fg_mulhi64(M_lo, a) + M_hi * a;
-    const uint64_t bottom = fg_mulhi64(lo, d);
-    const uint64_t top_lo = hi * d;
-    const uint64_t top_hi = fg_mulhi64(hi, d);
-    const uint64_t sum = bottom + top_lo;
-    return top_hi + (sum < bottom ? 1 : 0);
+/* a mod d for d < 2^32 with inv = floor(2^64 / d) (image.h): q = mulhi(a, inv) is floor(a / d) or one less, so one
+   conditional subtraction gives the exact remainder -- the value the reference's fastmod_u64
+   (pthash/external/fastmod/fastmod.h:159-162) returns. */
+FG_HD uint64_t mod_by_inverse(uint64_t a, uint64_t inv, uint64_t d) {
+    const uint64_t q = fg_mulhi64(a, inv);
+    uint64_t r = a - q * d;
+    if (r >= d) r -= d;
+    return r;
 }
 
 /* partitioned_phf::operator() (pthash/partitioned_phf.hpp:150-159) -> single_phf::position
@@ -138,12 +137,12 @@ FG_HD uint64_t phf_lookup(const dev_index& I, uint32_t phf_id, uint64_t key) {
     const uint64_t num_dense = FG_LDG(&P->num_dense);
     uint64_t bucket;
     if (first < I.bucketer_T) {
-        bucket = fastmod_u64(first, FG_LDG(&P->M_dense_lo), FG_LDG(&P->M_dense_hi), num_dense);
+        bucket = mod_by_inverse(first, FG_LDG(&P->inv_dense), num_dense);
     } else {
-        bucket = num_dense + fastmod_u64(first, FG_LDG(&P->M_sparse_lo), FG_LDG(&P->M_sparse_hi), FG_LDG(&P->num_sparse));
+        bucket = num_dense + mod_by_inverse(first, FG_LDG(&P->inv_sparse), FG_LDG(&P->num_sparse));
     }
     const uint64_t hashed_pilot = FG_LDG(I.hashed_pilots + FG_LDG(&P->pilot_base) + bucket);
-    uint64_t pos = fastmod_u64(second ^ hashed_pilot, FG_LDG(&P->M_table_lo), FG_LDG(&P->M_table_hi), FG_LDG(&P->table_size));
+    uint64_t pos = mod_by_inverse(second ^ hashed_pilot, FG_LDG(&P->inv_table), FG_LDG(&P->table_size));
     const uint64_t num_keys = FG_LDG(&P->num_keys);
     if (pos >= num_keys) pos = FG_LDG(I.free_slots + FG_LDG(&P->free_base) + (pos - num_keys));
     return FG_LDG(&P->offset) + pos;
@@ -159,56 +158,108 @@ FG_HD uint64_t revcomp(uint64_t x, uint32_t k) {
     return y >> (64 - 2 * k);
 }
 
-/* util::compute_minimizer (sshash/util.hpp:220-239) with mixer_64 (sshash/hash_util.hpp:97) */
-template <int W /* k - m + 1, 0 = runtime */>
-FG_HD uint64_t kmer_minimizer(uint64_t x, uint32_t window, uint64_t mmer_mask, uint64_t magic) {
-    uint64_t best_h = UINT64_MAX, best = UINT64_MAX;
-    const int n = W ? W : int(window);
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
+/* canonical minimizer of a k-mer and WHERE it sits. value = min over both strands (compared as integers,
+   sshash/streaming_query.hpp:76-79) of util::compute_minimizer (sshash/util.hpp:220-239: the m-mer with the smallest
+   mixer_64 hash, sshash/hash_util.hpp:97; first one wins). cpos = base offset of that m-mer inside the k-mer in forward
+   coordinates; ambiguous = both strands yield the same value, so the position is not unique. */
+struct minimizer_t {
+    uint64_t value;
+    uint32_t cpos;
+    bool ambiguous;
+};
+
+FG_HD minimizer_t combine_strands(uint64_t vf, uint32_t jf, uint64_t vr, uint32_t jr, uint32_t k, uint32_t m) {
+    minimizer_t r;
+    r.ambiguous = vf == vr;
+    if (vf <= vr) {
+        r.value = vf;
+        r.cpos = jf;
+    } else {
+        r.value = vr;
+        r.cpos = (k - m) - jr;
+    }
+    return r;
+}
+
+/* straight evaluation from the k-mer (host emulation, and the specification of the shared-memory pipeline below) */
+FG_HD void strand_minimizer(uint64_t x, uint32_t window, uint64_t mmer_mask, uint64_t magic, uint64_t& value, uint32_t& pos) {
+    uint64_t best_h = UINT64_MAX;
+    value = UINT64_MAX;
+    pos = 0;
+    for (uint32_t i = 0; i < window; ++i) {
         const uint64_t y = x & mmer_mask;
         const uint64_t h = (y * 0x517cc1b727220a95ULL) ^ magic;
         if (h < best_h) {
             best_h = h;
-            best = y;
+            value = y;
+            pos = i;
         }
         x >>= 2;
     }
-    return best;
+}
+FG_HD minimizer_t canonical_minimizer(uint64_t fwd, uint64_t rc, uint32_t k, uint32_t m, uint64_t magic) {
+    const uint64_t mmer_mask = (1ULL << (2 * m)) - 1;
+    uint64_t vf, vr;
+    uint32_t jf, jr;
+    strand_minimizer(fwd, k - m + 1, mmer_mask, magic, vf, jf);
+    strand_minimizer(rc, k - m + 1, mmer_mask, magic, vr, jr);
+    return combine_strands(vf, jf, vr, jr, k, m);
 }
 
 FG_HD uint32_t ceil_log2_u32(uint32_t v) { /* bits/util.hpp ceil_log2_uint32 */
     return v <= 1 ? 0u : 32u - fg_clz32(v - 1);
 }
 
-/* lookup_canonical_in_super_kmer (sshash/buckets.hpp:133-160) on the flattened record: compare the
-   k-mer and its reverse complement with the `window` consecutive k-mers that start at `offset` in the
-   2-bit strings. Returns the color-set id of the enclosing unitig, or FG_NOT_FOUND. */
-FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t rc, uint64_t kmask) {
+/* lookup_canonical_in_super_kmer (sshash/buckets.hpp:133-160) on the flattened record: is the k-mer (or its reverse
+   complement) one of the `window` consecutive k-mers that start at `offset` in the 2-bit strings? The reference compares
+   all of them. Here the record knows where the canonical minimizer of every k-mer of the super-k-mer sits (pm, relative to
+   the super-k-mer start; image.h), and the query knows where its own sits (mz.cpos): if the query equals the stored k-mer
+   at window index t in forward orientation then t + cpos = pm, in reverse orientation t + (k - m - cpos) = pm -- equal
+   k-mers have equal minimizers at equal positions -- so at most two positions can match and only those are compared.
+   Records whose k-mers disagree on the position (not pinned) and queries with an ambiguous position fall back to the full
+   scan. Returns the color-set id of the enclosing unitig, or FG_NOT_FOUND. */
+FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t rc, uint64_t kmask, const minimizer_t& mz) {
     const uint2 rec = FG_LDG(I.sk_records + sk);
-    const uint32_t window = rec.y >> FGI_SK_CID_BITS;
+    const uint32_t window = (rec.y >> FGI_SK_WINDOW_SHIFT) & 31u;
     const uint64_t bit = 2 * uint64_t(rec.x);
     const uint64_t* w = I.strings + (bit >> 6);
     const uint32_t sh = uint32_t(bit & 63);
     const uint64_t w0 = FG_LDG(w), w1 = FG_LDG(w + 1), w2 = FG_LDG(w + 2);
-    uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
-    uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
     bool hit = false;
-    for (uint32_t t = 0; t < window; ++t) {
-        const uint64_t cand = lo & kmask;
-        hit |= (cand == fwd) | (cand == rc);
-        lo = (lo >> 2) | (hi << 62);
-        hi >>= 2;
+    if ((rec.y >> FGI_SK_PINNED_SHIFT) && !mz.ambiguous) {
+        const uint32_t pm = (rec.y >> FGI_SK_PM_SHIFT) & 31u;
+        const uint32_t t_fwd = pm - mz.cpos, t_rc = pm - ((I.k - I.m) - mz.cpos); /* wrap around when negative */
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const uint32_t t = o ? t_rc : t_fwd;
+            if (t < window) {
+                const uint32_t s2 = sh + 2 * t;
+                const uint64_t a = (s2 & 64) ? w1 : w0, b = (s2 & 64) ? w2 : w1;
+                const uint32_t s = s2 & 63;
+                const uint64_t cand = (s ? (a >> s) | (b << (64 - s)) : a) & kmask;
+                hit |= cand == (o ? rc : fwd);
+            }
+        }
+    } else {
+        uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+        uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+        for (uint32_t t = 0; t < window; ++t) {
+            const uint64_t cand = lo & kmask;
+            hit |= (cand == fwd) | (cand == rc);
+            lo = (lo >> 2) | (hi << 62);
+            hi >>= 2;
+        }
     }
-    return hit ? (rec.y & FGI_SK_CID_MASK) : FG_NOT_FOUND;
+    if (!hit) return FG_NOT_FOUND;
+    return I.sk_cid ? FG_LDG(I.sk_cid + sk) : (rec.y & FGI_SK_CID_MASK);
 }
 
 /* dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:47-77) + buckets::lookup_canonical
    (sshash/buckets.hpp:162-209) + index::u2c. The "minimizer of the bucket's first k-mer must equal
    the target" test (buckets.hpp:168-180) is an early-out only: equal k-mers have equal minimizers,
    so a k-mer whose minimizer is absent cannot match any stored k-mer. */
-FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, uint64_t minimizer, uint64_t kmask) {
-    const uint64_t b = phf_lookup(I, 0, minimizer);
+FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, const minimizer_t& mz, uint64_t kmask) {
+    const uint64_t b = phf_lookup(I, 0, mz.value);
     const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
     const uint32_t n = end - begin;
     if (I.num_skew != 0) {
@@ -220,12 +271,12 @@ FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, u
             if (FG_LDG(&I.phfs[f].num_partitions) == 0) return FG_NOT_FOUND;
             const uint64_t h = phf_lookup(I, f, fwd < rc ? fwd : rc);
             const uint32_t pos = FG_LDG(I.skew_positions + I.skew_pos_base[pid] + h);
-            if (pos < n) return scan_super_kmer(I, begin + pos, fwd, rc, kmask);
+            if (pos < n) return scan_super_kmer(I, begin + pos, fwd, rc, kmask, mz);
             return FG_NOT_FOUND;
         }
     }
     for (uint32_t s = begin; s < end; ++s) {
-        const uint32_t cid = scan_super_kmer(I, s, fwd, rc, kmask);
+        const uint32_t cid = scan_super_kmer(I, s, fwd, rc, kmask, mz);
         if (cid != FG_NOT_FOUND) return cid;
     }
     return FG_NOT_FOUND;
@@ -249,59 +300,121 @@ __device__ __forceinline__ void pack_chars(uint32_t c, bool in_range, uint32_t l
     valid = __ballot_sync(FG_FULL, in_range && base_valid(c));
 }
 
+/* per-warp shared-memory staging of one read segment: 2-bit packed bases, validity bits, and the mixer_64 hash of the
+   m-mer that starts at every position, for both strands */
+#define FG_SEG_KMERS 160                  /* k-mers per segment (5 tiles) */
+#define FG_SEG_POS (FG_SEG_KMERS + 32)    /* m-mer start positions per segment: FG_SEG_KMERS + (k - m) <= +30 */
+#define FG_SEG_WORDS 8                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 pad */
+struct warp_stage {
+    uint64_t hf[FG_SEG_POS];  /* hash of the forward m-mer at position q */
+    uint64_t hr[FG_SEG_POS];  /* hash of its reverse complement */
+    uint64_t words[FG_SEG_WORDS];
+    uint32_t valid[FG_SEG_WORDS];
+};
+
 /* Walks one read in tiles of 32 consecutive k-mers: after next(), lane l holds the color-set id of the
    k-mer that starts at position t0 + l (FG_NOT_FOUND when negative, invalid or past the end).
    Replaces the per-k-mer loop around streaming_query::lookup_advanced (sshash/streaming_query.hpp:50-109,
    driven from src/ps_full_intersection.cpp:344-353): validity test (:53-59), 2-bit packing and reverse
-   complement (:62-74), canonical minimizer (:76-83), dictionary lookup (:144-190). */
+   complement (:62-74), canonical minimizer (:76-83), dictionary lookup (:144-190).
+   Per segment of FG_SEG_KMERS k-mers the warp first packs the bases and hashes every m-mer ONCE into shared
+   memory; a lane then takes the minimum over its k - m + 1 window from there (the k-mers of a read share
+   almost all their m-mers, which the reference exploits with its sliding minimizer_enumerator,
+   sshash/minimizer_enumerator.hpp:24-49). */
 template <int W>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
-    uint32_t len, lane, nk, t0;
-    uint64_t kmask, mmer_mask, w0, w1;
-    uint32_t window, kbits, v0, v1;
+    warp_stage& S;
+    uint32_t len, lane, nk, t0, seg0, seg_nk;
+    uint64_t kmask, mmer_mask;
+    uint32_t window, kbits;
 
-    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, uint32_t lane_)
-        : I(I_), seq(seq_), len(len_), lane(lane_) {
+    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, uint32_t lane_, warp_stage& S_)
+        : I(I_), seq(seq_), S(S_), len(len_), lane(lane_) {
         const uint32_t k = I.k;
         nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
         t0 = 0;
+        seg0 = 0;
+        seg_nk = 0;
         kmask = (1ULL << (2 * k)) - 1;
         mmer_mask = (1ULL << (2 * I.m)) - 1;
-        window = k - I.m + 1;
+        window = W ? W : k - I.m + 1;
         kbits = (1u << k) - 1u;
-        w1 = 0;
-        v1 = 0;
-        if (nk) {
-            const uint32_t c = lane < len ? seq[lane] : 0u;
-            pack_chars(c, lane < len, lane, w0, v0);
-        } else {
-            w0 = 0;
-            v0 = 0;
-        }
     }
     __device__ __forceinline__ bool done() const { return t0 >= nk; }
-    __device__ __forceinline__ uint32_t next() {
-        {
-            const uint32_t p = t0 + 32 + lane;
-            const uint32_t c = p < len ? seq[p] : 0u;
-            pack_chars(c, p < len, lane, w1, v1);
-        }
-        const uint32_t i = t0 + lane;
-        const bool valid = i < nk && ((__funnelshift_r(v0, v1, lane) & kbits) == kbits);
-        uint32_t cid = FG_NOT_FOUND;
-        if (valid) {
-            const uint32_t sh = 2 * lane;
-            const uint64_t fwd = (sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0) & kmask;
-            const uint64_t rc = revcomp(fwd, I.k);
-            const uint64_t a = kmer_minimizer<W>(fwd, window, mmer_mask, I.hash_magic);
-            const uint64_t b = kmer_minimizer<W>(rc, window, mmer_mask, I.hash_magic);
-            cid = lookup_color_set(I, fwd, rc, a < b ? a : b, kmask);
+
+    /* 2*nbases bits starting at base position p (segment-relative) of the packed words */
+    __device__ __forceinline__ uint64_t bases_at(uint32_t p) const {
+        const uint32_t wi = p >> 5, sh = (p & 31) * 2;
+        const uint64_t a = S.words[wi];
+        return sh ? (a >> sh) | (S.words[wi + 1] << (64 - sh)) : a;
+    }
+
+    __device__ __forceinline__ void load_segment() {
+        __syncwarp();
+        seg0 = t0;
+        seg_nk = min(uint32_t(FG_SEG_KMERS), nk - seg0);
+        const uint32_t nchars = seg_nk + I.k - 1, npos = seg_nk + window - 1;
+        const uint32_t nwords = (nchars + 31) >> 5;
+        for (uint32_t c = 0; c <= nwords; ++c) { /* one extra zero word so that bases_at may read words[wi + 1] */
+            const uint32_t p = seg0 + 32 * c + lane;
+            const bool in = c < nwords && 32 * c + lane < nchars;
+            const uint32_t ch = in ? seq[p] : 0u;
+            uint64_t w;
+            uint32_t v;
+            pack_chars(ch, in, lane, w, v);
+            if (lane == 0) {
+                S.words[c] = w;
+                S.valid[c] = v;
+            }
         }
         __syncwarp();
-        w0 = w1;
-        v0 = v1;
+        const uint32_t m = I.m;
+        for (uint32_t q = lane; q < npos; q += 32) {
+            const uint64_t y = bases_at(q) & mmer_mask;
+            S.hf[q] = (y * 0x517cc1b727220a95ULL) ^ I.hash_magic;
+            S.hr[q] = (revcomp(y, m) * 0x517cc1b727220a95ULL) ^ I.hash_magic;
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ uint32_t next() {
+        if (t0 == seg0 + seg_nk) load_segment();
+        const uint32_t i = t0 - seg0 + lane; /* segment-relative k-mer index */
+        bool valid = i < seg_nk;
+        if (valid) {
+            const uint32_t wi = i >> 5;
+            valid = (__funnelshift_r(S.valid[wi], S.valid[wi + 1], i & 31) & kbits) == kbits;
+        }
+        uint32_t cid = FG_NOT_FOUND;
+        if (valid) {
+            const uint64_t fwd = bases_at(i) & kmask;
+            const uint64_t rc = revcomp(fwd, I.k);
+            /* forward strand: m-mers in read order, first minimum wins; reverse strand: its j-th m-mer is the reverse
+               complement of the forward m-mer at read position i + window - 1 - j */
+            uint64_t bf = UINT64_MAX, br = UINT64_MAX;
+            uint32_t jf = 0, jr = 0;
+            const int n = W ? W : int(window);
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const uint64_t h = S.hf[i + j];
+                if (h < bf) {
+                    bf = h;
+                    jf = j;
+                }
+                const uint64_t g = S.hr[i + (n - 1 - j)];
+                if (g < br) {
+                    br = g;
+                    jr = j;
+                }
+            }
+            const uint64_t vf = bf == UINT64_MAX ? UINT64_MAX : (fwd >> (2 * jf)) & mmer_mask;
+            const uint64_t vr = br == UINT64_MAX ? UINT64_MAX : (rc >> (2 * jr)) & mmer_mask;
+            const minimizer_t mz = combine_strands(vf, jf, vr, jr, I.k, I.m);
+            cid = lookup_color_set(I, fwd, rc, mz, kmask);
+        }
+        __syncwarp();
         t0 += 32;
         return cid;
     }
@@ -388,7 +501,7 @@ __device__ __noinline__ void table_sort(uint2* tab, uint32_t n, uint32_t lane) {
    and one bitonic sort at the end. */
 template <int W>
 __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, uint32_t lane,
-                                                           uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
+                                                           warp_stage& stage, uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
     read_hits R;
     R.cid = FG_NOT_FOUND;
     R.cnt = 0;
@@ -397,7 +510,7 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
     R.tab = nullptr;
     R.cap = 0;
     R.failed = false;
-    kmer_tiles<W> tiles(I, seq, len, lane);
+    kmer_tiles<W> tiles(I, seq, len, lane, stage);
     while (!tiles.done()) {
         const uint32_t cid = tiles.next();
         const bool found = cid != FG_NOT_FOUND;

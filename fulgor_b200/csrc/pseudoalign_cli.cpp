@@ -347,7 +347,7 @@ int main(int argc, char** argv) {
         else std::cerr << "--deduplicate is not needed on the GPU path (results are identical without it). Remove --deduplicate flag." << std::endl;
         return 1;
     }
-    if (!(ends_with(a.index, ".fur"))) { /* .fur, .mfur, .dfur, .mdfur all end in "fur" (tools/util.cpp:5-19) */
+    if (!(ends_with(a.index, ".fur") || ends_with(a.index, ".mfur") || ends_with(a.index, ".dfur") || ends_with(a.index, ".mdfur"))) { /* tools/util.cpp:5-19 */
         std::cerr << "Wrong index filename supplied." << std::endl;
         return 1;
     }

@@ -20,6 +20,7 @@ static dev_index view_of(const uint8_t* base) {
     I.free_slots = reinterpret_cast<const uint32_t*>(base + H.off_free_slots);
     I.bucket_begin = reinterpret_cast<const uint32_t*>(base + H.off_bucket_begin);
     I.sk_records = reinterpret_cast<const uint2*>(base + H.off_sk_records);
+    I.sk_cid = H.off_sk_cid ? reinterpret_cast<const uint32_t*>(base + H.off_sk_cid) : nullptr;
     I.strings = reinterpret_cast<const uint64_t*>(base + H.off_strings);
     I.skew_positions = reinterpret_cast<const uint32_t*>(base + H.off_skew_positions);
     I.hybrids = reinterpret_cast<const fgi_hybrid*>(base + H.off_hybrids);
@@ -55,7 +56,7 @@ void emul_lookup_read(const uint8_t* image, const char* seq, uint64_t len, uint3
     const dev_index I = view_of(image);
     const uint32_t k = I.k;
     if (len < k) return;
-    const uint64_t kmask = (1ULL << (2 * k)) - 1, mmer_mask = (1ULL << (2 * I.m)) - 1;
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
     for (uint64_t i = 0; i + k <= len; ++i) {
         bool valid = true;
         uint64_t fwd = 0;
@@ -69,9 +70,8 @@ void emul_lookup_read(const uint8_t* image, const char* seq, uint64_t len, uint3
             continue;
         }
         const uint64_t rc = revcomp(fwd, k);
-        const uint64_t a = kmer_minimizer<0>(fwd, k - I.m + 1, mmer_mask, I.hash_magic);
-        const uint64_t b = kmer_minimizer<0>(rc, k - I.m + 1, mmer_mask, I.hash_magic);
-        cids[i] = lookup_color_set(I, fwd, rc, a < b ? a : b, kmask);
+        const minimizer_t mz = canonical_minimizer(fwd, rc, k, I.m, I.hash_magic);
+        cids[i] = lookup_color_set(I, fwd, rc, mz, kmask);
     }
 }
 
