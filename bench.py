@@ -281,9 +281,10 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_pseudoalign_small_dram_bytes_per_launch")
+            per_read = json.load(open(tpath)).get("k_pseudoalign_small_dram_bytes_per_read")
+            traffic = per_read * n if per_read else None  # ncu DRAM bytes per read of the same kernel x reads per launch
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "k_pseudoalign_small", "kernel_ms_per_launch": k1_ms_per_launch, "kernel_share_of_step": k1_ms / (dev_ms if world == 1 else k1_ms + 1e-9) if world == 1 else None,
+                    "kernel": "k_pseudoalign_small", "kernel_ms_per_launch": k1_ms_per_launch, "kernel_share_of_step": (k1_ms / dev_ms) if world == 1 else None,
                     "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src}
 
         cpu_baseline = None

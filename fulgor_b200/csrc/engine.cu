@@ -489,6 +489,8 @@ static dev_index make_view(const fgi_header& H, const uint8_t* base) {
     I.type = H.type;
     I.num_colors = H.num_colors;
     I.num_partitions = H.num_partitions;
+    I.main_seed = 0;
+    I.main_nparts = 0;
     return I;
 }
 
@@ -508,6 +510,13 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
     x->owns_image = owns;
     x->I = make_view(H, static_cast<const uint8_t*>(d_image));
     try {
+        /* the minimizer MPHF's descriptor goes into the kernel parameters */
+        fgi_phf main_phf;
+        FG_CUDA(cudaMemcpy(&main_phf, static_cast<const uint8_t*>(d_image) + H.off_phfs, sizeof(main_phf), cudaMemcpyDeviceToHost));
+        if (main_phf.first_part != 0 || main_phf.num_partitions == 0) throw std::runtime_error("unexpected minimizer MPHF layout in the image");
+        FG_CUDA(cudaMemcpy(&x->I.main_part, static_cast<const uint8_t*>(d_image) + H.off_phf_parts, sizeof(fgi_phf_part), cudaMemcpyDeviceToHost));
+        x->I.main_seed = main_phf.seed;
+        x->I.main_nparts = main_phf.num_partitions;
         cudaDeviceProp prop;
         FG_CUDA(cudaGetDeviceProperties(&prop, device));
         x->sm_count = prop.multiProcessorCount;

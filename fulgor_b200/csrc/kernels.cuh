@@ -93,6 +93,8 @@ struct dev_index {
     uint32_t skew_phf[FGI_MAX_SKEW];
     uint64_t skew_pos_base[FGI_MAX_SKEW];
     uint32_t type, num_colors, num_partitions, pad;
+    uint64_t main_seed, main_nparts; /* the minimizer MPHF (phfs[0]; its partitions are parts[0 .. main_nparts)) */
+    fgi_phf_part main_part;          /* parts[0] */
 };
 
 /* ------------------------------------------------------------------ hashing */
@@ -122,9 +124,38 @@ FG_HD uint64_t mod_by_inverse(uint64_t a, uint64_t inv, uint64_t d) {
     return r;
 }
 
-/* partitioned_phf::operator() (pthash/partitioned_phf.hpp:150-159) -> single_phf::position
-   (pthash/single_phf.hpp:79-101) with murmurhash2_128 (utils/hasher.hpp:203-207), skew_bucketer
-   (utils/bucketers.hpp:163-168), xor displacement, minimal (free slots) */
+/* single_phf::position (pthash/single_phf.hpp:79-101): skew_bucketer (utils/bucketers.hpp:163-168), pre-hashed pilot,
+   xor displacement, minimal (free slots) */
+FG_HD uint64_t phf_position(const dev_index& I, const fgi_phf_part& P, uint64_t first, uint64_t second) {
+    uint64_t bucket;
+    if (first < I.bucketer_T) {
+        bucket = mod_by_inverse(first, P.inv_dense, P.num_dense);
+    } else {
+        bucket = P.num_dense + mod_by_inverse(first, P.inv_sparse, P.num_sparse);
+    }
+    const uint64_t hashed_pilot = FG_LDG(I.hashed_pilots + P.pilot_base + bucket);
+    uint64_t pos = mod_by_inverse(second ^ hashed_pilot, P.inv_table, P.table_size);
+    if (pos >= P.num_keys) pos = FG_LDG(I.free_slots + P.free_base + (pos - P.num_keys));
+    return P.offset + pos;
+}
+
+FG_HD fgi_phf_part load_part(const fgi_phf_part* p) {
+    fgi_phf_part P;
+    P.num_keys = FG_LDG(&p->num_keys);
+    P.table_size = FG_LDG(&p->table_size);
+    P.inv_table = FG_LDG(&p->inv_table);
+    P.num_dense = FG_LDG(&p->num_dense);
+    P.inv_dense = FG_LDG(&p->inv_dense);
+    P.num_sparse = FG_LDG(&p->num_sparse);
+    P.inv_sparse = FG_LDG(&p->inv_sparse);
+    P.offset = FG_LDG(&p->offset);
+    P.pilot_base = FG_LDG(&p->pilot_base);
+    P.free_base = FG_LDG(&p->free_base);
+    return P;
+}
+
+/* partitioned_phf::operator() (pthash/partitioned_phf.hpp:150-159) with murmurhash2_128 (utils/hasher.hpp:203-207) and
+   range_bucketer (utils/bucketers.hpp:216-218) */
 FG_HD uint64_t phf_lookup(const dev_index& I, uint32_t phf_id, uint64_t key) {
     const fgi_phf* F = I.phfs + phf_id;
     const uint64_t seed = FG_LDG(&F->seed);
@@ -132,20 +163,18 @@ FG_HD uint64_t phf_lookup(const dev_index& I, uint32_t phf_id, uint64_t key) {
     const uint64_t first = murmur2_64(key, seed);
     const uint64_t second = murmur2_64(key, ~seed);
     uint64_t p = 0;
-    if (nparts > 1) p = (((first ^ second) >> 32) * nparts) >> 32; /* range_bucketer, bucketers.hpp:216-218 */
-    const fgi_phf_part* P = I.parts + FG_LDG(&F->first_part) + p;
-    const uint64_t num_dense = FG_LDG(&P->num_dense);
-    uint64_t bucket;
-    if (first < I.bucketer_T) {
-        bucket = mod_by_inverse(first, FG_LDG(&P->inv_dense), num_dense);
-    } else {
-        bucket = num_dense + mod_by_inverse(first, FG_LDG(&P->inv_sparse), FG_LDG(&P->num_sparse));
-    }
-    const uint64_t hashed_pilot = FG_LDG(I.hashed_pilots + FG_LDG(&P->pilot_base) + bucket);
-    uint64_t pos = mod_by_inverse(second ^ hashed_pilot, FG_LDG(&P->inv_table), FG_LDG(&P->table_size));
-    const uint64_t num_keys = FG_LDG(&P->num_keys);
-    if (pos >= num_keys) pos = FG_LDG(I.free_slots + FG_LDG(&P->free_base) + (pos - num_keys));
-    return FG_LDG(&P->offset) + pos;
+    if (nparts > 1) p = (((first ^ second) >> 32) * nparts) >> 32;
+    return phf_position(I, load_part(I.parts + FG_LDG(&F->first_part) + p), first, second);
+}
+
+/* minimizers::lookup (sshash/minimizers.hpp:36-39): the minimizer MPHF. With a single partition (up to ~3 M minimizers,
+   sshash/constants.hpp:13) its descriptor travels in the kernel parameters (constant bank), not through loads. */
+FG_HD uint64_t minimizer_bucket(const dev_index& I, uint64_t minimizer) {
+    const uint64_t first = murmur2_64(minimizer, I.main_seed);
+    const uint64_t second = murmur2_64(minimizer, ~I.main_seed);
+    if (I.main_nparts == 1) return phf_position(I, I.main_part, first, second);
+    const uint64_t p = (((first ^ second) >> 32) * I.main_nparts) >> 32;
+    return phf_position(I, load_part(I.parts + p), first, second);
 }
 
 /* ------------------------------------------------------------------ k-mers */
@@ -259,7 +288,7 @@ FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, ui
    the target" test (buckets.hpp:168-180) is an early-out only: equal k-mers have equal minimizers,
    so a k-mer whose minimizer is absent cannot match any stored k-mer. */
 FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, const minimizer_t& mz, uint64_t kmask) {
-    const uint64_t b = phf_lookup(I, 0, mz.value);
+    const uint64_t b = minimizer_bucket(I, mz.value);
     const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
     const uint32_t n = end - begin;
     if (I.num_skew != 0) {

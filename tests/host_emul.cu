@@ -45,6 +45,9 @@ static dev_index view_of(const uint8_t* base) {
     I.type = H.type;
     I.num_colors = H.num_colors;
     I.num_partitions = H.num_partitions;
+    I.main_seed = I.phfs[0].seed;
+    I.main_nparts = I.phfs[0].num_partitions;
+    I.main_part = I.parts[0];
     return I;
 }
 
