@@ -28,7 +28,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     if force or _stale(LIB, LIB_DEPS):
-        cmd = [NVCC] + ARCH + COMMON + ["-shared", "-o", LIB] + LIB_SOURCES
+        cmd = [NVCC] + ARCH + COMMON + os.environ.get("FG_NVCC_FLAGS", "").split() + ["-shared", "-o", LIB] + LIB_SOURCES
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

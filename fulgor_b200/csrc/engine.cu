@@ -4,7 +4,7 @@
  *
  * Per chunk of reads (host API) the stream order is
  *     H2D(bases, read_off) -> K1(+K2 fused when num_colors <= 32) -> [K2] -> scan -> emit -> D2H
- * with two slots so that the copies of one chunk overlap the kernels of the other. The only
+ * with three slots so that the copies of one chunk overlap the kernels of the others. The only
  * cross-chunk dependency is the running CSR offset, carried in device memory.
  */
 #include <cuda_runtime.h>
@@ -28,6 +28,9 @@ namespace fgb {
 
 #define FG_WARPS_PER_BLOCK 8
 #define FG_BLOCK (FG_WARPS_PER_BLOCK * 32)
+#ifndef FG_MIN_BLOCKS
+#define FG_MIN_BLOCKS 5 /* resident blocks per SM the lookup kernels are compiled for (register budget 65536 / (5 * 256) = 51) */
+#endif
 #define FG_STAGE_STRIDE FG_MAX_ENTRIES
 
 /* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask,
@@ -36,7 +39,7 @@ namespace fgb {
    Threshold union (src/ps_threshold_union.cpp:389 + merge :17-40 / merge_meta :43-120): color c is
    reported iff sum over positive k-mers of [c in set(k-mer)] >= uint64(double(npos) * threshold). */
 template <int W>
-__global__ void __launch_bounds__(FG_BLOCK) k_pseudoalign_small(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
                                                                const uint64_t* __restrict__ read_off, uint64_t read_off_base,
                                                                uint32_t n_reads, int algo, double threshold,
                                                                uint32_t* __restrict__ masks) {
@@ -102,7 +105,7 @@ __device__ __forceinline__ const uint2* entries_of(uint32_t r, uint32_t n, const
 
 /* K1 alone: per read, ascending distinct color-set ids with multiplicities */
 template <int W>
-__global__ void __launch_bounds__(FG_BLOCK) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
                                                               const uint64_t* __restrict__ read_off, uint64_t read_off_base,
                                                               uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
                                                               uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool) {
@@ -405,6 +408,7 @@ struct dev_buffer {
     T* as() const { return static_cast<T*>(p); }
 };
 
+#define FG_NUM_SLOTS 3 /* chunks in flight in the host pipeline: copy-in, compute, copy-out */
 struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
@@ -426,7 +430,7 @@ struct fulgor_gpu_index {
     void* d_image = nullptr;
     bool owns_image = false;
     dev_index I{};
-    slot slots[2];
+    slot slots[FG_NUM_SLOTS];
     uint64_t* d_carry = nullptr;
     int sm_count = 0;
     uint64_t pool_per_read = 8; /* entry-pool size per read of a chunk; grows (x4) when a launch exhausts it */
@@ -482,6 +486,8 @@ static dev_index make_view(const fgi_header& H, const uint8_t* base) {
     I.skew_max_log2 = H.skew_max_log2;
     I.skew_log2_max_bucket = H.skew_log2_max_bucket;
     I.num_skew = H.num_skew;
+    I.skew_threshold = H.num_skew ? (1u << H.skew_min_log2) : UINT32_MAX;
+    I.guard_max_hash = uint32_t(H.guard_max_hash);
     for (int i = 0; i < FGI_MAX_SKEW; ++i) {
         I.skew_phf[i] = H.skew_phf[i];
         I.skew_pos_base[i] = H.skew_pos_base[i];
@@ -554,7 +560,7 @@ static void dispatch_window(const fgi_header& H, F&& f) {
 
 static uint32_t read_grid(const fulgor_gpu_index* x, uint32_t n_reads) {
     const uint64_t blocks_needed = (uint64_t(n_reads) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK;
-    const uint64_t resident = uint64_t(x->sm_count) * 8; /* a multiple of the SM count; warps stride over reads */
+    const uint64_t resident = uint64_t(x->sm_count) * FG_MIN_BLOCKS * 2; /* a multiple of the SM count; warps stride over reads */
     return uint32_t(std::max<uint64_t>(1, std::min(blocks_needed, resident)));
 }
 
@@ -694,13 +700,6 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     if (op == op_kind::PSEUDOALIGN && !small)
         max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (((x->H.num_colors + 31) / 32) * 4)));
     struct pending { uint32_t first, n; int slot; emit_plan plan; };
-    std::vector<pending> chunks;
-    for (uint32_t first = 0; first < n_reads;) {
-        uint32_t n = 1;
-        while (first + n < n_reads && n < max_reads && read_off[first + n + 1] - read_off[first] <= CHUNK_MAX_BASES) ++n;
-        chunks.push_back({first, n, int(chunks.size() & 1), emit_plan()});
-        first += n;
-    }
     bool too_big = false, exhausted = false;
     cudaEvent_t prev_scanned = nullptr;
 
@@ -721,8 +720,27 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         FG_CUDA(cudaEventRecord(s.done, s.stream));
     };
 
-    for (size_t ci = 0; ci < chunks.size(); ++ci) {
-        pending& c = chunks[ci];
+    /* chunks are cut and validated on the fly, so the host-side O(n) work overlaps the GPU work of earlier chunks */
+    pending prev{};
+    bool have_prev = false;
+    uint32_t ci = 0;
+    for (uint32_t first = 0; first < n_reads; ++ci) {
+        uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
+        if (read_off[first + n] - read_off[first] > CHUNK_MAX_BASES) { /* largest n >= 1 within the byte budget */
+            uint32_t lo = 1, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo + 1) / 2;
+                if (read_off[first + mid] - read_off[first] <= CHUNK_MAX_BASES) lo = mid; else hi = mid - 1;
+            }
+            n = lo;
+        }
+        {
+            const uint64_t* ro = read_off + first;
+            uint64_t bad = 0;
+            for (uint32_t i = 0; i < n; ++i) bad |= (ro[i + 1] - ro[i]) >> 31; /* also catches decreasing offsets (wrap-around) */
+            if (bad) throw std::invalid_argument("read_off must be non-decreasing and reads shorter than 2^31 characters");
+        }
+        pending c{first, n, int(ci % FG_NUM_SLOTS), emit_plan()};
         slot& s = x->slots[c.slot];
         if (s.busy) FG_CUDA(cudaEventSynchronize(s.done));
         s.busy = true;
@@ -753,9 +771,12 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         FG_CUDA(cudaMemcpyAsync(out_off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
         if (op == op_kind::FETCH && num_positive)
             FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.npos.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (ci > 0) finalize(chunks[ci - 1]);
+        if (have_prev) finalize(prev);
+        prev = c;
+        have_prev = true;
+        first += n;
     }
-    finalize(chunks.back());
+    if (have_prev) finalize(prev);
     for (auto& s : x->slots) {
         FG_CUDA(cudaStreamSynchronize(s.stream));
         s.busy = false;
@@ -769,10 +790,6 @@ static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double thre
     FG_CUDA(cudaSetDevice(x->device));
     out_off[0] = 0;
     if (n_reads == 0) return 0;
-    for (uint32_t i = 0; i < n_reads; ++i) {
-        if (read_off[i + 1] < read_off[i]) throw std::invalid_argument("read_off must be non-decreasing");
-        if (read_off[i + 1] - read_off[i] >= (1ull << 31)) throw std::invalid_argument("reads of 2^31 characters or more are not supported");
-    }
     for (int attempt = 0; attempt < 12; ++attempt) {
         const int rc = run_host_batch_once(x, op, algo, threshold, bases, read_off, n_reads, out_off, out_vals, cap, num_positive);
         if (rc != RC_RETRY_LARGER_POOL) return rc;

@@ -498,6 +498,15 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
         if (!e.empty()) throw std::runtime_error(e);
     for (uint64_t v : unpinned) H.num_unpinned += v;
 
+    /* util::compute_minimizer (sshash/util.hpp:220-239) starts from min_hash = UINT64_MAX with a strict '<', so a k-mer whose
+       m-mers ALL hash to UINT64_MAX gets the sentinel UINT64_MAX as its "minimizer". The hash is a bijection, so this needs all
+       k-m+1 m-mers of the k-mer to be equal, i.e. one of the four homopolymers. Tell the kernels whether that can happen. */
+    for (uint64_t base = 0; base < 4; ++base) {
+        uint64_t y = 0;
+        for (uint32_t i = 0; i < H.m; ++i) y |= base << (2 * i);
+        if (((y * 0x517cc1b727220a95ULL) ^ H.hash_magic) == UINT64_MAX) H.guard_max_hash = 1;
+    }
+
     H.num_string_words = strings.words.size();
     H.num_phfs = uint32_t(F.phfs.size());
     H.num_phf_parts = uint32_t(F.parts.size());

@@ -101,7 +101,8 @@ struct fgi_header {
     uint64_t off_part_sets_before; /* u32[num_partitions + 1] */
     uint64_t off_sk_cid;         /* u32[num_super_kmers], only when num_color_sets > 2^21 (else 0): color-set ids that do not fit the record */
     uint64_t num_unpinned;       /* super-k-mers whose k-mers disagree on the minimizer position (full window scan) */
-    uint64_t reserved[6];
+    uint64_t guard_max_hash;     /* 1 iff some homopolymer m-mer hashes to UINT64_MAX (then compute_minimizer's "no minimum found" value matters) */
+    uint64_t reserved[5];
 };
 
 /* high word of a super-k-mer record */

@@ -90,9 +90,10 @@ struct dev_index {
     uint64_t hash_magic, bucketer_T;
     uint32_t k, m;
     uint32_t skew_min_log2, skew_max_log2, skew_log2_max_bucket, num_skew;
+    uint32_t skew_threshold, pad1; /* buckets with more super-k-mers go through the skew index; UINT32_MAX when there is none */
     uint32_t skew_phf[FGI_MAX_SKEW];
     uint64_t skew_pos_base[FGI_MAX_SKEW];
-    uint32_t type, num_colors, num_partitions, pad;
+    uint32_t type, num_colors, num_partitions, guard_max_hash;
     uint64_t main_seed, main_nparts; /* the minimizer MPHF (phfs[0]; its partitions are parts[0 .. main_nparts)) */
     fgi_phf_part main_part;          /* parts[0] */
 };
@@ -291,9 +292,9 @@ FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, c
     const uint64_t b = minimizer_bucket(I, mz.value);
     const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
     const uint32_t n = end - begin;
-    if (I.num_skew != 0) {
+    if (n > I.skew_threshold) { /* ceil_log2(n) > min_log2 and a skew index exists (sshash/../src/dictionary.cpp:61-63) */
         const uint32_t log2n = ceil_log2_u32(n);
-        if (log2n > I.skew_min_log2) { /* skew_index::lookup (sshash/skew_index.hpp:40-52) */
+        { /* skew_index::lookup (sshash/skew_index.hpp:40-52) */
             uint32_t pid = log2n - (I.skew_min_log2 + 1);
             if (log2n == I.skew_log2_max_bucket || log2n > I.skew_max_log2) pid = I.num_skew - 1;
             const uint32_t f = I.skew_phf[pid];
@@ -438,8 +439,12 @@ struct kmer_tiles {
                     jr = j;
                 }
             }
-            const uint64_t vf = bf == UINT64_MAX ? UINT64_MAX : (fwd >> (2 * jf)) & mmer_mask;
-            const uint64_t vr = br == UINT64_MAX ? UINT64_MAX : (rc >> (2 * jr)) & mmer_mask;
+            uint64_t vf = (fwd >> (2 * jf)) & mmer_mask;
+            uint64_t vr = (rc >> (2 * jr)) & mmer_mask;
+            if (I.guard_max_hash) { /* compute_minimizer's sentinel when no hash is below UINT64_MAX (image.h) */
+                if (bf == UINT64_MAX) vf = UINT64_MAX;
+                if (br == UINT64_MAX) vr = UINT64_MAX;
+            }
             const minimizer_t mz = combine_strands(vf, jf, vr, jr, I.k, I.m);
             cid = lookup_color_set(I, fwd, rc, mz, kmask);
         }

@@ -20,7 +20,7 @@ class Header(C.Structure):
         ("off_bucket_begin", C.c_uint64), ("off_sk_records", C.c_uint64), ("off_strings", C.c_uint64), ("off_skew_positions", C.c_uint64),
         ("off_hybrids", C.c_uint64), ("off_set_bit_off", C.c_uint64), ("off_color_words", C.c_uint64), ("off_meta_off", C.c_uint64),
         ("off_meta_vals", C.c_uint64), ("off_part_min_color", C.c_uint64), ("off_part_sets_before", C.c_uint64),
-        ("off_sk_cid", C.c_uint64), ("num_unpinned", C.c_uint64), ("reserved", C.c_uint64 * 6),
+        ("off_sk_cid", C.c_uint64), ("num_unpinned", C.c_uint64), ("guard_max_hash", C.c_uint64), ("reserved", C.c_uint64 * 5),
     ]
 
 

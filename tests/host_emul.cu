@@ -38,6 +38,8 @@ static dev_index view_of(const uint8_t* base) {
     I.skew_max_log2 = H.skew_max_log2;
     I.skew_log2_max_bucket = H.skew_log2_max_bucket;
     I.num_skew = H.num_skew;
+    I.skew_threshold = H.num_skew ? (1u << H.skew_min_log2) : UINT32_MAX;
+    I.guard_max_hash = uint32_t(H.guard_max_hash);
     for (int i = 0; i < FGI_MAX_SKEW; ++i) {
         I.skew_phf[i] = H.skew_phf[i];
         I.skew_pos_base[i] = H.skew_pos_base[i];
