@@ -14,7 +14,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter", "--cudart", "static"]
 
 LIB_SOURCES = [os.path.join(CSRC, f) for f in ("engine.cu", "fur_reader.cpp")]
-LIB_DEPS = LIB_SOURCES + [os.path.join(CSRC, f) for f in ("kernels.cuh", "image.h", "fur_reader.h")] + [
+LIB_DEPS = LIB_SOURCES + [os.path.join(CSRC, f) for f in ("kernels.cuh", "pipeline_kernels.cuh", "image.h", "fur_reader.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "fulgor_gpu.h")]
 CLI_SOURCES = [os.path.join(CSRC, "pseudoalign_cli.cpp")]
 

@@ -20,358 +20,9 @@
 
 #include "../../include/fulgor_gpu.h"
 #include "fur_reader.h"
-#include "kernels.cuh"
+#include "pipeline_kernels.cuh"
 
 namespace fgb {
-
-/* ================================================================== kernels */
-
-#define FG_WARPS_PER_BLOCK 8
-#define FG_BLOCK (FG_WARPS_PER_BLOCK * 32)
-#ifndef FG_MIN_BLOCKS
-#define FG_MIN_BLOCKS 5 /* resident blocks per SM the lookup kernels are compiled for (register budget 65536 / (5 * 256) = 51) */
-#endif
-#define FG_STAGE_STRIDE FG_MAX_ENTRIES
-
-/* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask,
-   accumulated tile by tile (no per-read table: AND is idempotent and scores are sums over k-mers).
-   Full intersection (src/ps_full_intersection.cpp:377-400 -> intersect :33-127): AND of the hit sets.
-   Threshold union (src/ps_threshold_union.cpp:389 + merge :17-40 / merge_meta :43-120): color c is
-   reported iff sum over positive k-mers of [c in set(k-mer)] >= uint64(double(npos) * threshold). */
-template <int W>
-__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
-                                                               const uint64_t* __restrict__ read_off, uint64_t read_off_base,
-                                                               uint32_t n_reads, int algo, double threshold,
-                                                               uint32_t* __restrict__ masks) {
-    __shared__ warp_stage stage[FG_WARPS_PER_BLOCK];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
-    for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
-        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, stage[threadIdx.x >> 5]);
-        uint32_t acc = ~0u, score = 0, npos = 0;
-        uint32_t cache_cid = FG_NOT_FOUND, cache_mask = 0;
-        while (!tiles.done()) {
-            const uint32_t cid = tiles.next();
-            const bool found = cid != FG_NOT_FOUND;
-            const uint32_t found_mask = __ballot_sync(FG_FULL, found);
-            if (!found_mask) continue;
-            npos += __popc(found_mask);
-            /* decode; the set of the previous tile's first hit is cached (reads mostly stay inside one color set) */
-            uint32_t mask = cache_mask;
-            if (found && cid != cache_cid) mask = color_set_mask(I, cid);
-            __syncwarp();
-            const int first = __ffs(int(found_mask)) - 1;
-            cache_cid = __shfl_sync(FG_FULL, cid, first);
-            cache_mask = __shfl_sync(FG_FULL, mask, first);
-            if (algo == FULGOR_GPU_FULL_INTERSECTION) {
-                acc &= __reduce_and_sync(FG_FULL, found ? mask : ~0u);
-            } else {
-                const uint32_t grp = __match_any_sync(FG_FULL, cid);
-                const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
-                uint32_t leaders = __ballot_sync(FG_FULL, leader);
-                while (leaders) {
-                    const int src = __ffs(int(leaders)) - 1;
-                    leaders &= leaders - 1;
-                    const uint32_t mj = __shfl_sync(FG_FULL, mask, src);
-                    const uint32_t wj = __shfl_sync(FG_FULL, uint32_t(__popc(grp)), src);
-                    score += ((mj >> lane) & 1u) ? wj : 0u;
-                }
-            }
-        }
-        uint32_t res = 0;
-        if (npos) {
-            if (algo == FULGOR_GPU_FULL_INTERSECTION) {
-                res = acc;
-            } else {
-                const uint64_t min_score = uint64_t(double(npos) * threshold);
-                res = __ballot_sync(FG_FULL, lane < I.num_colors && uint64_t(score) >= min_score);
-            }
-        }
-        if (lane == 0) masks[r] = res;
-    }
-}
-
-#define FG_SCRATCH_ENTRIES 256 /* per-warp shared-memory list for reads with more than 32 distinct color sets */
-
-/* where the sorted {color-set id, multiplicity} list of read r lives: counts[r] <= 32 -> stage[r*32 ..];
-   otherwise in the pool at the 64-bit entry offset stored in stage[r*32] */
-__device__ __forceinline__ const uint2* entries_of(uint32_t r, uint32_t n, const uint2* __restrict__ stage, const uint2* __restrict__ pool) {
-    const uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
-    if (n <= FG_STAGE_STRIDE) return s;
-    const uint2 o = s[0];
-    return pool + (uint64_t(o.x) | (uint64_t(o.y) << 32));
-}
-
-/* K1 alone: per read, ascending distinct color-set ids with multiplicities */
-template <int W>
-__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
-                                                              const uint64_t* __restrict__ read_off, uint64_t read_off_base,
-                                                              uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
-                                                              uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool) {
-    __shared__ uint2 scratch[FG_WARPS_PER_BLOCK][FG_SCRATCH_ENTRIES];
-    __shared__ warp_stage wstage[FG_WARPS_PER_BLOCK];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
-    for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
-        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, wstage[wib], scratch[wib], FG_SCRATCH_ENTRIES, pool);
-        uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
-        if (R.tab == nullptr) {
-            if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);
-        } else if (!R.failed) {
-            unsigned long long off;
-            if (R.tab == scratch[wib]) { /* the list must outlive this warp's shared memory */
-                if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)R.n);
-                off = __shfl_sync(FG_FULL, off, 0);
-                if (off + R.n > pool.cap) {
-                    if (lane == 0) *pool.exhausted = 1;
-                    R.failed = true;
-                } else {
-                    for (uint32_t i = lane; i < R.n; i += 32) pool.base[off + i] = R.tab[i];
-                }
-            } else {
-                off = (unsigned long long)(R.tab - pool.base);
-            }
-            if (lane == 0) s[0] = make_uint2(uint32_t(off), uint32_t(off >> 32));
-        }
-        if (lane == 0) {
-            counts[r] = R.failed ? 0u : R.n;
-            if (num_positive) num_positive[r] = R.npos;
-        }
-        __syncwarp();
-    }
-}
-
-/* K2 for indexes with more than 32 colors: one warp per read, per-color int32 scores in shared memory.
-   Full intersection = colors present in all n hit sets (weight 1 each, min_score = n) -- the same set as
-   the reference's intersect / meta_intersect (src/ps_full_intersection.cpp:33-127, 243-332);
-   threshold union = colors with score >= uint64(double(npos) * threshold) (src/ps_threshold_union.cpp:389,
-   merge :17-40, merge_meta :43-120). The result is a bitmap of num_colors bits per read + its popcount. */
-__global__ void __launch_bounds__(FG_BLOCK) k_color_sets_general(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
-                                                                const uint2* __restrict__ stage, const uint2* __restrict__ pool,
-                                                                const uint32_t* __restrict__ num_positive, uint32_t n_reads, int algo,
-                                                                double threshold, uint32_t words_per_read, uint32_t smem_ints_per_warp,
-                                                                uint32_t* __restrict__ res_bits, uint32_t* __restrict__ res_counts) {
-    extern __shared__ int smem[];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    int* scores = smem + size_t(wib) * smem_ints_per_warp;
-    int* base = scores + I.num_colors;
-    const uint32_t C = I.num_colors, P = I.num_partitions;
-    const uint32_t warps = gridDim.x * wpb;
-    for (uint32_t r = blockIdx.x * wpb + wib; r < n_reads; r += warps) {
-        const uint32_t n = __ldg(counts + r);
-        uint32_t* out = res_bits + uint64_t(r) * words_per_read;
-        if (n == 0) { /* no positive k-mer: empty result (src/ps_full_intersection.cpp:385, ps_threshold_union.cpp:355) */
-            for (uint32_t w = lane; w < words_per_read; w += 32) out[w] = 0;
-            if (lane == 0) res_counts[r] = 0;
-            continue;
-        }
-        const uint2* ents = entries_of(r, n, stage, pool);
-        for (uint32_t c = lane; c < C + P; c += 32) scores[c] = 0;
-        __syncwarp();
-        const bool fi = algo == FULGOR_GPU_FULL_INTERSECTION;
-        const uint64_t min_score = fi ? uint64_t(n) : uint64_t(double(__ldg(num_positive + r)) * threshold);
-        if (I.type == 0) {
-            for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                set_item it;
-                it.enc = FG_ENC_NONE;
-                if (j < n) {
-                    const uint2 e = ents[j];
-                    it = open_set(I, 0, e.x, 0, fi ? 1u : e.y);
-                }
-                apply_sets(I, j < n, it, scores, base, lane);
-            }
-        } else { /* meta: a color set is the list of its partial sets (include/color_sets/meta.hpp:93-236) */
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint2 e = ents[j];
-                const uint64_t b = __ldg(I.meta_off + e.x);
-                const uint32_t nm = __ldg(I.meta_vals + b);
-                for (uint32_t i0 = 0; i0 < nm; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    set_item it;
-                    it.enc = FG_ENC_NONE;
-                    if (i < nm) {
-                        const uint32_t mc = __ldg(I.meta_vals + b + 1 + i);
-                        uint32_t lo = 0, hi = P; /* largest p with sets_before[p] <= mc (meta.hpp:227-235) */
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (__ldg(I.part_sets_before + mid) <= mc) lo = mid; else hi = mid;
-                        }
-                        it = open_set(I, lo, mc - __ldg(I.part_sets_before + lo), __ldg(I.part_min_color + lo), fi ? 1u : e.y);
-                    }
-                    apply_sets(I, i < nm, it, scores, base, lane);
-                }
-            }
-        }
-        uint32_t total = 0, p = 0;
-        for (uint32_t w = 0; w < words_per_read; ++w) {
-            const uint32_t c = w * 32 + lane;
-            bool pass = false;
-            if (c < C) {
-                while (p + 1 < P && c >= __ldg(I.part_min_color + p + 1)) ++p;
-                const int sc = scores[c] + base[p];
-                pass = uint64_t(uint32_t(sc)) >= min_score;
-            }
-            const uint32_t word = __ballot_sync(FG_FULL, pass);
-            if (lane == 0) out[w] = word;
-            total += __popc(word);
-        }
-        if (lane == 0) res_counts[r] = total;
-        __syncwarp();
-    }
-}
-
-/* ---- CSR offsets: exclusive scan of per-read counts (three small kernels) ---- */
-#define FG_SCAN_ITEMS 8
-#define FG_SCAN_BLOCK 256
-#define FG_SCAN_TILE (FG_SCAN_ITEMS * FG_SCAN_BLOCK)
-
-template <bool POPC>
-__device__ __forceinline__ uint32_t count_of(const uint32_t* __restrict__ in, uint32_t i) {
-    const uint32_t v = __ldg(in + i);
-    return POPC ? uint32_t(__popc(v)) : v;
-}
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t warp_sums[FG_SCAN_BLOCK / 32];
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(FG_FULL, x, d);
-        if (lane >= uint32_t(d)) x += y;
-    }
-    if (lane == 31) warp_sums[w] = x;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t s = lane < FG_SCAN_BLOCK / 32 ? warp_sums[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(FG_FULL, s, d);
-            if (lane >= uint32_t(d)) s += y;
-        }
-        if (lane < FG_SCAN_BLOCK / 32) warp_sums[lane] = s;
-    }
-    __syncthreads();
-    const uint32_t before = w ? warp_sums[w - 1] : 0;
-    *total = warp_sums[FG_SCAN_BLOCK / 32 - 1];
-    __syncthreads();
-    return before + x - v;
-}
-
-template <bool POPC>
-__global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
-    const uint32_t base = blockIdx.x * FG_SCAN_TILE + threadIdx.x * FG_SCAN_ITEMS;
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < FG_SCAN_ITEMS; ++j)
-        if (base + j < n) s += count_of<POPC>(in, base + j);
-    uint32_t total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-/* one block: exclusive scan of the tile sums into 64-bit tile offsets; carries the running CSR
-   offset across chunks: carry[0] = running total, chunk_info = {base of this chunk, total of this chunk} */
-__global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_tile_offsets(const uint32_t* __restrict__ tile_sums, uint32_t n_tiles,
-                                                                    uint64_t* __restrict__ tile_off, uint64_t* __restrict__ carry,
-                                                                    uint64_t* __restrict__ chunk_info, uint64_t* __restrict__ off_last) {
-    __shared__ uint64_t running;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < n_tiles; t0 += FG_SCAN_BLOCK) {
-        const uint32_t i = t0 + threadIdx.x;
-        const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(v, &total);
-        if (i < n_tiles) tile_off[i] = running + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) running += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const uint64_t base = carry[0];
-        chunk_info[0] = base;
-        chunk_info[1] = running;
-        carry[0] = base + running;
-        *off_last = base + running;
-    }
-}
-
-template <bool POPC>
-__global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_write(const uint32_t* __restrict__ in, uint32_t n, const uint64_t* __restrict__ tile_off,
-                                                             const uint64_t* __restrict__ chunk_info, uint64_t* __restrict__ off) {
-    const uint32_t base = blockIdx.x * FG_SCAN_TILE + threadIdx.x * FG_SCAN_ITEMS;
-    uint32_t c[FG_SCAN_ITEMS];
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < FG_SCAN_ITEMS; ++j) {
-        c[j] = base + j < n ? count_of<POPC>(in, base + j) : 0;
-        s += c[j];
-    }
-    uint32_t total;
-    uint64_t o = chunk_info[0] + tile_off[blockIdx.x] + block_exclusive_scan(s, &total);
-#pragma unroll
-    for (int j = 0; j < FG_SCAN_ITEMS; ++j) {
-        if (base + j < n) off[base + j] = o;
-        o += c[j];
-    }
-}
-
-/* ---- emit ---- */
-
-/* color masks -> ascending color lists at their CSR positions (chunk-local output buffer) */
-__global__ void __launch_bounds__(256) k_emit_masks(const uint32_t* __restrict__ masks, const uint64_t* __restrict__ off,
-                                                   const uint64_t* __restrict__ chunk_info, uint32_t n, uint32_t* __restrict__ out,
-                                                   uint64_t out_cap) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    uint32_t m = __ldg(masks + r);
-    uint64_t o = __ldg(off + r) - chunk_info[0];
-    while (m) {
-        const uint32_t c = uint32_t(__ffs(int(m))) - 1u;
-        m &= m - 1;
-        if (o < out_cap) out[o] = c;
-        ++o;
-    }
-}
-
-/* per-read {color-set id, multiplicity} lists (stage or pool) -> CSR of color-set ids */
-__global__ void __launch_bounds__(256) k_emit_entries(const uint2* __restrict__ stage, const uint2* __restrict__ pool, const uint32_t* __restrict__ counts,
-                                                     const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
-                                                     uint32_t* __restrict__ out, uint64_t out_cap) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n) return;
-    const uint32_t c = __ldg(counts + r);
-    if (c == 0) return;
-    const uint64_t o = __ldg(off + r) - chunk_info[0];
-    const uint2* e = entries_of(r, c, stage, pool);
-    for (uint32_t i = lane; i < c; i += 32)
-        if (o + i < out_cap) out[o + i] = e[i].x;
-}
-
-/* per-read color bitmaps -> ascending color lists at their CSR positions */
-__global__ void __launch_bounds__(256) k_emit_bits(const uint32_t* __restrict__ res_bits, uint32_t words_per_read, const uint32_t* __restrict__ counts,
-                                                  const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
-                                                  uint32_t* __restrict__ out, uint64_t out_cap) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n) return;
-    if (__ldg(counts + r) == 0) return;
-    uint64_t o = __ldg(off + r) - chunk_info[0];
-    const uint32_t* bits = res_bits + uint64_t(r) * words_per_read;
-    for (uint32_t w = 0; w < words_per_read; ++w) {
-        const uint32_t word = __ldg(bits + w);
-        if ((word >> lane) & 1u) {
-            const uint64_t at = o + __popc(word & ((1u << lane) - 1u));
-            if (at < out_cap) out[at] = w * 32 + lane;
-        }
-        o += __popc(word);
-    }
-}
 
 /* ================================================================== host side */
 
@@ -650,13 +301,12 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     }
     *launches += enqueue_k1(x, s, a, true);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
-    const uint32_t C = x->H.num_colors, P = x->H.num_partitions;
-    const uint32_t ints = (C + P + 1) & ~1u;
-    if (size_t(ints) * 4 > 200 * 1024) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
-    uint32_t wpb = uint32_t(std::min<size_t>(FG_WARPS_PER_BLOCK, std::max<size_t>(1, (96 * 1024) / (size_t(ints) * 4))));
-    const size_t smem = size_t(wpb) * ints * 4;
+    const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions);
+    if (!g.ok) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
+    const uint32_t wpb = g.warps_per_block, ints = g.ints_per_warp;
+    const size_t smem = g.smem_bytes;
     FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
-    e.words_per_read = (C + 31) / 32;
+    e.words_per_read = g.words_per_read;
     s.res_bits.reserve(size_t(a.n) * e.words_per_read * 4);
     s.res_counts.reserve(size_t(a.n) * 4);
     const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;

@@ -16,7 +16,9 @@
 #ifndef FULGOR_B200_KERNELS_CUH
 #define FULGOR_B200_KERNELS_CUH
 
+#ifndef FG_SIMT_EMUL /* tests/simt_emul.h supplies the CUDA vocabulary when the kernels are compiled for the host */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "image.h"
@@ -284,14 +286,12 @@ FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, ui
     return I.sk_cid ? FG_LDG(I.sk_cid + sk) : (rec.y & FGI_SK_CID_MASK);
 }
 
-/* dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:47-77) + buckets::lookup_canonical
-   (sshash/buckets.hpp:162-209) + index::u2c. The "minimizer of the bucket's first k-mer must equal
-   the target" test (buckets.hpp:168-180) is an early-out only: equal k-mers have equal minimizers,
-   so a k-mer whose minimizer is absent cannot match any stored k-mer. */
-FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, const minimizer_t& mz, uint64_t kmask) {
-    const uint64_t b = minimizer_bucket(I, mz.value);
-    const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
-    const uint32_t n = end - begin;
+/* buckets::lookup_canonical (sshash/buckets.hpp:162-209) + index::u2c on the super-k-mers [begin, begin + n) of one
+   bucket, with the skew-index dispatch of dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:61-73).
+   The "minimizer of the bucket's first k-mer must equal the target" test (buckets.hpp:168-180) is an early-out only:
+   equal k-mers have equal minimizers, so a k-mer whose minimizer is absent cannot match any stored k-mer. */
+FG_HD uint32_t lookup_in_bucket(const dev_index& I, uint32_t begin, uint32_t n, uint64_t fwd, uint64_t rc, const minimizer_t& mz,
+                                uint64_t kmask) {
     if (n > I.skew_threshold) { /* ceil_log2(n) > min_log2 and a skew index exists (sshash/../src/dictionary.cpp:61-63) */
         const uint32_t log2n = ceil_log2_u32(n);
         { /* skew_index::lookup (sshash/skew_index.hpp:40-52) */
@@ -305,19 +305,28 @@ FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, c
             return FG_NOT_FOUND;
         }
     }
-    for (uint32_t s = begin; s < end; ++s) {
+    for (uint32_t s = begin; s < begin + n; ++s) {
         const uint32_t cid = scan_super_kmer(I, s, fwd, rc, kmask, mz);
         if (cid != FG_NOT_FOUND) return cid;
     }
     return FG_NOT_FOUND;
 }
 
+/* dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:47-77): minimizer -> bucket (minimizers.hpp:36-39,
+   buckets::locate_bucket buckets.hpp:62-67) -> lookup inside the bucket */
+FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, const minimizer_t& mz, uint64_t kmask) {
+    const uint64_t b = minimizer_bucket(I, mz.value);
+    const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
+    return lookup_in_bucket(I, begin, end - begin, fwd, rc, mz, kmask);
+}
+
 /* ------------------------------------------------------------------ stage 1 for one read, one warp */
 
-/* valid characters are exactly ACGTacgt (sshash/kmer.hpp:214-224,258-260); code = (c >> 1) & 3 (kmer.hpp:199) */
+/* valid characters are exactly ACGTacgt (sshash/kmer.hpp:214-224,258-260); code = (c >> 1) & 3 (kmer.hpp:199).
+   With case folded, A C G T are 0x41 + {0, 2, 6, 19}: one range test and one bit test of 0x80045. */
 FG_HD bool base_valid(uint32_t c) {
-    const uint32_t u = c & 0xDFu; /* fold case */
-    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+    const uint32_t d = (c & 0xDFu) - 0x41u;
+    return d < 20u && ((0x80045u >> d) & 1u);
 }
 
 /* 32 characters (one per lane) -> one 64-bit word of 2-bit codes (char j at bits [2j, 2j+1]) + validity mask */
@@ -330,33 +339,100 @@ __device__ __forceinline__ void pack_chars(uint32_t c, bool in_range, uint32_t l
     valid = __ballot_sync(FG_FULL, in_range && base_valid(c));
 }
 
-/* per-warp shared-memory staging of one read segment: 2-bit packed bases, validity bits, and the mixer_64 hash of the
-   m-mer that starts at every position, for both strands */
-#define FG_SEG_KMERS 160                  /* k-mers per segment (5 tiles) */
-#define FG_SEG_POS (FG_SEG_KMERS + 32)    /* m-mer start positions per segment: FG_SEG_KMERS + (k - m) <= +30 */
-#define FG_SEG_WORDS 8                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 pad */
+/* mixer_64 (sshash/hash_util.hpp:88-111) is h(y) = (y * FG_MIX_MUL) ^ magic: a bijection of 64-bit words, so the
+   m-mer is recovered from its hash with the inverse multiplier (FG_MIX_MUL * FG_MIX_INV == 1 mod 2^64). */
+#define FG_MIX_MUL 0x517cc1b727220a95ULL
+FG_HD constexpr uint64_t fg_inverse_odd(uint64_t a) {
+    uint64_t x = a; /* Newton: correct to 3 bits, doubles per step */
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+#define FG_MIX_INV (fgb::fg_inverse_odd(FG_MIX_MUL))
+static_assert(FG_MIX_MUL * fg_inverse_odd(FG_MIX_MUL) == 1ULL, "mixer_64 multiplier inverse");
+
+/* Per-warp shared-memory staging of one read segment of up to FG_SEG_KMERS k-mers.
+   The lanes own the k-mers of a segment in BLOCKS: lane l owns k-mers 4l .. 4l+3 ("tile" t = the t-th k-mer of every
+   lane), so the sliding-window minimum and the run detection below are sequential inside a lane and need no exchange.
+   Position p of the per-m-mer hash arrays is stored at slot p + p/4: lane l's 16 positions then start at slot 5l, an
+   odd stride, which keeps the blocked 64-bit reads free of bank conflicts. */
+#define FG_SEG_B 4                        /* k-mers per lane per segment */
+#define FG_SEG_KMERS (32 * FG_SEG_B)      /* k-mers per segment */
+#define FG_HASH_SLOTS 200                 /* >= slot(FG_SEG_KMERS + 30) + 1 */
+#define FG_SEG_WORDS 6                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 pad */
 struct warp_stage {
-    uint64_t hf[FG_SEG_POS];  /* hash of the forward m-mer at position q */
-    uint64_t hr[FG_SEG_POS];  /* hash of its reverse complement */
+    uint64_t hf[FG_HASH_SLOTS];       /* mixer_64 hash of the forward m-mer starting at every position; afterwards the
+                                         segment's seed list: {minimizer} -> {first super-k-mer, bucket size} */
+    uint64_t hr[FG_HASH_SLOTS];       /* hash of its reverse complement */
+    uint32_t info[FG_SEG_KMERS];      /* [t * 32 + lane]: seed slot | minimizer position << 8 | ambiguous << 13 | valid << 14 */
     uint64_t words[FG_SEG_WORDS];
     uint32_t valid[FG_SEG_WORDS];
 };
 
-/* Walks one read in tiles of 32 consecutive k-mers: after next(), lane l holds the color-set id of the
-   k-mer that starts at position t0 + l (FG_NOT_FOUND when negative, invalid or past the end).
-   Replaces the per-k-mer loop around streaming_query::lookup_advanced (sshash/streaming_query.hpp:50-109,
-   driven from src/ps_full_intersection.cpp:344-353): validity test (:53-59), 2-bit packing and reverse
-   complement (:62-74), canonical minimizer (:76-83), dictionary lookup (:144-190).
-   Per segment of FG_SEG_KMERS k-mers the warp first packs the bases and hashes every m-mer ONCE into shared
-   memory; a lane then takes the minimum over its k - m + 1 window from there (the k-mers of a read share
-   almost all their m-mers, which the reference exploits with its sliding minimizer_enumerator,
-   sshash/minimizer_enumerator.hpp:24-49). */
+FG_HD constexpr uint32_t fg_hslot(uint32_t p) { return p + (p >> 2); }
+
+/* Minimum of every window of W consecutive hashes among the W + 3 that start at a lane's base slot, for the lane's four
+   k-mers: h[j] for j in [t, t + W). One suffix scan over the first window (its suffix minima are the left parts of the
+   other three windows) plus a running prefix over the three extra positions: W + 4 comparisons for four k-mers.
+   Ties: util::compute_minimizer (sshash/util.hpp:220-239) keeps the FIRST minimum of the strand it scans. For the forward
+   strand that is the leftmost position; the reverse strand's m-mers come in the opposite order, so there (REV) the
+   rightmost position in forward coordinates wins. mh = hash, mp = position relative to the lane's base. */
+template <int W, bool REV>
+__device__ __forceinline__ void window_minima(const uint64_t* __restrict__ h, uint64_t (&mh)[FG_SEG_B], uint32_t (&mp)[FG_SEG_B]) {
+    uint64_t sh[FG_SEG_B];
+    uint32_t sp[FG_SEG_B];
+    uint64_t ch = h[fg_hslot(W - 1)];
+    uint32_t cp = W - 1;
+#pragma unroll
+    for (int j = W - 2; j >= 0; --j) {
+        const uint64_t x = h[fg_hslot(j)];
+        const bool take = REV ? (x < ch) : (x <= ch);
+        ch = take ? x : ch;
+        cp = take ? uint32_t(j) : cp;
+        if (j < FG_SEG_B) {
+            sh[j] = ch;
+            sp[j] = cp;
+        }
+    }
+    mh[0] = sh[0];
+    mp[0] = sp[0];
+    uint64_t ph = 0;
+    uint32_t pp = 0;
+#pragma unroll
+    for (int t = 1; t < FG_SEG_B; ++t) {
+        const uint64_t x = h[fg_hslot(W - 1 + t)];
+        const bool take = t == 1 || (REV ? (x <= ph) : (x < ph));
+        ph = take ? x : ph;
+        pp = take ? uint32_t(W - 1 + t) : pp;
+        const bool right = REV ? (ph <= sh[t]) : (ph < sh[t]);
+        mh[t] = right ? ph : sh[t];
+        mp[t] = right ? pp : sp[t];
+    }
+}
+
+/* Walks one read: after next(), lane l holds the color-set id of one of its k-mers (FG_NOT_FOUND when negative, invalid or
+   past the end); over the calls until done() every k-mer of the read is reported exactly once (in no particular order:
+   the consumers -- intersection, per-color scores, distinct-set table -- are order-free).
+   Replaces the per-k-mer loop around streaming_query::lookup_advanced (sshash/streaming_query.hpp:50-109, driven from
+   src/ps_full_intersection.cpp:344-353): validity test (:53-59), 2-bit packing and reverse complement (:62-74),
+   canonical minimizer (:76-83), dictionary lookup (:144-190).
+
+   Per segment of FG_SEG_KMERS k-mers the warp
+     0. packs the bases (2 bits each) and their validity bits into shared memory;
+     1. hashes every m-mer ONCE, both strands (the k-mers of a read share almost all their m-mers, which the reference
+        exploits with its sliding minimizer_enumerator, sshash/minimizer_enumerator.hpp:24-49);
+     2. takes the sliding-window minima (window_minima) and from them every k-mer's canonical minimizer;
+     3. cuts the k-mers into runs with the same minimizer and makes the first k-mer of each run a SEED: only seeds go
+        through the minimizer MPHF and the bucket table, all seeds of the segment at once, one per lane. This is the
+        device analogue of the reference's seed-and-extend: ~1 hash lookup per 7 k-mers instead of 1 per k-mer;
+     4. (next) every k-mer compares itself with the super-k-mers of its run's bucket.
+   A lookup answer is a pure function of the k-mer (streaming_query.hpp:107 asserts it), so sharing the bucket between
+   the k-mers of a run changes no result. */
 template <int W>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
     warp_stage& S;
-    uint32_t len, lane, nk, t0, seg0, seg_nk;
+    uint32_t len, lane, nk, seg_end, t;
     uint64_t kmask, mmer_mask;
     uint32_t window, kbits;
 
@@ -364,15 +440,14 @@ struct kmer_tiles {
         : I(I_), seq(seq_), S(S_), len(len_), lane(lane_) {
         const uint32_t k = I.k;
         nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
-        t0 = 0;
-        seg0 = 0;
-        seg_nk = 0;
+        seg_end = 0;
+        t = FG_SEG_B;
         kmask = (1ULL << (2 * k)) - 1;
         mmer_mask = (1ULL << (2 * I.m)) - 1;
         window = W ? W : k - I.m + 1;
         kbits = (1u << k) - 1u;
     }
-    __device__ __forceinline__ bool done() const { return t0 >= nk; }
+    __device__ __forceinline__ bool done() const { return t == FG_SEG_B && seg_end >= nk; }
 
     /* 2*nbases bits starting at base position p (segment-relative) of the packed words */
     __device__ __forceinline__ uint64_t bases_at(uint32_t p) const {
@@ -380,13 +455,23 @@ struct kmer_tiles {
         const uint64_t a = S.words[wi];
         return sh ? (a >> sh) | (S.words[wi + 1] << (64 - sh)) : a;
     }
+    __device__ __forceinline__ uint2* seeds() const { return reinterpret_cast<uint2*>(S.hf); }
+
+    /* m-mer behind a window minimum; compute_minimizer's "nothing below UINT64_MAX" sentinel when that can occur (image.h) */
+    __device__ __forceinline__ uint64_t mmer_of_hash(uint64_t h) const {
+        uint64_t y = (h ^ I.hash_magic) * FG_MIX_INV;
+        if (I.guard_max_hash && h == UINT64_MAX) y = UINT64_MAX;
+        return y;
+    }
 
     __device__ __forceinline__ void load_segment() {
         __syncwarp();
-        seg0 = t0;
-        seg_nk = min(uint32_t(FG_SEG_KMERS), nk - seg0);
+        const uint32_t seg0 = seg_end;
+        const uint32_t seg_nk = min(uint32_t(FG_SEG_KMERS), nk - seg0);
+        seg_end = seg0 + seg_nk;
         const uint32_t nchars = seg_nk + I.k - 1, npos = seg_nk + window - 1;
         const uint32_t nwords = (nchars + 31) >> 5;
+        /* 0. bases */
         for (uint32_t c = 0; c <= nwords; ++c) { /* one extra zero word so that bases_at may read words[wi + 1] */
             const uint32_t p = seg0 + 32 * c + lane;
             const bool in = c < nwords && 32 * c + lane < nchars;
@@ -400,56 +485,114 @@ struct kmer_tiles {
             }
         }
         __syncwarp();
+        /* 1. m-mer hashes */
         const uint32_t m = I.m;
         for (uint32_t q = lane; q < npos; q += 32) {
             const uint64_t y = bases_at(q) & mmer_mask;
-            S.hf[q] = (y * 0x517cc1b727220a95ULL) ^ I.hash_magic;
-            S.hr[q] = (revcomp(y, m) * 0x517cc1b727220a95ULL) ^ I.hash_magic;
+            S.hf[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
+            S.hr[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
+        }
+        __syncwarp();
+        /* 2. canonical minimizer of the lane's k-mers i0 .. i0+3: value = min over both strands, compared as integers
+              (sshash/streaming_query.hpp:76-79); cpos = where it starts inside the k-mer, forward coordinates */
+        const uint32_t i0 = FG_SEG_B * lane;
+        uint64_t val[FG_SEG_B];
+        uint32_t inf[FG_SEG_B]; /* cpos << 8 | ambiguous << 13 | valid << 14 */
+        {
+            uint64_t hf[FG_SEG_B], hr[FG_SEG_B];
+            uint32_t pf[FG_SEG_B], pr[FG_SEG_B];
+            if (W) {
+                window_minima<W ? W : 13, false>(S.hf + 5 * lane, hf, pf);
+                window_minima<W ? W : 13, true>(S.hr + 5 * lane, hr, pr);
+            } else { /* any other (k, m): plain scan of each window */
+#pragma unroll
+                for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                    hf[tt] = hr[tt] = UINT64_MAX;
+                    pf[tt] = pr[tt] = tt;
+                    for (uint32_t j = 0; j < window; ++j) {
+                        const uint64_t a = S.hf[fg_hslot(i0 + tt + j)], b = S.hr[fg_hslot(i0 + tt + j)];
+                        if (a < hf[tt]) hf[tt] = a, pf[tt] = tt + j;
+                        if (b <= hr[tt]) hr[tt] = b, pr[tt] = tt + j;
+                    }
+                }
+            }
+            /* i0 is a multiple of 4, so the lane's four k-mers start in the same 32-character word */
+            const uint32_t vw0 = S.valid[i0 >> 5], vw1 = S.valid[(i0 >> 5) + 1];
+#pragma unroll
+            for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                const uint32_t i = i0 + tt;
+                const uint32_t bits = __funnelshift_r(vw0, vw1, i & 31);
+                const bool valid = i < seg_nk && (bits & kbits) == kbits;
+                const uint64_t vf = mmer_of_hash(hf[tt]), vr = mmer_of_hash(hr[tt]);
+                const bool fwd_wins = vf <= vr;
+                val[tt] = fwd_wins ? vf : vr;
+                const uint32_t cpos = (fwd_wins ? pf[tt] : pr[tt]) - tt;
+                inf[tt] = (cpos << 8) | (uint32_t(vf == vr) << 13) | (uint32_t(valid) << 14);
+            }
+        }
+        __syncwarp(); /* every lane is done with the hash arrays: the seed list may overwrite them */
+        /* 3. seeds: the first k-mer of every run of valid k-mers with the same minimizer */
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        uint64_t prev_val = __shfl_up_sync(FG_FULL, val[FG_SEG_B - 1], 1);
+        bool prev_valid = __shfl_up_sync(FG_FULL, inf[FG_SEG_B - 1], 1) >> 14;
+        if (lane == 0) prev_valid = false;
+        uint32_t nseeds = 0, cur_slot = 0xffu;
+        bool has_leader = false;
+        bool leader[FG_SEG_B];
+#pragma unroll
+        for (int tt = 0; tt < FG_SEG_B; ++tt) {
+            const bool valid = inf[tt] >> 14;
+            leader[tt] = valid && !(prev_valid && prev_val == val[tt]);
+            prev_valid = valid;
+            prev_val = val[tt];
+            const uint32_t b = __ballot_sync(FG_FULL, leader[tt]);
+            if (leader[tt]) {
+                cur_slot = nseeds + __popc(b & lt_mask);
+                seeds()[cur_slot] = make_uint2(uint32_t(val[tt]), uint32_t(val[tt] >> 32));
+                has_leader = true;
+            }
+            inf[tt] |= cur_slot; /* 0xff for now when the run started in an earlier lane */
+            nseeds += __popc(b);
+        }
+        { /* runs that continue from an earlier lane: the slot in effect at the end of the nearest lane that has a seed */
+            const uint32_t hb = __ballot_sync(FG_FULL, has_leader) & lt_mask;
+            const uint32_t inherited = __shfl_sync(FG_FULL, cur_slot, hb ? 31 - __clz(int(hb)) : 0);
+#pragma unroll
+            for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                if ((inf[tt] & 0xffu) == 0xffu) inf[tt] = (inf[tt] & ~0xffu) | (inherited & 0xffu);
+                S.info[tt * 32 + lane] = inf[tt];
+            }
+        }
+        __syncwarp();
+        /* minimizers::lookup + buckets::locate_bucket for every seed, one per lane */
+        for (uint32_t s = lane; s < nseeds; s += 32) {
+            const uint2 v = seeds()[s];
+            const uint64_t b = minimizer_bucket(I, uint64_t(v.x) | (uint64_t(v.y) << 32));
+            const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
+            seeds()[s] = make_uint2(begin, end - begin);
         }
         __syncwarp();
     }
 
     __device__ __forceinline__ uint32_t next() {
-        if (t0 == seg0 + seg_nk) load_segment();
-        const uint32_t i = t0 - seg0 + lane; /* segment-relative k-mer index */
-        bool valid = i < seg_nk;
-        if (valid) {
-            const uint32_t wi = i >> 5;
-            valid = (__funnelshift_r(S.valid[wi], S.valid[wi + 1], i & 31) & kbits) == kbits;
+        if (t == FG_SEG_B) {
+            load_segment();
+            t = 0;
         }
+        const uint32_t inf = S.info[t * 32 + lane];
         uint32_t cid = FG_NOT_FOUND;
-        if (valid) {
-            const uint64_t fwd = bases_at(i) & kmask;
+        if (inf >> 14) {
+            const uint64_t fwd = bases_at(FG_SEG_B * lane + t) & kmask;
             const uint64_t rc = revcomp(fwd, I.k);
-            /* forward strand: m-mers in read order, first minimum wins; reverse strand: its j-th m-mer is the reverse
-               complement of the forward m-mer at read position i + window - 1 - j */
-            uint64_t bf = UINT64_MAX, br = UINT64_MAX;
-            uint32_t jf = 0, jr = 0;
-            const int n = W ? W : int(window);
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                const uint64_t h = S.hf[i + j];
-                if (h < bf) {
-                    bf = h;
-                    jf = j;
-                }
-                const uint64_t g = S.hr[i + (n - 1 - j)];
-                if (g < br) {
-                    br = g;
-                    jr = j;
-                }
-            }
-            uint64_t vf = (fwd >> (2 * jf)) & mmer_mask;
-            uint64_t vr = (rc >> (2 * jr)) & mmer_mask;
-            if (I.guard_max_hash) { /* compute_minimizer's sentinel when no hash is below UINT64_MAX (image.h) */
-                if (bf == UINT64_MAX) vf = UINT64_MAX;
-                if (br == UINT64_MAX) vr = UINT64_MAX;
-            }
-            const minimizer_t mz = combine_strands(vf, jf, vr, jr, I.k, I.m);
-            cid = lookup_color_set(I, fwd, rc, mz, kmask);
+            const uint2 bucket = seeds()[inf & 0xffu];
+            minimizer_t mz;
+            mz.value = 0;
+            mz.cpos = (inf >> 8) & 31u;
+            mz.ambiguous = (inf >> 13) & 1u;
+            cid = lookup_in_bucket(I, bucket.x, bucket.y, fwd, rc, mz, kmask);
         }
         __syncwarp();
-        t0 += 32;
+        t += 1;
         return cid;
     }
 };

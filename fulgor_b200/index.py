@@ -18,7 +18,7 @@ import numpy as np
 from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfulgor_gpu.so")
+LIB_PATH = os.environ.get("FULGOR_GPU_LIB") or os.path.join(_HERE, "libfulgor_gpu.so")  # the override is for kernel-variant A/B runs
 
 FULL_INTERSECTION = 0
 THRESHOLD_UNION = 1

@@ -1,5 +1,6 @@
-"""CPU tier: the index loader / flattener (host C++ inside libfulgor_gpu.so) and the per-lane device arithmetic
-compiled for the host (tests/host_emul.cu), both against the oracle; and the C ABI surface."""
+"""CPU tier: the index loader / flattener (host C++ inside libfulgor_gpu.so); the CUDA kernels themselves compiled for the
+host on a lock-step warp emulator (tests/simt_emul.{h,cpp}: per-lane arithmetic AND the whole K1 -> K2 -> scan -> emit
+pipeline with its shuffles, ballots and shared-memory staging), all against the oracle; and the C ABI surface."""
 import ctypes as C
 import os
 import re
@@ -11,23 +12,52 @@ import pytest
 import _checkers as ck
 
 ROOT = ck.ROOT
-EMUL_SO = os.path.join(ROOT, "build", "libfg_host_emul.so")
+EMUL_SO = os.path.join(ROOT, "build", "libfg_simt_emul.so")
 INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]
 
 
 @pytest.fixture(scope="module")
 def emul():
-    src = os.path.join(ROOT, "tests", "host_emul.cu")
-    deps = [src, os.path.join(ROOT, "fulgor_b200", "csrc", "kernels.cuh"), os.path.join(ROOT, "fulgor_b200", "csrc", "image.h")]
+    src = os.path.join(ROOT, "tests", "simt_emul.cpp")
+    csrc = os.path.join(ROOT, "fulgor_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "tests", "simt_emul.h")] + [os.path.join(csrc, f) for f in ("kernels.cuh", "pipeline_kernels.cuh", "image.h")]
     if not os.path.exists(EMUL_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_SO) for d in deps):
         os.makedirs(os.path.dirname(EMUL_SO), exist_ok=True)
-        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
-                               "-Xcompiler", "-fPIC,-w", "-shared", "-o", EMUL_SO, src])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-o", EMUL_SO, src])
     E = C.CDLL(EMUL_SO)
     E.emul_lookup_read.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p]
     E.emul_color_set_mask.restype = C.c_uint32
     E.emul_color_set_mask.argtypes = [C.c_void_p, C.c_uint32]
+    E.emul_base_valid.argtypes = [C.c_uint32]
+    E.emul_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                   C.c_uint, C.c_int]
+    E.emul_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.c_uint, C.c_int]
     return E
+
+
+def emul_pseudoalign(E, img, reads, algo, thr, num_colors, grid=1, generic=0):
+    bases, off = reads
+    n = len(off) - 1
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    cap = max(1, n * num_colors)
+    vals = np.zeros(cap, dtype=np.uint32)
+    rc = E.emul_pseudoalign(img.ctypes.data, algo, thr, bases.ctypes.data, off.ctypes.data, n, out_off.ctypes.data, vals.ctypes.data, cap, grid, generic)
+    assert rc == 0, rc
+    return out_off, vals[: int(out_off[n])]
+
+
+def emul_fetch(E, img, reads, grid=1, generic=0):
+    bases, off = reads
+    n = len(off) - 1
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    cap = max(1, int(off[n]))
+    vals = np.zeros(cap, dtype=np.uint32)
+    npos = np.zeros(n, dtype=np.uint32)
+    rc = E.emul_fetch_color_set_ids(img.ctypes.data, bases.ctypes.data, off.ctypes.data, n, out_off.ctypes.data, vals.ctypes.data, cap,
+                                    npos.ctypes.data, grid, generic)
+    assert rc == 0, rc
+    return out_off, vals[: int(out_off[n])], npos
 
 
 @pytest.fixture(scope="module", params=INDEXES)
@@ -83,6 +113,48 @@ def test_per_kmer_lookup_like_the_oracle(loaded, emul):
         got = np.full(len(exp), 0xFFFFFFFF, dtype=np.uint32)
         emul.emul_lookup_read(img.ctypes.data, seq, len(seq), got.ctypes.data)
         assert np.array_equal(got, exp), i
+
+
+def test_base_validity_is_exactly_ACGTacgt(emul):
+    """sshash/kmer.hpp:214-224,258-260"""
+    for c in range(256):
+        assert bool(emul.emul_base_valid(c)) == (chr(c) in "ACGTacgt"), c
+
+
+def _edge_reads(genomes):
+    rng = np.random.default_rng(5)
+    g = ck.gen_reads(48, 150, 150, seed=99, genomes=genomes)
+    seqs = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(48)]
+    out = [b"", b"A", b"ACGT" * 7 + b"AC", seqs[0][:31], seqs[1][:32], seqs[2].lower(), seqs[3][:75] + b"N" + seqs[3][76:],
+           b"N" * 150, seqs[4][:30] + b"n" + seqs[4][31:], b"A" * 200, b"ACGT" * 50, seqs[5] + seqs[6] + seqs[7],
+           bytes(rng.choice(list(b"ACGT"), 500).astype(np.uint8)), seqs[8][:149] + b"X", b"-" + seqs[9][1:],
+           seqs[10][:158], seqs[11] + seqs[12][:9], seqs[13] + seqs[14][:8], seqs[15][:127 + 30], seqs[16] + seqs[17][:128 + 30 - 150 + 1]]
+    return ck.reads_from_list(out + seqs[18:30])
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+def test_emulated_kernels_stage1_like_the_oracle(loaded, emul, generic):
+    """k_fetch_color_sets on emulated warps (segment pipeline: sliding-window minimizers, seeds, bucket compare, the
+    per-read table with its shared-memory and pool spill) == index::fetch_color_set_ids"""
+    fg, img, o = loaded
+    n = 400 if o.num_colors <= 32 else 150
+    for reads in (ck.gen_reads(n, 75, 300, seed=11, genomes=o.name.split(".")[0]), _edge_reads(o.name.split(".")[0])):
+        got = emul_fetch(emul, img, reads, grid=2, generic=generic)
+        exp = o.fetch_color_set_ids(reads, want_positive=True)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("algo,thr", [(0, 1.0), (1, 0.8), (1, 0.25)])
+def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr):
+    """the whole kernel pipeline (fused small-color kernel, or K1 + general color-set kernel, then scan + emit) on emulated
+    warps == pseudoalign_full_intersection / pseudoalign_threshold_union"""
+    fg, img, o = loaded
+    n = 400 if o.num_colors <= 32 else 120
+    for reads in (ck.gen_reads(n, 150, 150, seed=12, genomes=o.name.split(".")[0]), _edge_reads(o.name.split(".")[0])):
+        got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors)
+        exp = o.pseudoalign(reads, algo, thr)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
 
 
 def test_loader_rejects_bad_input(built_lib, tmp_path):
