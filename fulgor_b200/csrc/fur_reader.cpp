@@ -414,8 +414,8 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
     H.num_minimizers = nskb.size() - 1;
     H.num_super_kmers = offsets.size;
     if (u2c.num_bits != H.num_unitigs) throw std::runtime_error("u2c size does not match the number of unitigs");
-    if (H.num_super_kmers >= (1ULL << 32) || pieces.back() >= (1ULL << 32))
-        throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / string offsets");
+    if (H.num_super_kmers >= (1ULL << 32) || pieces.back() >= (1ULL << 31))
+        throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / 31-bit string offsets");
     if (H.k - H.m + 1 > 31) throw std::runtime_error("k - m + 1 > 31 is not supported");
 
     /* buckets::locate_bucket (sshash/buckets.hpp:62-67): begin(b) = EF[b] + b */
@@ -483,10 +483,17 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
                 pm = 0;
                 ++unpinned[tid];
             }
+            /* does the stored m-mer at the minimizer position read as the canonical minimizer itself (1) or as its reverse complement (0)? */
+            uint32_t canon_fwd = 0;
+            if (pinned) {
+                const uint64_t bit = 2 * (off + pm), w = bit >> 6, sh = bit & 63;
+                const uint64_t y = (sh ? (strings_padded[w] >> sh) | (strings_padded[w + 1] << (64 - sh)) : strings_padded[w]) & ((1ULL << (2 * H.m)) - 1);
+                canon_fwd = y == v0;
+            }
             uint32_t hi32 = (uint32_t(window) << FGI_SK_WINDOW_SHIFT) | (pm << FGI_SK_PM_SHIFT) | (uint32_t(pinned) << FGI_SK_PINNED_SHIFT);
             if (wide_cids) sk_cid[s] = unitig_cid[u];
             else hi32 |= unitig_cid[u];
-            sk_records[s] = uint64_t(uint32_t(off)) | (uint64_t(hi32) << 32);
+            sk_records[s] = uint64_t(uint32_t(off)) | (uint64_t(canon_fwd) << FGI_SK_CANON_FWD_SHIFT) | (uint64_t(hi32) << 32);
         }
     };
     {

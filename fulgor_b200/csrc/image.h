@@ -25,7 +25,7 @@
 
 #include <stdint.h>
 
-#define FGI_MAGIC 0x3130474D49475546ULL /* "FUGIMG01" */
+#define FGI_MAGIC 0x3230474D49475546ULL /* "FUGIMG02" */
 #define FGI_ALIGN 256
 
 /* one single_phf partition (pthash/include/single_phf.hpp:140-150). The three moduli (table size, dense / sparse bucket
@@ -105,6 +105,10 @@ struct fgi_header {
     uint64_t reserved[5];
 };
 
+/* low word of a super-k-mer record: base offset into `strings` (< 2^31) and, for pinned records, whether the stored m-mer at
+   the minimizer position reads as the canonical minimizer (1) or as its reverse complement (0) */
+#define FGI_SK_OFFSET_MASK 0x7fffffffu
+#define FGI_SK_CANON_FWD_SHIFT 31
 /* high word of a super-k-mer record */
 #define FGI_SK_CID_BITS 21
 #define FGI_SK_CID_MASK ((1u << FGI_SK_CID_BITS) - 1u)

@@ -253,7 +253,7 @@ FG_HD uint32_t ceil_log2_u32(uint32_t v) { /* bits/util.hpp ceil_log2_uint32 */
 FG_HD uint32_t scan_super_kmer(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t rc, uint64_t kmask, const minimizer_t& mz) {
     const uint2 rec = FG_LDG(I.sk_records + sk);
     const uint32_t window = (rec.y >> FGI_SK_WINDOW_SHIFT) & 31u;
-    const uint64_t bit = 2 * uint64_t(rec.x);
+    const uint64_t bit = 2 * uint64_t(rec.x & FGI_SK_OFFSET_MASK);
     const uint64_t* w = I.strings + (bit >> 6);
     const uint32_t sh = uint32_t(bit & 63);
     const uint64_t w0 = FG_LDG(w), w1 = FG_LDG(w + 1), w2 = FG_LDG(w + 2);
@@ -351,21 +351,35 @@ FG_HD constexpr uint64_t fg_inverse_odd(uint64_t a) {
 static_assert(FG_MIX_MUL * fg_inverse_odd(FG_MIX_MUL) == 1ULL, "mixer_64 multiplier inverse");
 
 /* Per-warp shared-memory staging of one read segment of up to FG_SEG_KMERS k-mers.
-   The lanes own the k-mers of a segment in BLOCKS: lane l owns k-mers 4l .. 4l+3 ("tile" t = the t-th k-mer of every
-   lane), so the sliding-window minimum and the run detection below are sequential inside a lane and need no exchange.
+   The lanes own the k-mers of a segment in BLOCKS: lane l owns k-mers 4l .. 4l+3, so the sliding-window minimum and the
+   run detection below are sequential inside a lane and need no exchange.
    Position p of the per-m-mer hash arrays is stored at slot p + p/4: lane l's 16 positions then start at slot 5l, an
    odd stride, which keeps the blocked 64-bit reads free of bank conflicts. */
 #define FG_SEG_B 4                        /* k-mers per lane per segment */
 #define FG_SEG_KMERS (32 * FG_SEG_B)      /* k-mers per segment */
-#define FG_HASH_SLOTS 200                 /* >= slot(FG_SEG_KMERS + 30) + 1 */
-#define FG_SEG_WORDS 6                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 pad */
+#define FG_HASH_SLOTS 256                 /* >= slot(FG_SEG_KMERS + 30) + 1; 2 * 8 * FG_HASH_SLOTS bytes also hold seeds and items */
+#define FG_SEG_WORDS 6                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 */
+#define FG_WORDS_PAD_BEFORE 1             /* readable words before / after the packed bases, for signed stretch offsets */
+#define FG_WORDS_PAD_AFTER 2
+
+/* One run of consecutive k-mers with the same minimizer occurrence, in k-mer order. Written by the run's first k-mer as
+   {minimizer, key}; the seed pass replaces the minimizer by its bucket. */
+struct seed_slot {
+    uint32_t begin; /* in: minimizer low word  | out: first super-k-mer of the bucket */
+    uint32_t n;     /* in: minimizer high word | out: number of super-k-mers to compare (0 when the run takes the per-k-mer path) */
+    uint32_t key;   /* read position of the minimizer | strand << 8 | index of the run's first k-mer << 16 | per-k-mer path << 31 */
+    uint32_t size;  /* out: bucket size */
+};
+#define FG_SEED_SLOW 0x80000000u
+static_assert((sizeof(seed_slot) + sizeof(uint2) + sizeof(uint32_t)) * FG_SEG_KMERS <= 2 * 8 * FG_HASH_SLOTS, "seeds + items + per-k-mer notes must fit in the hash arrays");
+
 struct warp_stage {
-    uint64_t hf[FG_HASH_SLOTS];       /* mixer_64 hash of the forward m-mer starting at every position; afterwards the
-                                         segment's seed list: {minimizer} -> {first super-k-mer, bucket size} */
-    uint64_t hr[FG_HASH_SLOTS];       /* hash of its reverse complement */
-    uint32_t info[FG_SEG_KMERS];      /* [t * 32 + lane]: seed slot | minimizer position << 8 | ambiguous << 13 | valid << 14 */
-    uint64_t words[FG_SEG_WORDS];
-    uint32_t valid[FG_SEG_WORDS];
+    uint64_t h[2 * FG_HASH_SLOTS];    /* [0, FG_HASH_SLOTS): mixer_64 hash of the forward m-mer starting at every position;
+                                         [FG_HASH_SLOTS, ..): hash of its reverse complement; afterwards seed slots and items */
+    uint64_t words[FG_WORDS_PAD_BEFORE + FG_SEG_WORDS + FG_WORDS_PAD_AFTER];  /* packed bases, base j of the segment at bits 2(j % 32) of word j / 32 */
+    uint64_t rcw[FG_WORDS_PAD_BEFORE + FG_SEG_WORDS + FG_WORDS_PAD_AFTER];    /* reverse complement of the 32 * nwords packed bases */
+    uint32_t valid[FG_SEG_WORDS + 2]; /* bit j: character j is one of ACGTacgt */
+    uint32_t vk[FG_SEG_B + 2];        /* bit i: k-mer i of the segment is valid */
 };
 
 FG_HD constexpr uint32_t fg_hslot(uint32_t p) { return p + (p >> 2); }
@@ -409,30 +423,52 @@ __device__ __forceinline__ void window_minima(const uint64_t* __restrict__ h, ui
     }
 }
 
-/* Walks one read: after next(), lane l holds the color-set id of one of its k-mers (FG_NOT_FOUND when negative, invalid or
-   past the end); over the calls until done() every k-mer of the read is reported exactly once (in no particular order:
-   the consumers -- intersection, per-color scores, distinct-set table -- are order-free).
+/* 64 bits (32 bases) of a packed base array starting at base position p, which may be negative or run past the end by
+   as much as the padding words allow; w points at the word of base 0 */
+__device__ __forceinline__ uint64_t stretch_at(const uint64_t* w, int p) {
+    const int wi = p >> 5; /* floor */
+    const uint32_t sh = uint32_t(p & 31) * 2;
+    const uint64_t a = w[wi];
+    return sh ? (a >> sh) | (w[wi + 1] << (64 - sh)) : a;
+}
+
+/* the bits of a 128-bit value {lo, hi} below bit position nb (0 <= nb <= 128) */
+__device__ __forceinline__ void mask_below(uint32_t nb, uint64_t& lo, uint64_t& hi) {
+    lo = nb >= 64 ? ~0ULL : ((1ULL << nb) - 1);
+    hi = nb <= 64 ? 0ULL : (nb >= 128 ? ~0ULL : ((1ULL << (nb - 64)) - 1));
+}
+
+/* Walks one read and reports its positive k-mers as ITEMS {color-set id, number of k-mers}: after next(), lane l holds one
+   item (cnt = 0: none). Over the calls until next() returns false every positive k-mer of the read is counted in exactly
+   one item; the consumers -- intersection, per-color scores, distinct-set table -- only need that multiset.
    Replaces the per-k-mer loop around streaming_query::lookup_advanced (sshash/streaming_query.hpp:50-109, driven from
-   src/ps_full_intersection.cpp:344-353): validity test (:53-59), 2-bit packing and reverse complement (:62-74),
-   canonical minimizer (:76-83), dictionary lookup (:144-190).
+   src/ps_full_intersection.cpp:344-353 and src/ps_threshold_union.cpp:327-347): validity test (:53-59), 2-bit packing and
+   reverse complement (:62-74), canonical minimizer (:76-83), dictionary lookup by seed (:144-190) and extend (:111-142).
 
    Per segment of FG_SEG_KMERS k-mers the warp
-     0. packs the bases (2 bits each) and their validity bits into shared memory;
+     0. packs the bases (2 bits each), their reverse complement and their validity bits into shared memory;
      1. hashes every m-mer ONCE, both strands (the k-mers of a read share almost all their m-mers, which the reference
         exploits with its sliding minimizer_enumerator, sshash/minimizer_enumerator.hpp:24-49);
      2. takes the sliding-window minima (window_minima) and from them every k-mer's canonical minimizer;
-     3. cuts the k-mers into runs with the same minimizer and makes the first k-mer of each run a SEED: only seeds go
-        through the minimizer MPHF and the bucket table, all seeds of the segment at once, one per lane. This is the
-        device analogue of the reference's seed-and-extend: ~1 hash lookup per 7 k-mers instead of 1 per k-mer;
-     4. (next) every k-mer compares itself with the super-k-mers of its run's bucket.
-   A lookup answer is a pure function of the k-mer (streaming_query.hpp:107 asserts it), so sharing the bucket between
-   the k-mers of a run changes no result. */
+     3. cuts the k-mers into runs that share one minimizer OCCURRENCE (same value, same read position, same strand) and
+        makes the first k-mer of each run a SEED;
+     4. seed pass, one seed per lane: minimizer MPHF -> bucket;
+     5. pair pass, one (seed, super-k-mer of its bucket) pair per lane: ONE comparison of the stored string with the read,
+        aligned on the minimizer (the record knows where the minimizer sits in the super-k-mer, the seed knows where it
+        sits in the read). The mismatch-free stretch around the minimizer gives the interval of read k-mers that are in
+        the dictionary; clipped to the run and counted over the valid k-mers it becomes one item. This is the device
+        analogue of the reference's seed-and-extend: ~1 hash lookup and ~1.2 string comparisons per run of ~5 k-mers.
+   A lookup answer is a pure function of the k-mer (streaming_query.hpp:107 asserts it) and every canonical k-mer is
+   stored once, so "read bases == stored bases over the k-mer's span, inside one super-k-mer" IS the lookup answer; a
+   k-mer can only be stored in the bucket of its own minimizer, so a run needs no other bucket.
+   Runs whose bucket is served by the skew index and k-mers whose minimizer value appears on both strands take the
+   per-k-mer path (lookup_in_bucket); super-k-mers without a single minimizer position are scanned k-mer by k-mer. */
 template <int W>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
     warp_stage& S;
-    uint32_t len, lane, nk, seg_end, t;
+    uint32_t len, lane, nk, seg_end, nitems, cursor;
     uint64_t kmask, mmer_mask;
     uint32_t window, kbits;
 
@@ -441,27 +477,95 @@ struct kmer_tiles {
         const uint32_t k = I.k;
         nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
         seg_end = 0;
-        t = FG_SEG_B;
+        nitems = cursor = 0;
         kmask = (1ULL << (2 * k)) - 1;
         mmer_mask = (1ULL << (2 * I.m)) - 1;
         window = W ? W : k - I.m + 1;
         kbits = (1u << k) - 1u;
     }
-    __device__ __forceinline__ bool done() const { return t == FG_SEG_B && seg_end >= nk; }
 
+    __device__ __forceinline__ const uint64_t* words() const { return S.words + FG_WORDS_PAD_BEFORE; }
+    __device__ __forceinline__ const uint64_t* rcwords() const { return S.rcw + FG_WORDS_PAD_BEFORE; }
     /* 2*nbases bits starting at base position p (segment-relative) of the packed words */
-    __device__ __forceinline__ uint64_t bases_at(uint32_t p) const {
-        const uint32_t wi = p >> 5, sh = (p & 31) * 2;
-        const uint64_t a = S.words[wi];
-        return sh ? (a >> sh) | (S.words[wi + 1] << (64 - sh)) : a;
-    }
-    __device__ __forceinline__ uint2* seeds() const { return reinterpret_cast<uint2*>(S.hf); }
+    __device__ __forceinline__ uint64_t bases_at(uint32_t p) const { return stretch_at(words(), int(p)); }
+    __device__ __forceinline__ uint64_t* hf() const { return S.h; }
+    __device__ __forceinline__ uint64_t* hr() const { return S.h + FG_HASH_SLOTS; }
+    __device__ __forceinline__ seed_slot* seeds() const { return reinterpret_cast<seed_slot*>(S.h); }
+    __device__ __forceinline__ uint2* items() const { return reinterpret_cast<uint2*>(seeds() + FG_SEG_KMERS); }
+    __device__ __forceinline__ uint32_t* notes() const { return reinterpret_cast<uint32_t*>(items() + FG_SEG_KMERS); } /* per k-mer, for the per-k-mer path */
 
-    /* m-mer behind a window minimum; compute_minimizer's "nothing below UINT64_MAX" sentinel when that can occur (image.h) */
-    __device__ __forceinline__ uint64_t mmer_of_hash(uint64_t h) const {
-        uint64_t y = (h ^ I.hash_magic) * FG_MIX_INV;
-        if (I.guard_max_hash && h == UINT64_MAX) y = UINT64_MAX;
-        return y;
+    /* m-mer behind a window minimum */
+    __device__ __forceinline__ uint64_t mmer_of_hash(uint64_t h) const { return (h ^ I.hash_magic) * FG_MIX_INV; }
+
+    /* number of valid k-mers with index in [lo, hi], hi - lo < 32 */
+    __device__ __forceinline__ uint32_t count_valid(uint32_t lo, uint32_t hi) const {
+        const uint32_t bits = __funnelshift_r(S.vk[lo >> 5], S.vk[(lo >> 5) + 1], lo & 31);
+        const uint32_t len = hi - lo + 1;
+        return __popc(len >= 32 ? bits : bits & ((1u << len) - 1u));
+    }
+
+    __device__ __forceinline__ void append_items(bool have, uint32_t cid, uint32_t cnt) {
+        const uint32_t b = __ballot_sync(FG_FULL, have);
+        if (have) items()[nitems + __popc(b & ((1u << lane) - 1u))] = make_uint2(cid, cnt);
+        nitems += __popc(b);
+    }
+
+    /* step 5 for one (seed, super-k-mer) pair: number of k-mers of the run [i_first, i_last] found in super-k-mer sk */
+    __device__ __forceinline__ uint32_t extend_pair(uint32_t sk, int p, bool fw, uint32_t i_first, uint32_t i_last, uint32_t nchars,
+                                                    uint32_t nwords, uint32_t& cid) const {
+        const int k = int(I.k), m = int(I.m);
+        const uint2 rec = FG_LDG(I.sk_records + sk);
+        cid = I.sk_cid ? FG_LDG(I.sk_cid + sk) : (rec.y & FGI_SK_CID_MASK);
+        const int win = int((rec.y >> FGI_SK_WINDOW_SHIFT) & 31u), pm = int((rec.y >> FGI_SK_PM_SHIFT) & 31u);
+        if (!(rec.y >> FGI_SK_PINNED_SHIFT)) { /* no single minimizer position: every k-mer of the run against every stored k-mer */
+            uint32_t cnt = 0;
+            minimizer_t mz;
+            mz.value = 0;
+            mz.cpos = 0;
+            mz.ambiguous = true;
+            for (uint32_t i = i_first; i <= i_last; ++i) {
+                if (!((S.vk[i >> 5] >> (i & 31)) & 1u)) continue;
+                const uint64_t fwd = bases_at(i) & kmask;
+                cnt += scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+            }
+            return cnt;
+        }
+        const uint64_t bit = 2 * uint64_t(rec.x & FGI_SK_OFFSET_MASK);
+        const uint64_t* w = I.strings + (bit >> 6);
+        const uint32_t sh = uint32_t(bit & 63);
+        const uint64_t w0 = FG_LDG(w), w1 = FG_LDG(w + 1), w2 = FG_LDG(w + 2);
+        const uint64_t s_lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0; /* the super-k-mer's win + k - 1 <= 61 bases */
+        const uint64_t s_hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+        /* the stored m-mer at the minimizer position reads as the minimizer itself or as its reverse complement (record bit);
+           so does the read's (fw). Same reading on both sides: the read aligns forward, otherwise reverse-complemented. */
+        const bool forward = bool(rec.x >> FGI_SK_CANON_FWD_SHIFT) == fw;
+        const int len_s = win + k - 1;
+        const int d = p - pm;               /* forward: stored base j <-> read base j + d, k-mer index i = t + d */
+        const int e = pm + p + m - k;       /* reverse: stored base j <-> complement of read base e + k - 1 - j, i = e - t */
+        const uint64_t* src = forward ? words() : rcwords();
+        const int off = forward ? d : int(32 * nwords) - e - k;
+        const int j_min = forward ? max(0, -d) : max(0, e + k - int(nchars));
+        const int j_max = forward ? min(len_s, int(nchars) - d) : min(len_s, e + k);
+        const uint64_t x_lo = s_lo ^ stretch_at(src, off), x_hi = s_hi ^ stretch_at(src, off + 32);
+        const uint64_t m_lo = (x_lo | (x_lo >> 1)) & 0x5555555555555555ULL, m_hi = (x_hi | (x_hi >> 1)) & 0x5555555555555555ULL;
+        /* a = first stored position after the last mismatch left of the minimizer's end; b = first mismatch at or right of
+           the minimizer's start. A k-mer at stored position t is present iff a <= t and t + k <= b. */
+        uint64_t q_lo, q_hi;
+        mask_below(2 * uint32_t(pm + m), q_lo, q_hi);
+        const uint64_t l_lo = m_lo & q_lo, l_hi = m_hi & q_hi;
+        int a = 0;
+        if (l_hi) a = 32 + ((64 - __clzll((long long)l_hi)) >> 1) + 1;
+        else if (l_lo) a = ((64 - __clzll((long long)l_lo)) >> 1) + 1;
+        mask_below(2 * uint32_t(pm), q_lo, q_hi);
+        const uint64_t g_lo = m_lo & ~q_lo, g_hi = m_hi & ~q_hi;
+        int b = 64;
+        if (g_lo) b = (__ffsll((long long)g_lo) - 1) >> 1;
+        else if (g_hi) b = 32 + ((__ffsll((long long)g_hi) - 1) >> 1);
+        const int t_lo = max(a, j_min), t_hi = min(min(b, j_max) - k, win - 1);
+        if (t_lo > t_hi) return 0;
+        const int lo = max(forward ? t_lo + d : e - t_hi, int(i_first)), hi = min(forward ? t_hi + d : e - t_lo, int(i_last));
+        if (lo > hi) return 0;
+        return count_valid(uint32_t(lo), uint32_t(hi));
     }
 
     __device__ __forceinline__ void load_segment() {
@@ -469,19 +573,31 @@ struct kmer_tiles {
         const uint32_t seg0 = seg_end;
         const uint32_t seg_nk = min(uint32_t(FG_SEG_KMERS), nk - seg0);
         seg_end = seg0 + seg_nk;
+        nitems = cursor = 0;
         const uint32_t nchars = seg_nk + I.k - 1, npos = seg_nk + window - 1;
         const uint32_t nwords = (nchars + 31) >> 5;
-        /* 0. bases */
-        for (uint32_t c = 0; c <= nwords; ++c) { /* one extra zero word so that bases_at may read words[wi + 1] */
+        /* 0. bases; characters past the end pack as zeros */
+        for (uint32_t c = 0; c < nwords; ++c) {
             const uint32_t p = seg0 + 32 * c + lane;
-            const bool in = c < nwords && 32 * c + lane < nchars;
+            const bool in = 32 * c + lane < nchars;
             const uint32_t ch = in ? seq[p] : 0u;
             uint64_t w;
             uint32_t v;
             pack_chars(ch, in, lane, w, v);
             if (lane == 0) {
-                S.words[c] = w;
+                S.words[FG_WORDS_PAD_BEFORE + c] = w;
                 S.valid[c] = v;
+                S.rcw[FG_WORDS_PAD_BEFORE + nwords - 1 - c] = revcomp(w, 32);
+            }
+        }
+        if (lane <= FG_WORDS_PAD_AFTER) { /* readable padding: values never reach a valid k-mer */
+            if (lane < FG_WORDS_PAD_AFTER) {
+                S.words[FG_WORDS_PAD_BEFORE + nwords + lane] = 0;
+                S.rcw[FG_WORDS_PAD_BEFORE + nwords + lane] = 0;
+                S.valid[nwords + lane] = 0;
+            } else {
+                S.words[0] = 0;
+                S.rcw[0] = 0;
             }
         }
         __syncwarp();
@@ -489,111 +605,185 @@ struct kmer_tiles {
         const uint32_t m = I.m;
         for (uint32_t q = lane; q < npos; q += 32) {
             const uint64_t y = bases_at(q) & mmer_mask;
-            S.hf[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
-            S.hr[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
+            hf()[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
+            hr()[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
         }
         __syncwarp();
         /* 2. canonical minimizer of the lane's k-mers i0 .. i0+3: value = min over both strands, compared as integers
               (sshash/streaming_query.hpp:76-79); cpos = where it starts inside the k-mer, forward coordinates */
         const uint32_t i0 = FG_SEG_B * lane;
         uint64_t val[FG_SEG_B];
-        uint32_t inf[FG_SEG_B]; /* cpos << 8 | ambiguous << 13 | valid << 14 */
+        uint32_t key[FG_SEG_B]; /* read position of the minimizer | strand << 8 | ambiguous << 13 | valid << 14 | cpos << 16 */
         {
-            uint64_t hf[FG_SEG_B], hr[FG_SEG_B];
+            uint64_t mhf[FG_SEG_B], mhr[FG_SEG_B];
             uint32_t pf[FG_SEG_B], pr[FG_SEG_B];
             if (W) {
-                window_minima<W ? W : 13, false>(S.hf + 5 * lane, hf, pf);
-                window_minima<W ? W : 13, true>(S.hr + 5 * lane, hr, pr);
+                window_minima<W ? W : 13, false>(hf() + 5 * lane, mhf, pf);
+                window_minima<W ? W : 13, true>(hr() + 5 * lane, mhr, pr);
             } else { /* any other (k, m): plain scan of each window */
 #pragma unroll
                 for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                    hf[tt] = hr[tt] = UINT64_MAX;
+                    mhf[tt] = mhr[tt] = UINT64_MAX;
                     pf[tt] = pr[tt] = tt;
                     for (uint32_t j = 0; j < window; ++j) {
-                        const uint64_t a = S.hf[fg_hslot(i0 + tt + j)], b = S.hr[fg_hslot(i0 + tt + j)];
-                        if (a < hf[tt]) hf[tt] = a, pf[tt] = tt + j;
-                        if (b <= hr[tt]) hr[tt] = b, pr[tt] = tt + j;
+                        const uint64_t a = hf()[fg_hslot(i0 + tt + j)], b = hr()[fg_hslot(i0 + tt + j)];
+                        if (a < mhf[tt]) mhf[tt] = a, pf[tt] = tt + j;
+                        if (b <= mhr[tt]) mhr[tt] = b, pr[tt] = tt + j;
                     }
                 }
             }
             /* i0 is a multiple of 4, so the lane's four k-mers start in the same 32-character word */
             const uint32_t vw0 = S.valid[i0 >> 5], vw1 = S.valid[(i0 >> 5) + 1];
+            uint32_t nibble = 0;
 #pragma unroll
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
                 const uint32_t i = i0 + tt;
                 const uint32_t bits = __funnelshift_r(vw0, vw1, i & 31);
                 const bool valid = i < seg_nk && (bits & kbits) == kbits;
-                const uint64_t vf = mmer_of_hash(hf[tt]), vr = mmer_of_hash(hr[tt]);
+                uint64_t vf = mmer_of_hash(mhf[tt]), vr = mmer_of_hash(mhr[tt]);
+                if (I.guard_max_hash) { /* compute_minimizer's "nothing below UINT64_MAX" sentinel when that can occur (image.h) */
+                    if (mhf[tt] == UINT64_MAX) vf = UINT64_MAX;
+                    if (mhr[tt] == UINT64_MAX) vr = UINT64_MAX;
+                }
                 const bool fwd_wins = vf <= vr;
                 val[tt] = fwd_wins ? vf : vr;
                 const uint32_t cpos = (fwd_wins ? pf[tt] : pr[tt]) - tt;
-                inf[tt] = (cpos << 8) | (uint32_t(vf == vr) << 13) | (uint32_t(valid) << 14);
+                key[tt] = (i + cpos) | (uint32_t(fwd_wins) << 8) | (uint32_t(vf == vr) << 13) | (uint32_t(valid) << 14) | (cpos << 16);
+                nibble |= uint32_t(valid) << tt;
             }
-        }
-        __syncwarp(); /* every lane is done with the hash arrays: the seed list may overwrite them */
-        /* 3. seeds: the first k-mer of every run of valid k-mers with the same minimizer */
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        uint64_t prev_val = __shfl_up_sync(FG_FULL, val[FG_SEG_B - 1], 1);
-        bool prev_valid = __shfl_up_sync(FG_FULL, inf[FG_SEG_B - 1], 1) >> 14;
-        if (lane == 0) prev_valid = false;
-        uint32_t nseeds = 0, cur_slot = 0xffu;
-        bool has_leader = false;
-        bool leader[FG_SEG_B];
+            /* valid-k-mer bitmap in k-mer order: 8 lanes per 32-bit word */
+            const uint32_t part = nibble << (4 * (lane & 7));
 #pragma unroll
-        for (int tt = 0; tt < FG_SEG_B; ++tt) {
-            const bool valid = inf[tt] >> 14;
-            leader[tt] = valid && !(prev_valid && prev_val == val[tt]);
-            prev_valid = valid;
-            prev_val = val[tt];
-            const uint32_t b = __ballot_sync(FG_FULL, leader[tt]);
-            if (leader[tt]) {
-                cur_slot = nseeds + __popc(b & lt_mask);
-                seeds()[cur_slot] = make_uint2(uint32_t(val[tt]), uint32_t(val[tt] >> 32));
-                has_leader = true;
+            for (int w = 0; w < FG_SEG_B; ++w) {
+                const uint32_t word = __reduce_or_sync(FG_FULL, (lane >> 3) == uint32_t(w) ? part : 0u);
+                if (lane == 0) S.vk[w] = word;
             }
-            inf[tt] |= cur_slot; /* 0xff for now when the run started in an earlier lane */
-            nseeds += __popc(b);
+            if (lane == 0) S.vk[FG_SEG_B] = S.vk[FG_SEG_B + 1] = 0;
         }
-        { /* runs that continue from an earlier lane: the slot in effect at the end of the nearest lane that has a seed */
-            const uint32_t hb = __ballot_sync(FG_FULL, has_leader) & lt_mask;
-            const uint32_t inherited = __shfl_sync(FG_FULL, cur_slot, hb ? 31 - __clz(int(hb)) : 0);
+        __syncwarp(); /* every lane is done with the hash arrays: seeds and items may overwrite them */
+        /* 3. seeds: the first k-mer of every run of valid k-mers with the same minimizer occurrence -- same value, at the same
+              read position, read off the same strand. A k-mer whose minimizer value shows up on both strands (ambiguous)
+              is a run of its own. Seeds are numbered in k-mer order. */
+        uint32_t nseeds;
+        {
+            uint64_t prev_val = __shfl_up_sync(FG_FULL, val[FG_SEG_B - 1], 1);
+            uint32_t prev_key = __shfl_up_sync(FG_FULL, key[FG_SEG_B - 1], 1);
+            if (lane == 0) prev_key = 0;
+            uint32_t leaders = 0;
 #pragma unroll
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                if ((inf[tt] & 0xffu) == 0xffu) inf[tt] = (inf[tt] & ~0xffu) | (inherited & 0xffu);
-                S.info[tt * 32 + lane] = inf[tt];
+                /* same run: both valid, neither ambiguous, same position and strand, same value */
+                const bool same = ((key[tt] ^ prev_key) & 0xffffu) == 0 && (key[tt] & 0x6000u) == 0x4000u && prev_val == val[tt];
+                if (((key[tt] >> 14) & 1u) && !same) leaders |= 1u << tt;
+                prev_key = key[tt];
+                prev_val = val[tt];
+            }
+            uint32_t incl = __popc(leaders); /* inclusive prefix sum over the lanes */
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t y = __shfl_up_sync(FG_FULL, incl, dlt);
+                if (lane >= uint32_t(dlt)) incl += y;
+            }
+            nseeds = __shfl_sync(FG_FULL, incl, 31);
+            uint32_t s = incl - __popc(leaders); /* seeds before this lane */
+#pragma unroll
+            for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                if ((leaders >> tt) & 1u) {
+                    seed_slot& slot = seeds()[s];
+                    slot.begin = uint32_t(val[tt]);
+                    slot.n = uint32_t(val[tt] >> 32);
+                    slot.key = (key[tt] & 0x1ffu) | ((i0 + tt) << 16) | (((key[tt] >> 13) & 1u) ? FG_SEED_SLOW : 0u);
+                    s += 1;
+                }
+                /* note for the per-k-mer path: run | ambiguous << 13 | valid << 14 | cpos << 16 (the run wraps to 0xff before the
+                   first seed: such k-mers are invalid) */
+                notes()[tt * 32 + lane] = ((s - 1) & 0xffu) | (key[tt] & 0x001f6000u);
             }
         }
         __syncwarp();
-        /* minimizers::lookup + buckets::locate_bucket for every seed, one per lane */
-        for (uint32_t s = lane; s < nseeds; s += 32) {
-            const uint2 v = seeds()[s];
-            const uint64_t b = minimizer_bucket(I, uint64_t(v.x) | (uint64_t(v.y) << 32));
-            const uint32_t begin = FG_LDG(I.bucket_begin + b), end = FG_LDG(I.bucket_begin + b + 1);
-            seeds()[s] = make_uint2(begin, end - begin);
+        /* 4. + 5. in groups of 32 seeds */
+        bool any_slow = false;
+        for (uint32_t g0 = 0; g0 < nseeds; g0 += 32) {
+            /* minimizers::lookup + buckets::locate_bucket, one seed per lane */
+            uint32_t n = 0;
+            if (g0 + lane < nseeds) {
+                seed_slot& slot = seeds()[g0 + lane];
+                const uint64_t b = minimizer_bucket(I, uint64_t(slot.begin) | (uint64_t(slot.n) << 32));
+                const uint32_t begin = FG_LDG(I.bucket_begin + b), size = FG_LDG(I.bucket_begin + b + 1) - begin;
+                if (size > I.skew_threshold) slot.key |= FG_SEED_SLOW; /* skew index: per-k-mer path */
+                n = (slot.key & FG_SEED_SLOW) ? 0u : size;
+                any_slow |= (slot.key & FG_SEED_SLOW) != 0;
+                slot.begin = begin;
+                slot.n = n;
+                slot.size = size;
+            }
+            uint32_t end = n; /* inclusive prefix sum of the pair counts */
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t y = __shfl_up_sync(FG_FULL, end, dlt);
+                if (lane >= uint32_t(dlt)) end += y;
+            }
+            const uint32_t total = __shfl_sync(FG_FULL, end, 31);
+            __syncwarp();
+            /* one (seed, super-k-mer) pair per lane */
+            for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+                const uint32_t q = q0 + lane;
+                uint32_t owner = 0; /* the lane whose seed owns pair q: the first with end > q */
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(FG_FULL, end, owner + step - 1);
+                    if (probe <= q) owner += step;
+                }
+                const uint32_t owner_end = __shfl_sync(FG_FULL, end, owner & 31u);
+                uint32_t cid = 0, cnt = 0;
+                if (q < total) {
+                    const seed_slot slot = seeds()[g0 + owner];
+                    const uint32_t j = q - (owner_end - slot.n);
+                    const uint32_t i_first = (slot.key >> 16) & 0xffu;
+                    const uint32_t i_last = (g0 + owner + 1 < nseeds ? ((seeds()[g0 + owner + 1].key >> 16) & 0xffu) : seg_nk) - 1;
+                    cnt = extend_pair(slot.begin + j, int(slot.key & 0xffu), (slot.key >> 8) & 1u, i_first, i_last, nchars, nwords, cid);
+                }
+                append_items(cnt != 0, cid, cnt);
+            }
+        }
+        /* per-k-mer path: ambiguous k-mers and runs behind the skew index */
+        if (__ballot_sync(FG_FULL, any_slow)) {
+#pragma unroll
+            for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                uint32_t cid = FG_NOT_FOUND;
+                const uint32_t note = notes()[tt * 32 + lane];
+                if ((note >> 14) & 1u) {
+                    const seed_slot slot = seeds()[note & 0xffu];
+                    if (slot.key & FG_SEED_SLOW) {
+                        const uint64_t fwd = bases_at(FG_SEG_B * lane + tt) & kmask;
+                        minimizer_t mz;
+                        mz.value = 0;
+                        mz.cpos = (note >> 16) & 31u;
+                        mz.ambiguous = (note >> 13) & 1u;
+                        cid = lookup_in_bucket(I, slot.begin, slot.size, fwd, revcomp(fwd, I.k), mz, kmask);
+                    }
+                }
+                append_items(cid != FG_NOT_FOUND, cid, 1);
+            }
         }
         __syncwarp();
     }
 
-    __device__ __forceinline__ uint32_t next() {
-        if (t == FG_SEG_B) {
+    /* the next batch of items, one per lane (cnt = 0: none); false when the read is exhausted (warp-uniform) */
+    __device__ __forceinline__ bool next(uint32_t& cid, uint32_t& cnt) {
+        while (cursor >= nitems) {
+            if (seg_end >= nk) return false;
             load_segment();
-            t = 0;
         }
-        const uint32_t inf = S.info[t * 32 + lane];
-        uint32_t cid = FG_NOT_FOUND;
-        if (inf >> 14) {
-            const uint64_t fwd = bases_at(FG_SEG_B * lane + t) & kmask;
-            const uint64_t rc = revcomp(fwd, I.k);
-            const uint2 bucket = seeds()[inf & 0xffu];
-            minimizer_t mz;
-            mz.value = 0;
-            mz.cpos = (inf >> 8) & 31u;
-            mz.ambiguous = (inf >> 13) & 1u;
-            cid = lookup_in_bucket(I, bucket.x, bucket.y, fwd, rc, mz, kmask);
+        cid = FG_NOT_FOUND;
+        cnt = 0;
+        if (cursor + lane < nitems) {
+            const uint2 it = items()[cursor + lane];
+            cid = it.x;
+            cnt = it.y;
         }
-        __syncwarp();
-        t += 1;
-        return cid;
+        cursor += 32;
+        return true;
     }
 };
 
@@ -688,21 +878,18 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
     R.cap = 0;
     R.failed = false;
     kmer_tiles<W> tiles(I, seq, len, lane, stage);
-    while (!tiles.done()) {
-        const uint32_t cid = tiles.next();
-        const bool found = cid != FG_NOT_FOUND;
-        const uint32_t found_mask = __ballot_sync(FG_FULL, found);
-        R.npos += __popc(found_mask);
-        if (!found_mask) continue;
+    uint32_t cid, cnt;
+    while (tiles.next(cid, cnt)) {
+        const bool found = cnt != 0;
+        R.npos += __reduce_add_sync(FG_FULL, cnt);
         const uint32_t grp = __match_any_sync(FG_FULL, cid);
         const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
-        const uint32_t gcnt = __popc(grp);
         uint32_t leaders = __ballot_sync(FG_FULL, leader);
         while (leaders) {
             const int src = __ffs(int(leaders)) - 1;
             leaders &= leaders - 1;
             const uint32_t kk = __shfl_sync(FG_FULL, cid, src);
-            const uint32_t cc = __shfl_sync(FG_FULL, gcnt, src);
+            const uint32_t cc = __reduce_add_sync(FG_FULL, cid == kk ? cnt : 0u);
             if (R.tab == nullptr) {
                 const uint32_t hit = __ballot_sync(FG_FULL, R.cid == kk);
                 if (hit) {

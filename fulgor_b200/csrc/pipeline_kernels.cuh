@@ -18,12 +18,12 @@ namespace fgb {
 #define FG_WARPS_PER_BLOCK 8
 #define FG_BLOCK (FG_WARPS_PER_BLOCK * 32)
 #ifndef FG_MIN_BLOCKS
-#define FG_MIN_BLOCKS 5 /* resident blocks per SM the lookup kernels are compiled for (register budget 65536 / (5 * 256) = 51) */
+#define FG_MIN_BLOCKS 4 /* resident blocks per SM the lookup kernels are compiled for (register budget 65536 / (4 * 256) = 64) */
 #endif
 #define FG_STAGE_STRIDE FG_MAX_ENTRIES
 
 /* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask,
-   accumulated tile by tile (no per-read table: AND is idempotent and scores are sums over k-mers).
+   accumulated item by item (no per-read table: AND is idempotent and scores are sums over k-mers).
    Full intersection (src/ps_full_intersection.cpp:377-400 -> intersect :33-127): AND of the hit sets.
    Threshold union (src/ps_threshold_union.cpp:389 + merge :17-40 / merge_meta :43-120): color c is
    reported iff sum over positive k-mers of [c in set(k-mer)] >= uint64(double(npos) * threshold). */
@@ -39,31 +39,21 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(c
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
         kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, stage[threadIdx.x >> 5]);
         uint32_t acc = ~0u, score = 0, npos = 0;
-        uint32_t cache_cid = FG_NOT_FOUND, cache_mask = 0;
-        while (!tiles.done()) {
-            const uint32_t cid = tiles.next();
-            const bool found = cid != FG_NOT_FOUND;
-            const uint32_t found_mask = __ballot_sync(FG_FULL, found);
-            if (!found_mask) continue;
-            npos += __popc(found_mask);
-            /* decode; the set of the previous tile's first hit is cached (reads mostly stay inside one color set) */
-            uint32_t mask = cache_mask;
-            if (found && cid != cache_cid) mask = color_set_mask(I, cid);
+        uint32_t cid, cnt;
+        while (tiles.next(cid, cnt)) { /* items {color-set id, number of k-mers}: every lane decodes its own set */
+            const bool found = cnt != 0;
+            const uint32_t mask = found ? color_set_mask(I, cid) : ~0u;
             __syncwarp();
-            const int first = __ffs(int(found_mask)) - 1;
-            cache_cid = __shfl_sync(FG_FULL, cid, first);
-            cache_mask = __shfl_sync(FG_FULL, mask, first);
+            npos += __reduce_add_sync(FG_FULL, cnt);
             if (algo == FULGOR_GPU_FULL_INTERSECTION) {
-                acc &= __reduce_and_sync(FG_FULL, found ? mask : ~0u);
+                acc &= __reduce_and_sync(FG_FULL, mask);
             } else {
-                const uint32_t grp = __match_any_sync(FG_FULL, cid);
-                const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
-                uint32_t leaders = __ballot_sync(FG_FULL, leader);
-                while (leaders) {
-                    const int src = __ffs(int(leaders)) - 1;
-                    leaders &= leaders - 1;
+                uint32_t todo = __ballot_sync(FG_FULL, found);
+                while (todo) {
+                    const int src = __ffs(int(todo)) - 1;
+                    todo &= todo - 1;
                     const uint32_t mj = __shfl_sync(FG_FULL, mask, src);
-                    const uint32_t wj = __shfl_sync(FG_FULL, uint32_t(__popc(grp)), src);
+                    const uint32_t wj = __shfl_sync(FG_FULL, cnt, src);
                     score += ((mj >> lane) & 1u) ? wj : 0u;
                 }
             }
@@ -81,7 +71,7 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(c
     }
 }
 
-#define FG_SCRATCH_ENTRIES 256 /* per-warp shared-memory list for reads with more than 32 distinct color sets */
+#define FG_SCRATCH_ENTRIES 128 /* per-warp shared-memory list for reads with more than 32 distinct color sets */
 
 /* where the sorted {color-set id, multiplicity} list of read r lives: counts[r] <= 32 -> stage[r*32 ..];
    otherwise in the pool at the 64-bit entry offset stored in stage[r*32] */

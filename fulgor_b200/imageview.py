@@ -30,7 +30,7 @@ HYBRID_DTYPE = np.dtype([("num_colors", "<u4"), ("sparse_thr", "<u4"), ("very_de
 
 def header(image):
     h = Header.from_buffer_copy(image[: C.sizeof(Header)].tobytes())
-    assert h.magic == 0x3130474D49475546 and h.total_bytes == image.size, "not a fulgor-b200 image"
+    assert h.magic == 0x3230474D49475546 and h.total_bytes == image.size, "not a fulgor-b200 image"
     return h
 
 

@@ -198,6 +198,7 @@ static inline T __ldg(const T* p) { return *p; }
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return uint64_t((unsigned __int128)a * b >> 64); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __clz(int x) { return x ? __builtin_clz(unsigned(x)) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
@@ -290,6 +291,14 @@ static inline unsigned __reduce_and_sync(unsigned mask, unsigned v) {
         uint64_t r = ~0ULL;
         for (int l = 0; l < 32; ++l) r &= w.vals[l];
         for (int l = 0; l < 32; ++l) w.out[l] = r;
+    }));
+}
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    fg_emul_check_mask(mask);
+    return unsigned(simt::collective(9, v, 0, [](simt::warp_state& w) {
+        uint64_t r = 0;
+        for (int l = 0; l < 32; ++l) r += w.vals[l];
+        for (int l = 0; l < 32; ++l) w.out[l] = r & 0xffffffffu;
     }));
 }
 static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
