@@ -329,16 +329,6 @@ FG_HD bool base_valid(uint32_t c) {
     return d < 20u && ((0x80045u >> d) & 1u);
 }
 
-/* 32 characters (one per lane) -> one 64-bit word of 2-bit codes (char j at bits [2j, 2j+1]) + validity mask */
-__device__ __forceinline__ void pack_chars(uint32_t c, bool in_range, uint32_t lane, uint64_t& word, uint32_t& valid) {
-    const uint32_t code = (c >> 1) & 3u;
-    const uint32_t sh = (lane & 15u) * 2u;
-    const uint32_t lo = __reduce_or_sync(FG_FULL, lane < 16 ? code << sh : 0u);
-    const uint32_t hi = __reduce_or_sync(FG_FULL, lane >= 16 ? code << sh : 0u);
-    word = uint64_t(lo) | (uint64_t(hi) << 32);
-    valid = __ballot_sync(FG_FULL, in_range && base_valid(c));
-}
-
 /* mixer_64 (sshash/hash_util.hpp:88-111) is h(y) = (y * FG_MIX_MUL) ^ magic: a bijection of 64-bit words, so the
    m-mer is recovered from its hash with the inverse multiplier (FG_MIX_MUL * FG_MIX_INV == 1 mod 2^64). */
 #define FG_MIX_MUL 0x517cc1b727220a95ULL
@@ -360,7 +350,7 @@ static_assert(FG_MIX_MUL * fg_inverse_odd(FG_MIX_MUL) == 1ULL, "mixer_64 multipl
 #define FG_HASH_SLOTS 256                 /* >= slot(FG_SEG_KMERS + 30) + 1; 2 * 8 * FG_HASH_SLOTS bytes also hold seeds and items */
 #define FG_SEG_WORDS 6                    /* 64-bit words of packed bases: ceil((FG_SEG_KMERS + 30) / 32) + 1 */
 #define FG_WORDS_PAD_BEFORE 1             /* readable words before / after the packed bases, for signed stretch offsets */
-#define FG_WORDS_PAD_AFTER 2
+#define FG_WORDS_PAD_AFTER 3
 
 /* One run of consecutive k-mers with the same minimizer occurrence, in k-mer order. Written by the run's first k-mer as
    {minimizer, key}; the seed pass replaces the minimizer by its bucket. */
@@ -378,7 +368,7 @@ struct warp_stage {
                                          [FG_HASH_SLOTS, ..): hash of its reverse complement; afterwards seed slots and items */
     uint64_t words[FG_WORDS_PAD_BEFORE + FG_SEG_WORDS + FG_WORDS_PAD_AFTER];  /* packed bases, base j of the segment at bits 2(j % 32) of word j / 32 */
     uint64_t rcw[FG_WORDS_PAD_BEFORE + FG_SEG_WORDS + FG_WORDS_PAD_AFTER];    /* reverse complement of the 32 * nwords packed bases */
-    uint32_t valid[FG_SEG_WORDS + 2]; /* bit j: character j is one of ACGTacgt */
+    uint32_t valid[FG_SEG_WORDS + 2]; /* bit j: character j of the segment is one of ACGTacgt (only written when some character is not) */
     uint32_t vk[FG_SEG_B + 2];        /* bit i: k-mer i of the segment is valid */
 };
 
@@ -467,17 +457,21 @@ template <int W>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
+    const uint8_t *buf_begin, *buf_end; /* the bases buffer the read lives in: aligned 4-byte loads stay inside it */
     warp_stage& S;
     uint32_t len, lane, nk, seg_end, nitems, cursor;
+    uint32_t shift; /* the packed stream starts at the 4-byte aligned address at or below the segment: base j sits at stream position j + shift */
     uint64_t kmask, mmer_mask;
     uint32_t window, kbits;
 
-    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, uint32_t lane_, warp_stage& S_)
-        : I(I_), seq(seq_), S(S_), len(len_), lane(lane_) {
+    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, const uint8_t* buf_begin_, const uint8_t* buf_end_,
+                                          uint32_t lane_, warp_stage& S_)
+        : I(I_), seq(seq_), buf_begin(buf_begin_), buf_end(buf_end_), S(S_), len(len_), lane(lane_) {
         const uint32_t k = I.k;
         nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
         seg_end = 0;
         nitems = cursor = 0;
+        shift = 0;
         kmask = (1ULL << (2 * k)) - 1;
         mmer_mask = (1ULL << (2 * I.m)) - 1;
         window = W ? W : k - I.m + 1;
@@ -487,7 +481,7 @@ struct kmer_tiles {
     __device__ __forceinline__ const uint64_t* words() const { return S.words + FG_WORDS_PAD_BEFORE; }
     __device__ __forceinline__ const uint64_t* rcwords() const { return S.rcw + FG_WORDS_PAD_BEFORE; }
     /* 2*nbases bits starting at base position p (segment-relative) of the packed words */
-    __device__ __forceinline__ uint64_t bases_at(uint32_t p) const { return stretch_at(words(), int(p)); }
+    __device__ __forceinline__ uint64_t bases_at(uint32_t p) const { return stretch_at(words(), int(p + shift)); }
     __device__ __forceinline__ uint64_t* hf() const { return S.h; }
     __device__ __forceinline__ uint64_t* hr() const { return S.h + FG_HASH_SLOTS; }
     __device__ __forceinline__ seed_slot* seeds() const { return reinterpret_cast<seed_slot*>(S.h); }
@@ -543,7 +537,7 @@ struct kmer_tiles {
         const int d = p - pm;               /* forward: stored base j <-> read base j + d, k-mer index i = t + d */
         const int e = pm + p + m - k;       /* reverse: stored base j <-> complement of read base e + k - 1 - j, i = e - t */
         const uint64_t* src = forward ? words() : rcwords();
-        const int off = forward ? d : int(32 * nwords) - e - k;
+        const int off = forward ? d + int(shift) : int(32 * nwords) - int(shift) - e - k;
         const int j_min = forward ? max(0, -d) : max(0, e + k - int(nchars));
         const int j_max = forward ? min(len_s, int(nchars) - d) : min(len_s, e + k);
         const uint64_t x_lo = s_lo ^ stretch_at(src, off), x_hi = s_hi ^ stretch_at(src, off + 32);
@@ -575,38 +569,81 @@ struct kmer_tiles {
         seg_end = seg0 + seg_nk;
         nitems = cursor = 0;
         const uint32_t nchars = seg_nk + I.k - 1, npos = seg_nk + window - 1;
-        const uint32_t nwords = (nchars + 31) >> 5;
-        /* 0. bases; characters past the end pack as zeros */
-        for (uint32_t c = 0; c < nwords; ++c) {
-            const uint32_t p = seg0 + 32 * c + lane;
-            const bool in = 32 * c + lane < nchars;
-            const uint32_t ch = in ? seq[p] : 0u;
-            uint64_t w;
-            uint32_t v;
-            pack_chars(ch, in, lane, w, v);
-            if (lane == 0) {
-                S.words[FG_WORDS_PAD_BEFORE + c] = w;
-                S.valid[c] = v;
-                S.rcw[FG_WORDS_PAD_BEFORE + nwords - 1 - c] = revcomp(w, 32);
+        /* 0. bases. Lane l loads the l-th aligned 4-byte word at or after the segment's aligned floor, packs its four
+              characters to one byte (2 bits each) and stores it: the packed stream is the byte array over S.words. */
+        const uint8_t* p0 = seq + seg0;
+        shift = uint32_t(reinterpret_cast<uintptr_t>(p0) & 3u);
+        const uint32_t nstream = nchars + shift;
+        const uint32_t nwords = (nstream + 31) >> 5;
+        bool bad = false;
+        for (uint32_t w0 = 0; w0 < 8 * nwords; w0 += 32) {
+            const uint32_t wi = w0 + lane;
+            const int bo = int(4 * wi) - int(shift); /* segment index of the word's first character */
+            uint32_t x = 0x41414141u;                /* characters outside the segment read as 'A' (code 0) */
+            if (bo < int(nchars)) {
+                const uint8_t* q = p0 + bo;
+                if (q >= buf_begin && q + 4 <= buf_end) {
+                    x = __ldg(reinterpret_cast<const uint32_t*>(q));
+                } else { /* the word straddles an end of the buffer */
+                    x = 0;
+                    for (int bb = 0; bb < 4; ++bb) x |= uint32_t(q + bb >= buf_begin && q + bb < buf_end ? q[bb] : uint8_t('A')) << (8 * bb);
+                }
+                const uint32_t drop_lo = bo < 0 ? uint32_t(-bo) : 0u, drop_hi = bo + 4 > int(nchars) ? uint32_t(bo + 4 - int(nchars)) : 0u;
+                if (drop_lo | drop_hi) {
+                    const uint32_t keep = (0xffffffffu << (8 * drop_lo)) & (0xffffffffu >> (8 * drop_hi));
+                    x = (x & keep) | (0x41414141u & ~keep);
+                }
+            }
+            const uint32_t codes = (x >> 1) & 0x03030303u;                /* (c >> 1) & 3 per character (sshash/kmer.hpp:199) */
+            const uint32_t packed = (codes * 0x01041040u) >> 24;         /* c0 | c1 << 2 | c2 << 4 | c3 << 6 */
+            /* valid characters are exactly ACGTacgt: rebuild the upper-case letter of every code and compare */
+            uint32_t sel = (packed | (packed << 4)) & 0x0f0fu;
+            sel = (sel | (sel << 2)) & 0x3333u;
+            bad |= __byte_perm(0x47544341u, 0u, sel) != (x & 0xdfdfdfdfu);
+            if (wi < 8 * nwords) reinterpret_cast<uint8_t*>(S.words + FG_WORDS_PAD_BEFORE)[wi] = uint8_t(packed);
+        }
+        const bool all_valid = __ballot_sync(FG_FULL, bad) == 0;
+        if (!all_valid) { /* rare: per-character validity bits (segment coordinates) */
+            for (uint32_t c = 0; 32 * c < nchars + 32; ++c) {
+                const uint32_t j = 32 * c + lane;
+                const uint32_t v = __ballot_sync(FG_FULL, j < nchars && base_valid(p0[j < nchars ? j : 0]));
+                if (lane == 0) S.valid[c] = v;
             }
         }
+        __syncwarp();
+        if (lane < nwords) S.rcw[FG_WORDS_PAD_BEFORE + nwords - 1 - lane] = revcomp(S.words[FG_WORDS_PAD_BEFORE + lane], 32);
         if (lane <= FG_WORDS_PAD_AFTER) { /* readable padding: values never reach a valid k-mer */
             if (lane < FG_WORDS_PAD_AFTER) {
                 S.words[FG_WORDS_PAD_BEFORE + nwords + lane] = 0;
                 S.rcw[FG_WORDS_PAD_BEFORE + nwords + lane] = 0;
-                S.valid[nwords + lane] = 0;
             } else {
                 S.words[0] = 0;
                 S.rcw[0] = 0;
             }
         }
         __syncwarp();
-        /* 1. m-mer hashes */
+        /* 1. m-mer hashes. Lane l hashes the m-mers at positions 5l .. 5l+4 out of ONE 32-base window (m + 4 <= 32): the
+              reverse complement of the window holds the five reverse-complemented m-mers too. */
         const uint32_t m = I.m;
-        for (uint32_t q = lane; q < npos; q += 32) {
-            const uint64_t y = bases_at(q) & mmer_mask;
-            hf()[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
-            hr()[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
+        if (m <= 28) {
+            const uint32_t q0 = 5 * lane;
+            if (q0 < npos) {
+                const uint64_t x = bases_at(q0) & (m + 4 == 32 ? ~0ULL : ((1ULL << (2 * (m + 4))) - 1));
+                const uint64_t r = revcomp(x, m + 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    if (q0 + j < npos) {
+                        hf()[fg_hslot(q0 + j)] = (((x >> (2 * j)) & mmer_mask) * FG_MIX_MUL) ^ I.hash_magic;
+                        hr()[fg_hslot(q0 + j)] = (((r >> (2 * (4 - j))) & mmer_mask) * FG_MIX_MUL) ^ I.hash_magic;
+                    }
+                }
+            }
+        } else {
+            for (uint32_t q = lane; q < npos; q += 32) {
+                const uint64_t y = bases_at(q) & mmer_mask;
+                hf()[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
+                hr()[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
+            }
         }
         __syncwarp();
         /* 2. canonical minimizer of the lane's k-mers i0 .. i0+3: value = min over both strands, compared as integers
@@ -633,7 +670,7 @@ struct kmer_tiles {
                 }
             }
             /* i0 is a multiple of 4, so the lane's four k-mers start in the same 32-character word */
-            const uint32_t vw0 = S.valid[i0 >> 5], vw1 = S.valid[(i0 >> 5) + 1];
+            const uint32_t vw0 = all_valid ? ~0u : S.valid[i0 >> 5], vw1 = all_valid ? ~0u : S.valid[(i0 >> 5) + 1];
             uint32_t nibble = 0;
 #pragma unroll
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
@@ -652,13 +689,17 @@ struct kmer_tiles {
                 nibble |= uint32_t(valid) << tt;
             }
             /* valid-k-mer bitmap in k-mer order: 8 lanes per 32-bit word */
-            const uint32_t part = nibble << (4 * (lane & 7));
+            if (all_valid) {
+                if (lane < FG_SEG_B + 2) S.vk[lane] = seg_nk >= 32 * lane + 32 ? ~0u : (seg_nk > 32 * lane ? (1u << (seg_nk - 32 * lane)) - 1u : 0u);
+            } else {
+                const uint32_t part = nibble << (4 * (lane & 7));
 #pragma unroll
-            for (int w = 0; w < FG_SEG_B; ++w) {
-                const uint32_t word = __reduce_or_sync(FG_FULL, (lane >> 3) == uint32_t(w) ? part : 0u);
-                if (lane == 0) S.vk[w] = word;
+                for (int w = 0; w < FG_SEG_B; ++w) {
+                    const uint32_t word = __reduce_or_sync(FG_FULL, (lane >> 3) == uint32_t(w) ? part : 0u);
+                    if (lane == 0) S.vk[w] = word;
+                }
+                if (lane == 0) S.vk[FG_SEG_B] = S.vk[FG_SEG_B + 1] = 0;
             }
-            if (lane == 0) S.vk[FG_SEG_B] = S.vk[FG_SEG_B + 1] = 0;
         }
         __syncwarp(); /* every lane is done with the hash arrays: seeds and items may overwrite them */
         /* 3. seeds: the first k-mer of every run of valid k-mers with the same minimizer occurrence -- same value, at the same
@@ -867,7 +908,8 @@ __device__ __noinline__ void table_sort(uint2* tab, uint32_t n, uint32_t lane) {
    scratch_cap entries, a power of two) and then to the pool for reads with more distinct color sets --
    and one bitonic sort at the end. */
 template <int W>
-__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, uint32_t lane,
+__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, const uint8_t* buf_begin,
+                                                           const uint8_t* buf_end, uint32_t lane,
                                                            warp_stage& stage, uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
     read_hits R;
     R.cid = FG_NOT_FOUND;
@@ -877,7 +919,7 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
     R.tab = nullptr;
     R.cap = 0;
     R.failed = false;
-    kmer_tiles<W> tiles(I, seq, len, lane, stage);
+    kmer_tiles<W> tiles(I, seq, len, buf_begin, buf_end, lane, stage);
     uint32_t cid, cnt;
     while (tiles.next(cid, cnt)) {
         const bool found = cnt != 0;

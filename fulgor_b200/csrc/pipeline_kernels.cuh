@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(c
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, stage[threadIdx.x >> 5]);
+        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base), lane,
+                            stage[threadIdx.x >> 5]);
         uint32_t acc = ~0u, score = 0, npos = 0;
         uint32_t cid, cnt;
         while (tiles.next(cid, cnt)) { /* items {color-set id, number of k-mers}: every lane decodes its own set */
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(co
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
         const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), lane, wstage[wib], scratch[wib], FG_SCRATCH_ENTRIES, pool);
+        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base),
+                                               lane, wstage[wib], scratch[wib], FG_SCRATCH_ENTRIES, pool);
         uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
         if (R.tab == nullptr) {
             if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);

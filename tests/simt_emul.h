@@ -201,6 +201,17 @@ static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __clz(int x) { return x ? __builtin_clz(unsigned(x)) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const uint64_t v = (uint64_t(y) << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned sel = (s >> (4 * i)) & 0xf;
+        unsigned byte = unsigned(v >> (8 * (sel & 7))) & 0xff;
+        if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
     sh &= 31;
     return unsigned(((uint64_t(hi) << 32) | lo) >> sh);

@@ -2,7 +2,7 @@
 # dev helper (GPU box): GPU tests, then kernel timing of library variants build/lib_*.so, then an ncu capture of the default build
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 900 python -m pytest ${GPU_AB_TESTS:-tests} -m gpu -x -q 2>&1 | tail -5
 for lib in build/lib_*.so; do
   echo "== $lib"; FULGOR_GPU_LIB=$PWD/$lib timeout 300 python tools/quick_gpu.py 2000000 2>&1 | grep -v "^gen" | tail -9
 done
