@@ -12,6 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DATA = os.path.join(ROOT, "data")
+BIG = os.path.join(DATA, "big")  # large generated fixtures (tools/make_standin_4546.sh), git-ignored
 ORACLE_SO = os.path.join(ROOT, "oracle", "libfulgor_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfulgor_ref.so")
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "fulgor_ref")
@@ -185,6 +186,8 @@ def load_gpk(name="salmonella_10"):
     """Packed genomes (written by tools/mkdump) as a uint8 array; stored xz-compressed in data/."""
     if name not in _GPK_CACHE:
         path = os.path.join(DATA, name + ".gpk")
+        if not os.path.exists(path) and os.path.exists(os.path.join(BIG, name + ".gpk")):
+            path = os.path.join(BIG, name + ".gpk")
         if os.path.exists(path):
             raw = open(path, "rb").read()
         else:
@@ -225,6 +228,8 @@ def index_path(name):
     path = os.path.join(DATA, name)
     if os.path.exists(path):
         return path
+    if os.path.exists(os.path.join(BIG, name)):
+        return os.path.join(BIG, name)
     tail = path + ".tail"
     if name.endswith(".mfur") and os.path.exists(tail):
         base = path[: -len(".mfur")] + ".fur"

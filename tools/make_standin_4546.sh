@@ -1,0 +1,19 @@
+#!/bin/bash
+# Fixture tooling (not on the query path): builds the labelled STAND-IN for salmonella_4546 (the real 4,546 genomes are a Zenodo
+# download, unavailable offline): 4,546 synthetic genomes evolved along a random tree with substitutions,
+# indels and horizontal transfers (tools/synthgen.py), dumped to unitigs + color sets (tools/mkdump.cpp) and turned into a
+# genuine .fur / .mfur by the REFERENCE's own tools (oracle/_ref/fulgor_ref load -m 20, color --meta), like README.md:158-160.
+# Needs oracle/_ref (i.e. /root/reference at build time). Output: data/big/synth_4546.{fur,mfur,gpk} (git-ignored).
+#   tools/make_standin_4546.sh [GENOME_LEN=100000] [N=4546]
+set -euo pipefail
+cd "$(dirname "$0")/.."
+LEN=${1:-100000}; N=${2:-4546}
+OUT=data/big; TMP=${TMPDIR:-/tmp}/fg_standin_$N; NAME=synth_$N
+mkdir -p "$OUT" "$TMP" build
+[ -x build/mkdump ] && [ build/mkdump -nt tools/mkdump.cpp ] || g++ -O2 -std=c++17 tools/mkdump.cpp -o build/mkdump -lz
+python tools/synthgen.py "$TMP/genomes" "$N" "$LEN" --seed 4546 --sub 0.0005 --indel 0.10 --hgt 0.5
+build/mkdump "$TMP/$NAME" "@$TMP/genomes/list.txt"
+oracle/_ref/fulgor_ref load -i "$TMP/$NAME" -o "$TMP/$NAME" -m 20 -d "$TMP" -t 8 --verbose
+oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --meta --verbose
+mv "$TMP/$NAME.fur" "$TMP/$NAME.mfur" "$TMP/$NAME.gpk" "$OUT/"
+ls -la "$OUT"

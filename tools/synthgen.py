@@ -5,7 +5,7 @@ along a random binary tree (per-edge substitutions, clade-specific insertions an
 clades of every size and the color sets of the resulting index span all three hybrid encodings (sparse delta-gaps, bitmap,
 complemented delta-gaps). Deterministic for a given seed.
 
-    python tools/synthgen.py OUTDIR N GENOME_LEN [--seed 1] [--sub 0.004] [--indel 0.15]
+    python tools/synthgen.py OUTDIR N GENOME_LEN [--seed 1] [--sub 0.004] [--indel 0.15] [--hgt 0]
 writes OUTDIR/g00000.fa ... and OUTDIR/list.txt (for `mkdump BASE @OUTDIR/list.txt`)."""
 import argparse
 import os
@@ -13,8 +13,15 @@ import os
 import numpy as np
 
 
-def evolve(seq, rng, sub, indel):
+def evolve(seq, rng, sub, indel, pool=None, hgt=0.0):
     seq = seq.copy()
+    if pool and rng.random() < hgt:  # horizontal transfer: a stretch of another lineage replaces the same coordinates
+        donor = pool[int(rng.integers(0, len(pool)))]
+        n = int(rng.integers(500, 5000))
+        lim = min(seq.size, donor.size) - n
+        if lim > 0:
+            at = int(rng.integers(0, lim))
+            seq[at:at + n] = donor[at:at + n]
     nsub = rng.binomial(seq.size, sub)
     pos = rng.integers(0, seq.size, nsub)
     seq[pos] = (seq[pos] + rng.integers(1, 4, nsub)) % 4
@@ -35,6 +42,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--sub", type=float, default=0.004)
     ap.add_argument("--indel", type=float, default=0.15)
+    ap.add_argument("--hgt", type=float, default=0.0, help="probability per new lineage of a horizontal transfer from a random lineage")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     os.makedirs(a.outdir, exist_ok=True)
@@ -42,8 +50,12 @@ def main():
     while len(pool) < a.n:  # split a random lineage into two children (Yule tree)
         i = int(rng.integers(0, len(pool)))
         parent = pool.pop(i)
-        pool.append(evolve(parent, rng, a.sub, a.indel))
-        pool.append(evolve(parent, rng, a.sub, a.indel))
+        if a.hgt > 0:
+            pool.append(evolve(parent, rng, a.sub, a.indel, pool, a.hgt))
+            pool.append(evolve(parent, rng, a.sub, a.indel, pool, a.hgt))
+        else:  # (kept separate so that fixtures generated before --hgt existed stay byte-identical)
+            pool.append(evolve(parent, rng, a.sub, a.indel))
+            pool.append(evolve(parent, rng, a.sub, a.indel))
     lut = np.frombuffer(b"ACGT", dtype=np.uint8)
     names = []
     for g, seq in enumerate(pool):
