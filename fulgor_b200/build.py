@@ -17,6 +17,7 @@ LIB_SOURCES = [os.path.join(CSRC, f) for f in ("engine.cu", "fur_reader.cpp")]
 LIB_DEPS = LIB_SOURCES + [os.path.join(CSRC, f) for f in ("kernels.cuh", "pipeline_kernels.cuh", "image.h", "fur_reader.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "fulgor_gpu.h")]
 CLI_SOURCES = [os.path.join(CSRC, "pseudoalign_cli.cpp")]
+CLI_DEPS = CLI_SOURCES + [os.path.join(CSRC, "fastx_io.h"), os.path.join(os.path.dirname(HERE), "include", "fulgor_gpu.h")]
 
 
 def _stale(target, deps):
@@ -33,8 +34,8 @@ def build(force=False, verbose=False):
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
-    if all(os.path.exists(s) for s in CLI_SOURCES) and (force or _stale(CLI, CLI_SOURCES + [LIB])):
-        cmd = [NVCC] + COMMON + ["-o", CLI] + CLI_SOURCES + ["-L" + HERE, "-lfulgor_gpu", "-Xlinker", "-rpath=$ORIGIN", "-lz", "-lpthread"]
+    if all(os.path.exists(s) for s in CLI_SOURCES) and (force or _stale(CLI, CLI_DEPS + [LIB])):
+        cmd = [NVCC] + ARCH + COMMON + ["-o", CLI] + CLI_SOURCES + ["-L" + HERE, "-lfulgor_gpu", "-Xlinker", "-rpath=$ORIGIN", "-lz", "-lpthread"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -1,0 +1,530 @@
+/*
+ * fastx_io.h -- host side of the `pseudoalign` tool around the GPU call: the FASTA/FASTQ feeder and the three output
+ * formatters, both multi-threaded. Plain C++17, no CUDA: pseudoalign_cli.cpp uses it, and tests/fastx_io_test.cpp
+ * exposes it to the CPU-only test tier.
+ *
+ * Replaces, for this tool only:
+ *   - the FQFeeder producer/consumer parser the reference drives from tools/pseudoalign.cpp:54-77
+ *     (external/FQFeeder/src/FastxParser.cpp:138-260): here an uncompressed query file is memory-mapped and cut into
+ *     slabs at record boundaries that worker threads tokenise concurrently, straight into the (pinned) batch buffers the
+ *     GPU call reads; gzip input goes through one inflating reader;
+ *   - psa_{ascii,binary,compressed}_formatter (src/ps_utils.cpp:48-243): same bytes per record; a batch is split
+ *     between threads by output volume and the pieces are written in read order.
+ * Read ids are 0-based record positions in the query file.
+ */
+#ifndef FULGOR_B200_FASTX_IO_H
+#define FULGOR_B200_FASTX_IO_H
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace fgio {
+
+/* runs f(0) .. f(n-1) on n threads (f(0) on the caller's) */
+inline void parallel_for(unsigned n, const std::function<void(unsigned)>& f) {
+    if (n <= 1) {
+        if (n == 1) f(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n; ++t) th.emplace_back(f, t);
+    f(0);
+    for (auto& t : th) t.join();
+}
+
+/* a batch of reads in the layout the C ABI takes: concatenated bases + CSR offsets. The buffers belong to the caller
+   (pinned memory in the tool); grow() is called when a batch needs more room. */
+struct read_batch {
+    char* bases = nullptr;
+    uint64_t* off = nullptr;
+    uint64_t bases_cap = 0, reads_cap = 0;
+    uint32_t n = 0;
+    std::function<void(read_batch&, uint64_t /*bases*/, uint64_t /*reads*/)> grow;
+    void reserve(uint64_t nbases, uint64_t nreads) {
+        if (nbases > bases_cap || nreads > reads_cap) grow(*this, nbases, nreads);
+    }
+};
+
+/* ---------------------------------------------------------------- serial reader (gzip or plain; multi-line records) */
+struct serial_fastx_reader {
+    gzFile f = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    bool eof = false;
+    std::string line, pending_header;
+
+    bool open(const char* path) {
+        f = gzopen(path, "rb");
+        if (!f) return false;
+        gzbuffer(f, 1 << 20);
+        buf.resize(1 << 22);
+        return true;
+    }
+    ~serial_fastx_reader() {
+        if (f) gzclose(f);
+    }
+    bool fill() {
+        if (eof) return false;
+        const int n = gzread(f, buf.data(), unsigned(buf.size()));
+        if (n <= 0) {
+            eof = true;
+            return false;
+        }
+        pos = 0;
+        end = size_t(n);
+        return true;
+    }
+    /* next line without the terminator; false at end of file */
+    bool getline(std::string& out) {
+        out.clear();
+        bool any = false;
+        for (;;) {
+            if (pos == end && !fill()) return any;
+            any = true;
+            const char* p = buf.data() + pos;
+            const char* nl = static_cast<const char*>(std::memchr(p, '\n', end - pos));
+            if (nl) {
+                out.append(p, size_t(nl - p));
+                pos += size_t(nl - p) + 1;
+                if (!out.empty() && out.back() == '\r') out.pop_back();
+                return true;
+            }
+            out.append(p, end - pos);
+            pos = end;
+        }
+    }
+    /* appends the next record's sequence to `bases`; false when the file is exhausted */
+    bool next(std::vector<char>& bases) {
+        std::string header;
+        if (!pending_header.empty()) {
+            header.swap(pending_header);
+        } else {
+            do {
+                if (!getline(header)) return false;
+            } while (header.empty());
+        }
+        if (header[0] == '@') { /* FASTQ: sequence line(s), '+', as many quality characters */
+            if (!getline(line)) return false;
+            bases.insert(bases.end(), line.begin(), line.end());
+            size_t seq_len = line.size();
+            for (;;) { /* multi-line sequence until the '+' line */
+                if (!getline(line)) return true;
+                if (!line.empty() && line[0] == '+') break;
+                bases.insert(bases.end(), line.begin(), line.end());
+                seq_len += line.size();
+            }
+            size_t q = 0;
+            while (q < seq_len && getline(line)) q += line.size();
+            return true;
+        }
+        if (header[0] == '>') { /* FASTA: possibly multi-line */
+            while (getline(line)) {
+                if (!line.empty() && (line[0] == '>' || line[0] == '@')) {
+                    pending_header = line;
+                    break;
+                }
+                bases.insert(bases.end(), line.begin(), line.end());
+            }
+            return true;
+        }
+        return false;
+    }
+};
+
+/* ---------------------------------------------------------------- query source */
+class fastx_source {
+public:
+    ~fastx_source() {
+        if (map_ && map_ != MAP_FAILED) munmap(const_cast<char*>(map_), size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    /* threads = tokenising threads for memory-mapped input; span = bytes of file per batch */
+    bool open(const char* path, unsigned threads, uint64_t span_bytes, uint64_t max_reads_serial) {
+        threads_ = std::max(1u, threads);
+        span_ = std::max<uint64_t>(span_bytes, 1 << 16);
+        max_reads_serial_ = std::max<uint64_t>(1, max_reads_serial);
+        path_ = path;
+        fd_ = ::open(path, O_RDONLY);
+        if (fd_ < 0) return false;
+        struct stat st;
+        unsigned char magic[2] = {0, 0};
+        const bool regular = fstat(fd_, &st) == 0 && S_ISREG(st.st_mode);
+        if (regular && st.st_size >= 2 && pread(fd_, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+            size_ = size_t(st.st_size);
+            map_ = static_cast<const char*>(mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0));
+            if (map_ != MAP_FAILED) {
+                madvise(const_cast<char*>(map_), size_, MADV_SEQUENTIAL);
+                pos_ = skip_blank(0);
+                if (pos_ < size_ && (map_[pos_] == '@' || map_[pos_] == '>')) {
+                    fastq_ = map_[pos_] == '@';
+                    mapped_ = true;
+                    return true;
+                }
+                munmap(const_cast<char*>(map_), size_);
+            }
+            map_ = nullptr;
+        }
+        return serial_.open(path); /* gzip, pipes, empty or odd files */
+    }
+    bool mapped() const { return mapped_; }
+
+    /* fills b with the next reads; returns false when the input is exhausted and b is empty */
+    bool next_batch(read_batch& b) {
+        b.n = 0;
+        if (mapped_) {
+            while (b.n == 0 && pos_ < size_) {
+                if (!next_mapped(b)) mapped_ = false; /* a record the slab tokeniser does not handle (multi-line FASTQ): serial from here on */
+                if (!mapped_) break;
+            }
+            if (mapped_) return b.n != 0;
+        }
+        return next_serial(b);
+    }
+
+private:
+    size_t skip_blank(size_t p) const {
+        while (p < size_ && (map_[p] == '\n' || map_[p] == '\r')) ++p;
+        return p;
+    }
+    size_t next_line(size_t p) const { /* start of the line after the one containing p; size_ if none */
+        const char* nl = static_cast<const char*>(std::memchr(map_ + p, '\n', size_ - p));
+        return nl ? size_t(nl - map_) + 1 : size_;
+    }
+    /* first record start at or after p (p need not be a line start) */
+    size_t find_record(size_t p) const {
+        if (p >= size_) return size_;
+        if (p > 0 && map_[p - 1] != '\n') p = next_line(p);
+        while (p < size_) {
+            if (!fastq_) {
+                if (map_[p] == '>') return p;
+            } else if (map_[p] == '@') { /* a header, unless it is a quality line that happens to start with '@':
+                                            two lines below a header there is the '+' line */
+                const size_t l1 = next_line(p), l2 = l1 < size_ ? next_line(l1) : size_;
+                if (l2 < size_ && map_[l2] == '+') return p;
+                if (l2 >= size_) return p; /* truncated tail: let the tokeniser decide */
+            }
+            p = next_line(p);
+        }
+        return size_;
+    }
+
+    struct slab_out {
+        std::vector<char> bases;
+        std::vector<uint32_t> lens;
+        bool ok = true;
+    };
+
+    void tokenise(size_t p, size_t end, slab_out& o) const {
+        o.bases.reserve((end - p) / (fastq_ ? 2 : 1) + 64);
+        while (p < end) {
+            p = skip_blank(p);
+            if (p >= end) break;
+            const size_t l1 = next_line(p); /* header */
+            const size_t start = o.bases.size();
+            if (fastq_) {
+                if (map_[p] != '@') {
+                    o.ok = false;
+                    return;
+                }
+                if (l1 >= size_) return; /* a header without a sequence line ends the input, like the serial reader */
+                const size_t l2 = next_line(l1);
+                size_t s_end = l2 - (l2 > l1 && map_[l2 - 1] == '\n' ? 1 : 0);
+                if (s_end > l1 && map_[s_end - 1] == '\r') --s_end;
+                o.bases.insert(o.bases.end(), map_ + l1, map_ + s_end);
+                if (l2 >= size_) { /* no '+' line: the serial reader accepts this too */
+                    o.lens.push_back(uint32_t(o.bases.size() - start));
+                    return;
+                }
+                if (map_[l2] != '+') { /* multi-line sequence */
+                    o.bases.resize(start);
+                    o.ok = false;
+                    return;
+                }
+                const size_t l3 = next_line(l2), l4 = l3 < size_ ? next_line(l3) : size_;
+                size_t q_end = l4 - (l4 > l3 && map_[l4 - 1] == '\n' ? 1 : 0);
+                if (q_end > l3 && map_[q_end - 1] == '\r') --q_end;
+                if (q_end - l3 < s_end - l1 && l4 < size_) { /* quality shorter than the sequence: multi-line record */
+                    o.bases.resize(start);
+                    o.ok = false;
+                    return;
+                }
+                p = l4;
+            } else {
+                if (map_[p] != '>') {
+                    o.ok = false;
+                    return;
+                }
+                size_t q = l1;
+                while (q < size_ && map_[q] != '>' && map_[q] != '@') {
+                    const size_t nq = next_line(q);
+                    size_t e = nq - (nq > q && map_[nq - 1] == '\n' ? 1 : 0);
+                    if (e > q && map_[e - 1] == '\r') --e;
+                    o.bases.insert(o.bases.end(), map_ + q, map_ + e);
+                    q = nq;
+                }
+                p = q;
+            }
+            o.lens.push_back(uint32_t(o.bases.size() - start));
+        }
+    }
+
+    bool next_mapped(read_batch& b) {
+        const unsigned T = threads_;
+        const size_t begin = pos_, target = std::min<uint64_t>(size_, begin + span_);
+        std::vector<size_t> cut(T + 1);
+        cut[0] = begin;
+        for (unsigned t = 1; t <= T; ++t) cut[t] = std::max(cut[t - 1], find_record(begin + size_t((target - begin) * uint64_t(t) / T)));
+        if (target == size_) cut[T] = size_;
+        std::vector<slab_out> out(T);
+        parallel_for(T, [&](unsigned t) { tokenise(cut[t], cut[t + 1], out[t]); });
+        for (auto const& o : out)
+            if (!o.ok) return false;
+        std::vector<uint64_t> base_at(T + 1, 0), read_at(T + 1, 0);
+        for (unsigned t = 0; t < T; ++t) {
+            base_at[t + 1] = base_at[t] + out[t].bases.size();
+            read_at[t + 1] = read_at[t] + out[t].lens.size();
+        }
+        if (read_at[T] > 0xffffffffull) return false;
+        b.reserve(base_at[T] + 1, read_at[T] + 1);
+        parallel_for(T, [&](unsigned t) {
+            if (!out[t].bases.empty()) std::memcpy(b.bases + base_at[t], out[t].bases.data(), out[t].bases.size());
+            uint64_t o = base_at[t];
+            uint64_t* dst = b.off + read_at[t];
+            for (uint32_t len : out[t].lens) {
+                *dst++ = o;
+                o += len;
+            }
+        });
+        b.off[read_at[T]] = base_at[T];
+        b.n = uint32_t(read_at[T]);
+        reads_done_ += b.n;
+        pos_ = cut[T];
+        return true;
+    }
+
+    bool next_serial(read_batch& b) {
+        if (!serial_open_) {
+            if (map_) { /* fell back from the mapped path: reopen and skip what was consumed */
+                if (!serial_.open(path_.c_str())) return false;
+                std::vector<char> sink;
+                uint64_t skipped = 0;
+                while (skipped < reads_done_ && serial_.next(sink)) {
+                    sink.clear();
+                    ++skipped;
+                }
+            }
+            serial_open_ = true;
+        }
+        std::vector<char>& bases = serial_bases_;
+        bases.clear();
+        serial_off_.assign(1, 0);
+        while (serial_off_.size() - 1 < max_reads_serial_ && bases.size() < (1ull << 31)) {
+            if (!serial_.next(bases)) break;
+            serial_off_.push_back(bases.size());
+        }
+        const uint64_t n = serial_off_.size() - 1;
+        if (n == 0) return false;
+        b.reserve(bases.size() + 1, n + 1);
+        std::memcpy(b.bases, bases.data(), bases.size());
+        std::memcpy(b.off, serial_off_.data(), (n + 1) * 8);
+        b.n = uint32_t(n);
+        return true;
+    }
+
+    std::string path_;
+    int fd_ = -1;
+    const char* map_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+    bool mapped_ = false, fastq_ = true, serial_open_ = false;
+    unsigned threads_ = 1;
+    uint64_t span_ = 1ull << 30, max_reads_serial_ = 1u << 22, reads_done_ = 0;
+    serial_fastx_reader serial_;
+    std::vector<char> serial_bases_;
+    std::vector<uint64_t> serial_off_;
+};
+
+/* ---------------------------------------------------------------- output formats (src/ps_utils.cpp:48-243) */
+inline char* put_u32(char* p, uint32_t v) {
+    char tmp[10];
+    int n = 0;
+    do {
+        tmp[n++] = char('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+struct bit_writer { /* LSB-first, like bits::bit_vector::builder */
+    std::vector<uint64_t> words;
+    uint64_t num_bits = 0;
+    void append(uint64_t v, uint32_t len) {
+        if (!len) return;
+        if (len < 64) v &= (1ULL << len) - 1;
+        const uint32_t sh = uint32_t(num_bits & 63);
+        if (sh == 0) words.push_back(v);
+        else {
+            words.back() |= v << sh;
+            if (sh + len > 64) words.push_back(v >> (64 - sh));
+        }
+        num_bits += len;
+    }
+    /* bits::util::write_delta (bits/include/integer_codes.hpp:54-71): gamma(len) then the payload */
+    void gamma(uint64_t x) {
+        const uint64_t xx = x + 1;
+        const uint32_t b = 63 - uint32_t(__builtin_clzll(xx));
+        append(1ULL << b, b + 1); /* b zeros then a one */
+        append(xx ^ (1ULL << b), b);
+    }
+    void delta(uint64_t x) {
+        const uint64_t xx = x + 1;
+        const uint32_t b = 63 - uint32_t(__builtin_clzll(xx));
+        gamma(b);
+        append(xx ^ (1ULL << b), b);
+    }
+    void clear() {
+        words.clear();
+        num_bits = 0;
+    }
+};
+
+enum class out_format { ASCII, BINARY, COMPRESSED };
+
+class result_writer {
+public:
+    bool open(const char* path, out_format fm, uint32_t num_colors, unsigned threads) {
+        f_ = std::fopen(path, "wb");
+        fmt_ = fm;
+        num_colors_ = num_colors;
+        threads_ = std::max(1u, threads);
+        pieces_.resize(threads_);
+        if (!f_) return false;
+        if (fmt_ == out_format::COMPRESSED) { /* psa_compressed_formatter::set_num_colors, src/ps_utils.cpp:160-166 */
+            const uint64_t header = num_colors;
+            std::fwrite(&header, 8, 1, f_);
+            sparse_thr_ = uint32_t(0.25 * num_colors);
+            dense_thr_ = uint32_t(0.75 * num_colors);
+        }
+        return true;
+    }
+    /* records first_id .. first_id+n-1: colors[off[i] .. off[i+1]) each */
+    void write_batch(uint32_t first_id, uint32_t n, const uint64_t* off, const uint32_t* colors) {
+        if (n == 0) return;
+        /* cut the batch where the output volume (records + values) splits evenly */
+        const unsigned T = unsigned(std::min<uint64_t>(threads_, std::max<uint64_t>(1, n / 1024)));
+        std::vector<uint32_t> cut(T + 1, 0);
+        const uint64_t total = (off[n] - off[0]) + 2 * uint64_t(n);
+        for (unsigned t = 1; t < T; ++t) {
+            const uint64_t want = total * t / T;
+            uint32_t lo = cut[t - 1], hi = n;
+            while (lo < hi) { /* first i with volume(i) >= want */
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if ((off[mid] - off[0]) + 2 * uint64_t(mid) < want) lo = mid + 1; else hi = mid;
+            }
+            cut[t] = lo;
+        }
+        cut[T] = n;
+        parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, pieces_[t]); });
+        for (unsigned t = 0; t < T; ++t)
+            if (!pieces_[t].empty()) std::fwrite(pieces_[t].data(), 1, pieces_[t].size(), f_);
+    }
+    void close() {
+        if (f_) std::fclose(f_);
+        f_ = nullptr;
+    }
+
+private:
+    void format(uint32_t first_id, uint32_t lo, uint32_t hi, const uint64_t* off, const uint32_t* colors, std::vector<char>& out) const {
+        out.clear();
+        if (lo >= hi) return;
+        if (fmt_ == out_format::ASCII) { /* "id \t n [\t color]* \n", src/ps_utils.cpp:48-100 */
+            out.resize(size_t(hi - lo) * 24 + size_t(off[hi] - off[lo]) * 11 + 16);
+            char* p = out.data();
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint64_t b = off[i], e = off[i + 1];
+                p = put_u32(p, first_id + i);
+                *p++ = '\t';
+                p = put_u32(p, uint32_t(e - b));
+                for (uint64_t j = b; j < e; ++j) {
+                    *p++ = '\t';
+                    p = put_u32(p, colors[j]);
+                }
+                *p++ = '\n';
+            }
+            out.resize(size_t(p - out.data()));
+        } else if (fmt_ == out_format::BINARY) { /* u32 id, u32 n, n x u32, src/ps_utils.cpp:102-147 */
+            out.resize((size_t(hi - lo) * 2 + size_t(off[hi] - off[lo])) * 4);
+            uint32_t* p = reinterpret_cast<uint32_t*>(out.data());
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint64_t b = off[i], e = off[i + 1];
+                *p++ = first_id + i;
+                *p++ = uint32_t(e - b);
+                std::memcpy(p, colors + b, size_t(e - b) * 4);
+                p += e - b;
+            }
+        } else { /* blocks of {u64 num_bits, words}: delta(id) delta(n) then the list like a hybrid color set, src/ps_utils.cpp:149-243 */
+            bit_writer bw;
+            auto flush = [&]() {
+                if (!bw.num_bits) return;
+                const size_t at = out.size();
+                out.resize(at + 8 + bw.words.size() * 8);
+                std::memcpy(out.data() + at, &bw.num_bits, 8);
+                std::memcpy(out.data() + at + 8, bw.words.data(), bw.words.size() * 8);
+                bw.clear();
+            };
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint32_t* c = colors + off[i];
+                const uint32_t size = uint32_t(off[i + 1] - off[i]);
+                bw.delta(first_id + i);
+                bw.delta(size);
+                if (size == 0) {
+                } else if (size < sparse_thr_) {
+                    bw.delta(c[0]);
+                    for (uint32_t j = 1; j < size; ++j) bw.delta(c[j] - (c[j - 1] + 1));
+                } else if (size < dense_thr_) {
+                    const uint64_t start = bw.num_bits;
+                    for (uint32_t w = 0; w < num_colors_; w += 64) bw.append(0, std::min<uint32_t>(64, num_colors_ - w));
+                    for (uint32_t j = 0; j < size; ++j) {
+                        const uint64_t bit = start + c[j];
+                        bw.words[bit >> 6] |= 1ULL << (bit & 63);
+                    }
+                } else { /* the complement, delta-gap coded */
+                    bool first = true;
+                    uint32_t prev = 0, j = 0;
+                    for (uint32_t v = 0; v < num_colors_; ++v) {
+                        if (j < size && c[j] == v) {
+                            ++j;
+                            continue;
+                        }
+                        bw.delta(first ? v : v - (prev + 1));
+                        first = false;
+                        prev = v;
+                    }
+                }
+                if (bw.words.size() * 8 > (1u << 14)) flush(); /* formatter_buffer, src/ps_utils.cpp:31-38 */
+            }
+            flush();
+        }
+    }
+
+    FILE* f_ = nullptr;
+    out_format fmt_ = out_format::ASCII;
+    uint32_t num_colors_ = 0, sparse_thr_ = 0, dense_thr_ = 0;
+    unsigned threads_ = 1;
+    std::vector<std::vector<char>> pieces_;
+};
+
+}  // namespace fgio
+#endif

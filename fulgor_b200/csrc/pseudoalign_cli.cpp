@@ -8,13 +8,12 @@
  *                           [--format ascii|binary|compressed] [--verbose] [--gpus N] [--batch-reads B]
  *
  * Differences from the reference, all outside the results: records are written in read-id order (the
- * reference's order depends on thread scheduling, README.md:220); -t is accepted and only sizes the
- * host-side formatting; --deduplicate is rejected (it only changes how the reference schedules work).
+ * reference's order depends on thread scheduling, README.md:220); -t sizes the host side (parsing and formatting
+ * threads, fastx_io.h); --deduplicate is rejected (it only changes how the reference schedules work).
+ * Three batches are in flight: while the GPU works on batch i, batch i+1 is being parsed and batch i-1 formatted.
  * Read ids are 0-based positions in the query file. With --gpus N the index
  * image is uploaded to N devices and every batch is split N ways; no cross-GPU reduction exists.
  */
-#include <zlib.h>
-
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
@@ -27,231 +26,11 @@
 #include <vector>
 
 #include "../../include/fulgor_gpu.h"
+#include "fastx_io.h"
 
 namespace {
 
-/* ---------------------------------------------------------------- FASTA/FASTQ(.gz) reader */
-struct fastx_reader {
-    gzFile f = nullptr;
-    std::vector<char> buf;
-    size_t pos = 0, end = 0;
-    bool eof = false;
-
-    bool open(const char* path) {
-        f = gzopen(path, "rb");
-        if (!f) return false;
-        gzbuffer(f, 1 << 20);
-        buf.resize(1 << 22);
-        return true;
-    }
-    ~fastx_reader() {
-        if (f) gzclose(f);
-    }
-    bool fill() {
-        if (eof) return false;
-        const int n = gzread(f, buf.data(), unsigned(buf.size()));
-        if (n <= 0) {
-            eof = true;
-            return false;
-        }
-        pos = 0;
-        end = size_t(n);
-        return true;
-    }
-    /* next line without the terminator; false at end of file */
-    bool getline(std::string& line) {
-        line.clear();
-        bool any = false;
-        for (;;) {
-            if (pos == end && !fill()) return any;
-            any = true;
-            const char* p = buf.data() + pos;
-            const char* nl = static_cast<const char*>(std::memchr(p, '\n', end - pos));
-            if (nl) {
-                line.append(p, size_t(nl - p));
-                pos += size_t(nl - p) + 1;
-                if (!line.empty() && line.back() == '\r') line.pop_back();
-                return true;
-            }
-            line.append(p, end - pos);
-            pos = end;
-        }
-    }
-    /* appends the next record's sequence to `bases`; false when the file is exhausted */
-    std::string line, pending_header;
-    bool next(std::vector<char>& bases) {
-        std::string header;
-        if (!pending_header.empty()) {
-            header.swap(pending_header);
-        } else {
-            do {
-                if (!getline(header)) return false;
-            } while (header.empty());
-        }
-        if (header[0] == '@') { /* FASTQ: sequence, '+', quality (single-line records, like kseq on typical files) */
-            if (!getline(line)) return false;
-            bases.insert(bases.end(), line.begin(), line.end());
-            const size_t seq_len = line.size();
-            if (!getline(line)) return true; /* '+' */
-            size_t q = 0;
-            while (q < seq_len && getline(line)) q += line.size();
-            return true;
-        }
-        if (header[0] == '>') { /* FASTA: possibly multi-line */
-            while (getline(line)) {
-                if (!line.empty() && (line[0] == '>' || line[0] == '@')) {
-                    pending_header = line;
-                    break;
-                }
-                bases.insert(bases.end(), line.begin(), line.end());
-            }
-            return true;
-        }
-        return false;
-    }
-};
-
-/* ---------------------------------------------------------------- output formats (src/ps_utils.cpp:48-243) */
-inline char* put_u32(char* p, uint32_t v) {
-    char tmp[10];
-    int n = 0;
-    do {
-        tmp[n++] = char('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
-}
-
-struct bit_writer { /* LSB-first, like bits::bit_vector::builder */
-    std::vector<uint64_t> words;
-    uint64_t num_bits = 0;
-    void append(uint64_t v, uint32_t len) {
-        if (!len) return;
-        if (len < 64) v &= (1ULL << len) - 1;
-        const uint32_t sh = uint32_t(num_bits & 63);
-        if (sh == 0) words.push_back(v);
-        else {
-            words.back() |= v << sh;
-            if (sh + len > 64) words.push_back(v >> (64 - sh));
-        }
-        num_bits += len;
-    }
-    /* bits::util::write_delta (bits/include/integer_codes.hpp:54-71): gamma(len) then the payload */
-    void gamma(uint64_t x) {
-        const uint64_t xx = x + 1;
-        const uint32_t b = 63 - uint32_t(__builtin_clzll(xx));
-        append(1ULL << b, b + 1); /* b zeros then a one */
-        append(xx ^ (1ULL << b), b);
-    }
-    void delta(uint64_t x) {
-        const uint64_t xx = x + 1;
-        const uint32_t b = 63 - uint32_t(__builtin_clzll(xx));
-        gamma(b);
-        append(xx ^ (1ULL << b), b);
-    }
-    void clear() {
-        words.clear();
-        num_bits = 0;
-    }
-};
-
-enum class out_format { ASCII, BINARY, COMPRESSED };
-
-struct writer {
-    FILE* f = nullptr;
-    out_format fmt = out_format::ASCII;
-    uint32_t num_colors = 0, sparse_thr = 0, dense_thr = 0;
-    std::vector<char> text;
-    bit_writer bw;
-
-    bool open(const char* path, out_format fm, uint32_t nc) {
-        f = std::fopen(path, "wb");
-        fmt = fm;
-        num_colors = nc;
-        if (!f) return false;
-        if (fmt == out_format::COMPRESSED) { /* psa_compressed_formatter::set_num_colors, src/ps_utils.cpp:160-166 */
-            const uint64_t header = nc;
-            std::fwrite(&header, 8, 1, f);
-            sparse_thr = uint32_t(0.25 * nc);
-            dense_thr = uint32_t(0.75 * nc);
-        }
-        return true;
-    }
-    void flush_bits() {
-        if (!bw.num_bits) return;
-        std::fwrite(&bw.num_bits, 8, 1, f);
-        std::fwrite(bw.words.data(), 8, bw.words.size(), f);
-        bw.clear();
-    }
-    void write_batch(uint32_t first_id, uint32_t n, const uint64_t* off, const uint32_t* colors) {
-        if (fmt == out_format::ASCII) {
-            text.resize(size_t(n) * 24 + size_t(off[n] - off[0]) * 11 + 16);
-            char* p = text.data();
-            for (uint32_t i = 0; i < n; ++i) {
-                const uint64_t b = off[i], e = off[i + 1];
-                p = put_u32(p, first_id + i);
-                *p++ = '\t';
-                p = put_u32(p, uint32_t(e - b));
-                for (uint64_t j = b; j < e; ++j) {
-                    *p++ = '\t';
-                    p = put_u32(p, colors[j]);
-                }
-                *p++ = '\n';
-            }
-            std::fwrite(text.data(), 1, size_t(p - text.data()), f);
-        } else if (fmt == out_format::BINARY) {
-            text.resize((size_t(n) * 2 + size_t(off[n] - off[0])) * 4);
-            uint32_t* p = reinterpret_cast<uint32_t*>(text.data());
-            for (uint32_t i = 0; i < n; ++i) {
-                const uint64_t b = off[i], e = off[i + 1];
-                *p++ = first_id + i;
-                *p++ = uint32_t(e - b);
-                std::memcpy(p, colors + b, size_t(e - b) * 4);
-                p += e - b;
-            }
-            std::fwrite(text.data(), 1, text.size(), f);
-        } else {
-            for (uint32_t i = 0; i < n; ++i) {
-                const uint32_t* c = colors + off[i];
-                const uint32_t size = uint32_t(off[i + 1] - off[i]);
-                bw.delta(first_id + i);
-                bw.delta(size);
-                if (size == 0) {
-                } else if (size < sparse_thr) {
-                    bw.delta(c[0]);
-                    for (uint32_t j = 1; j < size; ++j) bw.delta(c[j] - (c[j - 1] + 1));
-                } else if (size < dense_thr) {
-                    const uint64_t start = bw.num_bits;
-                    for (uint32_t w = 0; w < num_colors; w += 64) bw.append(0, std::min<uint32_t>(64, num_colors - w));
-                    for (uint32_t j = 0; j < size; ++j) {
-                        const uint64_t bit = start + c[j];
-                        bw.words[bit >> 6] |= 1ULL << (bit & 63);
-                    }
-                } else { /* the complement, delta-gap coded */
-                    bool first = true;
-                    uint32_t prev = 0, j = 0;
-                    for (uint32_t v = 0; v < num_colors; ++v) {
-                        if (j < size && c[j] == v) {
-                            ++j;
-                            continue;
-                        }
-                        bw.delta(first ? v : v - (prev + 1));
-                        first = false;
-                        prev = v;
-                    }
-                }
-                if (bw.words.size() * 8 > (1u << 14)) flush_bits(); /* formatter_buffer, src/ps_utils.cpp:31-38 */
-            }
-        }
-    }
-    void close() {
-        if (!f) return;
-        if (fmt == out_format::COMPRESSED) flush_bits();
-        std::fclose(f);
-        f = nullptr;
-    }
-};
+using fgio::out_format;
 
 /* ---------------------------------------------------------------- arguments (cmd_line_parser semantics) */
 struct args_t {
@@ -401,13 +180,15 @@ int main(int argc, char** argv) {
     if (a.verbose) std::cout << "*** DONE: loading the index" << std::endl;
     if (a.verbose) std::cout << "performing queries from file '" << a.query << "'..." << std::endl;
 
-    fastx_reader reader;
-    if (!reader.open(a.query.c_str())) {
+    /* host threads: half of -t parse, half format (the two stages overlap each other and the GPU call) */
+    const unsigned host_threads = unsigned(std::max<uint64_t>(1, a.threads / 2));
+    fgio::fastx_source reader;
+    if (!reader.open(a.query.c_str(), host_threads, std::min<uint64_t>(1ull << 30, a.batch_reads * 320), a.batch_reads)) {
         std::cerr << "cannot open query file '" << a.query << "'" << std::endl;
         return 1;
     }
-    writer out;
-    if (!out.open(a.output.c_str(), fmt, info.num_colors)) {
+    fgio::result_writer out;
+    if (!out.open(a.output.c_str(), fmt, info.num_colors, host_threads)) {
         std::cerr << "cannot open output file '" << a.output << "'" << std::endl;
         return 1;
     }
@@ -415,51 +196,51 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     if (a.verbose) std::cout << "*** START: pseudoalignment" << std::endl;
     uint64_t num_reads = 0, num_mapped = 0;
-    std::vector<char> bases;
-    std::vector<uint64_t> read_off;
-    pinned p_bases, p_off, p_coff, p_colors;
-    uint64_t colors_cap = 0;
-    bool more = true;
-    int rc_all = 0;
-    while (more) {
-        bases.clear();
-        read_off.assign(1, 0);
-        while (read_off.size() - 1 < a.batch_reads && bases.size() < (1ull << 31)) {
-            if (!reader.next(bases)) {
-                more = false;
-                break;
-            }
-            read_off.push_back(bases.size());
-        }
-        const uint32_t n = uint32_t(read_off.size() - 1);
-        if (n == 0) break;
-        if (num_reads + n > (1ull << 32)) {
-            std::cerr << "more than 2^32 reads: read ids do not fit the output formats" << std::endl;
-            return 1;
-        }
-        char* hb = p_bases.get<char>(bases.size() + 1);
-        std::memcpy(hb, bases.data(), bases.size());
-        uint64_t* ho = p_off.get<uint64_t>(n + 1);
-        std::memcpy(ho, read_off.data(), (n + 1) * 8);
-        uint64_t* hc = p_coff.get<uint64_t>(n + 1);
-        if (colors_cap == 0) colors_cap = std::max<uint64_t>(uint64_t(n) * std::min<uint32_t>(info.num_colors, 16), 1024);
-        uint32_t* hv = p_colors.get<uint32_t>(colors_cap);
+
+    /* one batch in flight per pipeline stage */
+    struct batch_ctx {
+        pinned p_bases, p_off, p_coff, p_colors;
+        fgio::read_batch reads;
+        uint64_t* hc = nullptr;
+        uint32_t* hv = nullptr;
+        uint64_t colors_cap = 0, first_id = 0;
+        bool full = false, failed = false;
+    } ctx[3];
+    for (auto& c : ctx) {
+        c.reads.grow = [&c](fgio::read_batch& r, uint64_t nb, uint64_t nr) {
+            /* growing discards the old contents: the feeder only grows before it fills */
+            r.bases = c.p_bases.get<char>(nb + nb / 8 + 64);
+            r.off = c.p_off.get<uint64_t>(nr + nr / 8 + 64);
+            r.bases_cap = nb + nb / 8 + 64;
+            r.reads_cap = nr + nr / 8 + 64;
+        };
+    }
+    uint64_t colors_per_read = std::min<uint32_t>(info.num_colors, 16); /* first guess; E2BIG reports the exact need */
+
+    auto gpu_stage = [&](batch_ctx& c) {
+        const uint32_t n = c.reads.n;
+        char* hb = c.reads.bases;
+        uint64_t* ho = c.reads.off;
+        c.hc = c.p_coff.get<uint64_t>(uint64_t(n) + 1);
+        if (c.colors_cap < uint64_t(n) * colors_per_read + 1024) c.colors_cap = uint64_t(n) * colors_per_read + 1024;
+        c.hv = c.p_colors.get<uint32_t>(c.colors_cap);
+        uint64_t* hc = c.hc;
         /* split the batch over the GPUs: contiguous ranges balanced by k-mer count */
         const int G = a.gpus;
         std::vector<uint32_t> cut(G + 1, 0);
-        {
+        if (G > 1) {
             const uint64_t k = info.k;
-            std::vector<uint64_t> work(n + 1, 0);
+            std::vector<uint64_t> work(uint64_t(n) + 1, 0);
             for (uint32_t i = 0; i < n; ++i) {
-                const uint64_t len = read_off[i + 1] - read_off[i];
+                const uint64_t len = ho[i + 1] - ho[i];
                 work[i + 1] = work[i] + (len >= k ? len - k + 1 : 0) + 8;
             }
             for (int g = 1; g < G; ++g) {
                 const uint64_t target = work[n] / G * g;
                 cut[g] = uint32_t(std::lower_bound(work.begin(), work.end(), target) - work.begin());
             }
-            cut[G] = n;
         }
+        cut[G] = n;
         for (;;) {
             std::vector<int> rcs(G, 0);
             std::vector<std::string> errs(G);
@@ -468,10 +249,10 @@ int main(int argc, char** argv) {
             auto run = [&](int g) {
                 const uint32_t lo = cut[g], hi = cut[g + 1];
                 if (G == 1) {
-                    rcs[g] = fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho, n, hc, hv, colors_cap);
+                    rcs[g] = fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho, n, hc, c.hv, c.colors_cap);
                 } else { /* each device fills its own CSR; spliced below */
                     g_off[g].assign(hi - lo + 1, 0);
-                    uint64_t cap = std::max<uint64_t>(uint64_t(hi - lo) * std::min<uint32_t>(info.num_colors, 16), 1024);
+                    uint64_t cap = std::max<uint64_t>(uint64_t(hi - lo) * colors_per_read, 1024);
                     for (;;) {
                         g_val[g].resize(cap);
                         rcs[g] = fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho + lo, hi - lo, g_off[g].data(), g_val[g].data(), cap);
@@ -490,38 +271,76 @@ int main(int argc, char** argv) {
             bool retry = false;
             for (int g = 0; g < G; ++g) {
                 if (rcs[g] == FULGOR_GPU_E2BIG && G == 1) { /* grow the values buffer to the reported size and retry */
-                    colors_cap = hc[n] + hc[n] / 8;
-                    hv = p_colors.get<uint32_t>(colors_cap);
+                    c.colors_cap = hc[n] + hc[n] / 8;
+                    c.hv = c.p_colors.get<uint32_t>(c.colors_cap);
                     retry = true;
                 } else if (rcs[g]) {
                     std::cerr << errs[g] << std::endl;
-                    rc_all = 1;
+                    c.failed = true;
                 }
             }
-            if (rc_all) return 1;
+            if (c.failed) return;
             if (retry) continue;
             if (G > 1) { /* splice the per-device CSRs in read order */
                 uint64_t total = 0;
                 for (int g = 0; g < G; ++g) total += g_off[g].back();
-                if (total > colors_cap) {
-                    colors_cap = total + total / 8;
-                    hv = p_colors.get<uint32_t>(colors_cap);
+                if (total > c.colors_cap) {
+                    c.colors_cap = total + total / 8;
+                    c.hv = c.p_colors.get<uint32_t>(c.colors_cap);
                 }
                 uint64_t base = 0;
                 hc[0] = 0;
                 for (int g = 0; g < G; ++g) {
                     const uint32_t lo = cut[g], cnt = cut[g + 1] - cut[g];
                     for (uint32_t i = 1; i <= cnt; ++i) hc[lo + i] = base + g_off[g][i];
-                    std::memcpy(hv + base, g_val[g].data(), g_off[g].back() * 4);
+                    std::memcpy(c.hv + base, g_val[g].data(), g_off[g].back() * 4);
                     base += g_off[g].back();
                 }
             }
             break;
         }
-        for (uint32_t i = 0; i < n; ++i) num_mapped += hc[i + 1] > hc[i];
-        out.write_batch(uint32_t(num_reads), n, hc, hv);
-        num_reads += n;
-        if (a.verbose) std::cout << "processed " << num_reads << " reads" << std::endl;
+        if (n) colors_per_read = std::max<uint64_t>(colors_per_read, hc[n] / n + 1);
+    };
+    auto format_stage = [&](batch_ctx& c) {
+        const uint32_t n = c.reads.n;
+        uint64_t mapped = 0;
+        for (uint32_t i = 0; i < n; ++i) mapped += c.hc[i + 1] > c.hc[i];
+        num_mapped += mapped;
+        out.write_batch(uint32_t(c.first_id), n, c.hc, c.hv);
+    };
+
+    /* step i: parse batch i | GPU on batch i-1 | format batch i-2, each on its own thread */
+    bool more = true, too_many = false;
+    for (uint64_t step = 0;; ++step) {
+        batch_ctx& cp = ctx[step % 3];
+        batch_ctx& cg = ctx[(step + 2) % 3];
+        batch_ctx& cf = ctx[(step + 1) % 3];
+        const bool do_gpu = step >= 1 && cg.full, do_fmt = step >= 2 && cf.full;
+        if (!more && !do_gpu && !do_fmt) break;
+        std::thread tg, tf;
+        if (do_gpu) tg = std::thread(gpu_stage, std::ref(cg));
+        if (do_fmt) tf = std::thread(format_stage, std::ref(cf));
+        cp.full = false;
+        if (more) {
+            more = reader.next_batch(cp.reads);
+            if (more) {
+                cp.full = true;
+                cp.first_id = num_reads;
+                num_reads += cp.reads.n;
+                if (num_reads > (1ull << 32)) too_many = true;
+            }
+        }
+        if (tg.joinable()) tg.join();
+        if (tf.joinable()) tf.join();
+        if (do_fmt) {
+            cf.full = false;
+            if (a.verbose) std::cout << "processed " << cf.first_id + cf.reads.n << " reads" << std::endl;
+        }
+        if (do_gpu && cg.failed) return 1;
+        if (too_many) {
+            std::cerr << "more than 2^32 reads: read ids do not fit the output formats" << std::endl;
+            return 1;
+        }
     }
     out.close();
     const auto t1 = std::chrono::high_resolution_clock::now();

@@ -1,0 +1,57 @@
+/* TEST INFRASTRUCTURE: exposes fulgor_b200/csrc/fastx_io.h (the tool's feeder and formatters, host C++ without CUDA) to
+   the CPU-only test tier through a C interface. Built into build/libfg_fastx_io_test.so by tests/test_fastx_io.py. */
+#include "../fulgor_b200/csrc/fastx_io.h"
+
+#include <cstdlib>
+
+extern "C" {
+
+/* parses a whole file; *bases / *off are malloc'ed (free with fxio_free). Returns the number of reads, -1 on error. */
+long long fxio_parse(const char* path, unsigned threads, unsigned long long span, unsigned long long max_reads_serial, char** bases,
+                     unsigned long long** off, int* was_mapped) {
+    fgio::fastx_source src;
+    if (!src.open(path, threads, span, max_reads_serial)) return -1;
+    *was_mapped = src.mapped();
+    std::vector<char> all;
+    std::vector<unsigned long long> offs(1, 0);
+    fgio::read_batch b;
+    std::vector<char> bb;
+    std::vector<uint64_t> bo;
+    b.grow = [&](fgio::read_batch& x, uint64_t nb, uint64_t nr) {
+        bb.resize(nb + 16);
+        bo.resize(nr + 16);
+        x.bases = bb.data();
+        x.off = bo.data();
+        x.bases_cap = bb.size();
+        x.reads_cap = bo.size();
+    };
+    while (src.next_batch(b)) {
+        const unsigned long long base = all.size();
+        all.insert(all.end(), b.bases, b.bases + b.off[b.n]);
+        for (uint32_t i = 1; i <= b.n; ++i) offs.push_back(base + b.off[i]);
+    }
+    *was_mapped = *was_mapped && src.mapped();
+    *bases = static_cast<char*>(std::malloc(all.size() + 1));
+    std::memcpy(*bases, all.data(), all.size());
+    *off = static_cast<unsigned long long*>(std::malloc(offs.size() * 8));
+    std::memcpy(*off, offs.data(), offs.size() * 8);
+    return (long long)(offs.size() - 1);
+}
+void fxio_free(void* p) { std::free(p); }
+
+/* formats one CSR batch to a file, in `pieces` calls of write_batch */
+int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads, unsigned n, const unsigned long long* off, const unsigned* colors,
+                unsigned pieces) {
+    fgio::result_writer w;
+    if (!w.open(path, fmt == 0 ? fgio::out_format::ASCII : fmt == 1 ? fgio::out_format::BINARY : fgio::out_format::COMPRESSED, num_colors, threads))
+        return -1;
+    if (pieces < 1) pieces = 1;
+    for (unsigned p = 0; p < pieces; ++p) {
+        const unsigned lo = unsigned((unsigned long long)n * p / pieces), hi = unsigned((unsigned long long)n * (p + 1) / pieces);
+        std::vector<uint64_t> o(off + lo, off + hi + 1);
+        w.write_batch(lo, hi - lo, o.data(), reinterpret_cast<const uint32_t*>(colors));
+    }
+    w.close();
+    return 0;
+}
+}

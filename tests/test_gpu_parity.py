@@ -124,3 +124,28 @@ def test_long_reads_many_color_sets(pair):
     assert _same(got, exp) and np.array_equal(got[2], exp[2])
     for algo, thr in ((0, 1.0), (1, 0.7)):
         assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+
+
+BIG = ["synth_4546.fur", "synth_4546.mfur", "synth_4546_dense.fur", "synth_4546_dense.mfur"]
+
+
+@pytest.mark.parametrize("index", BIG)
+def test_4546_color_standin(index, built_lib):
+    """the 4,546-color stand-ins for salmonella_4546 (tools/make_standin_4546.sh; generated, git-ignored, skipped when absent):
+    wide bitmaps, complemented sets and 145+ meta partitions through the general color-set kernel"""
+    import fulgor_b200 as fg
+
+    try:
+        path = ck.index_path(index)
+    except FileNotFoundError:
+        pytest.skip("data/big fixture not generated on this machine")
+    genomes = index.split(".")[0]
+    reads = ck.gen_reads(3000, 75, 300, seed=21, genomes=genomes)
+    o = ck.Oracle(path)
+    with fg.Index.open(path, 0) as gpu:
+        got = gpu.fetch_color_set_ids(reads, want_positive=True)
+        exp = o.fetch_color_set_ids(reads, want_positive=True)
+        assert _same(got, exp) and np.array_equal(got[2], exp[2])
+        for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.3)):
+            assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+    o.close()
