@@ -67,6 +67,7 @@ struct slot {
     uint64_t* chunk_info = nullptr;        /* device: {base, total} */
     uint64_t* h_info = nullptr;            /* pinned host: {base, total, pool exhausted} */
     uint32_t* exhausted = nullptr;         /* device flag: the entry pool was too small */
+    uint32_t* max_positive = nullptr;      /* device: largest number of positive k-mers of a read (sizes the color-set kernel's counters) */
     unsigned long long* pool_used = nullptr; /* device: entries handed out */
     bool busy = false;
 };
@@ -185,6 +186,7 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
             FG_CUDA(cudaEventCreateWithFlags(&s.info_ready, cudaEventDisableTiming));
             FG_CUDA(cudaMalloc(&s.chunk_info, 16));
             FG_CUDA(cudaMalloc(&s.exhausted, 4));
+            FG_CUDA(cudaMalloc(&s.max_positive, 4));
             FG_CUDA(cudaMalloc(&s.pool_used, 8));
             FG_CUDA(cudaHostAlloc(&s.h_info, 32, cudaHostAllocDefault));
             std::memset(s.h_info, 0, 32);
@@ -220,6 +222,7 @@ struct chunk_args {
     const uint64_t* d_read_off;
     uint64_t read_off_base;
     uint32_t n;
+    uint32_t max_len; /* longest read of the chunk when the host knows it, else 0 */
 };
 
 /* enqueue scan (counts -> CSR offsets with the cross-chunk carry) */
@@ -268,11 +271,13 @@ static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool wa
     s.pool.reserve(size_t(pool_entries) * sizeof(uint2));
     FG_CUDA(cudaMemsetAsync(s.exhausted, 0, 4, s.stream));
     FG_CUDA(cudaMemsetAsync(s.pool_used, 0, 8, s.stream));
+    FG_CUDA(cudaMemsetAsync(s.max_positive, 0, 4, s.stream));
     entry_pool pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted};
     const uint32_t grid = read_grid(x, a.n);
     dispatch_window(x->H, [&](auto w) {
         k_fetch_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, s.stage.as<uint2>(),
-                                                                                  s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr, pool);
+                                                                                  s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr, pool,
+                                                                                  a.max_len ? nullptr : s.max_positive);
     });
     FG_CUDA(cudaGetLastError());
     return 1;
@@ -301,7 +306,15 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     }
     *launches += enqueue_k1(x, s, a, true);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
-    const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions);
+    /* the counters of the color-set kernel must hold the largest score: at most the k-mers of the longest read. Chunks that
+       come from host buffers know that length; for device-resident reads K1 reports the largest number of positive k-mers. */
+    uint32_t max_kmers = a.max_len;
+    if (max_kmers == 0) {
+        FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
+        FG_CUDA(cudaStreamSynchronize(s.stream));
+        max_kmers = std::max<uint32_t>(1, uint32_t(s.h_info[3]));
+    }
+    const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions, algo, max_kmers);
     if (!g.ok) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
     const uint32_t wpb = g.warps_per_block, ints = g.ints_per_warp;
     const size_t smem = g.smem_bytes;
@@ -312,7 +325,7 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
     const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
     k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
-                                                           a.n, algo, threshold, e.words_per_read, ints, s.res_bits.as<uint32_t>(),
+                                                           a.n, algo, threshold, e.words_per_read, g.planes, ints, s.res_bits.as<uint32_t>(),
                                                            s.res_counts.as<uint32_t>());
     FG_CUDA(cudaGetLastError());
     *launches += 1;
@@ -376,6 +389,7 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     uint32_t ci = 0;
     for (uint32_t first = 0; first < n_reads; ++ci) {
         uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
+        uint32_t chunk_max_len = 1;
         if (read_off[first + n] - read_off[first] > CHUNK_MAX_BASES) { /* largest n >= 1 within the byte budget */
             uint32_t lo = 1, hi = n;
             while (lo < hi) {
@@ -386,9 +400,14 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         }
         {
             const uint64_t* ro = read_off + first;
-            uint64_t bad = 0;
-            for (uint32_t i = 0; i < n; ++i) bad |= (ro[i + 1] - ro[i]) >> 31; /* also catches decreasing offsets (wrap-around) */
+            uint64_t bad = 0, longest = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint64_t len = ro[i + 1] - ro[i];
+                bad |= len >> 31; /* also catches decreasing offsets (wrap-around) */
+                longest = std::max(longest, len);
+            }
             if (bad) throw std::invalid_argument("read_off must be non-decreasing and reads shorter than 2^31 characters");
+            chunk_max_len = uint32_t(std::max<uint64_t>(1, longest));
         }
         pending c{first, n, int(ci % FG_NUM_SLOTS), emit_plan()};
         slot& s = x->slots[c.slot];
@@ -404,7 +423,7 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
         FG_CUDA(cudaMemcpyAsync(s.read_off.p, read_off + c.first, size_t(c.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
         if (prev_scanned) FG_CUDA(cudaStreamWaitEvent(s.stream, prev_scanned, 0));
-        chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, c.n};
+        chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, c.n, chunk_max_len};
         int launches = 0;
         if (op == op_kind::FETCH) {
             c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), &launches);
@@ -586,6 +605,7 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
             b->release();
         if (s.chunk_info) cudaFree(s.chunk_info);
         if (s.exhausted) cudaFree(s.exhausted);
+        if (s.max_positive) cudaFree(s.max_positive);
         if (s.pool_used) cudaFree(s.pool_used);
         if (s.h_info) cudaFreeHost(s.h_info);
         if (s.scanned) cudaEventDestroy(s.scanned);
@@ -650,7 +670,7 @@ int fulgor_gpu_pseudoalign_device(fulgor_gpu_index* x, int algo, double threshol
             x->last_launches = 0;
             return 0;
         }
-        chunk_args a{reinterpret_cast<const uint8_t*>(d_bases), d_read_off, read_off_base, n_reads};
+        chunk_args a{reinterpret_cast<const uint8_t*>(d_bases), d_read_off, read_off_base, n_reads, 0};
         for (int attempt = 0;; ++attempt) {
             FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
             FG_CUDA(cudaEventRecord(x->ev[0], s.stream));

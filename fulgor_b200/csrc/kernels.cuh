@@ -1041,28 +1041,64 @@ FG_HD uint32_t color_set_mask(const dev_index& I, uint32_t cid) {
 
 enum { FG_ENC_DELTA = 0, FG_ENC_BITMAP = 1, FG_ENC_COMPLEMENT = 2, FG_ENC_NONE = 3 };
 
-/* one partial color set to be applied to the per-read score array */
+/* Sequential reader of an LSB-first bit stream (bits/bit_vector.hpp:234-294) that keeps 33..64 bits in a register and
+   refills 32 bits at a time, so a run of delta codes costs one 32-bit load per 32 bits instead of two 64-bit loads per code. */
+struct bit_cursor {
+    const uint32_t* next; /* next 32-bit word to load */
+    uint64_t buf;         /* the stream's next `avail` bits, LSB first */
+    uint32_t avail;
+
+    __device__ __forceinline__ void open(const uint64_t* words, uint64_t pos) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(words) + (pos >> 5);
+        const uint32_t sh = uint32_t(pos & 31);
+        buf = uint64_t(FG_LDG(w)) >> sh;
+        avail = 32 - sh;
+        next = w + 1;
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (avail <= 32) {
+            buf |= uint64_t(FG_LDG(next)) << avail;
+            next += 1;
+            avail += 32;
+        }
+    }
+    __device__ __forceinline__ void skip(uint32_t n) {
+        buf >>= n;
+        avail -= n;
+        refill();
+    }
+    /* Elias delta (bits/integer_codes.hpp:54-71), values < 2^32: gamma(b) (at most 11 bits) then b <= 32 payload bits */
+    __device__ __forceinline__ uint32_t delta() {
+        const uint32_t lo = uint32_t(buf);
+        const uint32_t u = uint32_t(__ffs(int(lo))) - 1u; /* unary: u zeros, then a one */
+        const uint32_t b = (((lo >> (u + 1)) & ((1u << u) - 1u)) | (1u << u)) - 1u;
+        skip(2 * u + 1);
+        const uint64_t payload = b >= 32 ? (buf & 0xffffffffULL) : (buf & ((1ULL << b) - 1));
+        skip(b);
+        return uint32_t((payload | (1ULL << b)) - 1);
+    }
+};
+
+/* one partial color set (a hybrid set of one container) */
 struct set_item {
     uint64_t pos;        /* bit position right after the size header */
-    uint32_t container;  /* hybrid container (partition) */
+    const uint64_t* words; /* the container's bit stream */
     uint32_t color_base; /* first global color of the container */
     uint32_t num_colors; /* colors in the container */
     uint32_t nvals;      /* delta-coded values that follow (the set, or its complement) */
-    uint32_t weight;
     uint32_t enc;
 };
 
 /* hybrid::forward_iterator::rewind (include/color_sets/hybrid.hpp:162-188): size header -> encoding */
-__device__ __forceinline__ set_item open_set(const dev_index& I, uint32_t container, uint64_t local_id, uint32_t color_base, uint32_t weight) {
+__device__ __forceinline__ set_item open_set(const dev_index& I, uint32_t container, uint64_t local_id, uint32_t color_base) {
     set_item it;
     const fgi_hybrid* h = I.hybrids + container;
-    it.container = container;
     it.color_base = color_base;
     it.num_colors = FG_LDG(&h->num_colors);
-    it.weight = weight;
-    const uint64_t* words = I.color_words + FG_LDG(&h->word_base);
+    it.words = I.color_words + FG_LDG(&h->word_base);
     it.pos = FG_LDG(I.set_bit_off + FG_LDG(&h->set_off_base) + local_id);
-    const uint32_t size = read_delta(words, it.pos);
+    const uint32_t size = read_delta(it.words, it.pos);
     if (size < FG_LDG(&h->sparse_thr)) {
         it.enc = FG_ENC_DELTA;
         it.nvals = size;
@@ -1076,47 +1112,41 @@ __device__ __forceinline__ set_item open_set(const dev_index& I, uint32_t contai
     return it;
 }
 
-/* Adds one round of up to 32 partial sets (one per lane, `valid` lanes only) to the warp's score array:
-     scores[c] += weight for every color of a delta-coded or bitmap set,
-     base[container] += weight and scores[c] -= weight for every MISSING color of a complement-coded set
-   (the same trick as the reference's merge, src/ps_threshold_union.cpp:23-29, so the cost of a set is
-   proportional to its encoded length). Bitmap sets are expanded by the whole warp (one 32-bit chunk
-   per lane, no conflicts); delta-coded sets are decoded lane-parallel with shared-memory atomics. */
-__device__ __forceinline__ void apply_sets(const dev_index& I, bool valid, const set_item& it, int* scores, int* base, uint32_t lane) {
-    uint32_t bm = __ballot_sync(FG_FULL, valid && it.enc == FG_ENC_BITMAP);
-    while (bm) {
-        const int src = __ffs(int(bm)) - 1;
-        bm &= bm - 1;
-        const uint64_t pos = __shfl_sync(FG_FULL, it.pos, src);
-        const uint32_t container = __shfl_sync(FG_FULL, it.container, src);
-        const uint32_t cb = __shfl_sync(FG_FULL, it.color_base, src);
-        const uint32_t nc = __shfl_sync(FG_FULL, it.num_colors, src);
-        const int w = int(__shfl_sync(FG_FULL, it.weight, src));
-        const uint64_t* words = I.color_words + FG_LDG(&I.hybrids[container].word_base);
-        for (uint32_t c0 = lane * 32; c0 < nc; c0 += 32 * 32) {
-            uint32_t bits = uint32_t(bits_at(words, pos + c0));
-            if (nc - c0 < 32) bits &= (1u << (nc - c0)) - 1u;
-            while (bits) {
-                const uint32_t b = uint32_t(__ffs(int(bits))) - 1u;
-                bits &= bits - 1;
-                scores[cb + c0 + b] += w;
-            }
-        }
-        __syncwarp();
-    }
-    if (valid && it.enc != FG_ENC_BITMAP) {
-        const uint64_t* words = I.color_words + FG_LDG(&I.hybrids[it.container].word_base);
-        const int w = it.enc == FG_ENC_COMPLEMENT ? -int(it.weight) : int(it.weight);
-        if (it.enc == FG_ENC_COMPLEMENT) atomicAdd(base + it.container, int(it.weight));
-        uint64_t pos = it.pos;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < it.nvals; ++i) {
-            const uint32_t d = read_delta(words, pos);
-            v = i ? v + d + 1 : d;
-            atomicAdd(scores + it.color_base + v, w);
+/* Per-read, per-color counters kept BIT-SLICED in shared memory: plane j holds bit j of every color's counter, one bit per
+   color, so a bitmap-coded color set is added to all of its colors with a few word-wide logic operations per 32 colors
+   (ripple carry across the planes) instead of one read-modify-write per member, and a whole 4,546-color counter array of
+   7-bit counters takes 4 KB instead of 18 KB. Updates are atomic XORs, so lanes may work on different sets at once: a lane
+   that flips a bit from 1 to 0 owes the carry to the next plane, whatever other lanes do to the same word in between. */
+struct bit_planes {
+    uint32_t* base;    /* plane j, word w at base[j * stride + w] */
+    uint32_t stride;   /* words per plane */
+    uint32_t nplanes;
+
+    /* counter[32 w + b] += weight for every set bit b of `bits` */
+    __device__ __forceinline__ void add_word(uint32_t w, uint32_t bits, uint32_t weight) const {
+        for (uint32_t j = 0; weight; ++j, weight >>= 1) {
+            if (!(weight & 1u)) continue;
+            uint32_t carry = bits;
+            for (uint32_t k = j; carry && k < nplanes; ++k) carry &= atomicXor(base + k * stride + w, carry);
         }
     }
-    __syncwarp();
+    __device__ __forceinline__ void add_color(uint32_t c, uint32_t weight) const { add_word(c >> 5, 1u << (c & 31), weight); }
+    __device__ __forceinline__ uint32_t plane(uint32_t j, uint32_t w) const { return j < nplanes ? base[j * stride + w] : 0u; }
+};
+
+/* 32 bits of a bitmap-coded partial set, aligned to GLOBAL color word w: bit b = color 32 w + b. gmask = the bits of the
+   word that belong to the container's color range [color_base, color_base + num_colors). */
+__device__ __forceinline__ uint32_t bitmap_word(const set_item& it, uint32_t w, uint32_t& gmask) {
+    const int lo = int(32 * w) - int(it.color_base); /* local index of the word's first color */
+    const int first = lo < 0 ? -lo : 0;              /* first bit of the word inside the range */
+    const int last = min(32, int(it.num_colors) - lo); /* one past the last */
+    if (last <= first) {
+        gmask = 0;
+        return 0;
+    }
+    gmask = (last >= 32 ? ~0u : ((1u << last) - 1u)) & ~((1u << first) - 1u);
+    const uint64_t raw = lo >= 0 ? bits_at(it.words, it.pos + uint64_t(lo)) : bits_at(it.words, it.pos) << first;
+    return uint32_t(raw) & gmask;
 }
 
 }  // namespace fgb

@@ -88,7 +88,8 @@ template <int W>
 __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
                                                               const uint64_t* __restrict__ read_off, uint64_t read_off_base,
                                                               uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
-                                                              uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool) {
+                                                              uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool,
+                                                              uint32_t* __restrict__ max_positive /* nullable: running maximum of num_positive */) {
     __shared__ uint2 scratch[FG_WARPS_PER_BLOCK][FG_SCRATCH_ENTRIES];
     __shared__ warp_stage wstage[FG_WARPS_PER_BLOCK];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -119,109 +120,272 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(co
         if (lane == 0) {
             counts[r] = R.failed ? 0u : R.n;
             if (num_positive) num_positive[r] = R.npos;
+            if (max_positive && R.npos > *max_positive) atomicMax(max_positive, R.npos);
         }
         __syncwarp();
     }
 }
 
-/* launch shape of k_color_sets_general: per warp num_colors + num_partitions int32 (scores, then one base per partition),
-   as many warps per block as fit ~96 KB of shared memory */
+/* ---- K2 for indexes with more than 32 colors ---- */
+
+#define FG_K2_SETS_PER_ROUND 256 /* color sets of one read handled per round (unit prefix + deferred list live in shared memory) */
+#define FG_K2_WIDE_COLORS 96     /* bitmap-coded partial sets over more colors than this are expanded by the whole warp */
+
+/* launch shape of k_color_sets_general. Shared memory per warp, in 32-bit words: the intersection accumulator (W words,
+   W = ceil(num_colors / 32)), the counter planes (planes x W, twice for threshold-union: members and complement-misses),
+   two ints per partition, the per-round unit prefix and deferred list, two counters. `planes` = bits of the largest
+   possible score = bit_width(max k-mers of a read in the batch). */
 struct general_plan {
-    uint32_t ints_per_warp, warps_per_block, words_per_read;
+    uint32_t ints_per_warp, warps_per_block, words_per_read, planes;
     size_t smem_bytes;
     bool ok;
 };
-static inline general_plan plan_color_sets_general(uint32_t num_colors, uint32_t num_partitions) {
+static inline general_plan plan_color_sets_general(uint32_t num_colors, uint32_t num_partitions, int algo, uint32_t max_kmers) {
     general_plan g;
-    g.ints_per_warp = (num_colors + num_partitions + 1) & ~1u;
+    g.words_per_read = (num_colors + 31) / 32;
+    g.planes = 1;
+    while (g.planes < 32 && (uint64_t(1) << g.planes) <= max_kmers) g.planes += 1;
+    const uint32_t counters = algo == FULGOR_GPU_FULL_INTERSECTION ? 1u : 2u;
+    g.ints_per_warp = g.words_per_read * (1 + counters * g.planes) + 2 * num_partitions + (FG_K2_SETS_PER_ROUND + 1) + FG_K2_SETS_PER_ROUND / 2 + 4;
+    g.ints_per_warp = (g.ints_per_warp + 3) & ~3u;
     g.ok = size_t(g.ints_per_warp) * 4 <= 200 * 1024;
-    size_t w = (96 * 1024) / (size_t(g.ints_per_warp) * 4);
+    size_t w = (72 * 1024) / (size_t(g.ints_per_warp) * 4); /* ~3 blocks per SM */
     if (w < 1) w = 1;
     if (w > FG_WARPS_PER_BLOCK) w = FG_WARPS_PER_BLOCK;
     g.warps_per_block = uint32_t(w);
     g.smem_bytes = size_t(g.warps_per_block) * g.ints_per_warp * 4;
-    g.words_per_read = (num_colors + 31) / 32;
     return g;
 }
 
-/* K2 for indexes with more than 32 colors: one warp per read, per-color int32 scores in shared memory.
-   Full intersection = colors present in all n hit sets (weight 1 each, min_score = n) -- the same set as
-   the reference's intersect / meta_intersect (src/ps_full_intersection.cpp:33-127, 243-332);
-   threshold union = colors with score >= uint64(double(npos) * threshold) (src/ps_threshold_union.cpp:389,
-   merge :17-40, merge_meta :43-120). The result is a bitmap of num_colors bits per read + its popcount. */
+/* K2: one warp per read; the read's distinct color sets {id, multiplicity} come from K1.
+   Full intersection = colors present in all n hit sets -- the same set as the reference's intersect / meta_intersect
+   (src/ps_full_intersection.cpp:33-127, 243-332); threshold union = colors with score >= uint64(double(npos) * threshold)
+   (src/ps_threshold_union.cpp:389, merge :17-40, merge_meta :43-120). The result is a bitmap of num_colors bits per read +
+   its popcount.
+
+   The UNIT of work is one partial set (hybrid: the set itself; meta: one (partition, partial set) entry of the set's meta
+   list, include/color_sets/meta.hpp:93-236). Lanes draw units from a shared ticket, so long delta-coded lists and short
+   ones balance out; every lane decodes its own unit with a register-buffered bit cursor:
+     full intersection   bitmap: acc &= bitmap (inside the partition's color range)
+                         complement-coded: acc &= ~{missing colors}
+                         delta-coded (sparse): members counted in the bit-sliced planes, sets counted per partition;
+                                               a color survives iff its count equals the partition's number of sparse sets
+                         a partition that some set does not list at all is cleared (listed[p] < n)
+     threshold union     bitmap / delta-coded: score planes += multiplicity for every member
+                         complement-coded: base[p] += multiplicity, miss planes += multiplicity for every MISSING color
+                                           (the reference's trick, src/ps_threshold_union.cpp:23-29: cost ~ encoded length)
+                         final: score - miss + base[p] >= min_score, evaluated 32 colors at a time with bit-sliced adders
+   Bitmaps over more than FG_K2_WIDE_COLORS colors are deferred and expanded by the whole warp, one word per lane. */
 __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_general(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
                                                                 const uint2* __restrict__ stage, const uint2* __restrict__ pool,
                                                                 const uint32_t* __restrict__ num_positive, uint32_t n_reads, int algo,
-                                                                double threshold, uint32_t words_per_read, uint32_t smem_ints_per_warp,
-                                                                uint32_t* __restrict__ res_bits, uint32_t* __restrict__ res_counts) {
+                                                                double threshold, uint32_t words_per_read, uint32_t planes_cap,
+                                                                uint32_t smem_ints_per_warp, uint32_t* __restrict__ res_bits,
+                                                                uint32_t* __restrict__ res_counts) {
 #ifdef FG_SIMT_EMUL
-    int* smem = static_cast<int*>(fg_emul_dynamic_smem());
+    uint32_t* smem = static_cast<uint32_t*>(fg_emul_dynamic_smem());
 #else
-    extern __shared__ int smem[];
+    extern __shared__ uint32_t smem[];
 #endif
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    int* scores = smem + size_t(wib) * smem_ints_per_warp;
-    int* base = scores + I.num_colors;
-    const uint32_t C = I.num_colors, P = I.num_partitions;
+    const uint32_t C = I.num_colors, P = I.num_partitions, W = words_per_read;
+    const bool fi = algo == FULGOR_GPU_FULL_INTERSECTION;
+    uint32_t* acc = smem + size_t(wib) * smem_ints_per_warp;
+    uint32_t* planes_a = acc + W;
+    uint32_t* planes_m = planes_a + planes_cap * W; /* threshold union only */
+    uint32_t* pa = planes_m + (fi ? 0 : planes_cap * W); /* per partition: FI sets that list it | TU complement base weight */
+    uint32_t* pb = pa + P;                                /* per partition: FI sparse sets */
+    uint32_t* pref = pb + P;                              /* units before set j of the round (FG_K2_SETS_PER_ROUND + 1) */
+    uint16_t* wide = reinterpret_cast<uint16_t*>(pref + FG_K2_SETS_PER_ROUND + 1);
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(wide + FG_K2_SETS_PER_ROUND); /* [0] ticket, [1] deferred units */
     const uint32_t warps = gridDim.x * wpb;
     for (uint32_t r = blockIdx.x * wpb + wib; r < n_reads; r += warps) {
         const uint32_t n = __ldg(counts + r);
-        uint32_t* out = res_bits + uint64_t(r) * words_per_read;
+        uint32_t* out = res_bits + uint64_t(r) * W;
         if (n == 0) { /* no positive k-mer: empty result (src/ps_full_intersection.cpp:385, ps_threshold_union.cpp:355) */
-            for (uint32_t w = lane; w < words_per_read; w += 32) out[w] = 0;
+            for (uint32_t w = lane; w < W; w += 32) out[w] = 0;
             if (lane == 0) res_counts[r] = 0;
             continue;
         }
         const uint2* ents = entries_of(r, n, stage, pool);
-        for (uint32_t c = lane; c < C + P; c += 32) scores[c] = 0;
-        __syncwarp();
-        const bool fi = algo == FULGOR_GPU_FULL_INTERSECTION;
-        const uint64_t min_score = fi ? uint64_t(n) : uint64_t(double(__ldg(num_positive + r)) * threshold);
-        if (I.type == 0) {
-            for (uint32_t j0 = 0; j0 < n; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                set_item it;
-                it.enc = FG_ENC_NONE;
-                if (j < n) {
-                    const uint2 e = ents[j];
-                    it = open_set(I, 0, e.x, 0, fi ? 1u : e.y);
-                }
-                apply_sets(I, j < n, it, scores, base, lane);
-            }
-        } else { /* meta: a color set is the list of its partial sets (include/color_sets/meta.hpp:93-236) */
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint2 e = ents[j];
-                const uint64_t b = __ldg(I.meta_off + e.x);
-                const uint32_t nm = __ldg(I.meta_vals + b);
-                for (uint32_t i0 = 0; i0 < nm; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    set_item it;
-                    it.enc = FG_ENC_NONE;
-                    if (i < nm) {
-                        const uint32_t mc = __ldg(I.meta_vals + b + 1 + i);
-                        uint32_t lo = 0, hi = P; /* largest p with sets_before[p] <= mc (meta.hpp:227-235) */
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (__ldg(I.part_sets_before + mid) <= mc) lo = mid; else hi = mid;
-                        }
-                        it = open_set(I, lo, mc - __ldg(I.part_sets_before + lo), __ldg(I.part_min_color + lo), fi ? 1u : e.y);
-                    }
-                    apply_sets(I, i < nm, it, scores, base, lane);
-                }
-            }
+        const uint32_t npos = __ldg(num_positive + r);
+        const uint64_t min_score = fi ? uint64_t(n) : uint64_t(double(npos) * threshold);
+        uint32_t np = 1; /* planes this read needs: scores are at most n (FI) or npos (TU) */
+        while (np < planes_cap && (1u << np) <= (fi ? n : npos)) np += 1;
+        const bit_planes A{planes_a, W, np}, M{planes_m, W, np};
+        for (uint32_t w = lane; w < W; w += 32) acc[w] = w + 1 < W || (C & 31) == 0 ? ~0u : (1u << (C & 31)) - 1u;
+        for (uint32_t i = lane; i < np * W; i += 32) {
+            planes_a[i] = 0;
+            if (!fi) planes_m[i] = 0;
         }
-        uint32_t total = 0, p = 0;
-        for (uint32_t w = 0; w < words_per_read; ++w) {
-            const uint32_t c = w * 32 + lane;
-            bool pass = false;
-            if (c < C) {
-                while (p + 1 < P && c >= __ldg(I.part_min_color + p + 1)) ++p;
-                const int sc = scores[c] + base[p];
-                pass = uint64_t(uint32_t(sc)) >= min_score;
+        for (uint32_t p = lane; p < 2 * P; p += 32) pa[p] = 0;
+        __syncwarp();
+
+        for (uint32_t j0 = 0; j0 < n; j0 += FG_K2_SETS_PER_ROUND) {
+            const uint32_t nb = min(uint32_t(FG_K2_SETS_PER_ROUND), n - j0);
+            /* units of this round: prefix of the sets' partial-set counts */
+            uint32_t carry = 0;
+            for (uint32_t b = 0; b < nb; b += 32) {
+                const uint32_t j = b + lane;
+                uint32_t units = 0;
+                if (j < nb) units = I.type == 0 ? 1u : __ldg(I.meta_vals + __ldg(I.meta_off + ents[j0 + j].x));
+                uint32_t incl = units;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FG_FULL, incl, d);
+                    if (lane >= uint32_t(d)) incl += y;
+                }
+                if (j < nb) pref[j] = carry + incl - units;
+                carry += __shfl_sync(FG_FULL, incl, 31);
             }
-            const uint32_t word = __ballot_sync(FG_FULL, pass);
-            if (lane == 0) out[w] = word;
-            total += __popc(word);
+            const uint32_t total = carry;
+            if (lane == 0) {
+                pref[nb] = total;
+                ctl[0] = 0;
+                ctl[1] = 0;
+            }
+            __syncwarp();
+            /* lane-parallel: every lane draws units until none is left */
+            for (;;) {
+                const uint32_t u = atomicAdd(ctl, 1u);
+                if (u >= total) break;
+                uint32_t lo = 0, hi = nb; /* the set j with pref[j] <= u < pref[j + 1] */
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (pref[mid] <= u) lo = mid; else hi = mid;
+                }
+                const uint2 e = ents[j0 + lo];
+                const uint32_t weight = fi ? 1u : e.y;
+                uint32_t part = 0;
+                set_item it;
+                if (I.type == 0) {
+                    it = open_set(I, 0, e.x, 0);
+                } else { /* meta: the (u - pref[lo])-th entry of the set's meta list -> (partition, local set id), meta.hpp:227-235 */
+                    const uint32_t mc = __ldg(I.meta_vals + __ldg(I.meta_off + e.x) + 1 + (u - pref[lo]));
+                    uint32_t plo = 0, phi = P; /* largest p with sets_before[p] <= mc */
+                    while (phi - plo > 1) {
+                        const uint32_t mid = (plo + phi) >> 1;
+                        if (__ldg(I.part_sets_before + mid) <= mc) plo = mid; else phi = mid;
+                    }
+                    part = plo;
+                    it = open_set(I, part, mc - __ldg(I.part_sets_before + part), __ldg(I.part_min_color + part));
+                }
+                if (fi) {
+                    atomicAdd(pa + part, 1u);
+                    if (it.enc == FG_ENC_DELTA) atomicAdd(pb + part, 1u);
+                } else if (it.enc == FG_ENC_COMPLEMENT) {
+                    atomicAdd(pa + part, weight);
+                }
+                if (it.enc == FG_ENC_BITMAP) {
+                    if (it.num_colors > FG_K2_WIDE_COLORS) {
+                        const uint32_t slot = atomicAdd(ctl + 1, 1u);
+                        if (slot < FG_K2_SETS_PER_ROUND && u < 65536u) { /* else: expanded right here, by this lane alone */
+                            wide[slot] = uint16_t(u);
+                            continue;
+                        }
+                    }
+                    for (uint32_t w = it.color_base >> 5; 32 * w < it.color_base + it.num_colors; ++w) {
+                        uint32_t gmask;
+                        const uint32_t bits = bitmap_word(it, w, gmask);
+                        if (fi) atomicAnd(acc + w, bits | ~gmask);
+                        else if (bits) A.add_word(w, bits, weight);
+                    }
+                    continue;
+                }
+                bit_cursor cur;
+                cur.open(it.words, it.pos);
+                uint32_t v = 0;
+                for (uint32_t i = 0; i < it.nvals; ++i) {
+                    const uint32_t d = cur.delta();
+                    v = i ? v + d + 1 : d;
+                    const uint32_t c = it.color_base + v;
+                    if (it.enc == FG_ENC_COMPLEMENT) {
+                        if (fi) atomicAnd(acc + (c >> 5), ~(1u << (c & 31)));
+                        else M.add_color(c, weight);
+                    } else {
+                        A.add_color(c, weight);
+                    }
+                }
+            }
+            __syncwarp();
+            /* the deferred wide bitmaps, one after the other, a word per lane */
+            const uint32_t nwide = min(ctl[1], uint32_t(FG_K2_SETS_PER_ROUND));
+            for (uint32_t x = 0; x < nwide; ++x) {
+                const uint32_t u = wide[x];
+                uint32_t lo = 0, hi = nb;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (pref[mid] <= u) lo = mid; else hi = mid;
+                }
+                const uint2 e = ents[j0 + lo];
+                set_item it;
+                if (I.type == 0) {
+                    it = open_set(I, 0, e.x, 0);
+                } else {
+                    const uint32_t mc = __ldg(I.meta_vals + __ldg(I.meta_off + e.x) + 1 + (u - pref[lo]));
+                    uint32_t plo = 0, phi = P;
+                    while (phi - plo > 1) {
+                        const uint32_t mid = (plo + phi) >> 1;
+                        if (__ldg(I.part_sets_before + mid) <= mc) plo = mid; else phi = mid;
+                    }
+                    it = open_set(I, plo, mc - __ldg(I.part_sets_before + plo), __ldg(I.part_min_color + plo));
+                }
+                for (uint32_t w = (it.color_base >> 5) + lane; 32 * w < it.color_base + it.num_colors; w += 32) {
+                    uint32_t gmask;
+                    const uint32_t bits = bitmap_word(it, w, gmask);
+                    if (fi) atomicAnd(acc + w, bits | ~gmask); /* neighbouring lanes may share the range's edge words with no one: plain AND would do, the atomic keeps it simple */
+                    else if (bits) A.add_word(w, bits, e.y);
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+
+        /* final: 32 colors per lane and step; a word may straddle partitions */
+        uint32_t total = 0;
+        for (uint32_t w0 = 0; w0 < W; w0 += 32) {
+            const uint32_t w = w0 + lane;
+            uint32_t word = 0;
+            if (w < W) {
+                uint32_t p = 0;
+                if (P > 1) { /* the partition of the word's first color: largest p with min_color[p] <= 32 w */
+                    uint32_t plo = 0, phi = P;
+                    while (phi - plo > 1) {
+                        const uint32_t mid = (plo + phi) >> 1;
+                        if (__ldg(I.part_min_color + mid) <= 32 * w) plo = mid; else phi = mid;
+                    }
+                    p = plo;
+                }
+                for (;; ++p) {
+                    const uint32_t cb = P > 1 ? __ldg(I.part_min_color + p) : 0u, ce = P > 1 ? __ldg(I.part_min_color + p + 1) : C;
+                    const int first = cb > 32 * w ? int(cb - 32 * w) : 0, last = min(32, int(ce) - int(32 * w));
+                    if (last > first) {
+                        const uint32_t rm = (last >= 32 ? ~0u : ((1u << last) - 1u)) & ~((1u << first) - 1u);
+                        uint32_t ok;
+                        if (fi) {
+                            ok = pa[p] == n ? acc[w] : 0u;
+                            const uint32_t ns = pb[p];
+                            for (uint32_t j = 0; j < np; ++j) ok &= ((ns >> j) & 1u) ? A.plane(j, w) : ~A.plane(j, w);
+                        } else { /* sign of (A - M + K), K = base[p] - min_score, in np + 3 bits of two's complement */
+                            const int64_t K = int64_t(pa[p]) - int64_t(min_score);
+                            uint32_t c1 = ~0u, c2 = 0u, sign = 0u; /* A + ~M + 1, then + K */
+                            for (uint32_t j = 0; j < np + 3; ++j) {
+                                const uint32_t a = A.plane(j, w), m = ~M.plane(j, w);
+                                const uint32_t s1 = a ^ m ^ c1;
+                                c1 = (a & m) | (a & c1) | (m & c1);
+                                const uint32_t kb = ((K >> j) & 1) ? ~0u : 0u;
+                                sign = s1 ^ kb ^ c2;
+                                c2 = (s1 & kb) | (s1 & c2) | (kb & c2);
+                            }
+                            ok = ~sign;
+                        }
+                        word |= ok & rm;
+                    }
+                    if (P <= 1 || p + 1 >= P || ce >= 32 * w + 32) break;
+                }
+                out[w] = word;
+            }
+            total += __reduce_add_sync(FG_FULL, uint32_t(__popc(word)));
         }
         if (lane == 0) res_counts[r] = total;
         __syncwarp();

@@ -12,7 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DATA = os.path.join(ROOT, "data")
-BIG = os.path.join(DATA, "big")  # large generated fixtures (tools/make_standin_4546.sh), git-ignored
+BIG = os.path.join(ROOT, "fixtures_big")  # large generated fixtures (tools/make_standin_4546.sh), git-ignored
 ORACLE_SO = os.path.join(ROOT, "oracle", "libfulgor_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfulgor_ref.so")
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "fulgor_ref")

@@ -90,7 +90,7 @@ static int run_k1(const dev_index& I, const uint8_t* bases, const uint64_t* read
     entry_pool pool{o.pool.data(), &used, pool_entries, &exhausted};
     dispatch_window(I, force_generic, [&](auto w) {
         simt::launch(grid, FG_BLOCK, 0, [&] {
-            k_fetch_color_sets<decltype(w)::value>(I, bases, read_off, read_off[0], n, o.stage.data(), o.counts.data(), o.npos.data(), pool);
+            k_fetch_color_sets<decltype(w)::value>(I, bases, read_off, read_off[0], n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
         });
     });
     return int(exhausted);
@@ -152,11 +152,13 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     k1_out k1;
     uint64_t pool_entries = 1u << 12; /* small on purpose: exercises the grow-and-rerun path */
     while (run_k1(I, bases, read_off, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
-    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions);
+    uint32_t max_kmers = 1;
+    for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
+    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
     if (!g.ok) return FULGOR_GPU_EINVAL;
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     simt::launch(grid, g.warps_per_block * 32, g.smem_bytes, [&] {
-        k_color_sets_general(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, algo, threshold, g.words_per_read,
+        k_color_sets_general(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, algo, threshold, g.words_per_read, g.planes,
                              g.ints_per_warp, res_bits.data(), res_counts.data());
     });
     run_scan<false>(res_counts.data(), n, out_off);

@@ -232,6 +232,25 @@ static inline T atomicAdd(T* p, T v) { /* fibers are cooperative: no preemption 
     return old;
 }
 
+template <typename T>
+static inline T atomicAnd(T* p, T v) {
+    const T old = *p;
+    *p = old & v;
+    return old;
+}
+template <typename T>
+static inline T atomicXor(T* p, T v) {
+    const T old = *p;
+    *p = old ^ v;
+    return old;
+}
+template <typename T>
+static inline T atomicMax(T* p, T v) {
+    const T old = *p;
+    if (v > old) *p = v;
+    return old;
+}
+
 /* ---- warp collectives (full mask only, like every call site in the kernels) ---- */
 static inline void fg_emul_check_mask(unsigned mask) {
     if (mask != 0xffffffffu) {

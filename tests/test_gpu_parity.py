@@ -138,7 +138,7 @@ def test_4546_color_standin(index, built_lib):
     try:
         path = ck.index_path(index)
     except FileNotFoundError:
-        pytest.skip("data/big fixture not generated on this machine")
+        pytest.skip("fixtures_big fixture not generated on this machine")
     genomes = index.split(".")[0]
     reads = ck.gen_reads(3000, 75, 300, seed=21, genomes=genomes)
     o = ck.Oracle(path)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# dev helper (GPU box): parity + bench + ncu launch list on a 4,546-color stand-in (needs data/big/ in the snapshot)
+# dev helper (GPU box): parity + bench + ncu launch list on a 4,546-color stand-in (needs fixtures_big/ in the snapshot)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 IDX=${1:-synth_4546_dense.fur}; READS=${2:-200000}
