@@ -86,6 +86,7 @@ struct fulgor_gpu_index {
     uint64_t* d_carry = nullptr;
     int sm_count = 0;
     uint64_t pool_per_read = 8; /* entry-pool size per read of a chunk; grows (x4) when a launch exhausts it */
+    uint32_t* d_table = nullptr; /* decoded color-set table (dev_index::set_table), owned */
     /* timing of the last *_device call */
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[3] = {0, 0, 0};
@@ -160,6 +161,30 @@ static void use_device(int device) {
     FG_CUDA(cudaSetDevice(device));
 }
 
+/* Decodes every color set into a bitmap row once (k_expand_color_sets) when the table fits the budget: FULGOR_GPU_TABLE_MAX_MB
+   (default 65536) and half of the free device memory. Without the table the color-set kernels decode the compressed sets per read. */
+static void build_color_set_table(fulgor_gpu_index* x) {
+    const char* env = std::getenv("FULGOR_GPU_TABLE_MAX_MB");
+    const uint64_t budget = (env ? std::strtoull(env, nullptr, 10) : 65536ull) << 20;
+    const uint64_t stride = table_stride_words(x->H.num_colors);
+    const uint64_t bytes = x->H.num_color_sets * stride * 4;
+    size_t free_b = 0, total_b = 0;
+    FG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes == 0 || bytes > budget || bytes > free_b / 2 || stride * 4 > 48 * 1024) return;
+    FG_CUDA(cudaMalloc(&x->d_table, bytes));
+    const uint32_t wpb = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(FG_WARPS_PER_BLOCK, (48 * 1024) / (stride * 4))));
+    const uint64_t per_launch = 1u << 22;
+    for (uint64_t first = 0; first < x->H.num_color_sets; first += per_launch) {
+        const uint32_t n = uint32_t(std::min<uint64_t>(per_launch, x->H.num_color_sets - first));
+        const uint32_t grid = uint32_t(std::min<uint64_t>((n + wpb - 1) / wpb, uint64_t(x->sm_count) * 16));
+        k_expand_color_sets<<<grid, wpb * 32, size_t(wpb) * stride * 4, x->slots[0].stream>>>(x->I, first, n, uint32_t(stride), x->d_table + first * stride);
+        FG_CUDA(cudaGetLastError());
+    }
+    FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
+    x->I.set_table = x->d_table;
+    x->I.table_stride = stride;
+}
+
 static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool owns, int device) {
     auto* x = new fulgor_gpu_index();
     x->device = device;
@@ -179,6 +204,7 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
         FG_CUDA(cudaGetDeviceProperties(&prop, device));
         x->sm_count = prop.multiProcessorCount;
         FG_CUDA(cudaMalloc(&x->d_carry, 8));
+        build_color_set_table(x);
         for (auto& s : x->slots) {
             FG_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             FG_CUDA(cudaEventCreateWithFlags(&s.scanned, cudaEventDisableTiming));
@@ -306,27 +332,41 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     }
     *launches += enqueue_k1(x, s, a, true);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
-    /* the counters of the color-set kernel must hold the largest score: at most the k-mers of the longest read. Chunks that
+    /* the counters of the color-set kernels must hold the largest score: at most the k-mers of the longest read. Chunks that
        come from host buffers know that length; for device-resident reads K1 reports the largest number of positive k-mers. */
     uint32_t max_kmers = a.max_len;
-    if (max_kmers == 0) {
+    if (max_kmers == 0 && algo != FULGOR_GPU_FULL_INTERSECTION) {
         FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
         FG_CUDA(cudaStreamSynchronize(s.stream));
         max_kmers = std::max<uint32_t>(1, uint32_t(s.h_info[3]));
     }
-    const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions, algo, max_kmers);
-    if (!g.ok) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
-    const uint32_t wpb = g.warps_per_block, ints = g.ints_per_warp;
-    const size_t smem = g.smem_bytes;
-    FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
-    e.words_per_read = g.words_per_read;
+    e.words_per_read = (x->H.num_colors + 31) / 32;
     s.res_bits.reserve(size_t(a.n) * e.words_per_read * 4);
     s.res_counts.reserve(size_t(a.n) * 4);
-    const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
-    const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
-    k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
-                                                           a.n, algo, threshold, e.words_per_read, g.planes, ints, s.res_bits.as<uint32_t>(),
-                                                           s.res_counts.as<uint32_t>());
+    if (x->I.set_table) { /* decoded table: registers only */
+        const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
+        dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
+            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, 0, s.stream>>>(
+                x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(), a.n, threshold, e.words_per_read,
+                s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
+        });
+    } else { /* compressed sets decoded per read */
+        if (max_kmers == 0) { /* full intersection counts sets, at most as many as positive k-mers */
+            FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            max_kmers = std::max<uint32_t>(1, uint32_t(s.h_info[3]));
+        }
+        const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions, algo, max_kmers);
+        if (!g.ok) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
+        const uint32_t wpb = g.warps_per_block, ints = g.ints_per_warp;
+        const size_t smem = g.smem_bytes;
+        FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
+        const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
+        const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
+        k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
+                                                               a.n, algo, threshold, e.words_per_read, g.planes, ints, s.res_bits.as<uint32_t>(),
+                                                               s.res_counts.as<uint32_t>());
+    }
     FG_CUDA(cudaGetLastError());
     *launches += 1;
     if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
@@ -616,6 +656,7 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
     for (auto& e : x->ev)
         if (e) cudaEventDestroy(e);
     if (x->d_carry) cudaFree(x->d_carry);
+    if (x->d_table) cudaFree(x->d_table);
     if (x->owns_image && x->d_image) cudaFree(x->d_image);
     delete x;
 }

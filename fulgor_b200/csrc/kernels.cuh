@@ -98,6 +98,10 @@ struct dev_index {
     uint32_t type, num_colors, num_partitions, guard_max_hash;
     uint64_t main_seed, main_nparts; /* the minimizer MPHF (phfs[0]; its partitions are parts[0 .. main_nparts)) */
     fgi_phf_part main_part;          /* parts[0] */
+    /* the decoded color-set table: row i = color set i as a bitmap of num_colors bits padded to table_stride 32-bit words.
+       Built on each GPU from the compressed sets when it fits the HBM budget (k_expand_color_sets); nullptr otherwise. */
+    const uint32_t* set_table;
+    uint64_t table_stride;
 };
 
 /* ------------------------------------------------------------------ hashing */

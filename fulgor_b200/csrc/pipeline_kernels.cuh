@@ -10,6 +10,8 @@
 #ifndef FULGOR_B200_PIPELINE_KERNELS_CUH
 #define FULGOR_B200_PIPELINE_KERNELS_CUH
 
+#include <type_traits>
+
 #include "../../include/fulgor_gpu.h"
 #include "kernels.cuh"
 
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(c
         uint32_t cid, cnt;
         while (tiles.next(cid, cnt)) { /* items {color-set id, number of k-mers}: every lane decodes its own set */
             const bool found = cnt != 0;
-            const uint32_t mask = found ? color_set_mask(I, cid) : ~0u;
+            const uint32_t mask = !found ? ~0u : (I.set_table ? __ldg(I.set_table + uint64_t(cid) * I.table_stride) : color_set_mask(I, cid));
             __syncwarp();
             npos += __reduce_add_sync(FG_FULL, cnt);
             if (algo == FULGOR_GPU_FULL_INTERSECTION) {
@@ -390,6 +392,165 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_general(const __grid_co
         if (lane == 0) res_counts[r] = total;
         __syncwarp();
     }
+}
+
+/* ---- the decoded color-set table ---- */
+
+/* words per table row: the color bitmap padded to a whole number of 32-word (128-byte) warp loads */
+static inline uint64_t table_stride_words(uint32_t num_colors) { return (uint64_t(num_colors) + 1023) / 1024 * 32; }
+
+/* Decodes color sets [first_set, first_set + n_sets) into bitmap rows, one warp per set: hybrid::forward_iterator
+   (include/color_sets/hybrid.hpp:151-305) / meta<hybrid>::forward_iterator (include/color_sets/meta.hpp:93-236) run once per
+   set at load time instead of once per read and set at query time. 180 GB of HBM hold the table of any index Fulgor builds
+   today (salmonella_4546: 972,178 sets x 640 B = 0.6 GB); the queries then read plain, coalesced bitmaps.
+   The row is assembled in shared memory: lanes take the set's partial sets (one for a hybrid index), set member bits with
+   atomic ORs -- a complement-coded partial set first fills its partition's color range, then clears the missing colors. */
+__global__ void __launch_bounds__(FG_BLOCK) k_expand_color_sets(const __grid_constant__ dev_index I, uint64_t first_set, uint32_t n_sets,
+                                                               uint32_t stride, uint32_t* __restrict__ table) {
+#ifdef FG_SIMT_EMUL
+    uint32_t* smem = static_cast<uint32_t*>(fg_emul_dynamic_smem());
+#else
+    extern __shared__ uint32_t smem[];
+#endif
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t* row = smem + size_t(wib) * stride;
+    const uint32_t P = I.num_partitions;
+    for (uint32_t s = blockIdx.x * wpb + wib; s < n_sets; s += gridDim.x * wpb) {
+        const uint64_t cid = first_set + s;
+        for (uint32_t w = lane; w < stride; w += 32) row[w] = 0;
+        __syncwarp();
+        uint64_t list = 0;
+        uint32_t units = 1;
+        if (I.type != 0) {
+            list = __ldg(I.meta_off + cid);
+            units = __ldg(I.meta_vals + list);
+        }
+        for (uint32_t u = lane; u < units; u += 32) {
+            set_item it;
+            if (I.type == 0) {
+                it = open_set(I, 0, cid, 0);
+            } else { /* meta.hpp:227-235 */
+                const uint32_t mc = __ldg(I.meta_vals + list + 1 + u);
+                uint32_t plo = 0, phi = P;
+                while (phi - plo > 1) {
+                    const uint32_t mid = (plo + phi) >> 1;
+                    if (__ldg(I.part_sets_before + mid) <= mc) plo = mid; else phi = mid;
+                }
+                it = open_set(I, plo, mc - __ldg(I.part_sets_before + plo), __ldg(I.part_min_color + plo));
+            }
+            if (it.enc != FG_ENC_DELTA) { /* bitmap: its bits; complement: the whole range first */
+                for (uint32_t w = it.color_base >> 5; 32 * w < it.color_base + it.num_colors; ++w) {
+                    uint32_t gmask;
+                    const uint32_t bits = bitmap_word(it, w, gmask);
+                    atomicOr(row + w, it.enc == FG_ENC_BITMAP ? bits : gmask);
+                }
+            }
+            if (it.enc != FG_ENC_BITMAP) {
+                bit_cursor cur;
+                cur.open(it.words, it.pos);
+                uint32_t v = 0;
+                for (uint32_t i = 0; i < it.nvals; ++i) {
+                    const uint32_t d = cur.delta();
+                    v = i ? v + d + 1 : d;
+                    const uint32_t c = it.color_base + v;
+                    if (it.enc == FG_ENC_COMPLEMENT) atomicAnd(row + (c >> 5), ~(1u << (c & 31)));
+                    else atomicOr(row + (c >> 5), 1u << (c & 31));
+                }
+            }
+        }
+        __syncwarp();
+        for (uint32_t w = lane; w < stride; w += 32) table[uint64_t(s) * stride + w] = row[w];
+        __syncwarp();
+    }
+}
+
+/* K2 on the decoded table: one warp per read, the read's result accumulated IN REGISTERS, 32 * T colors-words per pass
+   (lane l owns words l, l + 32, ...). Every hit set costs T coalesced 128-byte loads and, for full intersection, T ANDs;
+   for threshold union the bitmap is added to NP bit-sliced counter planes (kernels.cuh: bit_planes, here in registers,
+   no atomics: a lane owns its words) and the threshold test is one bit-sliced subtraction. Same results as
+   k_color_sets_general. NP = counter bits (scores < 2^NP), T = words per lane and pass. */
+template <bool FI, int NP, int T>
+__global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
+                                                              const uint2* __restrict__ stage, const uint2* __restrict__ pool,
+                                                              const uint32_t* __restrict__ num_positive, uint32_t n_reads, double threshold,
+                                                              uint32_t words_per_read, uint32_t* __restrict__ res_bits,
+                                                              uint32_t* __restrict__ res_counts) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const uint32_t C = I.num_colors, W = words_per_read;
+    const uint32_t* __restrict__ table = I.set_table;
+    const uint64_t stride = I.table_stride;
+    for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * wpb) {
+        const uint32_t n = __ldg(counts + r);
+        uint32_t* out = res_bits + uint64_t(r) * W;
+        if (n == 0) { /* no positive k-mer: empty result (src/ps_full_intersection.cpp:385, ps_threshold_union.cpp:355) */
+            for (uint32_t w = lane; w < W; w += 32) out[w] = 0;
+            if (lane == 0) res_counts[r] = 0;
+            continue;
+        }
+        const uint2* ents = entries_of(r, n, stage, pool);
+        const uint64_t min_score = FI ? uint64_t(n) : uint64_t(double(__ldg(num_positive + r)) * threshold);
+        uint32_t total = 0;
+        for (uint32_t w0 = 0; w0 < W; w0 += 32 * T) {
+            uint32_t pl[FI ? 1 : NP][T]; /* FI: the running intersection; TU: counter planes */
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+                for (int k = 0; k < (FI ? 1 : NP); ++k) pl[k][t] = FI ? ~0u : 0u;
+            }
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e = ents[j];
+                const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
+                uint32_t x[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
+                if (FI) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) pl[0][t] &= x[t];
+                } else { /* counter += multiplicity for every member: one full adder per plane, 32 colors wide */
+                    const uint32_t wt = e.y;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        uint32_t carry = 0;
+#pragma unroll
+                        for (int k = 0; k < (FI ? 1 : NP); ++k) {
+                            const uint32_t y = ((wt >> k) & 1u) ? x[t] : 0u, a = pl[k][t];
+                            pl[k][t] = a ^ y ^ carry;
+                            carry = (a & y) | (a & carry) | (y & carry);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const uint32_t w = w0 + 32 * t + lane;
+                uint32_t word = pl[0][t];
+                if (!FI) { /* score >= min_score <=> carry out of score + ~min_score + 1 over NP bits */
+                    uint32_t carry = ~0u;
+#pragma unroll
+                    for (int k = 0; k < (FI ? 1 : NP); ++k) {
+                        const uint32_t nb = ((min_score >> k) & 1u) ? 0u : ~0u;
+                        carry = (pl[k][t] & nb) | (pl[k][t] & carry) | (nb & carry);
+                    }
+                    word = (min_score >> NP) ? 0u : carry; /* a threshold beyond the counters' range is never met */
+                }
+                if (w + 1 == W && (C & 31)) word &= (1u << (C & 31)) - 1u;
+                if (w < W) out[w] = word; else word = 0;
+                total += __popc(word);
+            }
+        }
+        total = __reduce_add_sync(FG_FULL, total);
+        if (lane == 0) res_counts[r] = total;
+    }
+}
+
+/* counter bits and words per lane for reads of at most max_kmers k-mers */
+template <typename F>
+static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {
+    if (algo == FULGOR_GPU_FULL_INTERSECTION) f(std::true_type(), std::integral_constant<int, 1>(), std::integral_constant<int, 5>());
+    else if (max_kmers < (1u << 7)) f(std::false_type(), std::integral_constant<int, 7>(), std::integral_constant<int, 5>());
+    else if (max_kmers < (1u << 10)) f(std::false_type(), std::integral_constant<int, 10>(), std::integral_constant<int, 4>());
+    else if (max_kmers < (1u << 16)) f(std::false_type(), std::integral_constant<int, 16>(), std::integral_constant<int, 2>());
+    else f(std::false_type(), std::integral_constant<int, 32>(), std::integral_constant<int, 1>());
 }
 
 /* ---- CSR offsets: exclusive scan of per-read counts (three small kernels) ---- */

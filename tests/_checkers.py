@@ -12,7 +12,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DATA = os.path.join(ROOT, "data")
-BIG = os.path.join(ROOT, "fixtures_big")  # large generated fixtures (tools/make_standin_4546.sh), git-ignored
+# large generated fixtures (tools/make_standin_4546.sh), git-ignored: in the tree when they should travel to the GPU box, else parked outside
+BIG_DIRS = [os.path.join(ROOT, "fixtures_big"), os.environ.get("FG_FIXTURES_BIG", "/tmp/fg_fixtures/big")]
 ORACLE_SO = os.path.join(ROOT, "oracle", "libfulgor_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfulgor_ref.so")
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "fulgor_ref")
@@ -186,8 +187,9 @@ def load_gpk(name="salmonella_10"):
     """Packed genomes (written by tools/mkdump) as a uint8 array; stored xz-compressed in data/."""
     if name not in _GPK_CACHE:
         path = os.path.join(DATA, name + ".gpk")
-        if not os.path.exists(path) and os.path.exists(os.path.join(BIG, name + ".gpk")):
-            path = os.path.join(BIG, name + ".gpk")
+        for d in BIG_DIRS:
+            if not os.path.exists(path) and os.path.exists(os.path.join(d, name + ".gpk")):
+                path = os.path.join(d, name + ".gpk")
         if os.path.exists(path):
             raw = open(path, "rb").read()
         else:
@@ -228,8 +230,9 @@ def index_path(name):
     path = os.path.join(DATA, name)
     if os.path.exists(path):
         return path
-    if os.path.exists(os.path.join(BIG, name)):
-        return os.path.join(BIG, name)
+    for d in BIG_DIRS:
+        if os.path.exists(os.path.join(d, name)):
+            return os.path.join(d, name)
     tail = path + ".tail"
     if name.endswith(".mfur") and os.path.exists(tail):
         base = path[: -len(".mfur")] + ".fur"

@@ -133,8 +133,18 @@ int emul_base_valid(uint32_t c) { return base_valid(c) ? 1 : 0; }
 
 /* the whole pseudoalignment pipeline on emulated warps. Returns 0, or -7 when cap is too small (out_off complete). */
 int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uint8_t* bases, const uint64_t* read_off, uint32_t n,
-                     uint64_t* out_off, uint32_t* out_vals, uint64_t cap, unsigned grid, int force_generic) {
-    const dev_index I = view_of(image);
+                     uint64_t* out_off, uint32_t* out_vals, uint64_t cap, unsigned grid, int force_generic, int use_table) {
+    dev_index I = view_of(image);
+    std::vector<uint32_t> table;
+    if (use_table) { /* decode every color set once, like fulgor_gpu_index_open does on the device */
+        fgi_header H;
+        std::memcpy(&H, image, sizeof(H));
+        const uint64_t stride = table_stride_words(I.num_colors);
+        table.assign(H.num_color_sets * stride, 0xdeadbeefu);
+        simt::launch(2, 64, 2 * stride * 4, [&] { k_expand_color_sets(I, 0, uint32_t(H.num_color_sets), uint32_t(stride), table.data()); });
+        I.set_table = table.data();
+        I.table_stride = stride;
+    }
     out_off[0] = 0;
     if (n == 0) return 0;
     uint64_t chunk_info[2] = {0, 0};
@@ -157,10 +167,19 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
     if (!g.ok) return FULGOR_GPU_EINVAL;
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
-    simt::launch(grid, g.warps_per_block * 32, g.smem_bytes, [&] {
-        k_color_sets_general(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, algo, threshold, g.words_per_read, g.planes,
-                             g.ints_per_warp, res_bits.data(), res_counts.data());
-    });
+    if (use_table) {
+        dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
+            simt::launch(grid, FG_BLOCK, 0, [&] {
+                k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
+                    I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, threshold, g.words_per_read, res_bits.data(), res_counts.data());
+            });
+        });
+    } else {
+        simt::launch(grid, g.warps_per_block * 32, g.smem_bytes, [&] {
+            k_color_sets_general(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, algo, threshold, g.words_per_read, g.planes,
+                                 g.ints_per_warp, res_bits.data(), res_counts.data());
+        });
+    }
     run_scan<false>(res_counts.data(), n, out_off);
     if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
     simt::launch(uint32_t((uint64_t(n) * 32 + 255) / 256), 256, 0,

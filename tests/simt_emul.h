@@ -239,6 +239,12 @@ static inline T atomicAnd(T* p, T v) {
     return old;
 }
 template <typename T>
+static inline T atomicOr(T* p, T v) {
+    const T old = *p;
+    *p = old | v;
+    return old;
+}
+template <typename T>
 static inline T atomicXor(T* p, T v) {
     const T old = *p;
     *p = old ^ v;

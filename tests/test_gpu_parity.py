@@ -149,3 +149,22 @@ def test_4546_color_standin(index, built_lib):
         for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.3)):
             assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
     o.close()
+
+
+@pytest.mark.parametrize("index", ["salmonella_10.mfur", "synth_200.fur", "synth_200.mfur", "synth_4546.mfur"])
+def test_without_the_decoded_table(index, built_lib, monkeypatch):
+    """FULGOR_GPU_TABLE_MAX_MB=0: no decoded color-set table, the kernels decode the compressed sets per read
+    (color_set_mask in the fused kernel, k_color_sets_general otherwise)"""
+    import fulgor_b200 as fg
+
+    try:
+        path = ck.index_path(index)
+    except FileNotFoundError:
+        pytest.skip("fixtures_big not generated on this machine")
+    monkeypatch.setenv("FULGOR_GPU_TABLE_MAX_MB", "0")
+    reads = ck.gen_reads(4000, 75, 300, seed=23, genomes=index.split(".")[0])
+    o = ck.Oracle(path)
+    with fg.Index.open(path, 0) as gpu:
+        for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.2)):
+            assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+    o.close()

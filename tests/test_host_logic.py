@@ -30,19 +30,19 @@ def emul():
     E.emul_color_set_mask.argtypes = [C.c_void_p, C.c_uint32]
     E.emul_base_valid.argtypes = [C.c_uint32]
     E.emul_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
-                                   C.c_uint, C.c_int]
+                                   C.c_uint, C.c_int, C.c_int]
     E.emul_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                            C.c_uint, C.c_int]
     return E
 
 
-def emul_pseudoalign(E, img, reads, algo, thr, num_colors, grid=1, generic=0):
+def emul_pseudoalign(E, img, reads, algo, thr, num_colors, grid=1, generic=0, table=0):
     bases, off = reads
     n = len(off) - 1
     out_off = np.zeros(n + 1, dtype=np.uint64)
     cap = max(1, n * num_colors)
     vals = np.zeros(cap, dtype=np.uint32)
-    rc = E.emul_pseudoalign(img.ctypes.data, algo, thr, bases.ctypes.data, off.ctypes.data, n, out_off.ctypes.data, vals.ctypes.data, cap, grid, generic)
+    rc = E.emul_pseudoalign(img.ctypes.data, algo, thr, bases.ctypes.data, off.ctypes.data, n, out_off.ctypes.data, vals.ctypes.data, cap, grid, generic, table)
     assert rc == 0, rc
     return out_off, vals[: int(out_off[n])]
 
@@ -145,14 +145,16 @@ def test_emulated_kernels_stage1_like_the_oracle(loaded, emul, generic):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("table", [0, 1])
 @pytest.mark.parametrize("algo,thr", [(0, 1.0), (1, 0.8), (1, 0.25)])
-def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr):
-    """the whole kernel pipeline (fused small-color kernel, or K1 + general color-set kernel, then scan + emit) on emulated
-    warps == pseudoalign_full_intersection / pseudoalign_threshold_union"""
+def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr, table):
+    """the whole kernel pipeline (fused small-color kernel, or K1 + color-set kernel, then scan + emit) on emulated warps ==
+    pseudoalign_full_intersection / pseudoalign_threshold_union; table = with the decoded color-set table
+    (k_expand_color_sets + k_color_sets_table) or decoding the compressed sets per read (k_color_sets_general)"""
     fg, img, o = loaded
     n = 400 if o.num_colors <= 32 else 120
     for reads in (ck.gen_reads(n, 150, 150, seed=12, genomes=o.name.split(".")[0]), _edge_reads(o.name.split(".")[0])):
-        got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors)
+        got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors, table=table)
         exp = o.pseudoalign(reads, algo, thr)
         assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
 

@@ -18,9 +18,9 @@ python tools/synthgen.py "$TMP/genomes" "$N" "$LEN" --seed 4546 --sub "$SUB" --i
 build/mkdump "$TMP/$NAME" "@$TMP/genomes/list.txt"
 oracle/_ref/fulgor_ref load -i "$TMP/$NAME" -o "$TMP/$NAME" -m 20 -d "$TMP" -t 8 --verbose
 oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --meta --verbose
-mkdir -p fixtures_full
+mkdir -p ${FG_FULL_DIR:-/tmp/fg_fixtures/full}
 mv "$TMP/$NAME.fur" "$TMP/$NAME.mfur" "$OUT/"
-mv "$TMP/$NAME.gpk" fixtures_full/
-# reads are drawn from every 20th genome: a small file that travels to the GPU box (the full pack stays in fixtures_full/)
-python tools/gpk_subset.py "fixtures_full/$NAME.gpk" "$OUT/$NAME.gpk" 20
+mv "$TMP/$NAME.gpk" ${FG_FULL_DIR:-/tmp/fg_fixtures/full}/
+# reads are drawn from every 20th genome: a small file that travels to the GPU box (the full pack stays in ${FG_FULL_DIR:-/tmp/fg_fixtures/full}/)
+python tools/gpk_subset.py "${FG_FULL_DIR:-/tmp/fg_fixtures/full}/$NAME.gpk" "$OUT/$NAME.gpk" 20
 ls -la "$OUT"
