@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -45,7 +46,7 @@ inline void parallel_for(unsigned n, const std::function<void(unsigned)>& f) {
 }
 
 /* a batch of reads in the layout the C ABI takes: concatenated bases + CSR offsets. The buffers belong to the caller
-   (pinned memory in the tool); grow() is called when a batch needs more room. */
+   (pinned memory in the tool); grow() is called when a batch needs more room and must keep what the batch already holds. */
 struct read_batch {
     char* bases = nullptr;
     uint64_t* off = nullptr;
@@ -152,6 +153,7 @@ public:
     }
     /* threads = tokenising threads for memory-mapped input; span = bytes of file per batch */
     bool open(const char* path, unsigned threads, uint64_t span_bytes, uint64_t max_reads_serial) {
+        if (const char* e = std::getenv("FULGOR_SLAB_KB")) slab_bytes_ = std::max<size_t>(64, std::strtoull(e, nullptr, 10)) << 10;
         threads_ = std::max(1u, threads);
         span_ = std::max<uint64_t>(span_bytes, 1 << 16);
         max_reads_serial_ = std::max<uint64_t>(1, max_reads_serial);
@@ -221,57 +223,69 @@ private:
     }
 
     struct slab_out {
+        std::vector<char> raw;   /* the slab's bytes (pread scales across threads where first-touch faults of one mapping do not) */
         std::vector<char> bases;
         std::vector<uint32_t> lens;
         bool ok = true;
     };
 
-    void tokenise(size_t p, size_t end, slab_out& o) const {
-        o.bases.reserve((end - p) / (fastq_ ? 2 : 1) + 64);
-        while (p < end) {
-            p = skip_blank(p);
-            if (p >= end) break;
-            const size_t l1 = next_line(p); /* header */
+    static size_t line_after(const char* d, size_t n, size_t p) { /* start of the line after the one containing p; n if none */
+        const char* nl = static_cast<const char*>(std::memchr(d + p, '\n', n - p));
+        return nl ? size_t(nl - d) + 1 : n;
+    }
+
+    /* tokenises the whole records in d[0, n): n is a record boundary or the end of the file */
+    void tokenise(const char* d, size_t n, slab_out& o) const {
+        o.bases.clear(); /* the slabs' buffers persist across batches: no reallocation, no fresh pages after the first batch */
+        o.lens.clear();
+        o.ok = true;
+        o.bases.reserve(n / (fastq_ ? 2 : 1) + 64);
+        o.lens.reserve(n / (fastq_ ? 64 : 32) + 64);
+        size_t p = 0;
+        while (p < n) {
+            while (p < n && (d[p] == '\n' || d[p] == '\r')) ++p;
+            if (p >= n) break;
+            const size_t l1 = line_after(d, n, p); /* header */
             const size_t start = o.bases.size();
             if (fastq_) {
-                if (map_[p] != '@') {
+                if (d[p] != '@') {
                     o.ok = false;
                     return;
                 }
-                if (l1 >= size_) return; /* a header without a sequence line ends the input, like the serial reader */
-                const size_t l2 = next_line(l1);
-                size_t s_end = l2 - (l2 > l1 && map_[l2 - 1] == '\n' ? 1 : 0);
-                if (s_end > l1 && map_[s_end - 1] == '\r') --s_end;
-                o.bases.insert(o.bases.end(), map_ + l1, map_ + s_end);
-                if (l2 >= size_) { /* no '+' line: the serial reader accepts this too */
+                if (l1 >= n) return; /* a header without a sequence line ends the input, like the serial reader */
+                const size_t l2 = line_after(d, n, l1);
+                size_t s_end = l2 - (l2 > l1 && d[l2 - 1] == '\n' ? 1 : 0);
+                if (s_end > l1 && d[s_end - 1] == '\r') --s_end;
+                o.bases.insert(o.bases.end(), d + l1, d + s_end);
+                if (l2 >= n) { /* no '+' line: the serial reader accepts this too */
                     o.lens.push_back(uint32_t(o.bases.size() - start));
                     return;
                 }
-                if (map_[l2] != '+') { /* multi-line sequence */
+                if (d[l2] != '+') { /* multi-line sequence */
                     o.bases.resize(start);
                     o.ok = false;
                     return;
                 }
-                const size_t l3 = next_line(l2), l4 = l3 < size_ ? next_line(l3) : size_;
-                size_t q_end = l4 - (l4 > l3 && map_[l4 - 1] == '\n' ? 1 : 0);
-                if (q_end > l3 && map_[q_end - 1] == '\r') --q_end;
-                if (q_end - l3 < s_end - l1 && l4 < size_) { /* quality shorter than the sequence: multi-line record */
+                const size_t l3 = line_after(d, n, l2), l4 = l3 < n ? line_after(d, n, l3) : n;
+                size_t q_end = l4 - (l4 > l3 && d[l4 - 1] == '\n' ? 1 : 0);
+                if (q_end > l3 && d[q_end - 1] == '\r') --q_end;
+                if (q_end - l3 < s_end - l1 && l4 < n) { /* quality shorter than the sequence: multi-line record */
                     o.bases.resize(start);
                     o.ok = false;
                     return;
                 }
                 p = l4;
             } else {
-                if (map_[p] != '>') {
+                if (d[p] != '>') {
                     o.ok = false;
                     return;
                 }
                 size_t q = l1;
-                while (q < size_ && map_[q] != '>' && map_[q] != '@') {
-                    const size_t nq = next_line(q);
-                    size_t e = nq - (nq > q && map_[nq - 1] == '\n' ? 1 : 0);
-                    if (e > q && map_[e - 1] == '\r') --e;
-                    o.bases.insert(o.bases.end(), map_ + q, map_ + e);
+                while (q < n && d[q] != '>' && d[q] != '@') {
+                    const size_t nq = line_after(d, n, q);
+                    size_t e = nq - (nq > q && d[nq - 1] == '\n' ? 1 : 0);
+                    if (e > q && d[e - 1] == '\r') --e;
+                    o.bases.insert(o.bases.end(), d + q, d + e);
                     q = nq;
                 }
                 p = q;
@@ -280,37 +294,65 @@ private:
         }
     }
 
+    bool load_slab(size_t begin, size_t end, slab_out& o) const {
+        o.raw.resize(end - begin);
+        size_t got = 0;
+        while (got < o.raw.size()) {
+            const ssize_t r = pread(fd_, o.raw.data() + got, o.raw.size() - got, off_t(begin + got));
+            if (r <= 0) return false;
+            got += size_t(r);
+        }
+        return true;
+    }
+
+    /* One batch = up to span_ bytes of the file, produced in ROUNDS of threads_ cache-sized slabs: a slab is read (pread),
+       tokenised while still hot in the cache, and its reads appended to the batch buffers. */
     bool next_mapped(read_batch& b) {
         const unsigned T = threads_;
-        const size_t begin = pos_, target = std::min<uint64_t>(size_, begin + span_);
+        const size_t batch_end = std::min<uint64_t>(size_, pos_ + span_);
+        std::vector<slab_out>& out = slabs_;
+        out.resize(T);
+        uint64_t nbases = 0, nreads = 0;
         std::vector<size_t> cut(T + 1);
-        cut[0] = begin;
-        for (unsigned t = 1; t <= T; ++t) cut[t] = std::max(cut[t - 1], find_record(begin + size_t((target - begin) * uint64_t(t) / T)));
-        if (target == size_) cut[T] = size_;
-        std::vector<slab_out> out(T);
-        parallel_for(T, [&](unsigned t) { tokenise(cut[t], cut[t + 1], out[t]); });
-        for (auto const& o : out)
-            if (!o.ok) return false;
-        std::vector<uint64_t> base_at(T + 1, 0), read_at(T + 1, 0);
-        for (unsigned t = 0; t < T; ++t) {
-            base_at[t + 1] = base_at[t] + out[t].bases.size();
-            read_at[t + 1] = read_at[t] + out[t].lens.size();
-        }
-        if (read_at[T] > 0xffffffffull) return false;
-        b.reserve(base_at[T] + 1, read_at[T] + 1);
-        parallel_for(T, [&](unsigned t) {
-            if (!out[t].bases.empty()) std::memcpy(b.bases + base_at[t], out[t].bases.data(), out[t].bases.size());
-            uint64_t o = base_at[t];
-            uint64_t* dst = b.off + read_at[t];
-            for (uint32_t len : out[t].lens) {
-                *dst++ = o;
-                o += len;
+        std::vector<uint64_t> base_at(T + 1), read_at(T + 1);
+        while (pos_ < batch_end) {
+            const size_t begin = pos_, target = std::min<uint64_t>(size_, begin + uint64_t(T) * slab_bytes_);
+            cut[0] = begin;
+            for (unsigned t = 1; t <= T; ++t) cut[t] = std::max(cut[t - 1], find_record(begin + size_t((target - begin) * uint64_t(t) / T)));
+            if (target == size_) cut[T] = size_;
+            parallel_for(T, [&](unsigned t) {
+                if (load_slab(cut[t], cut[t + 1], out[t])) tokenise(out[t].raw.data(), out[t].raw.size(), out[t]);
+                else out[t].ok = false;
+            });
+            for (auto const& o : out)
+                if (!o.ok) { /* hand over to the serial reader from the start of this batch */
+                    reads_done_ -= nreads;
+                    return false;
+                }
+            base_at[0] = nbases;
+            read_at[0] = nreads;
+            for (unsigned t = 0; t < T; ++t) {
+                base_at[t + 1] = base_at[t] + out[t].bases.size();
+                read_at[t + 1] = read_at[t] + out[t].lens.size();
             }
-        });
-        b.off[read_at[T]] = base_at[T];
-        b.n = uint32_t(read_at[T]);
-        reads_done_ += b.n;
-        pos_ = cut[T];
+            if (read_at[T] > 0xffffffffull) return false;
+            b.reserve(base_at[T] + 1, read_at[T] + 1);
+            parallel_for(T, [&](unsigned t) {
+                if (!out[t].bases.empty()) std::memcpy(b.bases + base_at[t], out[t].bases.data(), out[t].bases.size());
+                uint64_t o = base_at[t];
+                uint64_t* dst = b.off + read_at[t];
+                for (uint32_t len : out[t].lens) {
+                    *dst++ = o;
+                    o += len;
+                }
+            });
+            reads_done_ += read_at[T] - nreads;
+            nbases = base_at[T];
+            nreads = read_at[T];
+            pos_ = cut[T];
+        }
+        b.off[nreads] = nbases;
+        b.n = uint32_t(nreads);
         return true;
     }
 
@@ -349,8 +391,10 @@ private:
     size_t size_ = 0, pos_ = 0;
     bool mapped_ = false, fastq_ = true, serial_open_ = false;
     unsigned threads_ = 1;
-    uint64_t span_ = 1ull << 30, max_reads_serial_ = 1u << 22, reads_done_ = 0;
+    uint64_t span_ = 1ull << 28, max_reads_serial_ = 1u << 22, reads_done_ = 0;
+    size_t slab_bytes_ = 2u << 20;
     serial_fastx_reader serial_;
+    std::vector<slab_out> slabs_;
     std::vector<char> serial_bases_;
     std::vector<uint64_t> serial_off_;
 };

@@ -39,7 +39,7 @@ struct args_t {
     double threshold = -1.0;
     bool has_threshold = false, verbose = false, deduplicate = false;
     int gpus = 1;
-    uint64_t batch_reads = 4u << 20;
+    uint64_t batch_reads = 1u << 20;
 };
 
 void usage() {
@@ -199,20 +199,33 @@ int main(int argc, char** argv) {
 
     /* one batch in flight per pipeline stage */
     struct batch_ctx {
-        pinned p_bases, p_off, p_coff, p_colors;
-        fgio::read_batch reads;
+        pinned p_coff, p_colors;
+        fgio::read_batch reads; /* pinned, owned here */
         uint64_t* hc = nullptr;
         uint32_t* hv = nullptr;
         uint64_t colors_cap = 0, first_id = 0;
         bool full = false, failed = false;
     } ctx[3];
     for (auto& c : ctx) {
-        c.reads.grow = [&c](fgio::read_batch& r, uint64_t nb, uint64_t nr) {
-            /* growing discards the old contents: the feeder only grows before it fills */
-            r.bases = c.p_bases.get<char>(nb + nb / 8 + 64);
-            r.off = c.p_off.get<uint64_t>(nr + nr / 8 + 64);
-            r.bases_cap = nb + nb / 8 + 64;
-            r.reads_cap = nr + nr / 8 + 64;
+        c.reads.grow = [&c](fgio::read_batch& r, uint64_t nb, uint64_t nr) { /* keeps the batch's contents */
+            if (nb > r.bases_cap) {
+                const uint64_t cap = nb + nb / 4 + (1u << 20);
+                char* p = static_cast<char*>(fulgor_gpu_host_alloc(cap));
+                if (!p) { std::cerr << "cannot allocate pinned host memory\n"; std::exit(1); }
+                if (r.bases) std::memcpy(p, r.bases, r.bases_cap);
+                fulgor_gpu_host_free(r.bases);
+                r.bases = p;
+                r.bases_cap = cap;
+            }
+            if (nr > r.reads_cap) {
+                const uint64_t cap = nr + nr / 4 + (1u << 16);
+                uint64_t* p = static_cast<uint64_t*>(fulgor_gpu_host_alloc(cap * 8));
+                if (!p) { std::cerr << "cannot allocate pinned host memory\n"; std::exit(1); }
+                if (r.off) std::memcpy(p, r.off, r.reads_cap * 8);
+                fulgor_gpu_host_free(r.off);
+                r.off = p;
+                r.reads_cap = cap;
+            }
         };
     }
     uint64_t colors_per_read = std::min<uint32_t>(info.num_colors, 16); /* first guess; E2BIG reports the exact need */
