@@ -38,10 +38,15 @@ using namespace fulgor;
 namespace {
 
 struct ref_handle {
-    int type;  // 0 = hybrid (.fur), 1 = meta (.mfur)
-    hfur_index_t h;
-    mfur_index_t m;
+    int type;  // 0 = hybrid (.fur), 1 = meta (.mfur), 2 = differential (.dfur), 3 = meta-differential (.mdfur)
+    std::variant<hfur_index_t, mfur_index_t, dfur_index_t, mdfur_index_t> index;
 };
+
+/* run f on the loaded index, whatever its color-set type (like std::visit in tools/pseudoalign.cpp:335) */
+template <typename F>
+auto on_index(void* hp, F&& f) {
+    return std::visit(std::forward<F>(f), static_cast<ref_handle*>(hp)->index);
+}
 
 bool ends_with(std::string const& s, std::string const& p) {
     return s.size() >= p.size() && std::equal(p.begin(), p.end(), s.end() - p.size());
@@ -115,12 +120,19 @@ void* fref_open(const char* path) {
     try {
         auto* h = new ref_handle();
         std::string p(path);
-        if (ends_with(p, ".mfur")) {
+        /* type by suffix, like tools/util.cpp:5-19 */
+        if (ends_with(p, ".mdfur")) {
+            h->type = 3;
+            essentials::load(h->index.emplace<mdfur_index_t>(), path);
+        } else if (ends_with(p, ".dfur")) {
+            h->type = 2;
+            essentials::load(h->index.emplace<dfur_index_t>(), path);
+        } else if (ends_with(p, ".mfur")) {
             h->type = 1;
-            essentials::load(h->m, path);
+            essentials::load(h->index.emplace<mfur_index_t>(), path);
         } else if (ends_with(p, ".fur")) {
             h->type = 0;
-            essentials::load(h->h, path);
+            essentials::load(h->index.emplace<hfur_index_t>(), path);
         } else {
             delete h;
             return nullptr;
@@ -146,25 +158,21 @@ void fref_info(void* hp, uint64_t* out) {
         out[5] = idx.num_color_sets();
         out[6] = h->type;
     };
-    if (h->type == 0) fill(h->h); else fill(h->m);
+    on_index(hp, fill);
 }
 
 /* per-k-mer streaming lookup of one read; contig_ids has len-k+1 slots; -1 = negative */
 void fref_lookup_read(void* hp, const char* seq, uint64_t len, uint64_t* contig_ids) {
-    auto* h = static_cast<ref_handle*>(hp);
-    if (h->type == 0) lookup_read(h->h, seq, len, contig_ids);
-    else lookup_read(h->m, seq, len, contig_ids);
+    on_index(hp, [&](auto const& idx) { lookup_read(idx, seq, len, contig_ids); });
 }
 
 /* unitig id -> color set id (include/index.hpp:37) */
 uint64_t fref_u2c(void* hp, uint64_t unitig_id) {
-    auto* h = static_cast<ref_handle*>(hp);
-    return h->type == 0 ? h->h.u2c(unitig_id) : h->m.u2c(unitig_id);
+    return on_index(hp, [&](auto const& idx) -> uint64_t { return idx.u2c(unitig_id); });
 }
 
 /* decode color set `id` with the reference iterator; returns its size (writes min(size,cap)) */
 int64_t fref_color_set(void* hp, uint64_t id, uint32_t* out, uint64_t cap) {
-    auto* h = static_cast<ref_handle*>(hp);
     uint64_t n = 0;
     auto dec = [&](auto const& idx) {
         auto it = idx.color_set(id);
@@ -174,28 +182,26 @@ int64_t fref_color_set(void* hp, uint64_t id, uint32_t* out, uint64_t cap) {
             ++n;
         }
     };
-    if (h->type == 0) dec(h->h); else dec(h->m);
+    on_index(hp, dec);
     return int64_t(n);
 }
 
 /* stage 1 for a batch: CSR of sorted distinct color-set ids per read */
 int fref_fetch_color_set_ids(void* hp, const char* bases, const uint64_t* read_off, uint32_t n,
                              uint64_t* cid_off, uint32_t* cids, uint64_t cap, int nthreads) {
-    auto* h = static_cast<ref_handle*>(hp);
     auto run = [&](auto const& idx) {
         return run_batch(n, nthreads, cid_off, cids, cap, [&](uint64_t i, std::vector<uint32_t>& res) {
             std::string seq(bases + read_off[i], read_off[i + 1] - read_off[i]);
             idx.fetch_color_set_ids(seq, res);
         });
     };
-    return h->type == 0 ? run(h->h) : run(h->m);
+    return on_index(hp, run);
 }
 
 /* whole path for a batch; algo 0 = full intersection, 1 = threshold union */
 int fref_pseudoalign(void* hp, int algo, double threshold, const char* bases,
                      const uint64_t* read_off, uint32_t n, uint64_t* color_off, uint32_t* colors,
                      uint64_t cap, int nthreads) {
-    auto* h = static_cast<ref_handle*>(hp);
     auto run = [&](auto const& idx) {
         return run_batch(n, nthreads, color_off, colors, cap,
                          [&](uint64_t i, std::vector<uint32_t>& res) {
@@ -213,7 +219,7 @@ int fref_pseudoalign(void* hp, int algo, double threshold, const char* bases,
                              }
                          });
     };
-    return h->type == 0 ? run(h->h) : run(h->m);
+    return on_index(hp, run);
 }
 
 }  // extern "C"
