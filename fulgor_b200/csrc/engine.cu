@@ -145,7 +145,8 @@ static dev_index make_view(const fgi_header& H, const uint8_t* base) {
         I.skew_phf[i] = H.skew_phf[i];
         I.skew_pos_base[i] = H.skew_pos_base[i];
     }
-    I.type = H.type;
+    I.type = H.type & 1u;
+    I.diff = (H.type >> 1) & 1u;
     I.num_colors = H.num_colors;
     I.num_partitions = H.num_partitions;
     I.main_seed = 0;
@@ -351,6 +352,9 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
                 s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */
+        if (x->I.diff)
+            throw std::runtime_error("differential indexes (.dfur/.mdfur) with more than 32 colors need the decoded color-set table "
+                                     "(it did not fit FULGOR_GPU_TABLE_MAX_MB / the free device memory)");
         if (max_kmers == 0) { /* full intersection counts sets, at most as many as positive k-mers */
             FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
             FG_CUDA(cudaStreamSynchronize(s.stream));

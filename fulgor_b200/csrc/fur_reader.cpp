@@ -294,6 +294,70 @@ struct flattener {
         color_words.push_back(0);
         hybrids.push_back(h);
     }
+
+    /* include/color_sets/differential.hpp:322-339. A set is stored as its symmetric difference with the representative of
+       its cluster (:8-96); color_set(i) pairs m_color_set_offsets[i] with m_representative_offsets[rank1(m_clusters, i)]
+       (:289-295), where m_clusters has a one at the last set of every cluster. Both offset sequences become plain arrays
+       here: num_sets + 1 bit offsets of the difference lists (the last one = end of the stream), then num_sets bit offsets
+       of the representative each set refers to. */
+    void read_differential(byte_reader& r) {
+        fgi_hybrid h{};
+        h.num_colors = r.pod<uint32_t>();
+        h.kind = FGI_SETS_DIFFERENTIAL;
+        elias_fano rep_offs, set_offs;
+        rep_offs.read(r);
+        set_offs.read(r);
+        bit_vector bits, clusters;
+        bits.read(r);
+        clusters.read(r);
+        r.vec<uint64_t>(); /* rank9 index over m_clusters: replaced by the sequential pass below */
+        h.num_sets = set_offs.size();
+        if (clusters.num_bits != h.num_sets) throw std::runtime_error("differential color sets: clusters/offsets size mismatch");
+        h.set_off_base = set_bit_off.size();
+        h.word_base = color_words.size();
+        for (uint64_t v : set_offs.decode()) set_bit_off.push_back(v);
+        set_bit_off.push_back(bits.num_bits);
+        const std::vector<uint64_t> reps = rep_offs.decode();
+        uint64_t cluster = 0;
+        for (uint64_t i = 0; i < h.num_sets; ++i) {
+            if (cluster >= reps.size()) throw std::runtime_error("differential color sets: more clusters than representatives");
+            set_bit_off.push_back(reps[cluster]);
+            cluster += (clusters.words[i >> 6] >> (i & 63)) & 1;
+        }
+        color_words.insert(color_words.end(), bits.words.begin(), bits.words.end());
+        color_words.push_back(0);
+        color_words.push_back(0);
+        hybrids.push_back(h);
+    }
+};
+
+/* LSB-first reader over a bit_vector for the load-time decoding of the meta-differential lists
+   (bits/bit_vector.hpp:234-294, Elias delta bits/integer_codes.hpp:54-71) */
+struct host_bit_cursor {
+    const bit_vector& b;
+    uint64_t pos;
+    uint64_t take(uint64_t l) {
+        if (l == 0) return 0;
+        if (pos + l > b.num_bits) throw std::runtime_error("bit stream overrun while decoding color-set lists");
+        const uint64_t w = pos >> 6, s = pos & 63;
+        uint64_t v = b.words[w] >> s;
+        if (s + l > 64) v |= b.words[w + 1] << (64 - s);
+        pos += l;
+        return l == 64 ? v : (v & ((1ULL << l) - 1));
+    }
+    uint64_t unary() {
+        uint64_t n = 0;
+        while (take(1) == 0) ++n;
+        return n;
+    }
+    uint64_t gamma() {
+        const uint64_t n = unary();
+        return (take(n) | (1ULL << n)) - 1;
+    }
+    uint64_t delta() {
+        const uint64_t n = gamma();
+        return (take(n) | (1ULL << n)) - 1;
+    }
 };
 
 bool ends_with(std::string const& s, const char* suf) {
@@ -401,6 +465,81 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
             part_sets_before.push_back(e.num_color_sets_before);
         }
     }
+    if (type == 2) { /* include/color_sets/differential.hpp:322-339 */
+        F.read_differential(r);
+        H.num_colors = F.hybrids[0].num_colors;
+        H.num_color_sets = F.hybrids[0].num_sets;
+        H.num_partitions = 1;
+    }
+    if (type == 3) { /* include/color_sets/meta_differential.hpp:306-331 */
+        H.num_colors = r.pod<uint32_t>();
+        r.pod<uint32_t>(); /* m_num_partition_sets */
+        elias_fano ps_offs, rel_offs;
+        ps_offs.read(r);
+        rel_offs.read(r);
+        struct endpoint { uint64_t min_color, num_color_sets; }; /* meta_differential.hpp:8-16 */
+        std::vector<endpoint> eps = r.vec<endpoint>();
+        const uint64_t np = r.pod<uint64_t>();
+        if (np > uint64_t(r.end - r.p)) throw std::runtime_error("index file truncated (partial color sets)");
+        if (eps.size() != np || np == 0) throw std::runtime_error("meta-differential color sets: endpoints/partitions size mismatch");
+        for (uint64_t i = 0; i < np; ++i) F.read_differential(r);
+        bit_vector relative_colors, partition_sets, ps_partitions;
+        relative_colors.read(r);
+        partition_sets.read(r);
+        ps_partitions.read(r);
+        r.vec<uint64_t>(); /* rank9 index over m_partition_sets_partitions */
+        const std::vector<uint64_t> pso = ps_offs.decode(), rco = rel_offs.decode();
+        if (rco.empty()) throw std::runtime_error("meta-differential color sets: empty offsets");
+        H.num_color_sets = rco.size() - 1;
+        H.num_partitions = uint32_t(np);
+        if (ps_partitions.num_bits != H.num_color_sets) throw std::runtime_error("meta-differential color sets: partition-set marks/offsets size mismatch");
+        uint64_t before = 0;
+        for (uint64_t p = 0; p < np; ++p) {
+            if (eps[p].num_color_sets != F.hybrids[p].num_sets) throw std::runtime_error("meta-differential color sets: endpoint/partition set count mismatch");
+            part_min_color.push_back(uint32_t(eps[p].min_color));
+            part_sets_before.push_back(uint32_t(before));
+            before += eps[p].num_color_sets;
+        }
+        part_min_color.push_back(H.num_color_sets ? H.num_colors : 0);
+        part_sets_before.push_back(uint32_t(before));
+        /* every set's list of partial sets, decoded once into the records the meta index uses ([n, meta color 1..n], meta
+           color = sets before its partition + relative id): the partition ids come from the delta-coded partition set shared
+           by a group of color sets (forward_iterator::init / read_partition_id, meta_differential.hpp:126-193; the group of
+           set i is rank1(m_partition_sets_partitions, i), :286-293), the relative ids from fixed-width fields of
+           msb(num_color_sets of the partition) + 1 bits (:184-191). */
+        uint64_t group = 0;
+        std::vector<uint32_t> parts_of_group;
+        bool group_loaded = false;
+        for (uint64_t i = 0; i < H.num_color_sets; ++i) {
+            if (!group_loaded) {
+                if (group >= pso.size()) throw std::runtime_error("meta-differential color sets: more groups than partition sets");
+                host_bit_cursor c{partition_sets, pso[group]};
+                const uint64_t n = c.delta();
+                parts_of_group.clear();
+                uint64_t pid = 0;
+                for (uint64_t j = 0; j < n; ++j) {
+                    pid += c.delta();
+                    if (pid >= np) throw std::runtime_error("meta-differential color sets: partition id out of range");
+                    parts_of_group.push_back(uint32_t(pid));
+                }
+                group_loaded = true;
+            }
+            meta_off.push_back(meta_vals.size());
+            meta_vals.push_back(uint32_t(parts_of_group.size()));
+            host_bit_cursor rc{relative_colors, rco[i]};
+            for (uint32_t pid : parts_of_group) {
+                const uint64_t width = 64 - uint64_t(__builtin_clzll(eps[pid].num_color_sets));
+                const uint64_t rel = rc.take(width);
+                if (rel >= eps[pid].num_color_sets) throw std::runtime_error("meta-differential color sets: relative id out of range");
+                meta_vals.push_back(part_sets_before[pid] + uint32_t(rel));
+            }
+            if ((ps_partitions.words[i >> 6] >> (i & 63)) & 1) {
+                ++group;
+                group_loaded = false;
+            }
+        }
+        meta_off.push_back(meta_vals.size());
+    }
     /* filenames (include/filenames.hpp:37-41) are not needed on the device */
     r.vec<uint32_t>();
     r.vec<char>();
@@ -413,7 +552,9 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
     H.num_unitigs = pieces.size() - 1;
     H.num_minimizers = nskb.size() - 1;
     H.num_super_kmers = offsets.size;
-    if (u2c.num_bits != H.num_unitigs) throw std::runtime_error("u2c size does not match the number of unitigs");
+    /* the differential builders allocate one bit more (include/builders/differential_builder.hpp:335-336) */
+    if (u2c.num_bits != H.num_unitigs && !(type >= 2 && u2c.num_bits == H.num_unitigs + 1))
+        throw std::runtime_error("u2c size does not match the number of unitigs");
     if (H.num_super_kmers >= (1ULL << 32) || pieces.back() >= (1ULL << 31))
         throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / 31-bit string offsets");
     if (H.k - H.m + 1 > 31) throw std::runtime_error("k - m + 1 > 31 is not supported");
@@ -546,8 +687,8 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
 int index_type_from_path(const char* path) {
     /* the reference infers the index type from the file suffix only (tools/util.cpp:5-19) */
     std::string p(path);
-    if (ends_with(p, ".mdfur")) return -2;
-    if (ends_with(p, ".dfur")) return -2;
+    if (ends_with(p, ".mdfur")) return 3;
+    if (ends_with(p, ".dfur")) return 2;
     if (ends_with(p, ".mfur")) return 1;
     if (ends_with(p, ".fur")) return 0;
     return -1;
@@ -555,7 +696,6 @@ int index_type_from_path(const char* path) {
 
 std::vector<uint8_t> build_image_from_file(const char* path) {
     const int type = index_type_from_path(path);
-    if (type == -2) throw std::runtime_error(std::string("differential indexes (.dfur/.mdfur) are not supported yet: ") + path);
     if (type < 0) throw std::runtime_error(std::string("Wrong index filename supplied: ") + path);
     FILE* f = std::fopen(path, "rb");
     if (!f) throw std::runtime_error(std::string("error in opening binary file: ") + path);

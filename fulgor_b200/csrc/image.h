@@ -25,7 +25,7 @@
 
 #include <stdint.h>
 
-#define FGI_MAGIC 0x3230474D49475546ULL /* "FUGIMG02" */
+#define FGI_MAGIC 0x3330474D49475546ULL /* "FUGIMG03" */
 #define FGI_ALIGN 256
 
 /* one single_phf partition (pthash/include/single_phf.hpp:140-150). The three moduli (table size, dense / sparse bucket
@@ -51,11 +51,16 @@ struct fgi_phf {
     uint64_t num_keys;
 };
 
-/* one hybrid color-set container (include/color_sets/hybrid.hpp:339-345) */
+/* one color-set container: hybrid (include/color_sets/hybrid.hpp:339-345) or differential
+   (include/color_sets/differential.hpp:322-339; sparse_thr / very_dense_thr unused) */
+#define FGI_SETS_HYBRID 0
+#define FGI_SETS_DIFFERENTIAL 1
 struct fgi_hybrid {
-    uint32_t num_colors, sparse_thr, very_dense_thr, pad;
+    uint32_t num_colors, sparse_thr, very_dense_thr, kind;
     uint64_t num_sets;
-    uint64_t set_off_base; /* first entry in set_bit_off[] (num_sets + 1 entries, bit offsets) */
+    uint64_t set_off_base; /* first entry in set_bit_off[]: num_sets + 1 bit offsets of the sets (hybrid) or of their difference
+                              lists (differential); a differential container adds num_sets more entries, the bit offset of
+                              the representative each set is coded against */
     uint64_t word_base;    /* first u64 word of this container's bit stream in color_words[] */
 };
 
@@ -78,7 +83,8 @@ struct fgi_header {
     uint32_t skew_phf[FGI_MAX_SKEW];      /* index into phfs[]; phfs[0] is the minimizer MPHF */
     uint64_t skew_pos_base[FGI_MAX_SKEW]; /* first entry in skew_positions[] */
     /* colors */
-    uint32_t type;            /* 0 hybrid (.fur), 1 meta (.mfur) */
+    uint32_t type;            /* 0 hybrid (.fur), 1 meta (.mfur), 2 differential (.dfur), 3 meta-differential (.mdfur):
+                                 bit 0 = a set is a list of partial sets, bit 1 = the containers are differential */
     uint32_t num_colors;
     uint64_t num_color_sets;
     uint32_t num_partitions;  /* meta: number of partial color-set containers; hybrid: 1 */

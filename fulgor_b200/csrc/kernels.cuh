@@ -92,10 +92,12 @@ struct dev_index {
     uint64_t hash_magic, bucketer_T;
     uint32_t k, m;
     uint32_t skew_min_log2, skew_max_log2, skew_log2_max_bucket, num_skew;
-    uint32_t skew_threshold, pad1; /* buckets with more super-k-mers go through the skew index; UINT32_MAX when there is none */
+    uint32_t skew_threshold; /* buckets with more super-k-mers go through the skew index; UINT32_MAX when there is none */
+    uint32_t diff;           /* 1: the containers are differential (.dfur / .mdfur), see fgi_hybrid */
     uint32_t skew_phf[FGI_MAX_SKEW];
     uint64_t skew_pos_base[FGI_MAX_SKEW];
-    uint32_t type, num_colors, num_partitions, guard_max_hash;
+    uint32_t type; /* 0: a color set is one set of container 0; 1: a list of partial sets (.mfur / .mdfur) */
+    uint32_t num_colors, num_partitions, guard_max_hash;
     uint64_t main_seed, main_nparts; /* the minimizer MPHF (phfs[0]; its partitions are parts[0 .. main_nparts)) */
     fgi_phf_part main_part;          /* parts[0] */
     /* the decoded color-set table: row i = color set i as a bitmap of num_colors bits padded to table_stride 32-bit words.
@@ -1025,17 +1027,43 @@ FG_HD uint32_t hybrid_set_mask(const dev_index& I, uint32_t container, uint64_t 
     return complement ? (~mask & cmask) : mask;
 }
 
+/* One differential color set (include/color_sets/differential.hpp:256-287) of a container with at most 32 colors: the
+   symmetric difference of its difference list and its cluster's representative (both delta-coded gap lists; the
+   difference list carries a second header, the size of the decoded set). */
+FG_HD uint32_t differential_set_mask(const dev_index& I, uint32_t container, uint64_t local_id) {
+    const fgi_hybrid* h = I.hybrids + container;
+    const uint64_t* words = I.color_words + FG_LDG(&h->word_base);
+    const uint64_t base = FG_LDG(&h->set_off_base);
+    uint32_t mask = 0;
+    for (uint32_t part = 0; part < 2; ++part) {
+        uint64_t pos = FG_LDG(I.set_bit_off + base + (part ? FG_LDG(&h->num_sets) + 1 : 0) + local_id);
+        const uint32_t n = read_delta(words, pos);
+        if (part == 0) read_delta(words, pos);
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t d = read_delta(words, pos);
+            v = i ? v + d + 1 : d;
+            mask ^= 1u << (v & 31);
+        }
+    }
+    return mask;
+}
+
+FG_HD uint32_t partial_set_mask(const dev_index& I, uint32_t container, uint64_t local_id) {
+    return I.diff ? differential_set_mask(I, container, local_id) : hybrid_set_mask(I, container, local_id);
+}
+
 /* color set `cid` of the index as a mask (num_colors <= 32). Meta (include/color_sets/meta.hpp:93-236):
    the set is the concatenation of its partial sets, each shifted by its partition's min_color. */
 FG_HD uint32_t color_set_mask(const dev_index& I, uint32_t cid) {
-    if (I.type == 0) return hybrid_set_mask(I, 0, cid);
+    if (I.type == 0) return partial_set_mask(I, 0, cid);
     const uint64_t b = FG_LDG(I.meta_off + cid);
     const uint32_t n = FG_LDG(I.meta_vals + b);
     uint32_t mask = 0, p = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t mc = FG_LDG(I.meta_vals + b + 1 + i);
         while (p + 1 < I.num_partitions && mc >= FG_LDG(I.part_sets_before + p + 1)) ++p; /* meta.hpp:227-235 */
-        mask |= hybrid_set_mask(I, p, mc - FG_LDG(I.part_sets_before + p)) << FG_LDG(I.part_min_color + p);
+        mask |= partial_set_mask(I, p, mc - FG_LDG(I.part_sets_before + p)) << FG_LDG(I.part_min_color + p);
     }
     return mask;
 }

@@ -426,18 +426,40 @@ __global__ void __launch_bounds__(FG_BLOCK) k_expand_color_sets(const __grid_con
             units = __ldg(I.meta_vals + list);
         }
         for (uint32_t u = lane; u < units; u += 32) {
-            set_item it;
-            if (I.type == 0) {
-                it = open_set(I, 0, cid, 0);
-            } else { /* meta.hpp:227-235 */
+            uint32_t container = 0, color_base = 0;
+            uint64_t local_id = cid;
+            if (I.type != 0) { /* meta.hpp:227-235 */
                 const uint32_t mc = __ldg(I.meta_vals + list + 1 + u);
                 uint32_t plo = 0, phi = P;
                 while (phi - plo > 1) {
                     const uint32_t mid = (plo + phi) >> 1;
                     if (__ldg(I.part_sets_before + mid) <= mc) plo = mid; else phi = mid;
                 }
-                it = open_set(I, plo, mc - __ldg(I.part_sets_before + plo), __ldg(I.part_min_color + plo));
+                container = plo;
+                local_id = mc - __ldg(I.part_sets_before + plo);
+                color_base = __ldg(I.part_min_color + plo);
             }
+            if (I.diff) { /* differential.hpp:256-287: the set = representative XOR difference list, both gap lists; the row's
+                             bits of this partition's color range are zero before, and no other unit touches them */
+                const fgi_hybrid* h = I.hybrids + container;
+                const uint64_t* words = I.color_words + __ldg(&h->word_base);
+                const uint64_t base = __ldg(&h->set_off_base);
+                for (uint32_t part = 0; part < 2; ++part) {
+                    bit_cursor cur;
+                    cur.open(words, __ldg(I.set_bit_off + base + (part ? __ldg(&h->num_sets) + 1 : 0) + local_id));
+                    const uint32_t n = cur.delta();
+                    if (part == 0) cur.delta(); /* size of the decoded set */
+                    uint32_t v = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint32_t d = cur.delta();
+                        v = i ? v + d + 1 : d;
+                        const uint32_t c = color_base + v;
+                        atomicXor(row + (c >> 5), 1u << (c & 31));
+                    }
+                }
+                continue;
+            }
+            const set_item it = open_set(I, container, local_id, color_base);
             if (it.enc != FG_ENC_DELTA) { /* bitmap: its bits; complement: the whole range first */
                 for (uint32_t w = it.color_base >> 5; 32 * w < it.color_base + it.num_colors; ++w) {
                     uint32_t gmask;

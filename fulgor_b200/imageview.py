@@ -24,13 +24,13 @@ class Header(C.Structure):
     ]
 
 
-HYBRID_DTYPE = np.dtype([("num_colors", "<u4"), ("sparse_thr", "<u4"), ("very_dense_thr", "<u4"), ("pad", "<u4"),
+HYBRID_DTYPE = np.dtype([("num_colors", "<u4"), ("sparse_thr", "<u4"), ("very_dense_thr", "<u4"), ("kind", "<u4"),
                          ("num_sets", "<u8"), ("set_off_base", "<u8"), ("word_base", "<u8")])
 
 
 def header(image):
     h = Header.from_buffer_copy(image[: C.sizeof(Header)].tobytes())
-    assert h.magic == 0x3230474D49475546 and h.total_bytes == image.size, "not a fulgor-b200 image"
+    assert h.magic == 0x3330474D49475546 and h.total_bytes == image.size, "not a fulgor-b200 image"
     return h
 
 
@@ -48,23 +48,35 @@ def bucket_sizes(image):
     return np.diff(section(image, h.off_bucket_begin, "<u4", h.num_minimizers + 1).astype(np.int64))
 
 
+def _container_set_bits(image, h, hy):
+    """compressed bits one query of each set of a container reads: the set itself (hybrid), or its difference list plus the
+    representative it is coded against (differential; the representative of a cluster sits right before the cluster's first set)"""
+    n = int(hy["num_sets"])
+    base = h.off_set_bit_off + 8 * int(hy["set_off_base"])
+    off = section(image, base, "<u8", n + 1).astype(np.int64)
+    bits = np.diff(off)
+    if int(hy["kind"]) == 1:
+        rep = section(image, base + 8 * (n + 1), "<u8", n).astype(np.int64)
+        first = np.ones(n, dtype=bool)
+        first[1:] = rep[1:] != rep[:-1]
+        rep_end = off[:-1][first][np.cumsum(first) - 1]  # offset of the first set of each set's cluster
+        bits = bits + (rep_end - rep)
+    return bits
+
+
 def color_set_bits(image):
     """compressed size in bits of every color set: m_offsets[c+1] - m_offsets[c] for a hybrid index (reference
     include/color_sets/hybrid.hpp:309-313); for a meta index the bits of the partial sets it visits plus 64 per meta list
-    (SURVEY.md 8(d))."""
+    (SURVEY.md 8(d)); differential containers add the representative's bits."""
     h = header(image)
     hy = hybrids(image)
-    if h.type == 0:
-        off = section(image, h.off_set_bit_off + 8 * int(hy[0]["set_off_base"]), "<u8", int(hy[0]["num_sets"]) + 1)
-        return np.diff(off.astype(np.int64))
+    if h.type in (0, 2):
+        return _container_set_bits(image, h, hy[0])
     meta_off = section(image, h.off_meta_off, "<u8", h.num_color_sets + 1).astype(np.int64)
     meta_vals = section(image, h.off_meta_vals, "<u4", int(meta_off[-1]))
     before = section(image, h.off_part_sets_before, "<u4", h.num_partitions + 1).astype(np.int64)
-    partial_bits = []
-    for p in range(h.num_partitions):
-        off = section(image, h.off_set_bit_off + 8 * int(hy[p]["set_off_base"]), "<u8", int(hy[p]["num_sets"]) + 1)
-        partial_bits.append(np.diff(off.astype(np.int64)))
-    partial_bits = np.concatenate(partial_bits)  # indexed by meta color (partitions are consecutive ranges of meta colors)
+    partial_bits = np.concatenate([_container_set_bits(image, h, hy[p]) for p in range(h.num_partitions)])
+    # indexed by meta color (partitions are consecutive ranges of meta colors)
     out = np.zeros(h.num_color_sets, dtype=np.int64)
     for c in range(h.num_color_sets):
         b = int(meta_off[c])

@@ -51,7 +51,7 @@ typedef struct fulgor_gpu_info {
     uint32_t k, m;
     uint64_t num_kmers, num_unitigs, num_color_sets;
     uint32_t num_colors;
-    uint32_t type;        /* 0 = hybrid (.fur), 1 = meta (.mfur) */
+    uint32_t type;        /* 0 = hybrid (.fur), 1 = meta (.mfur), 2 = differential (.dfur), 3 = meta-differential (.mdfur) */
     uint64_t image_bytes; /* size of the flattened device image */
     int32_t device;       /* CUDA device ordinal the handle is bound to; -1 for a host-only image */
     uint32_t pad;

@@ -258,10 +258,24 @@ static void rd_hybrid(rd* r, hybrid* h) {
     rd_ef(r, &h->offsets); rd_bitvec(r, &h->sets);
 }
 
+typedef struct { /* include/color_sets/differential.hpp:322-339 */
+    uint32_t num_colors;
+    efseq representative_offsets, color_set_offsets;
+    bitvec sets, clusters;
+    const uint8_t* rank9;
+    uint64_t rank9_words;
+} differential;
+static void rd_differential(rd* r, differential* d) {
+    d->num_colors = rd_u32(r);
+    rd_ef(r, &d->representative_offsets); rd_ef(r, &d->color_set_offsets);
+    rd_bitvec(r, &d->sets); rd_bitvec(r, &d->clusters);
+    d->rank9 = rd_vec(r, 8, &d->rank9_words);
+}
+
 struct fo_index {
     uint8_t* buf;
     uint64_t size;
-    int type; /* 0 hybrid, 1 meta */
+    int type; /* 0 hybrid, 1 meta, 2 differential, 3 meta-differential */
     /* sshash::dictionary (sshash/include/dictionary.hpp:141-154) */
     uint64_t num_kmers, k, m, magic;
     part_phf minimizers;
@@ -286,6 +300,17 @@ struct fo_index {
     hybrid* partial;
     uint64_t n_endpoints;
     const uint8_t* endpoints; /* {u32 min_color, u32 num_color_sets_before} */
+    differential dif;         /* .dfur */
+    /* include/color_sets/meta_differential.hpp:306-331 (.mdfur); meta_num_colors and n_partial are shared with .mfur */
+    uint32_t md_num_partition_sets;
+    efseq md_partition_sets_offsets, md_relative_colors_offsets;
+    uint64_t md_n_endpoints;
+    const uint8_t* md_endpoints; /* {u64 min_color, u64 num_color_sets} per partition */
+    differential* md_partial;
+    bitvec md_relative_colors, md_partition_sets, md_partition_sets_partitions;
+    const uint8_t* md_rank9;
+    uint64_t md_rank9_words;
+    uint64_t* md_sets_before;   /* prefix sums of num_color_sets (what forward_iterator::read_partition_id accumulates, :181-183) */
 };
 
 static int ends_with(const char* s, const char* suf) {
@@ -295,7 +320,9 @@ static int ends_with(const char* s, const char* suf) {
 
 fo_index* fo_open(const char* path) {
     int type;
-    if (ends_with(path, ".mfur")) type = 1;
+    if (ends_with(path, ".mdfur")) type = 3;
+    else if (ends_with(path, ".dfur")) type = 2;
+    else if (ends_with(path, ".mfur")) type = 1;
     else if (ends_with(path, ".fur")) type = 0;
     else { snprintf(g_err, sizeof g_err, "unsupported index suffix: %s", path); return NULL; }
     FILE* f = fopen(path, "rb");
@@ -338,6 +365,23 @@ fo_index* fo_open(const char* path) {
     x->rank9 = rd_vec(&r, 8, &x->rank9_words);
     if (type == 0) {
         rd_hybrid(&r, &x->hyb);
+    } else if (type == 2) {
+        rd_differential(&r, &x->dif);
+    } else if (type == 3) {
+        x->meta_num_colors = rd_u32(&r);
+        x->md_num_partition_sets = rd_u32(&r);
+        rd_ef(&r, &x->md_partition_sets_offsets); rd_ef(&r, &x->md_relative_colors_offsets);
+        x->md_endpoints = rd_vec(&r, 16, &x->md_n_endpoints);
+        x->n_partial = rd_u64(&r);
+        if (x->n_partial > (uint64_t)(r.end - r.p) || x->n_partial != x->md_n_endpoints) r.bad = 1;
+        if (!r.bad) {
+            x->md_partial = (differential*)calloc(x->n_partial ? x->n_partial : 1, sizeof(differential));
+            for (uint64_t i = 0; i < x->n_partial && !r.bad; ++i) rd_differential(&r, &x->md_partial[i]);
+            x->md_sets_before = (uint64_t*)calloc(x->n_partial + 1, sizeof(uint64_t));
+            for (uint64_t i = 0; i < x->n_partial; ++i) x->md_sets_before[i + 1] = x->md_sets_before[i] + ld64(x->md_endpoints + 16 * i + 8);
+        }
+        rd_bitvec(&r, &x->md_relative_colors); rd_bitvec(&r, &x->md_partition_sets); rd_bitvec(&r, &x->md_partition_sets_partitions);
+        x->md_rank9 = rd_vec(&r, 8, &x->md_rank9_words);
     } else {
         x->meta_num_colors = rd_u32(&r);
         rd_cvec(&r, &x->meta_sets);
@@ -365,15 +409,21 @@ void fo_close(fo_index* x) {
     if (!x) return;
     free_part(&x->minimizers);
     if (x->skew_mphfs) for (uint64_t i = 0; i < x->n_skew; ++i) free_part(&x->skew_mphfs[i]);
-    free(x->skew_mphfs); free(x->skew_positions); free(x->partial); free(x->buf); free(x);
+    free(x->skew_mphfs); free(x->skew_positions); free(x->partial); free(x->md_partial); free(x->md_sets_before); free(x->buf); free(x);
 }
 
-static uint32_t index_num_colors(const fo_index* x) { return x->type == 0 ? x->hyb.num_colors : x->meta_num_colors; }
+static uint32_t index_num_colors(const fo_index* x) {
+    return x->type == 0 ? x->hyb.num_colors : x->type == 2 ? x->dif.num_colors : x->meta_num_colors;
+}
 static uint64_t index_num_color_sets(const fo_index* x) {
+    if (x->type == 2) return ef_size(&x->dif.color_set_offsets);            /* differential.hpp:297 */
+    if (x->type == 3) return ef_size(&x->md_relative_colors_offsets) - 1;   /* meta_differential.hpp:296 */
     return (x->type == 0 ? ef_size(&x->hyb.offsets) : ef_size(&x->meta_offsets)) - 1;
 }
 void fo_info(const fo_index* x, uint64_t* out) {
-    out[0] = x->k; out[1] = x->m; out[2] = x->num_kmers; out[3] = x->u2c.num_bits;
+    out[0] = x->k; out[1] = x->m; out[2] = x->num_kmers;
+    out[3] = ef_size(&x->pieces) - 1; /* num_unitigs = m_k2u.num_contigs(), include/index.hpp:67 (the differential builders' u2c has one bit more) */
+   
     out[4] = index_num_colors(x); out[5] = index_num_color_sets(x); out[6] = (uint64_t)x->type;
 }
 
@@ -636,6 +686,43 @@ static uint32_t decoded_expand(const decoded* d, uint32_t num_colors, uint32_t a
     return n;
 }
 
+/* A differential set opened like differential::color_set + forward_iterator::init (differential.hpp:289-295, :256-278):
+   the difference list (header: its length, then the size of the decoded set) and the representative of the set's cluster
+   (cluster = rank1(m_clusters, id)), both as ascending values. */
+typedef struct {
+    uint64_t representative_begin;
+    uint32_t size;          /* colors in the decoded set */
+    uint32_t nd, nr;
+    uint32_t *dv, *rv;      /* difference list, representative */
+} diffset;
+static void gap_list(bitcur* c, uint32_t n, uint32_t* out) {
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < n; ++i) { v = i == 0 ? (uint32_t)cur_delta(c) : v + (uint32_t)cur_delta(c) + 1; out[i] = v; }
+}
+static void diff_open(const differential* d, uint64_t id, diffset* s) {
+    bitcur cd = {&d->sets, ef_access(&d->color_set_offsets, id)};
+    s->representative_begin = ef_access(&d->representative_offsets, rank9_rank1(d->rank9, d->rank9_words, &d->clusters, id));
+    bitcur cr = {&d->sets, s->representative_begin};
+    s->nd = (uint32_t)cur_delta(&cd);
+    s->nr = (uint32_t)cur_delta(&cr);
+    s->size = (uint32_t)cur_delta(&cd);
+    s->dv = (uint32_t*)malloc(sizeof(uint32_t) * (s->nd ? s->nd : 1));
+    s->rv = (uint32_t*)malloc(sizeof(uint32_t) * (s->nr ? s->nr : 1));
+    gap_list(&cd, s->nd, s->dv);
+    gap_list(&cr, s->nr, s->rv);
+}
+static void diff_close(diffset* s) { free(s->dv); free(s->rv); }
+/* the colors forward_iterator::next / update_curr_val enumerate (:203-217, :280-288): values in exactly one of the lists */
+static uint32_t diff_expand(const diffset* s, uint32_t add, uint32_t* out) {
+    uint32_t i = 0, j = 0, n = 0;
+    while (i < s->nd || j < s->nr) {
+        if (j == s->nr || (i < s->nd && s->dv[i] < s->rv[j])) out[n++] = s->dv[i++] + add;
+        else if (i == s->nd || s->rv[j] < s->dv[i]) out[n++] = s->rv[j++] + add;
+        else { ++i; ++j; }
+    }
+    return n;
+}
+
 /* include/color_sets/meta.hpp:227-235 */
 static uint32_t meta_partition_of(const fo_index* x, uint32_t meta_color, uint32_t partition_id) {
     while (partition_id + 1 < x->n_endpoints && meta_color >= ld32(x->endpoints + 8 * (partition_id + 1) + 4)) ++partition_id;
@@ -643,6 +730,43 @@ static uint32_t meta_partition_of(const fo_index* x, uint32_t meta_color, uint32
 }
 static uint32_t ep_min_color(const fo_index* x, uint32_t p) { return ld32(x->endpoints + 8 * p); }
 static uint32_t ep_sets_before(const fo_index* x, uint32_t p) { return ld32(x->endpoints + 8 * p + 4); }
+
+typedef struct { uint32_t n; uint32_t* mc; uint32_t* part; } meta_list; /* meta colors of one set + their partitions */
+static uint32_t md_min_color(const fo_index* x, uint32_t p) { return (uint32_t)ld64(x->md_endpoints + 16 * p); }
+static uint32_t md_sets_before(const fo_index* x, uint32_t p) { return (uint32_t)x->md_sets_before[p]; }
+static uint64_t msbll(uint64_t v) { return 63 - (uint64_t)__builtin_clzll(v); } /* bits/include/util.hpp msbll */
+/* meta_differential::color_set + forward_iterator::init / read_partition_id (meta_differential.hpp:286-293, :126-193): the set's
+   group of partitions is the delta-coded partition set number rank1(m_partition_sets_partitions, id) (gaps between partition
+   ids), its relative set ids are fields of msb(num_color_sets of the partition) + 1 bits; meta color = sets before + relative */
+static void md_list_load(const fo_index* x, uint64_t id, meta_list* l) {
+    uint64_t group = rank9_rank1(x->md_rank9, x->md_rank9_words, &x->md_partition_sets_partitions, id);
+    bitcur cp = {&x->md_partition_sets, ef_access(&x->md_partition_sets_offsets, group)};
+    bitcur cr = {&x->md_relative_colors, ef_access(&x->md_relative_colors_offsets, id)};
+    l->n = (uint32_t)cur_delta(&cp);
+    l->mc = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
+    l->part = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
+    uint64_t pid = 0;
+    for (uint32_t i = 0; i < l->n; ++i) {
+        pid += cur_delta(&cp);
+        uint64_t rel = cur_take(&cr, msbll(ld64(x->md_endpoints + 16 * pid + 8)) + 1);
+        l->part[i] = (uint32_t)pid;
+        l->mc[i] = md_sets_before(x, (uint32_t)pid) + (uint32_t)rel;
+    }
+}
+static void meta_list_load(const fo_index* x, uint64_t id, meta_list* l) {
+    if (x->type == 3) { md_list_load(x, id, l); return; }
+    uint64_t b = ef_access(&x->meta_offsets, id);
+    l->n = (uint32_t)cv_get(&x->meta_sets, b);
+    l->mc = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
+    l->part = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
+    uint32_t p = 0;
+    for (uint32_t i = 0; i < l->n; ++i) {
+        l->mc[i] = (uint32_t)cv_get(&x->meta_sets, b + 1 + i);
+        p = meta_partition_of(x, l->mc[i], p);
+        l->part[i] = p;
+    }
+}
+static int meta_find(const meta_list* l, uint32_t part) { for (uint32_t i = 0; i < l->n; ++i) if (l->part[i] == part) return (int)i; return -1; }
 
 int64_t fo_color_set(const fo_index* x, uint64_t id, uint32_t* out, uint64_t cap) {
     uint32_t C = index_num_colors(x);
@@ -652,6 +776,18 @@ int64_t fo_color_set(const fo_index* x, uint64_t id, uint32_t* out, uint64_t cap
         decoded d; hybrid_decode(&x->hyb, id, &d);
         n = decoded_expand(&d, C, 0, tmp);
         free(d.vals);
+    } else if (x->type == 2) {
+        diffset s; diff_open(&x->dif, id, &s);
+        n = diff_expand(&s, 0, tmp);
+        diff_close(&s);
+    } else if (x->type == 3) { /* meta_differential.hpp:93-268: the partial (differential) sets, shifted by min_color */
+        meta_list l; meta_list_load(x, id, &l);
+        for (uint32_t i = 0; i < l.n; ++i) {
+            diffset s; diff_open(&x->md_partial[l.part[i]], l.mc[i] - md_sets_before(x, l.part[i]), &s);
+            n += diff_expand(&s, md_min_color(x, l.part[i]), tmp + n);
+            diff_close(&s);
+        }
+        free(l.mc); free(l.part);
     } else { /* include/color_sets/meta.hpp:93-236: concatenation of the partial sets, shifted by min_color */
         uint64_t b = ef_access(&x->meta_offsets, id);
         uint32_t sz = (uint32_t)cv_get(&x->meta_sets, b), p = 0;
@@ -744,27 +880,65 @@ static uint64_t hybrid_intersect(const hybrid* h, decoded* its, uint64_t n, uint
 }
 
 /* ------------------------------------------------------------------ stage 2, meta: src/ps_full_intersection.cpp:243-332 */
-typedef struct { uint32_t n; uint32_t* mc; uint32_t* part; } meta_list; /* meta colors of one set + their partitions */
-static void meta_list_load(const fo_index* x, uint64_t id, meta_list* l) {
-    uint64_t b = ef_access(&x->meta_offsets, id);
-    l->n = (uint32_t)cv_get(&x->meta_sets, b);
-    l->mc = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
-    l->part = (uint32_t*)malloc(sizeof(uint32_t) * (l->n ? l->n : 1));
-    uint32_t p = 0;
-    for (uint32_t i = 0; i < l->n; ++i) {
-        l->mc[i] = (uint32_t)cv_get(&x->meta_sets, b + 1 + i);
-        p = meta_partition_of(x, l->mc[i], p);
-        l->part[i] = p;
-    }
+/* ------------------------------------------------------------------ stage 2, differential: src/ps_full_intersection.cpp:130-240 */
+static int cmp_diffset_rep(const void* a, const void* b) {
+    uint64_t x = ((const diffset*)a)->representative_begin, y = ((const diffset*)b)->representative_begin;
+    return x < y ? -1 : x > y;
 }
-static int meta_find(const meta_list* l, uint32_t part) { for (uint32_t i = 0; i < l->n; ++i) if (l->part[i] == part) return (int)i; return -1; }
+/* Sets that share a representative are intersected through it: counts[c] = how many difference lists contain c; c is in all
+   sets of the group iff (c not in the representative and all lists flip it in) or (c in the representative and no list
+   flips it out) (:166-195). A group of one is decoded (:155-163). The groups are then intersected smallest first (:200-239). */
+static uint64_t diff_intersect(const differential* d, diffset* its, uint64_t n, uint32_t lower_bound, uint32_t* out) {
+    if (n == 0) return 0;
+    const uint32_t C = d->num_colors;
+    qsort(its, n, sizeof(diffset), cmp_diffset_rep);                    /* :136-138 */
+    uint32_t** lists = (uint32_t**)malloc(sizeof(uint32_t*) * n);
+    uint32_t* lens = (uint32_t*)malloc(sizeof(uint32_t) * n);
+    uint32_t* counts = (uint32_t*)calloc(C ? C : 1, sizeof(uint32_t));
+    uint32_t ng = 0;
+    for (uint64_t a = 0; a < n;) {
+        uint64_t b = a + 1;
+        while (b < n && its[b].representative_begin == its[a].representative_begin) ++b;
+        uint32_t* l = (uint32_t*)malloc(sizeof(uint32_t) * (C ? C : 1));
+        uint32_t len = 0;
+        if (b - a == 1) {
+            len = diff_expand(&its[a], 0, l);
+        } else {
+            const uint32_t gsize = (uint32_t)(b - a);
+            for (uint64_t i = a; i < b; ++i) for (uint32_t j = 0; j < its[i].nd; ++j) ++counts[its[i].dv[j]];
+            const diffset* last = &its[b - 1];
+            uint32_t rp = 0;
+            for (uint32_t color = 0; color < C; ++color) {
+                while (rp < last->nr && last->rv[rp] < color) ++rp;
+                const int in_rep = rp < last->nr && last->rv[rp] == color;
+                if ((counts[color] == gsize && !in_rep) || (counts[color] == 0 && in_rep)) l[len++] = color;
+            }
+            memset(counts, 0, sizeof(uint32_t) * C);
+        }
+        lists[ng] = l; lens[ng] = len; ++ng;
+        a = b;
+    }
+    for (uint32_t a = 0; a < ng; ++a) for (uint32_t b = a + 1; b < ng; ++b) if (lens[b] < lens[a]) { /* :197-198 */
+        uint32_t t = lens[a]; lens[a] = lens[b]; lens[b] = t; uint32_t* tp = lists[a]; lists[a] = lists[b]; lists[b] = tp;
+    }
+    uint64_t cnt = 0;
+    int any_empty = 0;
+    for (uint32_t g = 0; g < ng; ++g) if (lens[g] == 0) any_empty = 1;  /* :201-204 */
+    if (!any_empty) {
+        cnt = leapfrog(lists, lens, ng, NULL, out);
+        for (uint64_t i = 0; i < cnt; ++i) out[i] += lower_bound;
+    }
+    for (uint32_t g = 0; g < ng; ++g) free(lists[g]);
+    free(lists); free(lens); free(counts);
+    return cnt;
+}
 
 static uint64_t meta_intersect(const fo_index* x, const uint32_t* cids, uint64_t n, uint32_t* out) {
     if (n == 0) return 0;
     meta_list* ls = (meta_list*)malloc(sizeof(meta_list) * n);
     for (uint64_t i = 0; i < n; ++i) meta_list_load(x, cids[i], &ls[i]);
     uint64_t cnt = 0;
-    const uint32_t P = (uint32_t)(x->n_endpoints - 1);
+    const uint32_t P = x->type == 3 ? (uint32_t)x->n_partial : (uint32_t)(x->n_endpoints - 1);
     for (uint32_t p = 0; p < P; ++p) {
         /* step 1 (:258-281): partition must be present in every set */
         int all = 1;
@@ -778,6 +952,16 @@ static uint64_t meta_intersect(const fo_index* x, const uint32_t* cids, uint64_t
             int dup = 0;
             for (uint32_t j = 0; j < nm; ++j) if (mcs[j] == mc) dup = 1;
             if (!dup) mcs[nm++] = mc;
+        }
+        if (x->type == 3) { /* meta_intersect<Iterator, true>: the partial sets are differential */
+            const differential* d = &x->md_partial[p];
+            diffset* ds = (diffset*)malloc(sizeof(diffset) * nm);
+            for (uint32_t j = 0; j < nm; ++j) diff_open(d, mcs[j] - md_sets_before(x, p), &ds[j]);
+            if (nm == 1) cnt += diff_expand(&ds[0], md_min_color(x, p), out + cnt);               /* :301-306 */
+            else cnt += diff_intersect(d, ds, nm, md_min_color(x, p), out + cnt);                 /* :322-329 */
+            for (uint32_t j = 0; j < nm; ++j) diff_close(&ds[j]);
+            free(ds); free(mcs);
+            continue;
         }
         const hybrid* h = &x->partial[p];
         const uint32_t base = ep_min_color(x, p), sets_before = ep_sets_before(x, p);
@@ -811,7 +995,15 @@ static uint64_t meta_intersect(const fo_index* x, const uint32_t* cids, uint64_t
 
 /* src/ps_full_intersection.cpp:377-400 */
 uint64_t fo_full_intersection(const fo_index* x, const uint32_t* cids, uint64_t n, uint32_t* out) {
-    if (x->type == 1) return meta_intersect(x, cids, n, out);
+    if (x->type == 1 || x->type == 3) return meta_intersect(x, cids, n, out);
+    if (x->type == 2) {
+        diffset* ds = (diffset*)malloc(sizeof(diffset) * (n ? n : 1));
+        for (uint64_t i = 0; i < n; ++i) diff_open(&x->dif, cids[i], &ds[i]);
+        uint64_t c = diff_intersect(&x->dif, ds, n, 0, out);
+        for (uint64_t i = 0; i < n; ++i) diff_close(&ds[i]);
+        free(ds);
+        return c;
+    }
     decoded* its = (decoded*)malloc(sizeof(decoded) * (n ? n : 1));
     for (uint64_t i = 0; i < n; ++i) hybrid_decode(&x->hyb, cids[i], &its[i]);
     uint64_t cnt = hybrid_intersect(&x->hyb, its, n, 0, out);
@@ -874,6 +1066,94 @@ static uint64_t tu_merge_meta(const fo_index* x, const scored* sets, uint64_t n,
     return cnt;
 }
 
+/* merge_diff (:123-186) for the sets of ONE differential container, adding into scores[add + color]: sets sharing a
+   representative are summed through it -- partition_scores[c] = sum of the scores of the lists that flip c, and a color of the
+   representative gets (group score - partition_scores[c]), any other color partition_scores[c] (:160-176); a group of one is
+   decoded (:148-155). */
+typedef struct { diffset s; uint32_t score; } scored_diffset;
+static int cmp_scored_diffset_rep(const void* a, const void* b) {
+    uint64_t x = ((const scored_diffset*)a)->s.representative_begin, y = ((const scored_diffset*)b)->s.representative_begin;
+    return x < y ? -1 : x > y;
+}
+static void tu_add_diff_sets(const differential* d, scored_diffset* its, uint64_t n, uint32_t add, uint32_t* scores) {
+    const uint32_t C = d->num_colors;
+    qsort(its, n, sizeof(scored_diffset), cmp_scored_diffset_rep);
+    uint32_t* partition_scores = (uint32_t*)calloc(C ? C : 1, sizeof(uint32_t));
+    uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * (C ? C : 1));
+    for (uint64_t a = 0; a < n;) {
+        uint64_t b = a + 1;
+        while (b < n && its[b].s.representative_begin == its[a].s.representative_begin) ++b;
+        if (b - a == 1) {
+            uint32_t m = diff_expand(&its[a].s, 0, tmp);
+            for (uint32_t t = 0; t < m; ++t) scores[add + tmp[t]] += its[a].score;
+        } else {
+            uint32_t score = 0;
+            for (uint64_t i = a; i < b; ++i) {
+                score += its[i].score;
+                for (uint32_t j = 0; j < its[i].s.nd; ++j) partition_scores[its[i].s.dv[j]] += its[i].score;
+            }
+            const diffset* last = &its[b - 1].s;
+            uint32_t rp = 0;
+            for (uint32_t color = 0; color < C; ++color) {
+                if (rp < last->nr && last->rv[rp] == color) { scores[add + color] += score - partition_scores[color]; ++rp; }
+                else scores[add + color] += partition_scores[color];
+            }
+            memset(partition_scores, 0, sizeof(uint32_t) * C);
+        }
+        a = b;
+    }
+    free(partition_scores); free(tmp);
+}
+static uint64_t tu_merge_diff(const fo_index* x, const scored* sets, uint64_t n, uint64_t min_score, uint32_t* out) {
+    if (n == 0) return 0;
+    const uint32_t C = x->dif.num_colors;
+    uint32_t* scores = (uint32_t*)calloc(C ? C : 1, sizeof(uint32_t));
+    scored_diffset* its = (scored_diffset*)malloc(sizeof(scored_diffset) * n);
+    for (uint64_t i = 0; i < n; ++i) { diff_open(&x->dif, sets[i].item, &its[i].s); its[i].score = sets[i].score; }
+    tu_add_diff_sets(&x->dif, its, n, 0, scores);
+    uint64_t cnt = 0;
+    for (uint32_t c = 0; c < C; ++c) if ((uint64_t)scores[c] >= min_score) out[cnt++] = c;  /* :183-185 */
+    for (uint64_t i = 0; i < n; ++i) diff_close(&its[i].s);
+    free(its); free(scores);
+    return cnt;
+}
+/* merge_metadiff (:188-318): partitions whose summed score reaches min_score (:200-223); inside such a partition, sets with the
+   same meta color count once with their scores summed (:272-278), then merge_diff's grouping by representative (:280-315) */
+static uint64_t tu_merge_metadiff(const fo_index* x, const scored* sets, uint64_t n, uint64_t min_score, uint32_t* out) {
+    if (n == 0) return 0;
+    const uint32_t C = x->meta_num_colors, P = (uint32_t)x->n_partial;
+    meta_list* ls = (meta_list*)malloc(sizeof(meta_list) * n);
+    for (uint64_t i = 0; i < n; ++i) meta_list_load(x, sets[i].item, &ls[i]);
+    uint32_t* scores = (uint32_t*)calloc(C ? C : 1, sizeof(uint32_t));
+    scored* mcs = (scored*)malloc(sizeof(scored) * n);
+    scored_diffset* its = (scored_diffset*)malloc(sizeof(scored_diffset) * n);
+    for (uint32_t p = 0; p < P; ++p) {
+        uint32_t pscore = 0; uint64_t nm = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            int j = meta_find(&ls[i], p);
+            if (j < 0) continue;
+            pscore += sets[i].score;
+            mcs[nm].item = ls[i].mc[j]; mcs[nm].score = sets[i].score; ++nm;
+        }
+        if (nm == 0 || (uint64_t)pscore < min_score) continue;
+        qsort(mcs, nm, sizeof(scored), cmp_scored);
+        uint64_t nd = 0;
+        for (uint64_t i = 0; i < nm; ++i) {
+            if (i && mcs[i].item == mcs[i - 1].item) { its[nd - 1].score += mcs[i].score; continue; }
+            diff_open(&x->md_partial[p], mcs[i].item - md_sets_before(x, p), &its[nd].s);
+            its[nd].score = mcs[i].score;
+            ++nd;
+        }
+        tu_add_diff_sets(&x->md_partial[p], its, nd, md_min_color(x, p), scores);
+        for (uint64_t i = 0; i < nd; ++i) diff_close(&its[i].s);
+    }
+    uint64_t cnt = 0;
+    for (uint32_t c = 0; c < C; ++c) if ((uint64_t)scores[c] >= min_score) out[cnt++] = c;  /* :315-317 */
+    for (uint64_t i = 0; i < n; ++i) { free(ls[i].mc); free(ls[i].part); }
+    free(ls); free(scores); free(mcs); free(its);
+    return cnt;
+}
+
 /* index::pseudoalign_threshold_union (:321-402) */
 uint64_t fo_threshold_union(const fo_index* x, const char* seq, uint64_t len, double threshold, uint32_t* out) {
     if (len < x->k) return 0;
@@ -902,8 +1182,10 @@ uint64_t fo_threshold_union(const fo_index* x, const char* seq, uint64_t len, do
         else csets[ns++] = csets[i];
     }
     const uint64_t min_score = (uint64_t)((double)npos * threshold);       /* :389 */
-    uint64_t cnt = x->type == 0 ? tu_merge_hybrid(&x->hyb, csets, ns, (int64_t)min_score, out)
-                                : tu_merge_meta(x, csets, ns, min_score, out);
+    uint64_t cnt = x->type == 0   ? tu_merge_hybrid(&x->hyb, csets, ns, (int64_t)min_score, out)
+                   : x->type == 1 ? tu_merge_meta(x, csets, ns, min_score, out)
+                   : x->type == 2 ? tu_merge_diff(x, csets, ns, min_score, out)
+                                  : tu_merge_metadiff(x, csets, ns, min_score, out);
     free(unitigs); free(csets);
     return cnt;
 }

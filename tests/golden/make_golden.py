@@ -22,13 +22,20 @@ CASES = [  # name, index, n, min_len, max_len, seed
     ("s10_mfur_mixed", "salmonella_10.mfur", 4000, 75, 300, 43),
     ("synth200_fur_mixed", "synth_200.fur", 3000, 75, 300, 44),
     ("synth200_mfur_mixed", "synth_200.mfur", 3000, 75, 300, 44),
+    ("s10_dfur_mixed", "salmonella_10.dfur", 4000, 75, 300, 45),
+    ("s10_mdfur_mixed", "salmonella_10.mdfur", 4000, 75, 300, 45),
+    ("synth200_dfur_mixed", "synth_200.dfur", 3000, 75, 300, 46),
+    ("synth200_mdfur_mixed", "synth_200.mdfur", 3000, 75, 300, 46),
 ]
 THRESHOLDS = [0.8, 1.0, 0.3]
 
 
 def main():
     assert ck.reference_available(), "build the reference first: make -C oracle ref"
+    only = set(sys.argv[1:])
     for name, index, n, lo, hi, seed in CASES:
+        if only and name not in only:
+            continue
         ref = ck.Reference(ck.index_path(index))
         reads = ck.gen_reads(n, lo, hi, seed=seed, genomes=index.split(".")[0])
         out = {"index": index, "n": n, "min_len": lo, "max_len": hi, "seed": seed, "thresholds": np.array(THRESHOLDS),

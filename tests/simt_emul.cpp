@@ -44,7 +44,8 @@ static dev_index view_of(const uint8_t* base) {
         I.skew_phf[i] = H.skew_phf[i];
         I.skew_pos_base[i] = H.skew_pos_base[i];
     }
-    I.type = H.type;
+    I.type = H.type & 1u;
+    I.diff = (H.type >> 1) & 1u;
     I.num_colors = H.num_colors;
     I.num_partitions = H.num_partitions;
     I.main_seed = I.phfs[0].seed;

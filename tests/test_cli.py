@@ -114,7 +114,9 @@ def csr_records(csr):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("index,algo_args", [("salmonella_10.fur", []), ("salmonella_10.fur", ["-r", "0.8"]), ("salmonella_10.mfur", []),
-                                             ("synth_200.fur", []), ("synth_200.mfur", ["-r", "0.6"])])
+                                             ("synth_200.fur", []), ("synth_200.mfur", ["-r", "0.6"]),
+                                             ("salmonella_10.dfur", ["-r", "0.7"]), ("salmonella_10.mdfur", []),
+                                             ("synth_200.dfur", []), ("synth_200.mdfur", ["-r", "0.5"])])
 def test_cli_matches_oracle_and_reference(index, algo_args, built_lib, tmp_path):
     genomes = index.split(".")[0]
     reads = ck.gen_reads(3000, 75, 300, seed=31, genomes=genomes)

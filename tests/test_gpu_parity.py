@@ -7,7 +7,7 @@ import _checkers as ck
 
 pytestmark = pytest.mark.gpu
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]  # 10 colors (fused kernel) and 200 colors (general kernels)
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]  # 10 colors (fused kernel) and 200 colors (general kernels)
 
 
 @pytest.fixture(scope="module", params=INDEXES)

@@ -13,7 +13,7 @@ import _checkers as ck
 
 ROOT = ck.ROOT
 EMUL_SO = os.path.join(ROOT, "build", "libfg_simt_emul.so")
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]
 
 
 @pytest.fixture(scope="module")
@@ -152,6 +152,8 @@ def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr, t
     pseudoalign_full_intersection / pseudoalign_threshold_union; table = with the decoded color-set table
     (k_expand_color_sets + k_color_sets_table) or decoding the compressed sets per read (k_color_sets_general)"""
     fg, img, o = loaded
+    if not table and o.type >= 2 and o.num_colors > 32:
+        pytest.skip("differential sets of more than 32 colors are only queried through the decoded table (the engine refuses otherwise)")
     n = 400 if o.num_colors <= 32 else 120
     for reads in (ck.gen_reads(n, 150, 150, seed=12, genomes=o.name.split(".")[0]), _edge_reads(o.name.split(".")[0])):
         got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors, table=table)

@@ -7,7 +7,7 @@ import _checkers as ck
 
 pytestmark = pytest.mark.skipif(not ck.reference_available(), reason="oracle/_ref/libfulgor_ref.so not built (needs /root/reference)")
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "synth_200.fur", "synth_200.mfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]
 
 
 @pytest.fixture(scope="module", params=INDEXES)
