@@ -63,7 +63,7 @@ struct dev_buffer {
 struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
-    dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out;
+    dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out, group_slots, rep, rep_counts;
     uint64_t* chunk_info = nullptr;        /* device: {base, total} */
     uint64_t* h_info = nullptr;            /* pinned host: {base, total, pool exhausted} */
     uint32_t* exhausted = nullptr;         /* device flag: the entry pool was too small */
@@ -310,6 +310,9 @@ static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool wa
     return 1;
 }
 
+static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const uint32_t* counts, int algo, double threshold,
+                                    uint64_t* d_off, cudaEvent_t after_k2, int* launches);
+
 /* whole path for a device-resident chunk, up to the CSR offsets (d_off, n+1 entries); returns how to emit the values */
 static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_args& a, int algo, double threshold, uint64_t* d_off,
                                      cudaEvent_t after_k1, cudaEvent_t after_k2, int* launches) {
@@ -333,6 +336,15 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     }
     *launches += enqueue_k1(x, s, a, true);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
+    return enqueue_color_sets(x, s, a, s.per_read.as<uint32_t>(), algo, threshold, d_off, after_k2, launches);
+}
+
+/* the color-set kernel (K2) over the per-read {color-set id, multiplicity} lists K1 left in stage/pool, then the CSR offsets.
+   `counts` = entries per read (K1's, or the deduplicated ones where only a group's representative keeps its list). */
+static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const uint32_t* counts, int algo, double threshold,
+                                    uint64_t* d_off, cudaEvent_t after_k2, int* launches) {
+    emit_plan e;
+    e.n = a.n;
     /* the counters of the color-set kernels must hold the largest score: at most the k-mers of the longest read. Chunks that
        come from host buffers know that length; for device-resident reads K1 reports the largest number of positive k-mers. */
     uint32_t max_kmers = a.max_len;
@@ -348,12 +360,12 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
             k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, 0, s.stream>>>(
-                x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(), a.n, threshold, e.words_per_read,
+                x->I, counts, s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(), a.n, threshold, e.words_per_read,
                 s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */
         if (x->I.diff)
-            throw std::runtime_error("differential indexes (.dfur/.mdfur) with more than 32 colors need the decoded color-set table "
+            throw std::runtime_error("differential indexes (.dfur/.mdfur) need the decoded color-set table for this operation "
                                      "(it did not fit FULGOR_GPU_TABLE_MAX_MB / the free device memory)");
         if (max_kmers == 0) { /* full intersection counts sets, at most as many as positive k-mers */
             FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
@@ -367,7 +379,7 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
         FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
         const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
-        k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
+        k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, counts, s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
                                                                a.n, algo, threshold, e.words_per_read, g.planes, ints, s.res_bits.as<uint32_t>(),
                                                                s.res_counts.as<uint32_t>());
     }
@@ -388,6 +400,25 @@ static emit_plan enqueue_fetch(fulgor_gpu_index* x, slot& s, const chunk_args& a
     return e;
 }
 
+/* full intersection computed once per distinct color-set-id list of the chunk (k_group_reads): K1 -> group -> K2 on the
+   representatives -> scan -> emit. Reads that are not representatives get an empty CSR range; rep (device, a.n entries)
+   receives the global index of every read's representative. */
+static emit_plan enqueue_dedup(fulgor_gpu_index* x, slot& s, const chunk_args& a, uint32_t read_base, uint64_t* d_off, int* launches) {
+    *launches += enqueue_k1(x, s, a, true);
+    uint32_t log2_slots = 10;
+    while ((1ull << log2_slots) < 2ull * a.n) ++log2_slots;
+    s.group_slots.reserve(size_t(4) << log2_slots);
+    s.rep.reserve(size_t(a.n) * 4);
+    s.rep_counts.reserve(size_t(a.n) * 4);
+    FG_CUDA(cudaMemsetAsync(s.group_slots.p, 0xff, size_t(4) << log2_slots, s.stream));
+    const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
+    k_group_reads<<<grid, FG_BLOCK, 0, s.stream>>>(s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), a.n, read_base,
+                                                   s.group_slots.as<uint32_t>(), log2_slots, s.rep.as<uint32_t>(), s.rep_counts.as<uint32_t>());
+    FG_CUDA(cudaGetLastError());
+    *launches += 1;
+    return enqueue_color_sets(x, s, a, s.rep_counts.as<uint32_t>(), FULGOR_GPU_FULL_INTERSECTION, 1.0, d_off, nullptr, launches);
+}
+
 /* ---- the chunked host pipeline ---- */
 
 static const uint64_t CHUNK_MAX_READS = 1u << 20;
@@ -395,16 +426,16 @@ static const uint64_t CHUNK_MAX_BASES = 256ull << 20;
 static const uint64_t CHUNK_MAX_RESULT_BITS_BYTES = 256ull << 20;
 static const int RC_RETRY_LARGER_POOL = 1;
 
-enum class op_kind { FETCH, PSEUDOALIGN };
+enum class op_kind { FETCH, PSEUDOALIGN, DEDUP };
 
 static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
                                uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
     FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, x->slots[0].stream));
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
-    const bool small = x->H.num_colors <= 32;
+    const bool small = x->H.num_colors <= 32 && op != op_kind::DEDUP;
     uint64_t max_reads = CHUNK_MAX_READS;
-    if (op == op_kind::PSEUDOALIGN && !small)
+    if (op != op_kind::FETCH && !small)
         max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (((x->H.num_colors + 31) / 32) * 4)));
     struct pending { uint32_t first, n; int slot; emit_plan plan; };
     bool too_big = false, exhausted = false;
@@ -471,6 +502,10 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         int launches = 0;
         if (op == op_kind::FETCH) {
             c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), &launches);
+        } else if (op == op_kind::DEDUP) {
+            c.plan = enqueue_dedup(x, s, a, c.first, s.off.as<uint64_t>(), &launches);
+            /* num_positive doubles as the rep_of_read output of this operation */
+            FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
         } else {
             c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, s.off.as<uint64_t>(), nullptr, nullptr, &launches);
         }
@@ -645,7 +680,7 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
     for (auto& s : x->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (dev_buffer* b : {&s.bases, &s.read_off, &s.per_read, &s.stage, &s.pool, &s.npos, &s.res_bits, &s.res_counts, &s.tile_sums, &s.tile_off,
-                              &s.off, &s.out})
+                              &s.off, &s.out, &s.group_slots, &s.rep, &s.rep_counts})
             b->release();
         if (s.chunk_info) cudaFree(s.chunk_info);
         if (s.exhausted) cudaFree(s.exhausted);
@@ -692,6 +727,18 @@ int fulgor_gpu_pseudoalign(fulgor_gpu_index* x, int algo, double threshold, cons
         if (algo == FULGOR_GPU_THRESHOLD_UNION && !(threshold > 0.0 && threshold <= 1.0))
             throw std::invalid_argument("threshold must be a float in (0.0,1.0]");
         int rc = run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, bases, read_off, n_reads, color_off, colors, colors_cap, nullptr);
+        if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
+        return rc;
+    });
+}
+
+int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index* x, const char* bases, const uint64_t* read_off, uint32_t n_reads, uint32_t* rep_of_read,
+                                 uint64_t* color_off, uint32_t* colors, uint64_t colors_cap) {
+    return guarded([&]() -> int {
+        if (!x || !read_off || !color_off || !rep_of_read || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!colors && colors_cap))
+            throw std::invalid_argument("null argument");
+        int rc = run_host_batch(x, op_kind::DEDUP, FULGOR_GPU_FULL_INTERSECTION, 1.0, bases, read_off, n_reads, color_off, colors, colors_cap,
+                                rep_of_read);
         if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
         return rc;
     });

@@ -463,24 +463,34 @@ public:
         }
         return true;
     }
-    /* records first_id .. first_id+n-1: colors[off[i] .. off[i+1]) each */
-    void write_batch(uint32_t first_id, uint32_t n, const uint64_t* off, const uint32_t* colors) {
+    /* records first_id .. first_id+n-1: colors[off[i] .. off[i+1]) each; with `rep` (deduplicated results: rep[i] = the read
+       of this batch whose range holds read i's colors) record i carries colors[off[rep[i]] .. off[rep[i]+1]) -- every read id
+       is written with its group's result, like the reference's preprocessed_query_reader path (tools/pseudoalign.cpp:39-44) */
+    void write_batch(uint32_t first_id, uint32_t n, const uint64_t* off, const uint32_t* colors, const uint32_t* rep = nullptr) {
         if (n == 0) return;
+        std::vector<uint64_t> fanned;
+        const uint64_t* vol = off; /* vol[i] - vol[0] = values written by records before i */
+        if (rep) {
+            fanned.resize(uint64_t(n) + 1);
+            fanned[0] = 0;
+            for (uint32_t i = 0; i < n; ++i) fanned[i + 1] = fanned[i] + (off[rep[i] + 1] - off[rep[i]]);
+            vol = fanned.data();
+        }
         /* cut the batch where the output volume (records + values) splits evenly */
         const unsigned T = unsigned(std::min<uint64_t>(threads_, std::max<uint64_t>(1, n / 1024)));
         std::vector<uint32_t> cut(T + 1, 0);
-        const uint64_t total = (off[n] - off[0]) + 2 * uint64_t(n);
+        const uint64_t total = (vol[n] - vol[0]) + 2 * uint64_t(n);
         for (unsigned t = 1; t < T; ++t) {
             const uint64_t want = total * t / T;
             uint32_t lo = cut[t - 1], hi = n;
             while (lo < hi) { /* first i with volume(i) >= want */
                 const uint32_t mid = lo + (hi - lo) / 2;
-                if ((off[mid] - off[0]) + 2 * uint64_t(mid) < want) lo = mid + 1; else hi = mid;
+                if ((vol[mid] - vol[0]) + 2 * uint64_t(mid) < want) lo = mid + 1; else hi = mid;
             }
             cut[t] = lo;
         }
         cut[T] = n;
-        parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, pieces_[t]); });
+        parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
         for (unsigned t = 0; t < T; ++t)
             if (!pieces_[t].empty()) std::fwrite(pieces_[t].data(), 1, pieces_[t].size(), f_);
     }
@@ -490,14 +500,16 @@ public:
     }
 
 private:
-    void format(uint32_t first_id, uint32_t lo, uint32_t hi, const uint64_t* off, const uint32_t* colors, std::vector<char>& out) const {
+    void format(uint32_t first_id, uint32_t lo, uint32_t hi, const uint64_t* off, const uint32_t* colors, const uint32_t* rep, uint64_t num_values,
+                std::vector<char>& out) const {
         out.clear();
         if (lo >= hi) return;
+        auto src = [rep](uint32_t i) { return rep ? rep[i] : i; };
         if (fmt_ == out_format::ASCII) { /* "id \t n [\t color]* \n", src/ps_utils.cpp:48-100 */
-            out.resize(size_t(hi - lo) * 24 + size_t(off[hi] - off[lo]) * 11 + 16);
+            out.resize(size_t(hi - lo) * 24 + size_t(num_values) * 11 + 16);
             char* p = out.data();
             for (uint32_t i = lo; i < hi; ++i) {
-                const uint64_t b = off[i], e = off[i + 1];
+                const uint64_t b = off[src(i)], e = off[src(i) + 1];
                 p = put_u32(p, first_id + i);
                 *p++ = '\t';
                 p = put_u32(p, uint32_t(e - b));
@@ -509,10 +521,10 @@ private:
             }
             out.resize(size_t(p - out.data()));
         } else if (fmt_ == out_format::BINARY) { /* u32 id, u32 n, n x u32, src/ps_utils.cpp:102-147 */
-            out.resize((size_t(hi - lo) * 2 + size_t(off[hi] - off[lo])) * 4);
+            out.resize((size_t(hi - lo) * 2 + size_t(num_values)) * 4);
             uint32_t* p = reinterpret_cast<uint32_t*>(out.data());
             for (uint32_t i = lo; i < hi; ++i) {
-                const uint64_t b = off[i], e = off[i + 1];
+                const uint64_t b = off[src(i)], e = off[src(i) + 1];
                 *p++ = first_id + i;
                 *p++ = uint32_t(e - b);
                 std::memcpy(p, colors + b, size_t(e - b) * 4);
@@ -529,8 +541,8 @@ private:
                 bw.clear();
             };
             for (uint32_t i = lo; i < hi; ++i) {
-                const uint32_t* c = colors + off[i];
-                const uint32_t size = uint32_t(off[i + 1] - off[i]);
+                const uint32_t* c = colors + off[src(i)];
+                const uint32_t size = uint32_t(off[src(i) + 1] - off[src(i)]);
                 bw.delta(first_id + i);
                 bw.delta(size);
                 if (size == 0) {

@@ -565,6 +565,65 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
     }
 }
 
+/* ---- cross-read deduplication of color-set-id lists (the reference's --deduplicate, tools/pseudoalign.cpp:92-226) ----
+   The reference sorts the reads' lists lexicographically, intersects each distinct list once and fans the result out to
+   every read that has it (preprocessed_query_reader, src/ps_utils.cpp:307-415). Here the distinct lists of a chunk are
+   found with an open-addressing table of read indexes: one warp per read hashes its sorted list (order-independent sum of
+   mixed ids, so lanes need no prefix), lane 0 claims a slot with a CAS or meets an earlier read there, whose list the
+   warp then compares entry by entry (exact: a hash collision only costs one more probe). The first read of a group is its
+   representative; every other read gets count 0 for the color-set kernel, so the intersection, the emit and the
+   device->host copy happen once per distinct list. rep_of_read[r] = GLOBAL index of r's representative (r itself when it
+   is one, and for reads without positive k-mers). slots: 2^log2_slots entries preset to 0xffffffff. */
+__global__ void __launch_bounds__(FG_BLOCK) k_group_reads(const uint32_t* __restrict__ counts, const uint2* __restrict__ stage,
+                                                         const uint2* __restrict__ pool, uint32_t n_reads, uint32_t read_base,
+                                                         uint32_t* __restrict__ slots, uint32_t log2_slots,
+                                                         uint32_t* __restrict__ rep_of_read, uint32_t* __restrict__ rep_counts) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const uint32_t mask = (1u << log2_slots) - 1u;
+    for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * wpb) {
+        const uint32_t n = __ldg(counts + r);
+        if (n == 0) {
+            if (lane == 0) {
+                rep_of_read[r] = read_base + r;
+                rep_counts[r] = 0;
+            }
+            continue;
+        }
+        const uint2* mine = entries_of(r, n, stage, pool);
+        uint32_t h = 0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            uint32_t x = mine[i].x * 0x9E3779B1u;
+            x ^= x >> 15;
+            x *= 0x85EBCA77u;
+            x ^= x >> 13;
+            h += x;
+        }
+        h = __reduce_add_sync(FG_FULL, h) + n * 0xC2B2AE3Du;
+        h ^= h >> 16;
+        uint32_t slot = h & mask, rep = r;
+        for (;;) {
+            uint32_t seen = 0;
+            if (lane == 0) seen = atomicCAS(slots + slot, 0xffffffffu, r);
+            seen = __shfl_sync(FG_FULL, seen, 0);
+            if (seen == 0xffffffffu) break; /* claimed: r represents a new list */
+            bool same = __ldg(counts + seen) == n;
+            if (same) {
+                const uint2* theirs = entries_of(seen, n, stage, pool);
+                for (uint32_t i = lane; i < n && same; i += 32) same = theirs[i].x == mine[i].x;
+            }
+            if (__all_sync(FG_FULL, same)) {
+                rep = seen;
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+        if (lane == 0) {
+            rep_of_read[r] = read_base + rep;
+            rep_counts[r] = rep == r ? n : 0;
+        }
+    }
+}
+
 /* counter bits and words per lane for reads of at most max_kmers k-mers */
 template <typename F>
 static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {

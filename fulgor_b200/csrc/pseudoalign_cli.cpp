@@ -9,7 +9,8 @@
  *
  * Differences from the reference, all outside the results: records are written in read-id order (the
  * reference's order depends on thread scheduling, README.md:220); -t sizes the host side (parsing and formatting
- * threads, fastx_io.h); --deduplicate is rejected (it only changes how the reference schedules work).
+ * threads, fastx_io.h); --deduplicate computes one intersection per distinct color-set-id list of a batch on the GPU
+ * (fulgor_gpu_pseudoalign_dedup) and fans the result out to every read id while formatting.
  * Three batches are in flight: while the GPU works on batch i, batch i+1 is being parsed and batch i-1 formatted.
  * Read ids are 0-based positions in the query file. With --gpus N the index
  * image is uploaded to N devices and every batch is split N ways; no cross-GPU reduction exists.
@@ -121,9 +122,8 @@ int main(int argc, char** argv) {
         return 1;
     }
     const int algo = a.has_threshold ? FULGOR_GPU_THRESHOLD_UNION : FULGOR_GPU_FULL_INTERSECTION;
-    if (a.deduplicate) {
-        if (a.has_threshold) std::cerr << "Deduplication not available for threshold < 1.0. Remove --deduplicate flag." << std::endl;
-        else std::cerr << "--deduplicate is not needed on the GPU path (results are identical without it). Remove --deduplicate flag." << std::endl;
+    if (a.deduplicate && a.has_threshold) { /* tools/pseudoalign.cpp:283-289 */
+        std::cerr << "Deduplication not available for threshold < 1.0. Remove --deduplicate flag." << std::endl;
         return 1;
     }
     if (!(ends_with(a.index, ".fur") || ends_with(a.index, ".mfur") || ends_with(a.index, ".dfur") || ends_with(a.index, ".mdfur"))) { /* tools/util.cpp:5-19 */
@@ -147,7 +147,7 @@ int main(int argc, char** argv) {
         std::cout << "[Output]    " << a.output << std::endl;
         std::cout << "[Algorithm] " << (algo == FULGOR_GPU_FULL_INTERSECTION ? std::string("full-intersection")
                                                                              : "threshold-union (threshold = " + std::to_string(a.threshold) + ")")
-                  << std::endl;
+                  << (a.deduplicate ? "(dedup.)" : "") << std::endl;
         std::cout << "---------------------------------\n" << std::endl;
     }
 
@@ -199,10 +199,11 @@ int main(int argc, char** argv) {
 
     /* one batch in flight per pipeline stage */
     struct batch_ctx {
-        pinned p_coff, p_colors;
+        pinned p_coff, p_colors, p_rep;
         fgio::read_batch reads; /* pinned, owned here */
         uint64_t* hc = nullptr;
         uint32_t* hv = nullptr;
+        uint32_t* hr = nullptr; /* --deduplicate: representative of every read (batch-local index) */
         uint64_t colors_cap = 0, first_id = 0;
         bool full = false, failed = false;
     } ctx[3];
@@ -237,7 +238,16 @@ int main(int argc, char** argv) {
         c.hc = c.p_coff.get<uint64_t>(uint64_t(n) + 1);
         if (c.colors_cap < uint64_t(n) * colors_per_read + 1024) c.colors_cap = uint64_t(n) * colors_per_read + 1024;
         c.hv = c.p_colors.get<uint32_t>(c.colors_cap);
+        c.hr = a.deduplicate ? c.p_rep.get<uint32_t>(uint64_t(n) + 1) : nullptr;
         uint64_t* hc = c.hc;
+        /* one full intersection per distinct color-set-id list (groups never span devices: each device deduplicates its range) */
+        auto pseudoalign = [&](int g, uint32_t lo, uint32_t cnt, uint64_t* off, uint32_t* vals, uint64_t cap) {
+            if (!a.deduplicate) return fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho + lo, cnt, off, vals, cap);
+            const int rc = fulgor_gpu_pseudoalign_dedup(gpu[g], hb, ho + lo, cnt, c.hr + lo, off, vals, cap);
+            if (rc == 0 && lo)
+                for (uint32_t i = lo; i < lo + cnt; ++i) c.hr[i] += lo;
+            return rc;
+        };
         /* split the batch over the GPUs: contiguous ranges balanced by k-mer count */
         const int G = a.gpus;
         std::vector<uint32_t> cut(G + 1, 0);
@@ -262,13 +272,13 @@ int main(int argc, char** argv) {
             auto run = [&](int g) {
                 const uint32_t lo = cut[g], hi = cut[g + 1];
                 if (G == 1) {
-                    rcs[g] = fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho, n, hc, c.hv, c.colors_cap);
+                    rcs[g] = pseudoalign(g, 0, n, hc, c.hv, c.colors_cap);
                 } else { /* each device fills its own CSR; spliced below */
                     g_off[g].assign(hi - lo + 1, 0);
                     uint64_t cap = std::max<uint64_t>(uint64_t(hi - lo) * colors_per_read, 1024);
                     for (;;) {
                         g_val[g].resize(cap);
-                        rcs[g] = fulgor_gpu_pseudoalign(gpu[g], algo, a.threshold, hb, ho + lo, hi - lo, g_off[g].data(), g_val[g].data(), cap);
+                        rcs[g] = pseudoalign(g, lo, hi - lo, g_off[g].data(), g_val[g].data(), cap);
                         if (rcs[g] != FULGOR_GPU_E2BIG) break;
                         cap = g_off[g][hi - lo];
                     }
@@ -317,9 +327,12 @@ int main(int argc, char** argv) {
     auto format_stage = [&](batch_ctx& c) {
         const uint32_t n = c.reads.n;
         uint64_t mapped = 0;
-        for (uint32_t i = 0; i < n; ++i) mapped += c.hc[i + 1] > c.hc[i];
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t r = c.hr ? c.hr[i] : i;
+            mapped += c.hc[r + 1] > c.hc[r];
+        }
         num_mapped += mapped;
-        out.write_batch(uint32_t(c.first_id), n, c.hc, c.hv);
+        out.write_batch(uint32_t(c.first_id), n, c.hc, c.hv, c.hr);
     };
 
     /* step i: parse batch i | GPU on batch i-1 | format batch i-2, each on its own thread */

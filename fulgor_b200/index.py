@@ -69,6 +69,7 @@ def lib():
         L.fulgor_gpu_index_info.argtypes = [C.c_void_p, C.POINTER(Info)]
         L.fulgor_gpu_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.fulgor_gpu_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.fulgor_gpu_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.fulgor_gpu_pseudoalign_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                                     C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
         L.fulgor_gpu_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
@@ -219,6 +220,19 @@ class Index:
             return L.fulgor_gpu_pseudoalign(self._h, algo, float(threshold), bases.ctypes.data, off.ctypes.data, n, o.ctypes.data, v.ctypes.data, c)
 
         return self._csr_call(fn, n, cap if cap is not None else 8 * n + 64)
+
+    def pseudoalign_dedup(self, reads, cap=None):
+        """full intersection computed once per distinct color-set-id list (the reference's --deduplicate):
+        returns (rep_of_read, color_off, colors); colors of read i = colors[color_off[rep[i]] : color_off[rep[i] + 1]]"""
+        bases, off, n = self._reads(reads)
+        rep = np.zeros(n, dtype=np.uint32)
+        L = lib()
+
+        def fn(o, v, c):
+            return L.fulgor_gpu_pseudoalign_dedup(self._h, bases.ctypes.data, off.ctypes.data, n, rep.ctypes.data, o.ctypes.data, v.ctypes.data, c)
+
+        o, v = self._csr_call(fn, n, cap if cap is not None else 8 * n + 64)
+        return rep, o, v
 
     def pseudoalign_full_intersection(self, reads, cap=None):
         return self.pseudoalign(reads, FULL_INTERSECTION, 1.0, cap)

@@ -97,6 +97,22 @@ int fulgor_gpu_pseudoalign(fulgor_gpu_index*, int algo, double threshold,
                            const char* bases, const uint64_t* read_off, uint32_t n_reads,
                            uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
 
+/* Full intersection with cross-read deduplication of the color-set-id lists. Replaces the reference's `--deduplicate` mode:
+   fetch_and_deduplicate_sets (tools/pseudoalign.cpp:92-226: fetch every read's list, sort the lists, keep one copy of each)
+   followed by pseudoalign_worker over preprocessed_query_reader (tools/pseudoalign.cpp:39-44, src/ps_utils.cpp:307-415: one
+   intersection per distinct list, written once per read id that has it). Here reads with the same list form a group inside
+   each chunk of <= 2^20 reads; the first one found is the group's representative and the only one whose intersection is
+   computed, emitted and copied back:
+     rep_of_read[i] = index of the read that represents read i (== i for a representative, and for every read without a
+                      positive k-mer);
+     colors of read i = colors[color_off[rep_of_read[i]] .. color_off[rep_of_read[i] + 1])  (reads that are not
+                      representatives own an empty range).
+   The per-read results are exactly those of fulgor_gpu_pseudoalign(FULL_INTERSECTION); like in the reference, which read of a
+   group does the work is not deterministic, and threshold-union cannot be deduplicated (tools/pseudoalign.cpp:283-289). */
+int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index*, const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                                 uint32_t* rep_of_read /* n_reads */,
+                                 uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
+
 /* ---- the same path on DEVICE-resident inputs (kernel-only timing, pipelines that keep reads on
         the GPU). All pointers are device pointers on the handle's device; offsets are CSR like above.
         *total_out (host) receives off[n_reads]. Runs on the handle's stream and synchronises it. */

@@ -247,3 +247,29 @@ def index_path(name):
         os.replace(tmp, path)
         return path
     raise FileNotFoundError(path)
+
+
+def check_dedup(rep, off, vals, expected, cids):
+    """a deduplicated full-intersection result (include/fulgor_gpu.h: fulgor_gpu_pseudoalign_dedup) against the per-read
+    results `expected` (CSR) and the per-read color-set-id lists `cids` (CSR): every read's result is its representative's
+    range, a representative represents itself, reads share a representative iff their (non-empty) lists are equal, and
+    only representatives own values."""
+    eoff, evals = expected
+    coff, cvals = cids
+    n = len(eoff) - 1
+    assert len(rep) == n and len(off) == n + 1
+    groups = {}
+    for i in range(n):
+        r = int(rep[i])
+        assert 0 <= r < n and int(rep[r]) == r, (i, r)
+        got = vals[int(off[r]):int(off[r + 1])]
+        assert np.array_equal(got, evals[int(eoff[i]):int(eoff[i + 1])]), i
+        if r != i:
+            assert off[i] == off[i + 1], i
+        key = cvals[int(coff[i]):int(coff[i + 1])].tobytes()
+        if len(key) == 0:
+            assert r == i
+        else:
+            assert groups.setdefault(key, r) == r, i
+    assert len(set(groups.values())) == len(groups)
+    return len(groups)

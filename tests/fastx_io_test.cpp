@@ -54,4 +54,15 @@ int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads
     w.close();
     return 0;
 }
+
+/* one write_batch call with deduplicated results: record i carries the range of read rep[i] */
+int fxio_format_dedup(const char* path, int fmt, unsigned num_colors, unsigned threads, unsigned n, const unsigned long long* off,
+                      const unsigned* colors, const unsigned* rep) {
+    fgio::result_writer w;
+    if (!w.open(path, fmt == 0 ? fgio::out_format::ASCII : fmt == 1 ? fgio::out_format::BINARY : fgio::out_format::COMPRESSED, num_colors, threads))
+        return -1;
+    w.write_batch(7, n, reinterpret_cast<const uint64_t*>(off), reinterpret_cast<const uint32_t*>(colors), reinterpret_cast<const uint32_t*>(rep));
+    w.close();
+    return 0;
+}
 }

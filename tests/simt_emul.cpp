@@ -188,6 +188,59 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     return 0;
 }
 
+/* full intersection once per distinct color-set-id list (engine.cu: enqueue_dedup): K1 -> k_group_reads -> color-set kernel on
+   the representatives -> scan -> emit. rep_of_read[i] = representative of read i. */
+int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uint64_t* read_off, uint32_t n, uint32_t* rep_of_read,
+                           uint64_t* out_off, uint32_t* out_vals, uint64_t cap, unsigned grid, int use_table) {
+    dev_index I = view_of(image);
+    std::vector<uint32_t> table;
+    if (use_table) {
+        fgi_header H;
+        std::memcpy(&H, image, sizeof(H));
+        const uint64_t stride = table_stride_words(I.num_colors);
+        table.assign(H.num_color_sets * stride, 0xdeadbeefu);
+        simt::launch(2, 64, 2 * stride * 4, [&] { k_expand_color_sets(I, 0, uint32_t(H.num_color_sets), uint32_t(stride), table.data()); });
+        I.set_table = table.data();
+        I.table_stride = stride;
+    }
+    out_off[0] = 0;
+    if (n == 0) return 0;
+    uint64_t chunk_info[2] = {0, 0};
+    k1_out k1;
+    uint64_t pool_entries = 1u << 12;
+    while (run_k1(I, bases, read_off, n, grid, 0, pool_entries, k1)) pool_entries *= 4;
+    uint32_t log2_slots = 4; /* small on purpose: long probe sequences */
+    while ((1ull << log2_slots) < 2ull * n) ++log2_slots;
+    std::vector<uint32_t> slots(size_t(1) << log2_slots, 0xffffffffu), rep_counts(n, 0xdeadbeefu);
+    simt::launch(grid, FG_BLOCK, 0, [&] {
+        k_group_reads(k1.counts.data(), k1.stage.data(), k1.pool.data(), n, 0, slots.data(), log2_slots, rep_of_read, rep_counts.data());
+    });
+    const int algo = FULGOR_GPU_FULL_INTERSECTION;
+    uint32_t max_kmers = 1;
+    for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
+    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
+    if (!g.ok) return FULGOR_GPU_EINVAL;
+    std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
+    if (use_table) {
+        dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
+            simt::launch(grid, FG_BLOCK, 0, [&] {
+                k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
+                    I, rep_counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, 1.0, g.words_per_read, res_bits.data(), res_counts.data());
+            });
+        });
+    } else {
+        simt::launch(grid, g.warps_per_block * 32, g.smem_bytes, [&] {
+            k_color_sets_general(I, rep_counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, algo, 1.0, g.words_per_read, g.planes,
+                                 g.ints_per_warp, res_bits.data(), res_counts.data());
+        });
+    }
+    run_scan<false>(res_counts.data(), n, out_off);
+    if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
+    simt::launch(uint32_t((uint64_t(n) * 32 + 255) / 256), 256, 0,
+                 [&] { k_emit_bits(res_bits.data(), g.words_per_read, res_counts.data(), out_off, chunk_info, n, out_vals, cap); });
+    return 0;
+}
+
 /* stage 1 alone: per read the ascending distinct color-set ids (+ number of positive k-mers) */
 int emul_fetch_color_set_ids(const uint8_t* image, const uint8_t* bases, const uint64_t* read_off, uint32_t n, uint64_t* out_off,
                              uint32_t* out_vals, uint64_t cap, uint32_t* num_positive, unsigned grid, int force_generic) {

@@ -251,6 +251,12 @@ static inline T atomicXor(T* p, T v) {
     return old;
 }
 template <typename T>
+static inline T atomicCAS(T* p, T expected, T desired) {
+    const T old = *p;
+    if (old == expected) *p = desired;
+    return old;
+}
+template <typename T>
 static inline T atomicMax(T* p, T v) {
     const T old = *p;
     if (v > old) *p = v;
@@ -276,6 +282,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
         for (int l = 0; l < 32; ++l) w.out[l] = b;
     }));
 }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
 template <typename T>
 static inline T __shfl_sync(unsigned mask, T v, int src) {
     fg_emul_check_mask(mask);

@@ -28,6 +28,7 @@ def fx():
     L.fxio_parse.argtypes = [C.c_char_p, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.fxio_free.argtypes = [C.c_void_p]
     L.fxio_format.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint]
+    L.fxio_format_dedup.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -143,6 +144,29 @@ def test_formatters(fx, tmp_path, num_colors, threads, pieces):
     else:
         C_, recs = compressed_records_prefix(outs["compressed"], 1500)
         assert C_ == num_colors and all(recs[i] == exp[i] for i in recs)
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_formatters_fan_out_deduplicated_results(fx, tmp_path, threads):
+    """write_batch with a representative map (--deduplicate): every read id is written with its group's list, like the
+    reference's preprocessed_query_reader path (tools/pseudoalign.cpp:39-44)"""
+    rng = np.random.default_rng(threads)
+    n, num_colors = 30000, 10
+    rep = np.arange(n, dtype=np.uint32)
+    members = rng.random(n) < 0.7
+    members[:10] = False
+    rep[members] = rng.choice(np.flatnonzero(~members), int(members.sum())).astype(np.uint32)
+    lists = [np.sort(rng.choice(num_colors, int(rng.integers(0, num_colors + 1)), replace=False)).astype(np.uint32) if not members[i]
+             else np.zeros(0, dtype=np.uint32) for i in range(n)]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(x) for x in lists])
+    colors = np.concatenate(lists + [np.zeros(1, dtype=np.uint32)])
+    exp = {7 + i: lists[int(rep[i])].tolist() for i in range(n)}
+    for fmt, (name, parse_fn) in enumerate((("ascii", ascii_records), ("binary", binary_records), ("compressed", compressed_records))):
+        path = str(tmp_path / name)
+        assert fx.fxio_format_dedup(path.encode(), fmt, num_colors, threads, n, off.ctypes.data, colors.ctypes.data, rep.ctypes.data) == 0
+        got = parse_fn(path)
+        assert (got[1] if fmt == 2 else got) == exp
 
 
 def compressed_records_prefix(path, limit):

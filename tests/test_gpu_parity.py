@@ -168,3 +168,22 @@ def test_without_the_decoded_table(index, built_lib, monkeypatch):
         for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.2)):
             assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
     o.close()
+
+
+@pytest.mark.gpu
+def test_deduplicated_full_intersection(pair):
+    """fulgor_gpu_pseudoalign_dedup (the reference's --deduplicate, tools/pseudoalign.cpp:92-226): reads drawn WITH repeats;
+    every read's colors through its representative == pseudoalign_full_intersection, the groups are exactly the distinct
+    color-set-id lists, only representatives own values (so the intersection ran once per group)"""
+    gpu, o = pair
+    base = ck.gen_reads(800, 100, 250, seed=77, genomes=o.name.split(".")[0])
+    seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(800)]
+    rng = np.random.default_rng(3)
+    picks = [seqs[j] for j in rng.integers(0, 800, 5000)] + [b"", b"ACGT" * 10, b"N" * 80, seqs[0].lower()]
+    reads = ck.reads_from_list(picks)
+    rep, off, vals = gpu.pseudoalign_dedup(reads)
+    groups = ck.check_dedup(rep, off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
+    assert groups <= 800
+    # E2BIG protocol: exact capacity reported, second call succeeds
+    rep2, off2, vals2 = gpu.pseudoalign_dedup(reads, cap=1)
+    ck.check_dedup(rep2, off2, vals2, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))

@@ -33,6 +33,7 @@ def emul():
                                    C.c_uint, C.c_int, C.c_int]
     E.emul_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                            C.c_uint, C.c_int]
+    E.emul_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int]
     return E
 
 
@@ -159,6 +160,32 @@ def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr, t
         got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors, table=table)
         exp = o.pseudoalign(reads, algo, thr)
         assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+
+
+@pytest.mark.parametrize("table", [0, 1])
+def test_emulated_kernels_deduplicate_like_the_reference(loaded, emul, table):
+    """K1 -> k_group_reads -> color-set kernel on the representatives only -> scan -> emit on emulated warps: every read's
+    result (through its representative) == pseudoalign_full_intersection, and the groups are exactly the distinct
+    color-set-id lists (tools/pseudoalign.cpp:92-226). The reads are drawn with repeats so that groups have several members."""
+    fg, img, o = loaded
+    if not table and o.type >= 2:
+        pytest.skip("the unfused color-set kernel reads differential sets only through the decoded table")
+    base = ck.gen_reads(60, 100, 200, seed=21, genomes=o.name.split(".")[0])
+    seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(60)]
+    rng = np.random.default_rng(5)
+    picks = [seqs[j] for j in rng.integers(0, 60, 150)] + [b"", b"ACGT" * 10, b"N" * 80]
+    reads = ck.reads_from_list(picks)
+    bases, off = reads
+    n = len(off) - 1
+    rep = np.zeros(n, dtype=np.uint32)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    cap = max(1, n * o.num_colors)
+    vals = np.zeros(cap, dtype=np.uint32)
+    rc = emul.emul_pseudoalign_dedup(img.ctypes.data, bases.ctypes.data, off.ctypes.data, n, rep.ctypes.data, out_off.ctypes.data,
+                                     vals.ctypes.data, cap, 2, table)
+    assert rc == 0
+    groups = ck.check_dedup(rep, out_off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
+    assert groups <= 60
 
 
 def test_loader_rejects_bad_input(built_lib, tmp_path):
