@@ -63,7 +63,7 @@ struct dev_buffer {
 struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
-    dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out, group_slots, rep, rep_counts;
+    dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out, group_slots, rep, rep_counts, kmer_off, per_kmer, word_off;
     uint64_t* chunk_info = nullptr;        /* device: {base, total} */
     uint64_t* h_info = nullptr;            /* pinned host: {base, total, pool exhausted} */
     uint32_t* exhausted = nullptr;         /* device flag: the entry pool was too small */
@@ -546,6 +546,112 @@ static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double thre
     throw std::runtime_error("entry pool kept overflowing");
 }
 
+/* ---- the per-k-mer tools (kmer-conservation, kmer-matches): one chunk at a time on slot 0 ---- */
+
+enum class kmer_tool { CONSERVATION, MATCHES };
+static const uint64_t TOOL_MAX_BASES = 64ull << 20;
+static const uint64_t TOOL_MAX_COUNT_BYTES = 256ull << 20;
+
+static int run_kmer_tool(fulgor_gpu_index* x, kmer_tool tool, const char* bases, const uint64_t* read_off, uint32_t n_reads, uint64_t* out_off,
+                         uint32_t* out_vals, uint64_t cap, uint32_t* counts) {
+    FG_CUDA(cudaSetDevice(x->device));
+    slot& s = x->slots[0];
+    const uint64_t k = x->H.k, C = x->H.num_colors;
+    auto kmers_of = [&](uint32_t i) -> uint64_t {
+        const uint64_t len = read_off[i + 1] - read_off[i];
+        if (len >> 31) throw std::invalid_argument("read_off must be non-decreasing and reads shorter than 2^31 characters");
+        return len >= k ? len - k + 1 : 0;
+    };
+    out_off[0] = 0;
+    if (tool == kmer_tool::MATCHES) {
+        if (!x->I.set_table)
+            throw std::runtime_error("kmer_matches needs the decoded color-set table (it did not fit FULGOR_GPU_TABLE_MAX_MB / the free device memory)");
+        for (uint32_t i = 0; i < n_reads; ++i) out_off[i + 1] = out_off[i] + (kmers_of(i) + 31) / 32;
+        if (out_off[n_reads] > cap) return FULGOR_GPU_E2BIG;
+    }
+    if (n_reads == 0) return 0;
+    FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
+    uint64_t max_reads = CHUNK_MAX_READS;
+    if (tool == kmer_tool::MATCHES) max_reads = std::max<uint64_t>(256, std::min<uint64_t>(max_reads, TOOL_MAX_COUNT_BYTES / (4 * std::max<uint64_t>(1, C))));
+    std::vector<uint64_t> koff, woff;
+    bool too_big = false;
+    for (uint32_t first = 0; first < n_reads;) {
+        uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
+        while (n > 1 && read_off[first + n] - read_off[first] > TOOL_MAX_BASES) n = (n + 1) / 2;
+        koff.assign(size_t(n) + 1, 0);
+        uint64_t longest = 1;
+        for (uint32_t i = 0; i < n; ++i) {
+            koff[i + 1] = koff[i] + kmers_of(first + i);
+            longest = std::max(longest, read_off[first + i + 1] - read_off[first + i]);
+        }
+        const uint64_t b0 = read_off[first], b1 = read_off[first + n], total_kmers = koff[n];
+        s.bases.reserve(size_t(b1 - b0) + 64);
+        s.read_off.reserve(size_t(n + 1) * 8);
+        s.kmer_off.reserve(size_t(n + 1) * 8);
+        s.per_kmer.reserve(size_t(total_kmers) * 4 + 4);
+        if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
+        FG_CUDA(cudaMemcpyAsync(s.read_off.p, read_off + first, size_t(n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        FG_CUDA(cudaMemcpyAsync(s.kmer_off.p, koff.data(), size_t(n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, n, uint32_t(longest)};
+        const uint32_t grid = read_grid(x, n);
+        dispatch_window(x->H, [&](auto w) {
+            k_kmer_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, n, s.kmer_off.as<uint64_t>(),
+                                                                                     s.per_kmer.as<uint32_t>());
+        });
+        FG_CUDA(cudaGetLastError());
+        const uint32_t warp_grid = uint32_t((uint64_t(n) * 32 + 255) / 256);
+        if (tool == kmer_tool::CONSERVATION) {
+            s.per_read.reserve(size_t(n) * 4);
+            s.off.reserve(size_t(n + 1) * 8);
+            k_kmer_runs<false><<<warp_grid, 256, 0, s.stream>>>(s.per_kmer.as<uint32_t>(), s.kmer_off.as<uint64_t>(), n, s.per_read.as<uint32_t>(), nullptr,
+                                                                 nullptr, nullptr, 0);
+            FG_CUDA(cudaGetLastError());
+            enqueue_scan<false>(x, s, s.per_read.as<uint32_t>(), n, s.off.as<uint64_t>());
+            FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaMemcpyAsync(out_off + first, s.off.p, size_t(n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            const uint64_t base = s.h_info[0], total = s.h_info[1];
+            if (base + total > cap) too_big = true;
+            if (!too_big && total) {
+                s.out.reserve(size_t(total) * 12);
+                k_kmer_runs<true><<<warp_grid, 256, 0, s.stream>>>(s.per_kmer.as<uint32_t>(), s.kmer_off.as<uint64_t>(), n, nullptr, s.off.as<uint64_t>(),
+                                                                    s.chunk_info, s.out.as<uint32_t>(), total);
+                FG_CUDA(cudaGetLastError());
+                FG_CUDA(cudaMemcpyAsync(out_vals + 3 * base, s.out.p, size_t(total) * 12, cudaMemcpyDeviceToHost, s.stream));
+            }
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+        } else {
+            /* the read's distinct {color-set id, multiplicity} list (K1) feeds the per-color counts */
+            for (int attempt = 0;; ++attempt) {
+                enqueue_k1(x, s, a, false);
+                FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
+                FG_CUDA(cudaStreamSynchronize(s.stream));
+                if (!uint32_t(s.h_info[2])) break;
+                if (attempt >= 12) throw std::runtime_error("entry pool kept overflowing");
+                x->pool_per_read *= 4;
+            }
+            woff.assign(size_t(n) + 1, 0);
+            for (uint32_t i = 0; i <= n; ++i) woff[i] = out_off[first + i] - out_off[first];
+            s.word_off.reserve(size_t(n + 1) * 8);
+            s.out.reserve(size_t(woff[n]) * 4 + 4);
+            s.res_bits.reserve(size_t(n) * C * 4 + 4);
+            FG_CUDA(cudaMemcpyAsync(s.word_off.p, woff.data(), size_t(n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            k_kmer_positive_bits<<<warp_grid, 256, 0, s.stream>>>(s.per_kmer.as<uint32_t>(), s.kmer_off.as<uint64_t>(), s.word_off.as<uint64_t>(), n,
+                                                                  s.out.as<uint32_t>());
+            FG_CUDA(cudaGetLastError());
+            const uint32_t cgrid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
+            k_kmer_match_counts<<<cgrid, FG_BLOCK, 0, s.stream>>>(x->I, s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), n,
+                                                                  s.res_bits.as<uint32_t>());
+            FG_CUDA(cudaGetLastError());
+            if (woff[n]) FG_CUDA(cudaMemcpyAsync(out_vals + out_off[first], s.out.p, size_t(woff[n]) * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (C) FG_CUDA(cudaMemcpyAsync(counts + uint64_t(first) * C, s.res_bits.p, size_t(n) * C * 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+        }
+        first += n;
+    }
+    return too_big ? FULGOR_GPU_E2BIG : 0;
+}
+
 template <typename F>
 static int guarded(F&& f) {
     try {
@@ -680,7 +786,7 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
     for (auto& s : x->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (dev_buffer* b : {&s.bases, &s.read_off, &s.per_read, &s.stage, &s.pool, &s.npos, &s.res_bits, &s.res_counts, &s.tile_sums, &s.tile_off,
-                              &s.off, &s.out, &s.group_slots, &s.rep, &s.rep_counts})
+                              &s.off, &s.out, &s.group_slots, &s.rep, &s.rep_counts, &s.kmer_off, &s.per_kmer, &s.word_off})
             b->release();
         if (s.chunk_info) cudaFree(s.chunk_info);
         if (s.exhausted) cudaFree(s.exhausted);
@@ -740,6 +846,28 @@ int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index* x, const char* bases, const u
         int rc = run_host_batch(x, op_kind::DEDUP, FULGOR_GPU_FULL_INTERSECTION, 1.0, bases, read_off, n_reads, color_off, colors, colors_cap,
                                 rep_of_read);
         if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
+        return rc;
+    });
+}
+
+int fulgor_gpu_kmer_conservation(fulgor_gpu_index* x, const char* bases, const uint64_t* read_off, uint32_t n_reads, uint64_t* triple_off,
+                                 uint32_t* triples, uint64_t triples_cap) {
+    return guarded([&]() -> int {
+        if (!x || !read_off || !triple_off || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!triples && triples_cap))
+            throw std::invalid_argument("null argument");
+        int rc = run_kmer_tool(x, kmer_tool::CONSERVATION, bases, read_off, n_reads, triple_off, triples, triples_cap, nullptr);
+        if (rc == FULGOR_GPU_E2BIG) return fail(rc, "triples_cap too small; triple_off[n_reads] holds the required capacity");
+        return rc;
+    });
+}
+
+int fulgor_gpu_kmer_matches(fulgor_gpu_index* x, const char* bases, const uint64_t* read_off, uint32_t n_reads, uint64_t* word_off,
+                            uint32_t* positive_words, uint64_t words_cap, uint32_t* counts) {
+    return guarded([&]() -> int {
+        if (!x || !read_off || !word_off || !counts || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!positive_words && words_cap))
+            throw std::invalid_argument("null argument");
+        int rc = run_kmer_tool(x, kmer_tool::MATCHES, bases, read_off, n_reads, word_off, positive_words, words_cap, counts);
+        if (rc == FULGOR_GPU_E2BIG) return fail(rc, "words_cap too small; word_off[n_reads] holds the required capacity");
         return rc;
     });
 }

@@ -459,7 +459,7 @@ __device__ __forceinline__ void mask_below(uint32_t nb, uint64_t& lo, uint64_t& 
    k-mer can only be stored in the bucket of its own minimizer, so a run needs no other bucket.
    Runs whose bucket is served by the skew index and k-mers whose minimizer value appears on both strands take the
    per-k-mer path (lookup_in_bucket); super-k-mers without a single minimizer position are scanned k-mer by k-mer. */
-template <int W>
+template <int W, bool PERK = false>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
@@ -469,6 +469,11 @@ struct kmer_tiles {
     uint32_t shift; /* the packed stream starts at the 4-byte aligned address at or below the segment: base j sits at stream position j + shift */
     uint64_t kmask, mmer_mask;
     uint32_t window, kbits;
+    /* PERK: besides the items, the color-set id of EVERY k-mer (FG_NOT_FOUND = negative or invalid) goes to per_kmer[i], i =
+       k-mer index in the read -- the per-k-mer view of streaming_query::lookup_advanced that index::kmer_conservation and
+       index::kmer_matches consume (src/kmer_conservation.cpp:31-47, src/kmer_matches.cpp:20-28). Set by the caller. */
+    uint32_t* per_kmer;
+    uint32_t seg_base; /* read index of the current segment's first k-mer */
 
     __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, const uint8_t* buf_begin_, const uint8_t* buf_end_,
                                           uint32_t lane_, warp_stage& S_)
@@ -482,6 +487,8 @@ struct kmer_tiles {
         mmer_mask = (1ULL << (2 * I.m)) - 1;
         window = W ? W : k - I.m + 1;
         kbits = (1u << k) - 1u;
+        per_kmer = nullptr;
+        seg_base = 0;
     }
 
     __device__ __forceinline__ const uint64_t* words() const { return S.words + FG_WORDS_PAD_BEFORE; }
@@ -512,7 +519,9 @@ struct kmer_tiles {
 
     /* step 5 for one (seed, super-k-mer) pair: number of k-mers of the run [i_first, i_last] found in super-k-mer sk */
     __device__ __forceinline__ uint32_t extend_pair(uint32_t sk, int p, bool fw, uint32_t i_first, uint32_t i_last, uint32_t nchars,
-                                                    uint32_t nwords, uint32_t& cid) const {
+                                                    uint32_t nwords, uint32_t& cid, int& found_lo, int& found_hi) const {
+        found_lo = 0;
+        found_hi = -1; /* PERK: the found k-mers are the valid ones in [found_lo, found_hi] (the unpinned path writes its own) */
         const int k = int(I.k), m = int(I.m);
         const uint2 rec = FG_LDG(I.sk_records + sk);
         cid = I.sk_cid ? FG_LDG(I.sk_cid + sk) : (rec.y & FGI_SK_CID_MASK);
@@ -526,7 +535,9 @@ struct kmer_tiles {
             for (uint32_t i = i_first; i <= i_last; ++i) {
                 if (!((S.vk[i >> 5] >> (i & 31)) & 1u)) continue;
                 const uint64_t fwd = bases_at(i) & kmask;
-                cnt += scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+                const bool found = scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+                cnt += found;
+                if (PERK && found) per_kmer[seg_base + i] = cid;
             }
             return cnt;
         }
@@ -565,6 +576,8 @@ struct kmer_tiles {
         if (t_lo > t_hi) return 0;
         const int lo = max(forward ? t_lo + d : e - t_hi, int(i_first)), hi = min(forward ? t_hi + d : e - t_lo, int(i_last));
         if (lo > hi) return 0;
+        found_lo = lo;
+        found_hi = hi;
         return count_valid(uint32_t(lo), uint32_t(hi));
     }
 
@@ -574,6 +587,10 @@ struct kmer_tiles {
         const uint32_t seg_nk = min(uint32_t(FG_SEG_KMERS), nk - seg0);
         seg_end = seg0 + seg_nk;
         nitems = cursor = 0;
+        if (PERK) { /* every k-mer starts negative; the warp barriers before the pair pass order these stores before the hits */
+            seg_base = seg0;
+            for (uint32_t i = lane; i < seg_nk; i += 32) per_kmer[seg0 + i] = FG_NOT_FOUND;
+        }
         const uint32_t nchars = seg_nk + I.k - 1, npos = seg_nk + window - 1;
         /* 0. bases. Lane l loads the l-th aligned 4-byte word at or after the segment's aligned floor, packs its four
               characters to one byte (2 bits each) and stores it: the packed stream is the byte array over S.words. */
@@ -788,7 +805,11 @@ struct kmer_tiles {
                     const uint32_t j = q - (owner_end - slot.n);
                     const uint32_t i_first = (slot.key >> 16) & 0xffu;
                     const uint32_t i_last = (g0 + owner + 1 < nseeds ? ((seeds()[g0 + owner + 1].key >> 16) & 0xffu) : seg_nk) - 1;
-                    cnt = extend_pair(slot.begin + j, int(slot.key & 0xffu), (slot.key >> 8) & 1u, i_first, i_last, nchars, nwords, cid);
+                    int found_lo, found_hi;
+                    cnt = extend_pair(slot.begin + j, int(slot.key & 0xffu), (slot.key >> 8) & 1u, i_first, i_last, nchars, nwords, cid, found_lo, found_hi);
+                    if (PERK && cnt)
+                        for (int i = found_lo; i <= found_hi; ++i)
+                            if ((S.vk[i >> 5] >> (i & 31)) & 1u) per_kmer[seg_base + uint32_t(i)] = cid;
                 }
                 append_items(cnt != 0, cid, cnt);
             }
@@ -808,6 +829,7 @@ struct kmer_tiles {
                         mz.cpos = (note >> 16) & 31u;
                         mz.ambiguous = (note >> 13) & 1u;
                         cid = lookup_in_bucket(I, slot.begin, slot.size, fwd, revcomp(fwd, I.k), mz, kmask);
+                        if (PERK && cid != FG_NOT_FOUND) per_kmer[seg_base + FG_SEG_B * lane + tt] = cid;
                     }
                 }
                 append_items(cid != FG_NOT_FOUND, cid, 1);

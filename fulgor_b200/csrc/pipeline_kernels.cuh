@@ -565,6 +565,121 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
     }
 }
 
+/* ---- the per-k-mer tools on the lookup kernel: kmer-conservation and kmer-matches ----
+   k_kmer_color_sets runs the same segment pipeline as the pseudoalignment kernels (kmer_tiles) in its per-k-mer mode: the
+   color-set id of every k-mer of every read, FG_NOT_FOUND for negative and invalid k-mers -- what the loops around
+   streaming_query::lookup_advanced + u2c see (src/kmer_conservation.cpp:31-36, src/kmer_matches.cpp:20-24).
+   kmer_off (n_reads + 1, chunk-local) = first k-mer slot of every read. */
+template <int W>
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_kmer_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
+                                                                            const uint64_t* __restrict__ read_off, uint64_t read_off_base,
+                                                                            uint32_t n_reads, const uint64_t* __restrict__ kmer_off,
+                                                                            uint32_t* __restrict__ per_kmer) {
+    __shared__ warp_stage wstage[FG_WARPS_PER_BLOCK];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
+    for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
+        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
+        kmer_tiles<W, true> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base), lane,
+                                  wstage[wib]);
+        tiles.per_kmer = per_kmer + __ldg(kmer_off + r);
+        uint32_t cid, cnt;
+        while (tiles.next(cid, cnt)) {}
+        __syncwarp();
+    }
+}
+
+/* index::kmer_conservation (src/kmer_conservation.cpp:7-54): maximal runs of consecutive positive k-mers with the same
+   color-set id, as triples {start_pos_in_query, num_kmers, color_set_id} (include/util.hpp:74-78). A run starts at a positive
+   k-mer whose predecessor is negative or has another color set, and ends likewise; the j-th start of a read pairs with its
+   j-th end, so both are placed by a running count. EMIT = false: only the number of runs per read (for the CSR offsets). */
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_kmer_runs(const uint32_t* __restrict__ per_kmer, const uint64_t* __restrict__ kmer_off, uint32_t n_reads,
+                                                  uint32_t* __restrict__ run_counts, const uint64_t* __restrict__ off,
+                                                  const uint64_t* __restrict__ chunk_info, uint32_t* __restrict__ triples, uint64_t cap_triples) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_reads) return;
+    const uint64_t k0 = __ldg(kmer_off + r);
+    const uint32_t nk = uint32_t(__ldg(kmer_off + r + 1) - k0);
+    const uint32_t* c = per_kmer + k0;
+    const uint64_t o = EMIT ? __ldg(off + r) - chunk_info[0] : 0;
+    uint32_t nstart = 0, nend = 0;
+    for (uint32_t i0 = 0; i0 < nk; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t cur = i < nk ? __ldg(c + i) : FG_NOT_FOUND;
+        const uint32_t prev = i > 0 && i < nk ? __ldg(c + i - 1) : FG_NOT_FOUND;
+        const uint32_t next = i + 1 < nk ? __ldg(c + i + 1) : FG_NOT_FOUND;
+        const bool is_start = cur != FG_NOT_FOUND && prev != cur, is_end = cur != FG_NOT_FOUND && next != cur;
+        const uint32_t bs = __ballot_sync(FG_FULL, is_start), be = __ballot_sync(FG_FULL, is_end);
+        if (EMIT) {
+            const uint32_t below = (1u << lane) - 1u;
+            if (is_start) {
+                const uint64_t t = o + nstart + __popc(bs & below);
+                if (t < cap_triples) {
+                    triples[3 * t] = i;
+                    triples[3 * t + 2] = cur;
+                }
+            }
+            if (is_end) {
+                const uint64_t t = o + nend + __popc(be & below);
+                if (t < cap_triples) triples[3 * t + 1] = i + 1; /* end (exclusive) for now; the length is fixed up below */
+            }
+        }
+        nstart += __popc(bs);
+        nend += __popc(be);
+    }
+    if (EMIT) {
+        __syncwarp();
+        for (uint32_t t = lane; t < nstart; t += 32)
+            if (o + t < cap_triples) triples[3 * (o + t) + 1] -= triples[3 * (o + t)];
+    } else if (lane == 0) {
+        run_counts[r] = nstart;
+    }
+}
+
+/* index::kmer_matches (src/kmer_matches.cpp:7-30), part 1: the positive-k-mer bit vector of every read, bit i = k-mer i is in
+   the index; read r owns the 32-bit words [word_off[r], word_off[r+1]) */
+__global__ void __launch_bounds__(256) k_kmer_positive_bits(const uint32_t* __restrict__ per_kmer, const uint64_t* __restrict__ kmer_off,
+                                                           const uint64_t* __restrict__ word_off, uint32_t n_reads, uint32_t* __restrict__ words) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_reads) return;
+    const uint64_t k0 = __ldg(kmer_off + r);
+    const uint32_t nk = uint32_t(__ldg(kmer_off + r + 1) - k0);
+    uint32_t* out = words + __ldg(word_off + r);
+    for (uint32_t i0 = 0; i0 < nk; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t b = __ballot_sync(FG_FULL, i < nk && __ldg(per_kmer + k0 + i) != FG_NOT_FOUND);
+        if (lane == 0) out[i0 >> 5] = b;
+    }
+}
+
+/* index::kmer_matches, part 2: counts[c] = number of positive k-mers whose color set contains c (:25-27), from the read's
+   distinct {color-set id, multiplicity} list (K1) and the decoded color-set table: lane l owns color 32 w + l of word w,
+   every row word is one broadcast load. counts: n_reads x num_colors. */
+__global__ void __launch_bounds__(FG_BLOCK) k_kmer_match_counts(const __grid_constant__ dev_index I, const uint32_t* __restrict__ list_counts,
+                                                               const uint2* __restrict__ stage, const uint2* __restrict__ pool, uint32_t n_reads,
+                                                               uint32_t* __restrict__ counts) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const uint32_t C = I.num_colors, W = (C + 31) / 32;
+    const uint32_t* __restrict__ table = I.set_table;
+    const uint64_t stride = I.table_stride;
+    for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * wpb) {
+        const uint32_t n = __ldg(list_counts + r);
+        const uint2* ents = n ? entries_of(r, n, stage, pool) : nullptr;
+        uint32_t* out = counts + uint64_t(r) * C;
+        for (uint32_t w = 0; w < W; ++w) {
+            uint32_t acc = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e = ents[j];
+                acc += ((__ldg(table + uint64_t(e.x) * stride + w) >> lane) & 1u) * e.y;
+            }
+            if (32 * w + lane < C) out[32 * w + lane] = acc;
+        }
+    }
+}
+
 /* ---- cross-read deduplication of color-set-id lists (the reference's --deduplicate, tools/pseudoalign.cpp:92-226) ----
    The reference sorts the reads' lists lexicographically, intersects each distinct list once and fans the result out to
    every read that has it (preprocessed_query_reader, src/ps_utils.cpp:307-415). Here the distinct lists of a chunk are

@@ -70,6 +70,8 @@ def lib():
         L.fulgor_gpu_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.fulgor_gpu_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.fulgor_gpu_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.fulgor_gpu_kmer_conservation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.fulgor_gpu_kmer_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.fulgor_gpu_pseudoalign_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                                     C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
         L.fulgor_gpu_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
@@ -233,6 +235,32 @@ class Index:
 
         o, v = self._csr_call(fn, n, cap if cap is not None else 8 * n + 64)
         return rep, o, v
+
+    def kmer_conservation(self, reads, cap=None):
+        """index::kmer_conservation for a batch: (triple_off[n+1], triples[t, 3] = start_pos_in_query, num_kmers, color_set_id)"""
+        bases, off, n = self._reads(reads)
+        L = lib()
+        toff = np.zeros(n + 1, dtype=np.uint64)
+        cap = cap if cap is not None else 4 * n + 64
+        while True:
+            tr = np.empty(3 * max(1, cap), dtype=np.uint32)
+            rc = L.fulgor_gpu_kmer_conservation(self._h, bases.ctypes.data, off.ctypes.data, n, toff.ctypes.data, tr.ctypes.data, cap)
+            if rc == E2BIG:
+                cap = int(toff[n])
+                continue
+            _check(rc)
+            return toff, tr[: 3 * int(toff[n])].reshape(-1, 3)
+
+    def kmer_matches(self, reads):
+        """index::kmer_matches for a batch: (word_off[n+1], positive_words uint32, counts[n, num_colors])"""
+        bases, off, n = self._reads(reads)
+        L = lib()
+        woff = np.zeros(n + 1, dtype=np.uint64)
+        counts = np.zeros((n, self.num_colors), dtype=np.uint32)
+        cap = int(off[n] - off[0]) // 32 + n + 1
+        words = np.zeros(max(1, cap), dtype=np.uint32)
+        _check(L.fulgor_gpu_kmer_matches(self._h, bases.ctypes.data, off.ctypes.data, n, woff.ctypes.data, words.ctypes.data, cap, counts.ctypes.data))
+        return woff, words[: int(woff[n])], counts
 
     def pseudoalign_full_intersection(self, reads, cap=None):
         return self.pseudoalign(reads, FULL_INTERSECTION, 1.0, cap)

@@ -113,6 +113,25 @@ int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index*, const char* bases, const uin
                                  uint32_t* rep_of_read /* n_reads */,
                                  uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
 
+/* ---- the per-k-mer tools that share the lookup kernel (reference tools/kmer_conservation.cpp, tools/kmer_matches.cpp) ---- */
+
+/* Replaces index::kmer_conservation (src/kmer_conservation.cpp:7-54, called tools/kmer_conservation.cpp:26) for a batch: per
+   read the maximal runs of consecutive positive k-mers with one color-set id, as kmer_conservation_triple
+   {start_pos_in_query, num_kmers, color_set_id} (include/util.hpp:74-78), in query order. Read i owns triples
+   [triple_off[i], triple_off[i+1]); triple t is triples[3t .. 3t+2]. triples_cap counts triples. */
+int fulgor_gpu_kmer_conservation(fulgor_gpu_index*, const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                                 uint64_t* triple_off /* n_reads+1 */, uint32_t* triples, uint64_t triples_cap);
+
+/* Replaces index::kmer_matches (src/kmer_matches.cpp:7-30, called tools/kmer_matches.cpp:25) for a batch:
+     positive k-mers: read i owns the 32-bit words [word_off[i], word_off[i+1]) of positive_words, ceil(num_kmers / 32) of
+                      them; bit j (LSB first) = k-mer j of the read is in the index (positive_kmers_in_sequence);
+     counts:          n_reads x num_colors, counts[i * num_colors + c] = positive k-mers of read i whose color set contains c.
+   Reads shorter than k have no k-mers: no words and zero counts (the reference returns early there and its caller prints
+   whatever the previous read left in the buffers, src/kmer_matches.cpp:11). Needs the decoded color-set table. */
+int fulgor_gpu_kmer_matches(fulgor_gpu_index*, const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                            uint64_t* word_off /* n_reads+1 */, uint32_t* positive_words, uint64_t words_cap,
+                            uint32_t* counts /* n_reads * num_colors */);
+
 /* ---- the same path on DEVICE-resident inputs (kernel-only timing, pipelines that keep reads on
         the GPU). All pointers are device pointers on the handle's device; offsets are CSR like above.
         *total_out (host) receives off[n_reads]. Runs on the handle's stream and synchronises it. */

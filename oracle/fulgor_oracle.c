@@ -1190,6 +1190,86 @@ uint64_t fo_threshold_union(const fo_index* x, const char* seq, uint64_t len, do
     return cnt;
 }
 
+/* ------------------------------------------------------------------ the per-k-mer tools */
+/* index::kmer_conservation (src/kmer_conservation.cpp:7-54): triples {start_pos_in_query, num_kmers, color_set_id} of the maximal
+   runs of consecutive positive k-mers with one color-set id. Returns the number of triples (3 uint32 each in out). */
+uint64_t fo_kmer_conservation(const fo_index* x, const char* seq, uint64_t len, uint32_t* out) {
+    if (len < x->k) return 0;                                            /* :14 */
+    const uint64_t nk = len - x->k + 1;
+    uint64_t n = 0, prev = FO_INVALID;
+    uint32_t start = 0, num = 0;
+    sq q; sq_init(&q, x);
+    for (uint64_t i = 0; i != nk; ++i) {
+        lookup_result r = sq_lookup(&q, seq + i);
+        if (r.kmer_id != FO_INVALID) {                                   /* :35-46 */
+            uint64_t cid = fo_u2c(x, r.contig_id);
+            if (prev != cid) {
+                if (prev != FO_INVALID) { out[3 * n] = start; out[3 * n + 1] = num; out[3 * n + 2] = (uint32_t)prev; ++n; }
+                num = 0; start = (uint32_t)i;
+            }
+            num += 1; prev = cid;
+        } else {                                                         /* :48-51 */
+            if (prev != FO_INVALID) { out[3 * n] = start; out[3 * n + 1] = num; out[3 * n + 2] = (uint32_t)prev; ++n; }
+            prev = FO_INVALID;
+        }
+    }
+    if (prev != FO_INVALID) { out[3 * n] = start; out[3 * n + 1] = num; out[3 * n + 2] = (uint32_t)prev; ++n; } /* :54 */
+    return n;
+}
+
+/* index::kmer_matches (src/kmer_matches.cpp:7-30): positive[i] = k-mer i is in the index (one byte each here), counts[c] +=1 for
+   every color of every positive k-mer's color set. Returns the number of k-mers. counts has num_colors entries, zeroed here. */
+uint64_t fo_kmer_matches(const fo_index* x, const char* seq, uint64_t len, uint8_t* positive, uint32_t* counts) {
+    const uint32_t C = index_num_colors(x);
+    memset(counts, 0, sizeof(uint32_t) * C);
+    if (len < x->k) return 0;
+    const uint64_t nk = len - x->k + 1;
+    uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * (C ? C : 1));
+    sq q; sq_init(&q, x);
+    for (uint64_t i = 0; i != nk; ++i) {
+        lookup_result r = sq_lookup(&q, seq + i);
+        positive[i] = r.kmer_id != FO_INVALID;
+        if (positive[i]) {
+            int64_t m = fo_color_set(x, fo_u2c(x, r.contig_id), tmp, C);
+            for (int64_t j = 0; j < m; ++j) counts[tmp[j]] += 1;
+        }
+    }
+    free(tmp);
+    return nk;
+}
+
+int fo_batch_kmer_conservation(const fo_index* x, const char* bases, const uint64_t* read_off, uint32_t n, uint64_t* triple_off,
+                               uint32_t* triples, uint64_t cap) {
+    uint64_t total = 0;
+    uint32_t* tmp = NULL; uint64_t tmp_cap = 0;
+    triple_off[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t len = read_off[i + 1] - read_off[i];
+        if (3 * (len + 1) > tmp_cap) { tmp_cap = 6 * len + 64; tmp = (uint32_t*)realloc(tmp, sizeof(uint32_t) * tmp_cap); }
+        uint64_t c = fo_kmer_conservation(x, bases + read_off[i], len, tmp);
+        if (total + c <= cap) memcpy(triples + 3 * total, tmp, sizeof(uint32_t) * 3 * c);
+        total += c;
+        triple_off[i + 1] = total;
+    }
+    free(tmp);
+    return total > cap ? -7 : 0;
+}
+
+/* positive: one byte per k-mer, reads concatenated (kmer_off[i] = first k-mer of read i, n+1 entries); counts: n x num_colors */
+int fo_batch_kmer_matches(const fo_index* x, const char* bases, const uint64_t* read_off, uint32_t n, uint64_t* kmer_off,
+                          uint8_t* positive, uint64_t cap, uint32_t* counts) {
+    const uint32_t C = index_num_colors(x);
+    kmer_off[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t len = read_off[i + 1] - read_off[i];
+        kmer_off[i + 1] = kmer_off[i] + (len >= x->k ? len - x->k + 1 : 0);
+    }
+    if (kmer_off[n] > cap) return -7;
+    for (uint32_t i = 0; i < n; ++i)
+        fo_kmer_matches(x, bases + read_off[i], read_off[i + 1] - read_off[i], positive + kmer_off[i], counts + (uint64_t)i * C);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ batch drivers */
 int fo_batch_fetch_color_set_ids(const fo_index* x, const char* bases, const uint64_t* read_off, uint32_t n,
                                  uint64_t* cid_off, uint32_t* cids, uint64_t cap, uint32_t* num_positive) {

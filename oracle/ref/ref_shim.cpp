@@ -8,6 +8,9 @@
  *     fetch_color_set_ids            src/ps_full_intersection.cpp:335-374
  *     pseudoalign_full_intersection  src/ps_full_intersection.cpp:377-400
  *     pseudoalign_threshold_union    src/ps_threshold_union.cpp:321-402
+ * the two per-k-mer tools that share the lookup:
+ *     kmer_conservation              src/kmer_conservation.cpp:7-54
+ *     kmer_matches                   src/kmer_matches.cpp:7-30
  * plus the per-k-mer `sshash::streaming_query::lookup_advanced`
  * (external/sshash/include/streaming_query.hpp:50-109) and color-set decoding, so
  * that tests can pin the C restatement (oracle/fulgor_oracle.c) and the CUDA path
@@ -32,6 +35,8 @@
 #include "src/color_sets.cpp"
 #include "src/ps_full_intersection.cpp"
 #include "src/ps_threshold_union.cpp"
+#include "src/kmer_conservation.cpp"
+#include "src/kmer_matches.cpp"
 
 using namespace fulgor;
 
@@ -218,6 +223,58 @@ int fref_pseudoalign(void* hp, int algo, double threshold, const char* bases,
                                  idx.pseudoalign_threshold_union(seq, res, threshold);
                              }
                          });
+    };
+    return on_index(hp, run);
+}
+
+/* index::kmer_conservation for a batch: CSR of triples {start_pos_in_query, num_kmers, color_set_id} */
+int fref_kmer_conservation(void* hp, const char* bases, const uint64_t* read_off, uint32_t n,
+                           uint64_t* triple_off, uint32_t* triples, uint64_t cap) {
+    auto run = [&](auto const& idx) {
+        uint64_t total = 0;
+        triple_off[0] = 0;
+        std::vector<kmer_conservation_triple> info;
+        for (uint32_t i = 0; i != n; ++i) {
+            std::string seq(bases + read_off[i], read_off[i + 1] - read_off[i]);
+            info.clear(); /* like tools/kmer_conservation.cpp:36 (the early return for short reads leaves it untouched) */
+            idx.kmer_conservation(seq, info);
+            for (auto const& t : info) {
+                if (total < cap) {
+                    triples[3 * total] = t.start_pos_in_query;
+                    triples[3 * total + 1] = t.num_kmers;
+                    triples[3 * total + 2] = t.color_set_id;
+                }
+                ++total;
+            }
+            triple_off[i + 1] = total;
+        }
+        return total > cap ? -7 : 0;
+    };
+    return on_index(hp, run);
+}
+
+/* index::kmer_matches for a batch: positive = one byte per k-mer (reads concatenated, kmer_off = n+1 offsets),
+   counts = n x num_colors. Reads shorter than k get zero counts here (the reference leaves its buffers untouched). */
+int fref_kmer_matches(void* hp, const char* bases, const uint64_t* read_off, uint32_t n,
+                      uint64_t* kmer_off, uint8_t* positive, uint64_t cap, uint32_t* counts) {
+    auto run = [&](auto const& idx) {
+        const uint64_t k = idx.k(), C = idx.num_colors();
+        kmer_off[0] = 0;
+        for (uint32_t i = 0; i != n; ++i) {
+            const uint64_t len = read_off[i + 1] - read_off[i];
+            kmer_off[i + 1] = kmer_off[i] + (len >= k ? len - k + 1 : 0);
+        }
+        if (kmer_off[n] > cap) return -7;
+        std::vector<count_type> c(C);
+        for (uint32_t i = 0; i != n; ++i) {
+            std::string seq(bases + read_off[i], read_off[i + 1] - read_off[i]);
+            bits::bit_vector::builder bvb;
+            std::fill(c.begin(), c.end(), 0);
+            idx.kmer_matches(seq, bvb, c);
+            for (uint64_t j = 0; j != bvb.num_bits(); ++j) positive[kmer_off[i] + j] = bvb.get(j);
+            std::memcpy(counts + uint64_t(i) * C, c.data(), C * sizeof(uint32_t));
+        }
+        return 0;
     };
     return on_index(hp, run);
 }

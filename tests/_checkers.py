@@ -57,6 +57,25 @@ class _Batch:
             cap = int(out_off[n])
 
 
+    def _kmer_tools(self, conservation_fn, matches_fn, reads, which):
+        """(triple_off, triples[n,3]) for which == 'conservation'; (kmer_off, positive uint8 per k-mer, counts[n, C]) for 'matches'"""
+        bases, off = reads
+        n = len(off) - 1
+        bp = bases.ctypes.data_as(C.c_char_p)
+        if which == "conservation":
+            toff = np.zeros(n + 1, dtype=np.uint64)
+            cap = max(1, int(off[n]))
+            tr = np.zeros(3 * cap, dtype=np.uint32)
+            assert conservation_fn(self.h, bp, _p(off, u64p), n, _p(toff, u64p), _p(tr, u32p), cap) == 0
+            return toff, tr[: 3 * int(toff[n])].reshape(-1, 3).copy()
+        koff = np.zeros(n + 1, dtype=np.uint64)
+        cap = max(1, int(off[n]))
+        pos = np.zeros(cap, dtype=np.uint8)
+        counts = np.zeros((n, self.num_colors), dtype=np.uint32)
+        assert matches_fn(self.h, bp, _p(off, u64p), n, _p(koff, u64p), _p(pos, u8p), cap, _p(counts, u32p)) == 0
+        return koff, pos[: int(koff[n])].copy(), counts
+
+
 class Oracle(_Batch):
     """The plain-C restatement (oracle/fulgor_oracle.c)."""
 
@@ -77,6 +96,8 @@ class Oracle(_Batch):
         L.fo_color_set.argtypes = [C.c_void_p, C.c_uint64, u32p, C.c_uint64]
         L.fo_batch_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64, u32p]
         L.fo_batch_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64]
+        L.fo_batch_kmer_conservation.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64]
+        L.fo_batch_kmer_matches.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u8p, C.c_uint64, u32p]
         self.L = L
         self.h = L.fo_open(path.encode())
         if not self.h:
@@ -120,6 +141,12 @@ class Oracle(_Batch):
         n = len(off) - 1
         return self._csr(lambda o, v, cap: self.L.fo_batch_pseudoalign(self.h, algo, threshold, bases.ctypes.data_as(C.c_char_p), _p(off, u64p), n, _p(o, u64p), _p(v, u32p), cap), reads)
 
+    def kmer_conservation(self, reads):
+        return self._kmer_tools(self.L.fo_batch_kmer_conservation, self.L.fo_batch_kmer_matches, reads, "conservation")
+
+    def kmer_matches(self, reads):
+        return self._kmer_tools(self.L.fo_batch_kmer_conservation, self.L.fo_batch_kmer_matches, reads, "matches")
+
 
 def reference_available():
     return os.path.exists(REF_SO)
@@ -141,6 +168,8 @@ class Reference(_Batch):
         L.fref_color_set.argtypes = [C.c_void_p, C.c_uint64, u32p, C.c_uint64]
         L.fref_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64, C.c_int]
         L.fref_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64, C.c_int]
+        L.fref_kmer_conservation.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u32p, C.c_uint64]
+        L.fref_kmer_matches.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint32, u64p, u8p, C.c_uint64, u32p]
         self.L = L
         self.h = L.fref_open(path.encode())
         if not self.h:
@@ -178,6 +207,12 @@ class Reference(_Batch):
         bases, off = reads
         n = len(off) - 1
         return self._csr(lambda o, v, cap: self.L.fref_pseudoalign(self.h, algo, threshold, bases.ctypes.data_as(C.c_char_p), _p(off, u64p), n, _p(o, u64p), _p(v, u32p), cap, threads), reads)
+
+    def kmer_conservation(self, reads):
+        return self._kmer_tools(self.L.fref_kmer_conservation, self.L.fref_kmer_matches, reads, "conservation")
+
+    def kmer_matches(self, reads):
+        return self._kmer_tools(self.L.fref_kmer_conservation, self.L.fref_kmer_matches, reads, "matches")
 
 
 _GPK_CACHE = {}
@@ -273,3 +308,17 @@ def check_dedup(rep, off, vals, expected, cids):
             assert groups.setdefault(key, r) == r, i
     assert len(set(groups.values())) == len(groups)
     return len(groups)
+
+
+def unpack_positive_words(word_off, words, kmer_off):
+    """fulgor_gpu_kmer_matches' per-read 32-bit words -> one byte per k-mer, reads concatenated (the checkers' layout)"""
+    n = len(kmer_off) - 1
+    out = np.zeros(int(kmer_off[n]), dtype=np.uint8)
+    for i in range(n):
+        nk = int(kmer_off[i + 1] - kmer_off[i])
+        w = words[int(word_off[i]):int(word_off[i + 1])]
+        assert w.size == (nk + 31) // 32
+        bits = np.unpackbits(w.view(np.uint8), bitorder="little")[:nk]
+        assert not np.unpackbits(w.view(np.uint8), bitorder="little")[nk:].any()
+        out[int(kmer_off[i]):int(kmer_off[i + 1])] = bits
+    return out

@@ -241,6 +241,50 @@ int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uin
     return 0;
 }
 
+/* the per-k-mer tools (engine.cu: run_kmer_tool) on emulated warps. which = 0: kmer-conservation -> out_off = triple offsets,
+   out_vals = triples (3 each, cap in triples); which = 1: kmer-matches -> out_off = word offsets, out_vals = positive words,
+   counts = n x num_colors (uses the decoded table). */
+int emul_kmer_tool(const uint8_t* image, int which, const uint8_t* bases, const uint64_t* read_off, uint32_t n, uint64_t* out_off,
+                   uint32_t* out_vals, uint64_t cap, uint32_t* counts, unsigned grid, int force_generic) {
+    dev_index I = view_of(image);
+    out_off[0] = 0;
+    if (n == 0) return 0;
+    std::vector<uint64_t> koff(size_t(n) + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = read_off[i + 1] - read_off[i];
+        koff[i + 1] = koff[i] + (len >= I.k ? len - I.k + 1 : 0);
+    }
+    std::vector<uint32_t> per_kmer(koff[n] + 1, 0xdeadbeefu);
+    dispatch_window(I, force_generic, [&](auto w) {
+        simt::launch(grid, FG_BLOCK, 0, [&] { k_kmer_color_sets<decltype(w)::value>(I, bases, read_off, read_off[0], n, koff.data(), per_kmer.data()); });
+    });
+    const uint32_t warp_grid = uint32_t((uint64_t(n) * 32 + 255) / 256);
+    uint64_t chunk_info[2] = {0, 0};
+    if (which == 0) {
+        std::vector<uint32_t> run_counts(n, 0xdeadbeefu);
+        simt::launch(warp_grid, 256, 0, [&] { k_kmer_runs<false>(per_kmer.data(), koff.data(), n, run_counts.data(), nullptr, nullptr, nullptr, 0); });
+        run_scan<false>(run_counts.data(), n, out_off);
+        if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
+        simt::launch(warp_grid, 256, 0, [&] { k_kmer_runs<true>(per_kmer.data(), koff.data(), n, nullptr, out_off, chunk_info, out_vals, cap); });
+        return 0;
+    }
+    fgi_header H;
+    std::memcpy(&H, image, sizeof(H));
+    const uint64_t stride = table_stride_words(I.num_colors);
+    std::vector<uint32_t> table(H.num_color_sets * stride, 0xdeadbeefu);
+    simt::launch(2, 64, 2 * stride * 4, [&] { k_expand_color_sets(I, 0, uint32_t(H.num_color_sets), uint32_t(stride), table.data()); });
+    I.set_table = table.data();
+    I.table_stride = stride;
+    for (uint32_t i = 0; i < n; ++i) out_off[i + 1] = out_off[i] + (koff[i + 1] - koff[i] + 31) / 32;
+    if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
+    k1_out k1;
+    uint64_t pool_entries = 1u << 12;
+    while (run_k1(I, bases, read_off, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
+    simt::launch(warp_grid, 256, 0, [&] { k_kmer_positive_bits(per_kmer.data(), koff.data(), out_off, n, out_vals); });
+    simt::launch(grid, FG_BLOCK, 0, [&] { k_kmer_match_counts(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), n, counts); });
+    return 0;
+}
+
 /* stage 1 alone: per read the ascending distinct color-set ids (+ number of positive k-mers) */
 int emul_fetch_color_set_ids(const uint8_t* image, const uint8_t* bases, const uint64_t* read_off, uint32_t n, uint64_t* out_off,
                              uint32_t* out_vals, uint64_t cap, uint32_t* num_positive, unsigned grid, int force_generic) {

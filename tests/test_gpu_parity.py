@@ -126,7 +126,7 @@ def test_long_reads_many_color_sets(pair):
         assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
 
 
-BIG = ["synth_4546.fur", "synth_4546.mfur", "synth_4546_dense.fur", "synth_4546_dense.mfur"]
+BIG = ["synth_4546.fur", "synth_4546.mfur", "synth_4546.dfur", "synth_4546.mdfur", "synth_4546_dense.fur", "synth_4546_dense.mfur"]
 
 
 @pytest.mark.parametrize("index", BIG)
@@ -151,7 +151,7 @@ def test_4546_color_standin(index, built_lib):
     o.close()
 
 
-@pytest.mark.parametrize("index", ["salmonella_10.mfur", "synth_200.fur", "synth_200.mfur", "synth_4546.mfur"])
+@pytest.mark.parametrize("index", ["salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_4546.mfur"])
 def test_without_the_decoded_table(index, built_lib, monkeypatch):
     """FULGOR_GPU_TABLE_MAX_MB=0: no decoded color-set table, the kernels decode the compressed sets per read
     (color_set_mask in the fused kernel, k_color_sets_general otherwise)"""
@@ -176,7 +176,7 @@ def test_deduplicated_full_intersection(pair):
     every read's colors through its representative == pseudoalign_full_intersection, the groups are exactly the distinct
     color-set-id lists, only representatives own values (so the intersection ran once per group)"""
     gpu, o = pair
-    base = ck.gen_reads(800, 100, 250, seed=77, genomes=o.name.split(".")[0])
+    base = ck.gen_reads(800, 100, 250, seed=77, genomes=gpu.genomes)
     seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(800)]
     rng = np.random.default_rng(3)
     picks = [seqs[j] for j in rng.integers(0, 800, 5000)] + [b"", b"ACGT" * 10, b"N" * 80, seqs[0].lower()]
@@ -187,3 +187,36 @@ def test_deduplicated_full_intersection(pair):
     # E2BIG protocol: exact capacity reported, second call succeeds
     rep2, off2, vals2 = gpu.pseudoalign_dedup(reads, cap=1)
     ck.check_dedup(rep2, off2, vals2, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
+
+
+def test_differential_sets_need_the_table_beyond_32_colors(built_lib, monkeypatch):
+    """no silent wrong answer: without the decoded table a differential index of more than 32 colors is refused loudly"""
+    import fulgor_b200 as fg
+
+    monkeypatch.setenv("FULGOR_GPU_TABLE_MAX_MB", "0")
+    reads = ck.gen_reads(100, 150, 150, seed=1, genomes="synth_200")
+    with fg.Index.open(ck.index_path("synth_200.dfur"), 0) as gpu:
+        with pytest.raises(fg.FulgorGpuError) as e:
+            gpu.pseudoalign(reads, 0)
+        assert "decoded color-set table" in str(e.value)
+        gpu.fetch_color_set_ids(reads)  # stage 1 does not touch the color sets
+
+
+def test_kmer_conservation_and_matches(pair):
+    """fulgor_gpu_kmer_conservation / fulgor_gpu_kmer_matches == index::kmer_conservation / index::kmer_matches
+    (src/kmer_conservation.cpp:7-54, src/kmer_matches.cpp:7-30) on mixed-length reads and the edge reads"""
+    gpu, o = pair
+    seqs = [b"", b"A", b"ACGT" * 8, b"N" * 100]
+    r0 = ck.gen_reads(50, 150, 150, seed=3, genomes=gpu.genomes)
+    one = r0[0][: int(r0[1][1])].tobytes()
+    seqs += [one[:31], one[:75] + b"N" + one[76:], one.lower(), one + one[:40]]
+    for reads in (ck.gen_reads(3000, 75, 300, seed=91, genomes=gpu.genomes), ck.reads_from_list(seqs)):
+        toff, tr = gpu.kmer_conservation(reads)
+        eoff, etr = o.kmer_conservation(reads)
+        assert np.array_equal(toff, eoff) and np.array_equal(tr, etr)
+        toff2, tr2 = gpu.kmer_conservation(reads, cap=1)  # E2BIG protocol
+        assert np.array_equal(toff2, eoff) and np.array_equal(tr2, etr)
+        woff, words, counts = gpu.kmer_matches(reads)
+        koff, pos, ecounts = o.kmer_matches(reads)
+        assert np.array_equal(ck.unpack_positive_words(woff, words, koff), pos)
+        assert np.array_equal(counts, ecounts)

@@ -33,6 +33,7 @@ def emul():
                                    C.c_uint, C.c_int, C.c_int]
     E.emul_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                            C.c_uint, C.c_int]
+    E.emul_kmer_tool.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint, C.c_int]
     E.emul_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int]
     return E
 
@@ -186,6 +187,34 @@ def test_emulated_kernels_deduplicate_like_the_reference(loaded, emul, table):
     assert rc == 0
     groups = ck.check_dedup(rep, out_off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
     assert groups <= 60
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+def test_emulated_kernels_kmer_tools_like_the_oracle(loaded, emul, generic):
+    """k_kmer_color_sets (the segment pipeline in per-k-mer mode) + k_kmer_runs / k_kmer_positive_bits / k_kmer_match_counts on
+    emulated warps == index::kmer_conservation / index::kmer_matches (src/kmer_conservation.cpp:7-54, src/kmer_matches.cpp:7-30)"""
+    fg, img, o = loaded
+    genomes = o.name.split(".")[0]
+    n = 300 if o.num_colors <= 32 else 100
+    for reads in (ck.gen_reads(n, 75, 300, seed=13, genomes=genomes), _edge_reads(genomes)):
+        bases, off = reads
+        nr = len(off) - 1
+        toff = np.zeros(nr + 1, dtype=np.uint64)
+        cap = max(1, int(off[nr]))
+        tr = np.zeros(3 * cap, dtype=np.uint32)
+        assert emul.emul_kmer_tool(img.ctypes.data, 0, bases.ctypes.data, off.ctypes.data, nr, toff.ctypes.data, tr.ctypes.data, cap, None, 2, generic) == 0
+        exp_off, exp_tr = o.kmer_conservation(reads)
+        assert np.array_equal(toff, exp_off) and np.array_equal(tr[: 3 * int(toff[nr])].reshape(-1, 3), exp_tr)
+        if generic:
+            continue
+        woff = np.zeros(nr + 1, dtype=np.uint64)
+        words = np.zeros(cap, dtype=np.uint32)
+        counts = np.full((nr, o.num_colors), 0xdeadbeef, dtype=np.uint32)
+        assert emul.emul_kmer_tool(img.ctypes.data, 1, bases.ctypes.data, off.ctypes.data, nr, woff.ctypes.data, words.ctypes.data, cap,
+                                   counts.ctypes.data, 2, 0) == 0
+        koff, pos, exp_counts = o.kmer_matches(reads)
+        assert np.array_equal(ck.unpack_positive_words(woff, words, koff), pos)
+        assert np.array_equal(counts, exp_counts)
 
 
 def test_loader_rejects_bad_input(built_lib, tmp_path):

@@ -76,3 +76,16 @@ def test_edge_reads(pair):
     for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.001)):
         assert _same(o.pseudoalign(reads, algo, thr), r.pseudoalign(reads, algo, thr))
     assert _same(o.fetch_color_set_ids(reads), r.fetch_color_set_ids(reads))
+
+
+def test_kmer_tools(pair):
+    """index::kmer_conservation / index::kmer_matches (src/kmer_conservation.cpp:7-54, src/kmer_matches.cpp:7-30)"""
+    o, r = pair
+    reads = ck.gen_reads(300, 75, 300, seed=61, genomes=o.genomes)
+    seqs = [b"", b"ACGT" * 5, reads[0][: int(reads[1][1])].tobytes()[:40] + b"N" + reads[0][: int(reads[1][1])].tobytes()[41:]]
+    extra = ck.reads_from_list(seqs)
+    for batch in (reads, extra):
+        a, b = o.kmer_conservation(batch), r.kmer_conservation(batch)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        a, b = o.kmer_matches(batch), r.kmer_matches(batch)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
