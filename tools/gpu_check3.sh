@@ -1,0 +1,5 @@
+#!/bin/bash
+# dev helper (GPU box): full GPU test tier
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -15
