@@ -182,6 +182,22 @@ public:
     }
     bool mapped() const { return mapped_; }
 
+    /* upper estimate of what the next batch holds, for sizing its buffers up front: the bases cannot exceed the bytes of the
+       span (half of them in a FASTQ file), the reads are estimated from the size of the first record ahead. False (and
+       zeros) for inputs that are read serially. */
+    bool estimate_batch(uint64_t& nbases, uint64_t& nreads) const {
+        nbases = nreads = 0;
+        if (!mapped_ || pos_ >= size_) return false;
+        const uint64_t bytes = std::min<uint64_t>(size_ - pos_, span_ + uint64_t(threads_) * slab_bytes_);
+        const size_t r0 = skip_blank(pos_);
+        size_t r1 = r0;
+        for (int l = 0; l < (fastq_ ? 4 : 2) && r1 < size_; ++l) r1 = next_line(r1);
+        const uint64_t rec = std::max<uint64_t>(fastq_ ? 8 : 4, r1 - r0);
+        nbases = bytes / (fastq_ ? 2 : 1) + 64;
+        nreads = bytes / rec + bytes / rec / 16 + 1024;
+        return true;
+    }
+
     /* fills b with the next reads; returns false when the input is exhausted and b is empty */
     bool next_batch(read_batch& b) {
         b.n = 0;
@@ -315,6 +331,12 @@ private:
         uint64_t nbases = 0, nreads = 0;
         std::vector<size_t> cut(T + 1);
         std::vector<uint64_t> base_at(T + 1), read_at(T + 1);
+        { /* size the batch buffers ONCE (they are pinned memory in the tool: growing them round by round would cost a pinned
+             allocation and a copy each time); the rounds below still grow the buffers if the estimate was short */
+            uint64_t eb = 0, er = 0;
+            estimate_batch(eb, er);
+            b.reserve(eb, er);
+        }
         while (pos_ < batch_end) {
             const size_t begin = pos_, target = std::min<uint64_t>(size_, begin + uint64_t(T) * slab_bytes_);
             cut[0] = begin;

@@ -193,8 +193,6 @@ int main(int argc, char** argv) {
         return 1;
     }
 
-    const auto t0 = std::chrono::high_resolution_clock::now();
-    if (a.verbose) std::cout << "*** START: pseudoalignment" << std::endl;
     uint64_t num_reads = 0, num_mapped = 0;
 
     /* one batch in flight per pipeline stage */
@@ -210,7 +208,7 @@ int main(int argc, char** argv) {
     for (auto& c : ctx) {
         c.reads.grow = [&c](fgio::read_batch& r, uint64_t nb, uint64_t nr) { /* keeps the batch's contents */
             if (nb > r.bases_cap) {
-                const uint64_t cap = nb + nb / 4 + (1u << 20);
+                const uint64_t cap = std::max<uint64_t>(nb + nb / 4 + (1u << 20), 2 * r.bases_cap);
                 char* p = static_cast<char*>(fulgor_gpu_host_alloc(cap));
                 if (!p) { std::cerr << "cannot allocate pinned host memory\n"; std::exit(1); }
                 if (r.bases) std::memcpy(p, r.bases, r.bases_cap);
@@ -219,7 +217,7 @@ int main(int argc, char** argv) {
                 r.bases_cap = cap;
             }
             if (nr > r.reads_cap) {
-                const uint64_t cap = nr + nr / 4 + (1u << 16);
+                const uint64_t cap = std::max<uint64_t>(nr + nr / 4 + (1u << 16), 2 * r.reads_cap);
                 uint64_t* p = static_cast<uint64_t*>(fulgor_gpu_host_alloc(cap * 8));
                 if (!p) { std::cerr << "cannot allocate pinned host memory\n"; std::exit(1); }
                 if (r.off) std::memcpy(p, r.off, r.reads_cap * 8);
@@ -230,6 +228,22 @@ int main(int argc, char** argv) {
         };
     }
     uint64_t colors_per_read = std::min<uint32_t>(info.num_colors, 16); /* first guess; E2BIG reports the exact need */
+    { /* set-up, like loading the index: the pinned buffers of the three batches in flight are sized for a whole batch before
+         the clock starts (a pinned allocation costs about as much as parsing the bytes it will hold) */
+        uint64_t eb = 0, er = 0;
+        if (reader.estimate_batch(eb, er)) {
+            for (auto& c : ctx) {
+                c.reads.grow(c.reads, eb, er);
+                c.p_coff.get<uint64_t>(er + 1);
+                c.colors_cap = er * colors_per_read + 1024;
+                c.p_colors.get<uint32_t>(c.colors_cap);
+                if (a.deduplicate) c.p_rep.get<uint32_t>(er + 1);
+            }
+        }
+    }
+
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    if (a.verbose) std::cout << "*** START: pseudoalignment" << std::endl;
 
     auto gpu_stage = [&](batch_ctx& c) {
         const uint32_t n = c.reads.n;
