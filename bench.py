@@ -196,6 +196,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # one process per GPU: keep this rank's pinned buffers and copy threads on the GPU's NUMA node (the cpu_baseline leg gets all cores back)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = fg.bind_host_thread(local_rank)
 
     # ---- index: rank 0 parses + flattens the .fur; one NCCL broadcast replicates the image; no other collective on the data path
     algo = fg.FULL_INTERSECTION if args.algo == "fi" else fg.THRESHOLD_UNION
@@ -314,7 +317,8 @@ def main():
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
         top = 0 if (fused or k_ms[0] >= k_ms[1]) else 1
-        kname = ("k_pseudoalign_small" if fused else "k_fetch_color_sets") if top == 0 else "k_color_sets_general"
+        table_off = os.environ.get("FULGOR_GPU_TABLE_MAX_MB", "") == "0"  # the decoded color-set table is built unless disabled / over budget
+        kname = ("k_pseudoalign_small" if fused else "k_fetch_color_sets") if top == 0 else ("k_color_sets_general" if table_off else "k_color_sets_table")
         top_ms_per_launch = k_ms[top] / args.steps
         path_ms_per_step = (k_ms[0] + k_ms[1]) / args.steps
         achieved = bytes_per_read * n / (path_ms_per_step / 1e3) / 1e9
@@ -335,6 +339,7 @@ def main():
 
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, all_cpus)  # the reference gets every core of the box
             if ck.reference_available():
                 ref, kind, threads = ck.Reference(ck.index_path(args.index)), "reference", cores
             else:
@@ -360,7 +365,8 @@ def main():
                        "reads_per_gpu": n, "read_len": [args.min_len, args.max_len], "index": args.index,
                        "l2": f"inputs ({nbases / 1e9:.2f} GB of reads per step) are larger than L2; the {image.size / 1e6:.0f} MB index image is L2-resident "
                              "by nature of the workload",
-                       "parallelism": f"reads sharded over {world} GPU(s), index replicated by one NCCL broadcast, no data-path collective"},
+                       "parallelism": f"reads sharded over {world} GPU(s), index replicated by one NCCL broadcast, no data-path collective",
+                       "host_numa_binding": f"{numa_cpus} CPUs next to the GPU" if numa_cpus else "none (single node or unknown topology)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_ms_per_step": wall_ms / args.steps, "results_total_colors": total_colors,
         }))

@@ -4,13 +4,17 @@
  *
  * Per chunk of reads (host API) the stream order is
  *     H2D(bases, read_off) -> K1(+K2 fused when num_colors <= 32) -> [K2] -> scan -> emit -> D2H
- * with three slots so that the copies of one chunk overlap the kernels of the others. The only
+ * with four slots so that the copies of one chunk overlap the kernels of the others. The only
  * cross-chunk dependency is the running CSR offset, carried in device memory.
  */
 #include <cuda_runtime.h>
+#include <sched.h>
+
+#include <cctype>
 
 #include <algorithm>
 #include <cstdio>
+#include <deque>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -59,7 +63,10 @@ struct dev_buffer {
     T* as() const { return static_cast<T*>(p); }
 };
 
-#define FG_NUM_SLOTS 3 /* chunks in flight in the host pipeline: copy-in, compute, copy-out */
+#define FG_NUM_SLOTS 4     /* chunks in flight in the host pipeline: copy-in, compute, copy-out + one of slack (see FG_FINALIZE_LAG) */
+#define FG_FINALIZE_LAG 2  /* the host reads a chunk's totals (and enqueues its values copy) two chunks behind the one it is
+                              enqueueing, so that wait never holds back the next host->device copy: the copy engine, the
+                              bottleneck of the host-buffer path, always has the next chunk queued */
 struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
@@ -421,7 +428,15 @@ static emit_plan enqueue_dedup(fulgor_gpu_index* x, slot& s, const chunk_args& a
 
 /* ---- the chunked host pipeline ---- */
 
-static const uint64_t CHUNK_MAX_READS = 1u << 20;
+/* Reads per chunk. Small chunks keep the pipeline's fill and drain short (measured on salmonella_10, 10 M reads per call:
+   2^20 -> 33.4 ms, 2^18 -> 31.8 ms, the host->device copy of the reads being the bottleneck); deduplication groups reads
+   inside a chunk, so it takes the largest one. FULGOR_GPU_CHUNK_READS overrides (tuning, tests of the multi-chunk path). */
+static uint64_t chunk_max_reads(bool dedup = false) {
+    const char* e = std::getenv("FULGOR_GPU_CHUNK_READS");
+    const uint64_t v = e ? std::strtoull(e, nullptr, 10) : 0;
+    return v ? std::min<uint64_t>(std::max<uint64_t>(v, 32), 1u << 22) : (dedup ? (1u << 20) : (1u << 18));
+}
+#define CHUNK_MAX_READS (chunk_max_reads())
 static const uint64_t CHUNK_MAX_BASES = 256ull << 20;
 static const uint64_t CHUNK_MAX_RESULT_BITS_BYTES = 256ull << 20;
 static const int RC_RETRY_LARGER_POOL = 1;
@@ -434,7 +449,7 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
     const bool small = x->H.num_colors <= 32 && op != op_kind::DEDUP;
-    uint64_t max_reads = CHUNK_MAX_READS;
+    uint64_t max_reads = chunk_max_reads(op == op_kind::DEDUP);
     if (op != op_kind::FETCH && !small)
         max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (((x->H.num_colors + 31) / 32) * 4)));
     struct pending { uint32_t first, n; int slot; emit_plan plan; };
@@ -459,8 +474,7 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     };
 
     /* chunks are cut and validated on the fly, so the host-side O(n) work overlaps the GPU work of earlier chunks */
-    pending prev{};
-    bool have_prev = false;
+    std::deque<pending> inflight;
     uint32_t ci = 0;
     for (uint32_t first = 0; first < n_reads; ++ci) {
         uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
@@ -519,12 +533,14 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         FG_CUDA(cudaMemcpyAsync(out_off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
         if (op == op_kind::FETCH && num_positive)
             FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.npos.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (have_prev) finalize(prev);
-        prev = c;
-        have_prev = true;
+        inflight.push_back(c);
+        while (inflight.size() > FG_FINALIZE_LAG) {
+            finalize(inflight.front());
+            inflight.pop_front();
+        }
         first += n;
     }
-    if (have_prev) finalize(prev);
+    for (auto const& c : inflight) finalize(c);
     for (auto& s : x->slots) {
         FG_CUDA(cudaStreamSynchronize(s.stream));
         s.busy = false;
@@ -683,6 +699,52 @@ int fulgor_gpu_device_count(void) {
         return 0;
     }
     return n;
+}
+
+/* CPUs on the same NUMA node / PCIe root as the device, from sysfs (local_cpulist of the device's PCI function) */
+static bool cpus_local_to_device(int device, cpu_set_t* set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, int(sizeof(bus)), device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; ++c) *c = char(std::tolower(*c));
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[4096] = {0};
+    const bool got = std::fgets(line, sizeof(line), f) != nullptr;
+    std::fclose(f);
+    if (!got) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char* p = line; *p && *p != '\n';) { /* "0-15,32-47" */
+        char* e = nullptr;
+        const long a = std::strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        p = e;
+        if (*p == '-') {
+            b = std::strtol(p + 1, &e, 10);
+            p = e;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET(int(c), set);
+            ++n;
+        }
+        if (*p == ',') ++p;
+    }
+    return n > 0;
+}
+
+int fulgor_gpu_bind_host_thread(int device) {
+    cpu_set_t local, current, both;
+    if (!cpus_local_to_device(device, &local)) return 0;
+    if (sched_getaffinity(0, sizeof(current), &current) != 0) return 0;
+    CPU_AND(&both, &local, &current);
+    const int n = CPU_COUNT(&both);
+    if (n == 0 || n == CPU_COUNT(&current)) return 0; /* nothing to narrow (one node, or the CPUs are not ours) */
+    return sched_setaffinity(0, sizeof(both), &both) == 0 ? n : 0;
 }
 
 void* fulgor_gpu_host_alloc(uint64_t bytes) {

@@ -58,6 +58,7 @@ def lib():
         L.fulgor_gpu_host_alloc.restype = C.c_void_p
         L.fulgor_gpu_host_alloc.argtypes = [C.c_uint64]
         L.fulgor_gpu_host_free.argtypes = [C.c_void_p]
+        L.fulgor_gpu_bind_host_thread.argtypes = [C.c_int]
         L.fulgor_gpu_image_build.argtypes = [C.c_char_p, C.POINTER(_u8p), _u64p]
         L.fulgor_gpu_image_free.argtypes = [_u8p]
         L.fulgor_gpu_image_info.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Info)]
@@ -101,6 +102,11 @@ def image_info(image):
     info = Info()
     _check(lib().fulgor_gpu_image_info(image.ctypes.data, image.size, C.byref(info)))
     return info
+
+
+def bind_host_thread(device):
+    """CPU affinity of the calling thread -> the CPUs next to `device` (NUMA-local pinned buffers); returns the CPUs bound or 0"""
+    return int(lib().fulgor_gpu_bind_host_thread(int(device)))
 
 
 class PinnedBuffer:

@@ -101,7 +101,7 @@ int fulgor_gpu_pseudoalign(fulgor_gpu_index*, int algo, double threshold,
    fetch_and_deduplicate_sets (tools/pseudoalign.cpp:92-226: fetch every read's list, sort the lists, keep one copy of each)
    followed by pseudoalign_worker over preprocessed_query_reader (tools/pseudoalign.cpp:39-44, src/ps_utils.cpp:307-415: one
    intersection per distinct list, written once per read id that has it). Here reads with the same list form a group inside
-   each chunk of <= 2^20 reads; the first one found is the group's representative and the only one whose intersection is
+   each chunk of reads (up to 2^20); the first one found is the group's representative and the only one whose intersection is
    computed, emitted and copied back:
      rep_of_read[i] = index of the read that represents read i (== i for a representative, and for every read without a
                       positive k-mer);
@@ -147,6 +147,12 @@ int fulgor_gpu_last_kernel_times(const fulgor_gpu_index*, float ms[3]);
 /* ---- utilities ----------------------------------------------------------------------------- */
 int fulgor_gpu_device_count(void);
 void* fulgor_gpu_host_alloc(uint64_t bytes); /* pinned host memory (cudaHostAlloc); NULL on failure */
+/* Narrows the calling thread's CPU affinity to the CPUs next to `device` (sysfs local_cpulist of its PCI function), so that the
+   pinned buffers the thread allocates afterwards and the copies it issues stay on the device's NUMA node: with one process or
+   thread per GPU on a multi-socket host this keeps N host->device streams from crossing the socket interconnect. Returns the
+   number of CPUs bound, 0 when there is nothing to narrow or the topology is unknown (never an error). Threads created
+   afterwards inherit the mask. */
+int fulgor_gpu_bind_host_thread(int device);
 void fulgor_gpu_host_free(void*);
 const char* fulgor_gpu_last_error(void);     /* thread-local */
 const char* fulgor_gpu_version(void);

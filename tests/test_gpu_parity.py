@@ -92,7 +92,7 @@ def test_e2big_reports_required_capacity(pair):
 
 
 def test_multi_chunk_large_batch(pair):
-    """more reads than one pipeline chunk (2^20): exercises the cross-chunk CSR carry; checked against the oracle on
+    """many pipeline chunks (2^18 reads each, more chunks than slots): exercises the cross-chunk CSR carry and the slot reuse; checked against the oracle on
     a sample and through size-independent properties on the whole batch"""
     gpu, o = pair
     n = (1 << 20) + 70000 if gpu.num_colors <= 32 else 300000
