@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -106,8 +107,9 @@ struct serial_fastx_reader {
             pos = end;
         }
     }
-    /* appends the next record's sequence to `bases`; false when the file is exhausted */
-    bool next(std::vector<char>& bases) {
+    /* appends the next record's sequence to `bases`; false when the file is exhausted. name (optional) receives the record's
+       name: the header without its first character, up to the first white space (klibpp, FQFeeder/include/kseq++.hpp:598) */
+    bool next(std::vector<char>& bases, std::string* name = nullptr) {
         std::string header;
         if (!pending_header.empty()) {
             header.swap(pending_header);
@@ -115,6 +117,11 @@ struct serial_fastx_reader {
             do {
                 if (!getline(header)) return false;
             } while (header.empty());
+        }
+        if (name) {
+            size_t e = 1;
+            while (e < header.size() && !std::isspace(static_cast<unsigned char>(header[e]))) ++e;
+            name->assign(header, 1, e - 1);
         }
         if (header[0] == '@') { /* FASTQ: sequence line(s), '+', as many quality characters */
             if (!getline(line)) return false;

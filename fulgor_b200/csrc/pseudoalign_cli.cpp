@@ -32,6 +32,7 @@
 namespace {
 
 using fgio::out_format;
+using fgio::put_u32;
 
 /* ---------------------------------------------------------------- arguments (cmd_line_parser semantics) */
 struct args_t {
@@ -105,9 +106,149 @@ struct pinned {
     ~pinned() { fulgor_gpu_host_free(p); }
 };
 
+/* ---------------------------------------------------------------- `kmer-conservation` / `kmer-matches`
+   The reference's two per-k-mer tools (tools/kmer_conservation.cpp, tools/kmer_matches.cpp) with the per-read body
+   (index::kmer_conservation / index::kmer_matches) replaced by one C-ABI call per batch. Same flags (-i -q -o -t --verbose),
+   same output lines, written in input order:
+       kmer-conservation:  name \t n [\t (start_pos_in_query num_kmers color_set_id)]*      (tools/kmer_conservation.cpp:27-37)
+       kmer-matches:       name \t num_kmers [\t 0|1]* [\t count]*num_colors                 (tools/kmer_matches.cpp:28-34)
+   These tools print the read NAMES, so the records come from the serial reader (one thread). A read shorter than k is a line
+   without k-mers (and, for kmer-matches, zero counts). */
+int kmer_tool_main(bool conservation, int argc, char** argv) {
+    args_t a;
+    if (!parse(argc, argv, a)) {
+        std::cerr << "Usage: fulgor_b200_pseudoalign " << (conservation ? "kmer-conservation" : "kmer-matches")
+                  << " -i index_filename -q query_filename -o output_filename [-t num_threads] [--verbose] [--batch-reads n]\n";
+        return 1;
+    }
+    if (a.threads == 1) std::cerr << "1 thread was specified, but an additional thread will be allocated for parsing" << std::endl;
+    if (!(ends_with(a.index, ".fur") || ends_with(a.index, ".mfur") || ends_with(a.index, ".dfur") || ends_with(a.index, ".mdfur"))) {
+        std::cerr << "Wrong index filename supplied." << std::endl;
+        return 1;
+    }
+    if (fulgor_gpu_device_count() < 1) {
+        std::cerr << "no usable CUDA device (this tool has no CPU path)" << std::endl;
+        return 1;
+    }
+    fulgor_gpu_index* gpu = nullptr;
+    if (fulgor_gpu_index_open(a.index.c_str(), 0, &gpu)) {
+        std::cerr << fulgor_gpu_last_error() << std::endl;
+        return 1;
+    }
+    fulgor_gpu_info info;
+    fulgor_gpu_index_info(gpu, &info);
+    fgio::serial_fastx_reader reader;
+    if (!reader.open(a.query.c_str())) {
+        std::cerr << "error in opening the file '" << a.query << "'" << std::endl;
+        return 1;
+    }
+    FILE* out = std::fopen(a.output.c_str(), "wb");
+    if (!out) {
+        std::cerr << "could not open output file " << a.output << std::endl;
+        return 1;
+    }
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    /* kmer-matches returns num_colors counts per read: keep a batch's counts within ~256 MB */
+    const uint64_t batch = conservation ? std::min<uint64_t>(a.batch_reads, 1u << 18)
+                                        : std::max<uint64_t>(64, std::min<uint64_t>(a.batch_reads, (64ull << 20) / std::max<uint32_t>(1, info.num_colors)));
+    std::vector<char> bases;
+    std::vector<uint64_t> off, res_off;
+    std::vector<std::string> names;
+    std::vector<uint32_t> vals, counts;
+    std::string line;
+    uint64_t num_reads = 0;
+    for (bool more = true; more;) {
+        bases.clear();
+        off.assign(1, 0);
+        names.clear();
+        std::string name;
+        while (names.size() < batch && bases.size() < (256ull << 20)) {
+            if (!reader.next(bases, &name)) {
+                more = false;
+                break;
+            }
+            off.push_back(bases.size());
+            names.push_back(name);
+        }
+        const uint32_t n = uint32_t(names.size());
+        if (n == 0) break;
+        res_off.assign(uint64_t(n) + 1, 0);
+        int rc;
+        if (conservation) {
+            if (vals.size() < 3 * (uint64_t(n) * 4 + 64)) vals.resize(3 * (uint64_t(n) * 4 + 64));
+            while ((rc = fulgor_gpu_kmer_conservation(gpu, bases.data(), off.data(), n, res_off.data(), vals.data(), vals.size() / 3)) == FULGOR_GPU_E2BIG)
+                vals.resize(3 * res_off[n]);
+        } else {
+            const uint64_t words = bases.size() / 32 + n + 1;
+            if (vals.size() < words) vals.resize(words);
+            counts.resize(uint64_t(n) * info.num_colors);
+            rc = fulgor_gpu_kmer_matches(gpu, bases.data(), off.data(), n, res_off.data(), vals.data(), vals.size(), counts.data());
+        }
+        if (rc) {
+            std::cerr << fulgor_gpu_last_error() << std::endl;
+            return 1;
+        }
+        line.clear();
+        char num[16];
+        auto put = [&](uint64_t v) { line.append(num, size_t(put_u32(num, uint32_t(v)) - num)); };
+        for (uint32_t i = 0; i < n; ++i) {
+            line += names[i];
+            line += '\t';
+            if (conservation) {
+                put(res_off[i + 1] - res_off[i]);
+                for (uint64_t t = res_off[i]; t < res_off[i + 1]; ++t) {
+                    line += "\t(";
+                    put(vals[3 * t]);
+                    line += ' ';
+                    put(vals[3 * t + 1]);
+                    line += ' ';
+                    put(vals[3 * t + 2]);
+                    line += ')';
+                }
+            } else {
+                const uint64_t len = off[i + 1] - off[i], nk = len >= info.k ? len - info.k + 1 : 0;
+                put(nk);
+                const uint32_t* w = vals.data() + res_off[i];
+                for (uint64_t j = 0; j < nk; ++j) {
+                    line += '\t';
+                    line += char('0' + ((w[j >> 5] >> (j & 31)) & 1u));
+                }
+                const uint32_t* c = counts.data() + uint64_t(i) * info.num_colors;
+                for (uint32_t j = 0; j < info.num_colors; ++j) {
+                    line += '\t';
+                    put(c[j]);
+                }
+            }
+            line += '\n';
+            if (line.size() > (1u << 22)) {
+                std::fwrite(line.data(), 1, line.size(), out);
+                line.clear();
+            }
+        }
+        std::fwrite(line.data(), 1, line.size(), out);
+        num_reads += n;
+        if (a.verbose) std::cout << "processed " << num_reads << " reads" << std::endl;
+    }
+    std::fclose(out);
+    const double ms = double(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count());
+    if (a.verbose) { /* tools/kmer_conservation.cpp:118-124 */
+        std::cout << "processed " << num_reads << " reads" << std::endl;
+        std::cout << "elapsed = " << ms << " millisec / " << ms / 1000 << " sec / " << ms / 1000 / 60 << " min / "
+                  << (ms * 1000) / double(std::max<uint64_t>(1, num_reads)) << " musec/read" << std::endl;
+    }
+    fulgor_gpu_index_close(gpu);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc > 1 && (std::strcmp(argv[1], "kmer-conservation") == 0 || std::strcmp(argv[1], "kmer-matches") == 0))
+        return kmer_tool_main(std::strcmp(argv[1], "kmer-conservation") == 0, argc - 1, argv + 1);
+    if (argc > 1 && std::strcmp(argv[1], "pseudoalign") == 0) { /* `fulgor pseudoalign ...` spelling */
+        --argc;
+        ++argv;
+    }
     args_t a;
     if (!parse(argc, argv, a)) {
         usage();

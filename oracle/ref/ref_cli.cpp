@@ -8,7 +8,7 @@
  * The three GGCAT (Rust) symbols referenced by tools/build.cpp are left
  * unresolved at link time (-Wl,--unresolved-symbols=ignore-all): `fulgor build`
  * therefore cannot run here, but `load`, `color`, `dump`, `stats`, `verify` and
- * `pseudoalign` are the reference's own code paths.
+ * `pseudoalign`, `kmer-conservation` and `kmer-matches` are the reference's own code paths.
  *
  * Built by oracle/Makefile into oracle/_ref/fulgor_ref (git-ignored).
  */
@@ -31,10 +31,12 @@
 #include "tools/util.cpp"
 #include "tools/build.cpp"
 #include "tools/pseudoalign.cpp"
+#include "tools/kmer_conservation.cpp"
+#include "tools/kmer_matches.cpp"
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        std::cerr << "usage: fulgor_ref <pseudoalign|load|dump|color|stats|verify|print-filenames|check> ...\n";
+        std::cerr << "usage: fulgor_ref <pseudoalign|kmer-conservation|kmer-matches|load|dump|color|stats|verify|print-filenames|check> ...\n";
         return 1;
     }
     auto tool = std::string(argv[1]);
@@ -46,6 +48,8 @@ int main(int argc, char** argv) {
     if (tool == "verify") return verify(argc - 1, argv + 1);
     if (tool == "check") return check(argc - 1, argv + 1);
     if (tool == "print-filenames") return print_filenames(argc - 1, argv + 1);
+    if (tool == "kmer-conservation") return kmer_conservation(argc - 1, argv + 1);
+    if (tool == "kmer-matches") return kmer_matches(argc - 1, argv + 1);
     std::cerr << "unsupported tool '" << tool << "'\n";
     return 1;
 }

@@ -187,6 +187,60 @@ def test_cli_deduplicate(index, built_lib, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_200.mdfur"])
+def test_cli_kmer_tools(index, built_lib, tmp_path):
+    """`kmer-conservation` / `kmer-matches` front-ends: the reference's output lines (tools/kmer_conservation.cpp:27-37,
+    tools/kmer_matches.cpp:28-34), checked against the oracle and, where it was built, against the reference's own tools
+    (their line order depends on thread scheduling: compared as sorted lines)"""
+    genomes = index.split(".")[0]
+    reads = ck.gen_reads(600, 75, 300, seed=51, genomes=genomes)
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path(index)
+    o = ck.Oracle(path)
+    n = len(reads[1]) - 1
+    out_c, out_m = str(tmp_path / "cons.txt"), str(tmp_path / "match.txt")
+    subprocess.check_call([CLI, "kmer-conservation", "-i", path, "-q", fq, "-o", out_c, "--batch-reads", "250"])
+    subprocess.check_call([CLI, "kmer-matches", "-i", path, "-q", fq, "-o", out_m, "--batch-reads", "250"])
+    toff, tr = o.kmer_conservation(reads)
+    want = []
+    for i in range(n):
+        t = tr[int(toff[i]):int(toff[i + 1])]
+        want.append("\t".join(["r%d" % i, str(len(t))] + ["(%d %d %d)" % tuple(x) for x in t]))
+    assert open(out_c).read().split("\n")[:-1] == want
+    koff, pos, counts = o.kmer_matches(reads)
+    want = []
+    for i in range(n):
+        p = pos[int(koff[i]):int(koff[i + 1])]
+        want.append("\t".join(["r%d" % i, str(len(p))] + [str(int(b)) for b in p] + [str(int(c)) for c in counts[i]]))
+    assert open(out_m).read().split("\n")[:-1] == want
+    if os.path.exists(ck.REF_CLI):
+        for tool, mine in (("kmer-conservation", out_c), ("kmer-matches", out_m)):
+            ref_out = str(tmp_path / ("ref_" + tool))
+            r = subprocess.run([ck.REF_CLI, tool, "-i", path, "-q", fq, "-o", ref_out, "-t", "3"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            if r.returncode != 0:
+                pytest.skip("this build of oracle/_ref/fulgor_ref has no " + tool)
+            ref_lines, my_lines = sorted(open(ref_out).read().split("\n")), sorted(open(mine).read().split("\n"))
+            if tool == "kmer-conservation":
+                assert ref_lines == my_lines
+                continue
+            # kmer-matches: each worker of the reference tool reuses one bit_vector::builder across its reads and builder::resize
+            # keeps the old words (bits/include/bit_vector.hpp:27-36), so its positive-k-mer column also shows stale ones from
+            # the worker's earlier reads (which depends on thread scheduling). Names, k-mer counts and per-color counts must be
+            # identical; the reference's bits must be a superset of ours (ours == index::kmer_matches on a fresh builder, checked
+            # against the oracle above).
+            assert len(ref_lines) == len(my_lines)
+            for a, b in zip(ref_lines, my_lines):
+                fa, fb = a.split("\t"), b.split("\t")
+                if len(fa) < 2:
+                    assert a == b
+                    continue
+                nk = int(fa[1])
+                assert fa[:2] == fb[:2] and fa[2 + nk:] == fb[2 + nk:]
+                assert all(x == y or (x == "1" and y == "0") for x, y in zip(fa[2:2 + nk], fb[2:2 + nk]))
+
+
+@pytest.mark.gpu
 def test_cli_gz_fasta_and_verbose_summary(built_lib, tmp_path):
     reads = ck.gen_reads(2000, seed=5)
     fa = str(tmp_path / "reads.fa.gz")
