@@ -195,7 +195,7 @@ def test_emulated_kernels_kmer_tools_like_the_oracle(loaded, emul, generic):
     emulated warps == index::kmer_conservation / index::kmer_matches (src/kmer_conservation.cpp:7-54, src/kmer_matches.cpp:7-30)"""
     fg, img, o = loaded
     genomes = o.name.split(".")[0]
-    n = 300 if o.num_colors <= 32 else 100
+    n = 120 if o.num_colors <= 32 else 50
     for reads in (ck.gen_reads(n, 75, 300, seed=13, genomes=genomes), _edge_reads(genomes)):
         bases, off = reads
         nr = len(off) - 1
