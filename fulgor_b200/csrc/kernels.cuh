@@ -70,6 +70,7 @@ FG_HD uint32_t fg_clz32(uint32_t x) {
 #define FG_FULL 0xffffffffu
 #define FG_NOT_FOUND 0xffffffffu
 #define FG_MAX_ENTRIES 32 /* distinct color sets per read held in registers (one per lane) */
+#define FG_DIVERSE_BATCH 10 /* distinct color sets in one batch of 32 items from which a read skips the register table */
 
 /* device view of the image: absolute pointers + the scalars the kernels need */
 struct dev_index {
@@ -876,34 +877,21 @@ struct read_hits {
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __clz(int(v - 1))); }
 
-/* slow path of the per-read table: more than 32 distinct color sets. Lanes stride over the list. */
-__device__ __noinline__ void table_insert(read_hits& R, uint32_t kk, uint32_t cc, uint32_t nk, const entry_pool& pool, uint32_t lane) {
-    uint32_t found = 0;
-    for (uint32_t i0 = 0; i0 < R.n && !found; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool eq = i < R.n && R.tab[i].x == kk;
-        found = __ballot_sync(FG_FULL, eq);
-        if (eq) R.tab[i].y += cc;
-    }
-    if (!found) {
-        if (R.n == R.cap) { /* grow into the pool: nk bounds the number of distinct color sets of this read */
-            const uint32_t want = next_pow2(nk);
-            unsigned long long off = 0;
-            if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)want);
-            off = __shfl_sync(FG_FULL, off, 0);
-            if (want <= R.cap || off + want > pool.cap) {
-                if (lane == 0) *pool.exhausted = 1;
-                R.failed = true;
-                return;
-            }
-            uint2* nt = pool.base + off;
-            for (uint32_t i = lane; i < R.n; i += 32) nt[i] = R.tab[i];
-            R.tab = nt;
-            R.cap = want;
-        }
-        if (lane == 0) R.tab[R.n] = make_uint2(kk, cc);
-        R.n += 1;
-    }
+/* The per-read list beyond 32 distinct color sets (shared memory first, then the pool). Entries are APPENDED without
+   looking for their color-set id -- a batch of items costs one ballot and one store per lane -- so the list may hold an id
+   several times; table_compact() sorts it and merges equal ids, at the end of the read and whenever the list is full. */
+
+/* room for `extra` more entries; false when the pool is exhausted (the host grows it and reruns) */
+__device__ __noinline__ bool table_reserve(read_hits& R, uint32_t extra, uint32_t nk, const entry_pool& pool, uint32_t lane);
+__device__ __noinline__ void table_compact(read_hits& R, uint32_t lane);
+
+/* appends {cid, cnt} of every lane with have = true, in lane order */
+__device__ __forceinline__ void table_append(read_hits& R, bool have, uint32_t cid, uint32_t cnt, uint32_t nk, const entry_pool& pool, uint32_t lane) {
+    const uint32_t b = __ballot_sync(FG_FULL, have);
+    if (b == 0) return;
+    if (R.n + 32 > R.cap && !table_reserve(R, 32, nk, pool, lane)) return;
+    if (have) R.tab[R.n + __popc(b & ((1u << lane) - 1u))] = make_uint2(cid, cnt);
+    R.n += __popc(b);
     __syncwarp();
 }
 
@@ -929,12 +917,60 @@ __device__ __noinline__ void table_sort(uint2* tab, uint32_t n, uint32_t lane) {
     }
 }
 
+/* sorts the list by color-set id and merges the entries with equal ids (their counts add up): n becomes the number of
+   distinct ids. The head of every run of equal ids sums the run, then the heads are packed to the front in order. */
+__device__ __noinline__ void table_compact(read_hits& R, uint32_t lane) {
+    uint2* tab = R.tab;
+    const uint32_t n = R.n;
+    table_sort(tab, n, lane);
+    uint32_t out_n = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint2 e = make_uint2(FG_NOT_FOUND, 0);
+        bool head = false;
+        if (i < n) {
+            e = tab[i];
+            head = i == 0 || tab[i - 1].x != e.x;
+            if (head)
+                for (uint32_t j = i + 1; j < n && tab[j].x == e.x; ++j) e.y += tab[j].y;
+        }
+        const uint32_t b = __ballot_sync(FG_FULL, head);
+        __syncwarp(); /* all reads of this block of entries are done before the packed entries overwrite it */
+        if (head) tab[out_n + __popc(b & ((1u << lane) - 1u))] = e;
+        out_n += __popc(b);
+        __syncwarp();
+    }
+    R.n = out_n;
+}
+
+__device__ __noinline__ bool table_reserve(read_hits& R, uint32_t extra, uint32_t nk, const entry_pool& pool, uint32_t lane) {
+    if (R.failed) return false;
+    table_compact(R, lane);
+    if (R.n + extra <= R.cap) return true;
+    /* grow into the pool: nk bounds the number of distinct color sets of this read, so a compacted list never needs more */
+    const uint32_t want = next_pow2(nk + extra);
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)want);
+    off = __shfl_sync(FG_FULL, off, 0);
+    if (want <= R.cap || off + want > pool.cap) {
+        if (lane == 0) *pool.exhausted = 1;
+        R.failed = true;
+        return false;
+    }
+    uint2* nt = pool.base + off;
+    for (uint32_t i = lane; i < R.n; i += 32) nt[i] = R.tab[i];
+    __syncwarp();
+    R.tab = nt;
+    R.cap = want;
+    return true;
+}
+
 /* index::fetch_color_set_ids (src/ps_full_intersection.cpp:335-374) and the counting half of
    index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read.
    The reference's two sort+unique passes become: warp match on the color-set id inside a tile, a
-   32-entry register table (one entry per lane) across tiles -- spilling to `scratch` (shared memory,
-   scratch_cap entries, a power of two) and then to the pool for reads with more distinct color sets --
-   and one bitonic sort at the end. */
+   32-entry register table (one entry per lane) across tiles; a read with more distinct color sets moves to
+   an append-only list in `scratch` (shared memory, scratch_cap entries, a power of two, >= 64) and then in
+   the pool, sorted and merged by table_compact() when it fills up and at the end. */
 template <int W>
 __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, const uint8_t* buf_begin,
                                                            const uint8_t* buf_end, uint32_t lane,
@@ -952,9 +988,22 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
     while (tiles.next(cid, cnt)) {
         const bool found = cnt != 0;
         R.npos += __reduce_add_sync(FG_FULL, cnt);
+        if (R.tab != nullptr) { /* the read already has more than 32 distinct color sets: append, merge later */
+            table_append(R, found, cid, cnt, tiles.nk, pool, lane);
+            continue;
+        }
         const uint32_t grp = __match_any_sync(FG_FULL, cid);
         const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
         uint32_t leaders = __ballot_sync(FG_FULL, leader);
+        if (__popc(leaders) >= FG_DIVERSE_BATCH) { /* a batch with many different ids: the register table would be walked once per
+                                                     id and overflow soon anyway -- go to the list now, with the batch as it is */
+            if (lane < R.n) scratch[lane] = make_uint2(R.cid, R.cnt);
+            R.tab = scratch;
+            R.cap = scratch_cap;
+            __syncwarp();
+            table_append(R, found, cid, cnt, tiles.nk, pool, lane);
+            continue;
+        }
         while (leaders) {
             const int src = __ffs(int(leaders)) - 1;
             leaders &= leaders - 1;
@@ -979,11 +1028,20 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
                 R.cap = scratch_cap;
                 __syncwarp();
             }
-            if (!R.failed) table_insert(R, kk, cc, tiles.nk, pool, lane);
+            table_append(R, lane == 0, kk, cc, tiles.nk, pool, lane); /* the rest of this batch: one merged entry per id */
         }
     }
     if (R.tab != nullptr) {
-        if (!R.failed) table_sort(R.tab, R.n, lane);
+        if (!R.failed) {
+            table_compact(R, lane);
+            if (R.n <= FG_MAX_ENTRIES) { /* few distinct ids after all: back to one entry per lane (already sorted) */
+                const uint2 e = lane < R.n ? R.tab[lane] : make_uint2(FG_NOT_FOUND, 0);
+                R.cid = e.x;
+                R.cnt = e.y;
+                R.tab = nullptr;
+                R.cap = 0;
+            }
+        }
     } else if (R.n > 1) { /* bitonic sort across lanes; unused lanes hold FG_NOT_FOUND and sink to the end */
 #pragma unroll
         for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
