@@ -444,7 +444,9 @@ static const int RC_RETRY_LARGER_POOL = 1;
 enum class op_kind { FETCH, PSEUDOALIGN, DEDUP };
 
 static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
-                               uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
+                               uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* per_read_out) {
+    /* per_read_out (n_reads entries, nullable): FETCH -> the reads' positive k-mer counts; DEDUP -> their representatives */
+    uint32_t* const num_positive = op == op_kind::FETCH ? per_read_out : nullptr;
     FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, x->slots[0].stream));
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
@@ -518,8 +520,7 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
             c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), &launches);
         } else if (op == op_kind::DEDUP) {
             c.plan = enqueue_dedup(x, s, a, c.first, s.off.as<uint64_t>(), &launches);
-            /* num_positive doubles as the rep_of_read output of this operation */
-            FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaMemcpyAsync(per_read_out + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
         } else {
             c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, s.off.as<uint64_t>(), nullptr, nullptr, &launches);
         }
@@ -550,12 +551,12 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
 }
 
 static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
-                          uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* num_positive) {
+                          uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* per_read_out) {
     FG_CUDA(cudaSetDevice(x->device));
     out_off[0] = 0;
     if (n_reads == 0) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
-        const int rc = run_host_batch_once(x, op, algo, threshold, bases, read_off, n_reads, out_off, out_vals, cap, num_positive);
+        const int rc = run_host_batch_once(x, op, algo, threshold, bases, read_off, n_reads, out_off, out_vals, cap, per_read_out);
         if (rc != RC_RETRY_LARGER_POOL) return rc;
         x->pool_per_read *= 4; /* reads with many distinct color sets: rerun with a larger entry pool (kept for later calls) */
     }

@@ -491,6 +491,67 @@ __global__ void __launch_bounds__(FG_BLOCK) k_expand_color_sets(const __grid_con
    for threshold union the bitmap is added to NP bit-sliced counter planes (kernels.cuh: bit_planes, here in registers,
    no atomics: a lane owns its words) and the threshold test is one bit-sliced subtraction. Same results as
    k_color_sets_general. NP = counter bits (scores < 2^NP), T = words per lane and pass. */
+/* Bit-sliced per-color counters in CARRY-SAVE form for the threshold union on the decoded table: plane k holds bit k of 32 T
+   colors' scores (acc) plus at most one PENDING vector of the same weight 2^k. A vector arriving at a plane that has no
+   pending one is just parked there (no arithmetic); when a second one arrives, the plane's 3:2 compressor folds
+   {acc, pending, new} into the new plane bit and one carry for the next plane. Which planes hold a pending vector depends
+   only on the multiplicities, which every lane shares, so the control flow is warp-uniform and the planes stay in registers
+   (compile-time indices). A hit set costs about one compressor (two LOP3 per word) per set bit of its multiplicity, however
+   many planes the counters have -- the ripple-carry adder this replaces paid a full adder per plane and word for every set. */
+template <int NP, int T>
+struct carry_save_counters {
+    uint32_t acc[NP][T], pend[NP][T];
+    uint32_t pending; /* bit k: plane k holds a pending vector (warp-uniform) */
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[k][t] = 0u;
+        }
+        pending = 0;
+    }
+    /* counters[c] += 2^b for every set bit c of v (v is consumed); a carry out of the top plane cannot happen (scores < 2^NP) */
+    __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) {
+        bool have = true;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            if (have && uint32_t(k) >= b) {
+                if ((pending >> k) & 1u) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const uint32_t a = acc[k][t], p = pend[k][t], x = v[t];
+                        acc[k][t] = a ^ p ^ x;
+                        v[t] = (a & p) | (a & x) | (p & x);
+                    }
+                    pending &= ~(1u << k);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) pend[k][t] = v[t];
+                    pending |= 1u << k;
+                    have = false;
+                }
+            }
+        }
+    }
+    /* folds the pending vectors in: afterwards acc[k] is bit k of the scores */
+    __device__ __forceinline__ void finish() {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            if ((pending >> k) & 1u) {
+                uint32_t c[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    c[t] = acc[k][t] & pend[k][t];
+                    acc[k][t] ^= pend[k][t];
+                }
+                pending &= ~(1u << k);
+                if (k + 1 < NP) add(c, uint32_t(k + 1));
+            }
+        }
+    }
+};
+
 template <bool FI, int NP, int T>
 __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
                                                               const uint2* __restrict__ stage, const uint2* __restrict__ pool,
@@ -513,12 +574,11 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
         const uint64_t min_score = FI ? uint64_t(n) : uint64_t(double(__ldg(num_positive + r)) * threshold);
         uint32_t total = 0;
         for (uint32_t w0 = 0; w0 < W; w0 += 32 * T) {
-            uint32_t pl[FI ? 1 : NP][T]; /* FI: the running intersection; TU: counter planes */
+            uint32_t acc[T];                                    /* FI: the running intersection */
+            carry_save_counters<FI ? 1 : NP, FI ? 1 : T> cs;   /* TU: the colors' scores, bit-sliced */
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-#pragma unroll
-                for (int k = 0; k < (FI ? 1 : NP); ++k) pl[k][t] = FI ? ~0u : 0u;
-            }
+            for (int t = 0; t < T; ++t) acc[t] = ~0u;
+            if (!FI) cs.clear();
             for (uint32_t j = 0; j < n; ++j) {
                 const uint2 e = ents[j];
                 const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
@@ -527,31 +587,27 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
                 for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
                 if (FI) {
 #pragma unroll
-                    for (int t = 0; t < T; ++t) pl[0][t] &= x[t];
-                } else { /* counter += multiplicity for every member: one full adder per plane, 32 colors wide */
-                    const uint32_t wt = e.y;
+                    for (int t = 0; t < T; ++t) acc[t] &= x[t];
+                } else { /* score += multiplicity for every member: the bitmap enters at the plane of every set bit of the multiplicity */
+                    for (uint32_t wt = e.y; wt; wt &= wt - 1) {
+                        uint32_t v[FI ? 1 : T];
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        uint32_t carry = 0;
-#pragma unroll
-                        for (int k = 0; k < (FI ? 1 : NP); ++k) {
-                            const uint32_t y = ((wt >> k) & 1u) ? x[t] : 0u, a = pl[k][t];
-                            pl[k][t] = a ^ y ^ carry;
-                            carry = (a & y) | (a & carry) | (y & carry);
-                        }
+                        for (int t = 0; t < (FI ? 1 : T); ++t) v[t] = x[t];
+                        cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
                 }
             }
+            if (!FI) cs.finish();
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 const uint32_t w = w0 + 32 * t + lane;
-                uint32_t word = pl[0][t];
+                uint32_t word = acc[t];
                 if (!FI) { /* score >= min_score <=> carry out of score + ~min_score + 1 over NP bits */
                     uint32_t carry = ~0u;
 #pragma unroll
                     for (int k = 0; k < (FI ? 1 : NP); ++k) {
-                        const uint32_t nb = ((min_score >> k) & 1u) ? 0u : ~0u;
-                        carry = (pl[k][t] & nb) | (pl[k][t] & carry) | (nb & carry);
+                        const uint32_t nb = ((min_score >> k) & 1u) ? 0u : ~0u, pk = cs.acc[k][FI ? 0 : t];
+                        carry = (pk & nb) | (pk & carry) | (nb & carry);
                     }
                     word = (min_score >> NP) ? 0u : carry; /* a threshold beyond the counters' range is never met */
                 }

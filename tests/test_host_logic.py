@@ -163,6 +163,26 @@ def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr, t
         assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
 
 
+def test_emulated_threshold_union_wide_counters(emul, built_lib):
+    """long reads with REPEATED content: multiplicities of dozens to thousands drive the carry-save counters of the table kernel
+    through their 10-, 16- and 32-plane variants (reads of up to 2^10, 2^16 and more k-mers)"""
+    import fulgor_b200 as fg
+
+    path = ck.index_path("synth_200.mfur")
+    img, o = fg.build_image(path), ck.Oracle(path)
+    base = ck.gen_reads(12, 120, 200, seed=33, genomes="synth_200")
+    seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(12)]
+    for batch in ([seqs[0] * 3 + seqs[1], seqs[2] * 5],                       # < 2^10 k-mers
+                  [seqs[3] * 9 + seqs[4] * 2, (seqs[5] + seqs[6]) * 6, seqs[7]],   # < 2^16
+                  [(seqs[8] + seqs[9][:77]) * 300, seqs[10]]):                  # >= 2^16 k-mers: 32 planes
+        reads = ck.reads_from_list(batch)
+        for thr in (0.9, 0.3):
+            got = emul_pseudoalign(emul, img, reads, 1, thr, o.num_colors, table=1)
+            exp = o.pseudoalign(reads, 1, thr)
+            assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+    o.close()
+
+
 @pytest.mark.parametrize("table", [0, 1])
 def test_emulated_kernels_deduplicate_like_the_reference(loaded, emul, table):
     """K1 -> k_group_reads -> color-set kernel on the representatives only -> scan -> emit on emulated warps: every read's
