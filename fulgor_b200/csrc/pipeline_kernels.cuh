@@ -52,12 +52,20 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(c
                 acc &= __reduce_and_sync(FG_FULL, mask);
             } else {
                 uint32_t todo = __ballot_sync(FG_FULL, found);
-                while (todo) {
-                    const int src = __ffs(int(todo)) - 1;
-                    todo &= todo - 1;
-                    const uint32_t mj = __shfl_sync(FG_FULL, mask, src);
-                    const uint32_t wj = __shfl_sync(FG_FULL, cnt, src);
-                    score += ((mj >> lane) & 1u) ? wj : 0u;
+                if (2 * __popc(todo) > I.num_colors) { /* more items than colors: one warp reduction per color (lane c keeps color c) */
+                    const uint32_t w = found ? cnt : 0u;
+                    for (uint32_t c = 0; c < I.num_colors; ++c) {
+                        const uint32_t sc = __reduce_add_sync(FG_FULL, ((mask >> c) & 1u) ? w : 0u);
+                        if (lane == c) score += sc;
+                    }
+                } else { /* few items: broadcast each one, lane c tests its color */
+                    while (todo) {
+                        const int src = __ffs(int(todo)) - 1;
+                        todo &= todo - 1;
+                        const uint32_t mj = __shfl_sync(FG_FULL, mask, src);
+                        const uint32_t wj = __shfl_sync(FG_FULL, cnt, src);
+                        score += ((mj >> lane) & 1u) ? wj : 0u;
+                    }
                 }
             }
         }
