@@ -2,8 +2,8 @@
 # Fixture tooling (not on the query path): builds the labelled STAND-IN for salmonella_4546 (the real 4,546 genomes are a Zenodo
 # download, unavailable offline): 4,546 synthetic genomes evolved along a random tree with substitutions,
 # indels and horizontal transfers (tools/synthgen.py), dumped to unitigs + color sets (tools/mkdump.cpp) and turned into a
-# genuine .fur / .mfur by the REFERENCE's own tools (oracle/_ref/fulgor_ref load -m 20, color --meta), like README.md:158-160.
-# Needs oracle/_ref (i.e. /root/reference at build time). Output: fixtures_big/NAME.{fur,mfur,gpk} (git-ignored).
+# genuine .fur / .mfur / .dfur / .mdfur by the REFERENCE's own tools (oracle/_ref/fulgor_ref load -m 20, color --meta / --diff / --meta --diff), like README.md:158-160.
+# Needs oracle/_ref (i.e. /root/reference at build time). Output: fixtures_big/NAME.{fur,mfur,dfur,mdfur,gpk} (git-ignored).
 #   tools/make_standin_4546.sh [GENOME_LEN=200000] [N=4546] [SUB=0.00003] [NAME=synth_N]
 # The default substitution rate gives ~0.4 unitigs per genome position, like the real collection (1.88 M unitigs over ~5 Mbp
 # genomes, reference README.md:158-160); SUB=0.0005 with GENOME_LEN=100000 gives a much more fragmented stress case
@@ -18,8 +18,11 @@ python tools/synthgen.py "$TMP/genomes" "$N" "$LEN" --seed 4546 --sub "$SUB" --i
 build/mkdump "$TMP/$NAME" "@$TMP/genomes/list.txt"
 oracle/_ref/fulgor_ref load -i "$TMP/$NAME" -o "$TMP/$NAME" -m 20 -d "$TMP" -t 8 --verbose
 oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --meta --verbose
+# the differential and meta-differential re-encodings (about a minute each); their dictionaries are rebuilt (permuted unitigs)
+oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --diff --verbose
+oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --meta --diff --verbose
 mkdir -p ${FG_FULL_DIR:-/tmp/fg_fixtures/full}
-mv "$TMP/$NAME.fur" "$TMP/$NAME.mfur" "$OUT/"
+mv "$TMP/$NAME.fur" "$TMP/$NAME.mfur" "$TMP/$NAME.dfur" "$TMP/$NAME.mdfur" "$OUT/"
 mv "$TMP/$NAME.gpk" ${FG_FULL_DIR:-/tmp/fg_fixtures/full}/
 # reads are drawn from every 20th genome: a small file that travels to the GPU box (the full pack stays in ${FG_FULL_DIR:-/tmp/fg_fixtures/full}/)
 python tools/gpk_subset.py "${FG_FULL_DIR:-/tmp/fg_fixtures/full}/$NAME.gpk" "$OUT/$NAME.gpk" 20
