@@ -519,45 +519,55 @@ struct carry_save_counters {
         }
         pending = 0;
     }
-    /* counters[c] += 2^b for every set bit c of v (v is consumed); a carry out of the top plane cannot happen (scores < 2^NP) */
-    __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) {
-        bool have = true;
+    /* the vector enters at plane K (compile-time): every plane with a pending vector compresses and passes the carry on, the
+       first one without parks it. Only the planes actually visited cost instructions; a carry out of the top plane cannot
+       happen (scores < 2^NP). */
+    template <int K>
+    __device__ __forceinline__ void add_from(uint32_t (&v)[T]) {
+        if constexpr (K < NP) {
+            if ((pending >> K) & 1u) {
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            if (have && uint32_t(k) >= b) {
-                if ((pending >> k) & 1u) {
-#pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        const uint32_t a = acc[k][t], p = pend[k][t], x = v[t];
-                        acc[k][t] = a ^ p ^ x;
-                        v[t] = (a & p) | (a & x) | (p & x);
-                    }
-                    pending &= ~(1u << k);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < T; ++t) pend[k][t] = v[t];
-                    pending |= 1u << k;
-                    have = false;
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a = acc[K][t], p = pend[K][t], x = v[t];
+                    acc[K][t] = a ^ p ^ x;
+                    v[t] = (a & p) | (a & x) | (p & x);
                 }
+                pending &= ~(1u << K);
+                add_from<K + 1>(v);
+            } else {
+#pragma unroll
+                for (int t = 0; t < T; ++t) pend[K][t] = v[t];
+                pending |= 1u << K;
             }
         }
     }
-    /* folds the pending vectors in: afterwards acc[k] is bit k of the scores */
-    __device__ __forceinline__ void finish() {
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            if ((pending >> k) & 1u) {
+    template <int K>
+    __device__ __forceinline__ void dispatch(uint32_t (&v)[T], uint32_t b) {
+        if constexpr (K < NP) {
+            if (b == uint32_t(K)) add_from<K>(v);
+            else dispatch<K + 1>(v, b);
+        }
+    }
+    /* counters[c] += 2^b for every set bit c of v (v is consumed) */
+    __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) { dispatch<0>(v, b); }
+    /* folds the pending vectors in, lowest plane first: afterwards acc[k] is bit k of the scores */
+    template <int K>
+    __device__ __forceinline__ void finish_from() {
+        if constexpr (K < NP) {
+            if ((pending >> K) & 1u) {
                 uint32_t c[T];
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    c[t] = acc[k][t] & pend[k][t];
-                    acc[k][t] ^= pend[k][t];
+                    c[t] = acc[K][t] & pend[K][t];
+                    acc[K][t] ^= pend[K][t];
                 }
-                pending &= ~(1u << k);
-                if (k + 1 < NP) add(c, uint32_t(k + 1));
+                pending &= ~(1u << K);
+                add_from<K + 1>(c);
             }
+            finish_from<K + 1>();
         }
     }
+    __device__ __forceinline__ void finish() { finish_from<0>(); }
 };
 
 template <bool FI, int NP, int T>

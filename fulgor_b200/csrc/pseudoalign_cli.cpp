@@ -111,7 +111,7 @@ struct pinned {
    (index::kmer_conservation / index::kmer_matches) replaced by one C-ABI call per batch. Same flags (-i -q -o -t --verbose),
    same output lines, written in input order:
        kmer-conservation:  name \t n [\t (start_pos_in_query num_kmers color_set_id)]*      (tools/kmer_conservation.cpp:27-37)
-       kmer-matches:       name \t num_kmers [\t 0|1]* [\t count]*num_colors                 (tools/kmer_matches.cpp:28-34)
+       kmer-matches:       "num_colors=C" once, then  name \t num_kmers [\t 0|1]* [\t count]*C  (tools/kmer_matches.cpp:98, 28-34)
    These tools print the read NAMES, so the records come from the serial reader (one thread). A read shorter than k is a line
    without k-mers (and, for kmer-matches, zero counts). */
 int kmer_tool_main(bool conservation, int argc, char** argv) {
@@ -147,6 +147,7 @@ int kmer_tool_main(bool conservation, int argc, char** argv) {
         std::cerr << "could not open output file " << a.output << std::endl;
         return 1;
     }
+    if (!conservation) std::fprintf(out, "num_colors=%u\n", info.num_colors); /* tools/kmer_matches.cpp:98 */
     const auto t0 = std::chrono::high_resolution_clock::now();
     /* kmer-matches returns num_colors counts per read: keep a batch's counts within ~256 MB */
     const uint64_t batch = conservation ? std::min<uint64_t>(a.batch_reads, 1u << 18)

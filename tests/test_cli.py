@@ -213,7 +213,7 @@ def test_cli_kmer_tools(index, built_lib, tmp_path):
     for i in range(n):
         p = pos[int(koff[i]):int(koff[i + 1])]
         want.append("\t".join(["r%d" % i, str(len(p))] + [str(int(b)) for b in p] + [str(int(c)) for c in counts[i]]))
-    assert open(out_m).read().split("\n")[:-1] == want
+    assert open(out_m).read().split("\n")[:-1] == ["num_colors=%d" % o.num_colors] + want
     if os.path.exists(ck.REF_CLI):
         for tool, mine in (("kmer-conservation", out_c), ("kmer-matches", out_m)):
             ref_out = str(tmp_path / ("ref_" + tool))
