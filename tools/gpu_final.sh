@@ -3,7 +3,7 @@
 # compute-sanitizer, one ncu capture of the threshold-union table kernel. Most important first: the call may be cut short.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x --durations=12 2>&1 | tail -22
+timeout 900 python -m pytest tests -m gpu -q --durations=12 2>&1 | tail -22
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cut -c1-200 gpurun_out/bench.json
 timeout 300 python bench.py --algo tu > gpurun_out/bench_tu.json 2>> gpurun_out/bench.err; cut -c1-200 gpurun_out/bench_tu.json
