@@ -284,6 +284,25 @@ def test_no_cpu_fallback_without_a_gpu(built_lib):
     assert e.value.code == fg.index.ENODEV
 
 
+def test_entry_points_reject_a_null_handle(built_lib):
+    """every compute entry point of include/fulgor_gpu.h returns EINVAL on a null handle instead of touching it (no GPU needed)"""
+    import fulgor_b200 as fg
+
+    L = fg.lib()
+    off = np.zeros(2, dtype=np.uint64)
+    out = np.zeros(2, dtype=np.uint64)
+    vals = np.zeros(8, dtype=np.uint32)
+    EINVAL = -22
+    assert L.fulgor_gpu_fetch_color_set_ids(None, b"A", off.ctypes.data, 1, out.ctypes.data, vals.ctypes.data, 8, None) == EINVAL
+    assert L.fulgor_gpu_pseudoalign(None, 0, 1.0, b"A", off.ctypes.data, 1, out.ctypes.data, vals.ctypes.data, 8) == EINVAL
+    assert L.fulgor_gpu_pseudoalign_dedup(None, b"A", off.ctypes.data, 1, vals.ctypes.data, out.ctypes.data, vals.ctypes.data, 8) == EINVAL
+    assert L.fulgor_gpu_kmer_conservation(None, b"A", off.ctypes.data, 1, out.ctypes.data, vals.ctypes.data, 2) == EINVAL
+    assert L.fulgor_gpu_kmer_matches(None, b"A", off.ctypes.data, 1, out.ctypes.data, vals.ctypes.data, 8, vals.ctypes.data) == EINVAL
+    assert b"null" in L.fulgor_gpu_last_error()
+    if L.fulgor_gpu_device_count() == 0:
+        assert fg.bind_host_thread(0) == 0  # unknown topology: nothing is narrowed, never an error
+
+
 def test_product_does_not_reference_the_oracle():
     """only tests/, __graft_entry__.smoke() and bench.py may touch oracle/"""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "fulgor_b200")):
