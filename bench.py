@@ -322,16 +322,21 @@ def main():
         top_ms_per_launch = k_ms[top] / args.steps
         path_ms_per_step = (k_ms[0] + k_ms[1]) / args.steps
         achieved = bytes_per_read * n / (path_ms_per_step / 1e3) / 1e9
-        traffic = None
+        traffic, ncu_view = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            per_read = json.load(open(tpath)).get(f"{kname}_dram_bytes_per_read@{args.index}")
-            traffic = per_read * n if per_read else None  # ncu DRAM bytes per read of the same kernel x reads per launch
+            try:
+                tj = json.load(open(tpath))
+                per_read = tj.get(f"{kname}_dram_bytes_per_read@{args.index}")
+                traffic = per_read * n if per_read else None  # ncu DRAM bytes per read of the same kernel x reads per launch
+                ncu_view = tj.get(f"{kname}_ncu@{args.index}")  # what actually bounds the kernel (pipe utilisation from the committed capture)
+            except (ValueError, OSError):
+                pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "kernel": kname, "kernel_ms_per_launch": top_ms_per_launch,
                     "kernel_share_of_step": (k_ms[top] / sum(k_ms)) if world == 1 else None,
                     "lookup_ms": k_ms[0] / args.steps, "color_sets_ms": k_ms[1] / args.steps, "scan_emit_ms": k_ms[2] / args.steps,
-                    "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src,
+                    "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src, "ncu": ncu_view,
                     "note": "algorithmic bytes = SURVEY.md 8(d) (independent lookups: 160 B per valid k-mer + hit color sets + output) over the "
                             "lookup + color-set kernels' time. The kernels use SEED-AND-EXTEND (one MPHF lookup and ~1.2 string comparisons per run "
                             "of ~5 k-mers), i.e. do less work than independent lookups, so frac may exceed 1; the index is L2-resident and the "
