@@ -16,6 +16,7 @@ DATA = os.path.join(ROOT, "data")
 BIG_DIRS = [os.path.join(ROOT, "fixtures_big"), os.environ.get("FG_FIXTURES_BIG", "/tmp/fg_fixtures/big")]
 ORACLE_SO = os.path.join(ROOT, "oracle", "libfulgor_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfulgor_ref.so")
+REF_DBG_SO = os.path.join(ROOT, "oracle", "_ref", "libfulgor_ref_dbg.so")  # the same shim with the reference's asserts compiled in
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "fulgor_ref")
 TOOLS_SO = os.path.join(ROOT, "build", "libfg_tools.so")
 
@@ -155,8 +156,8 @@ def reference_available():
 class Reference(_Batch):
     """The unmodified reference (oracle/_ref/libfulgor_ref.so, built by `make -C oracle ref`)."""
 
-    def __init__(self, path):
-        L = C.CDLL(REF_SO)
+    def __init__(self, path, self_checking=False):
+        L = C.CDLL(REF_DBG_SO if self_checking else REF_SO)
         L.fref_open.restype = C.c_void_p
         L.fref_open.argtypes = [C.c_char_p]
         L.fref_close.argtypes = [C.c_void_p]

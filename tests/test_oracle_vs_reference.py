@@ -1,5 +1,7 @@
 """Pins the plain-C oracle (oracle/fulgor_oracle.c) against the UNMODIFIED reference compiled from /root/reference
 (oracle/_ref/libfulgor_ref.so, built by `make -C oracle ref`). Skipped where that library was not built."""
+import os
+
 import numpy as np
 import pytest
 
@@ -89,3 +91,21 @@ def test_kmer_tools(pair):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         a, b = o.kmer_matches(batch), r.kmer_matches(batch)
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.skipif(not os.path.exists(ck.REF_DBG_SO), reason="oracle/_ref/libfulgor_ref_dbg.so not built")
+@pytest.mark.parametrize("index", INDEXES)
+def test_reference_self_checks_run_clean(index):
+    """SURVEY.md section 4, mechanism 1: the reference compiled WITHOUT -DNDEBUG checks itself on the hot path (every streamed
+    k-mer answer against an independent lookup, streaming_query.hpp:107; every full intersection against decode-all +
+    std::set_intersection, src/ps_full_intersection.cpp:399; every threshold union against a naive score array,
+    src/ps_threshold_union.cpp:401) and aborts on any disagreement. It must run clean on our fixtures and reads, and give
+    the oracle's answers."""
+    path = ck.index_path(index)
+    r, o = ck.Reference(path, self_checking=True), ck.Oracle(path)
+    reads = ck.gen_reads(1500 if index.startswith("salmonella") else 400, 75, 300, seed=123, genomes=index.split(".")[0])
+    assert _same(r.fetch_color_set_ids(reads), o.fetch_color_set_ids(reads))
+    for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.3)):
+        assert _same(r.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+    r.close()
+    o.close()
