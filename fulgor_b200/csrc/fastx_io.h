@@ -473,6 +473,53 @@ struct bit_writer { /* LSB-first, like bits::bit_vector::builder */
     }
 };
 
+/* ---------------------------------------------------------------- output lines of the per-k-mer tools
+   reads [lo, hi) of a batch, appended to `line`:
+     kmer-conservation  name \t n [\t (start_pos_in_query num_kmers color_set_id)]* \n      (tools/kmer_conservation.cpp:27-37)
+     kmer-matches       name \t num_kmers [\t 0|1]*num_kmers [\t count]*num_colors \n        (tools/kmer_matches.cpp:28-34) */
+inline void append_u32(std::string& line, uint64_t v) {
+    char num[16];
+    line.append(num, size_t(put_u32(num, uint32_t(v)) - num));
+}
+inline void format_kmer_conservation(const std::vector<std::string>& names, uint32_t lo, uint32_t hi, const uint64_t* triple_off,
+                                     const uint32_t* triples, std::string& line) {
+    for (uint32_t i = lo; i < hi; ++i) {
+        line += names[i];
+        line += '\t';
+        append_u32(line, triple_off[i + 1] - triple_off[i]);
+        for (uint64_t t = triple_off[i]; t < triple_off[i + 1]; ++t) {
+            line += "\t(";
+            append_u32(line, triples[3 * t]);
+            line += ' ';
+            append_u32(line, triples[3 * t + 1]);
+            line += ' ';
+            append_u32(line, triples[3 * t + 2]);
+            line += ')';
+        }
+        line += '\n';
+    }
+}
+inline void format_kmer_matches(const std::vector<std::string>& names, uint32_t lo, uint32_t hi, const uint64_t* read_off, uint32_t k,
+                                const uint64_t* word_off, const uint32_t* words, const uint32_t* counts, uint32_t num_colors, std::string& line) {
+    for (uint32_t i = lo; i < hi; ++i) {
+        const uint64_t len = read_off[i + 1] - read_off[i], nk = len >= k ? len - k + 1 : 0;
+        line += names[i];
+        line += '\t';
+        append_u32(line, nk);
+        const uint32_t* w = words + word_off[i];
+        for (uint64_t j = 0; j < nk; ++j) {
+            line += '\t';
+            line += char('0' + ((w[j >> 5] >> (j & 31)) & 1u));
+        }
+        const uint32_t* c = counts + uint64_t(i) * num_colors;
+        for (uint32_t j = 0; j < num_colors; ++j) {
+            line += '\t';
+            append_u32(line, c[j]);
+        }
+        line += '\n';
+    }
+}
+
 enum class out_format { ASCII, BINARY, COMPRESSED };
 
 class result_writer {

@@ -156,7 +156,7 @@ int kmer_tool_main(bool conservation, int argc, char** argv) {
     std::vector<uint64_t> off, res_off;
     std::vector<std::string> names;
     std::vector<uint32_t> vals, counts;
-    std::string line;
+    std::vector<std::string> pieces;
     uint64_t num_reads = 0;
     for (bool more = true; more;) {
         bases.clear();
@@ -189,44 +189,16 @@ int kmer_tool_main(bool conservation, int argc, char** argv) {
             std::cerr << fulgor_gpu_last_error() << std::endl;
             return 1;
         }
-        line.clear();
-        char num[16];
-        auto put = [&](uint64_t v) { line.append(num, size_t(put_u32(num, uint32_t(v)) - num)); };
-        for (uint32_t i = 0; i < n; ++i) {
-            line += names[i];
-            line += '\t';
-            if (conservation) {
-                put(res_off[i + 1] - res_off[i]);
-                for (uint64_t t = res_off[i]; t < res_off[i + 1]; ++t) {
-                    line += "\t(";
-                    put(vals[3 * t]);
-                    line += ' ';
-                    put(vals[3 * t + 1]);
-                    line += ' ';
-                    put(vals[3 * t + 2]);
-                    line += ')';
-                }
-            } else {
-                const uint64_t len = off[i + 1] - off[i], nk = len >= info.k ? len - info.k + 1 : 0;
-                put(nk);
-                const uint32_t* w = vals.data() + res_off[i];
-                for (uint64_t j = 0; j < nk; ++j) {
-                    line += '\t';
-                    line += char('0' + ((w[j >> 5] >> (j & 31)) & 1u));
-                }
-                const uint32_t* c = counts.data() + uint64_t(i) * info.num_colors;
-                for (uint32_t j = 0; j < info.num_colors; ++j) {
-                    line += '\t';
-                    put(c[j]);
-                }
-            }
-            line += '\n';
-            if (line.size() > (1u << 22)) {
-                std::fwrite(line.data(), 1, line.size(), out);
-                line.clear();
-            }
-        }
-        std::fwrite(line.data(), 1, line.size(), out);
+        /* the lines of the batch, formatted by up to T threads over contiguous read ranges and written in input order */
+        const unsigned T = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(a.threads, n / 256)));
+        pieces.resize(T);
+        fgio::parallel_for(T, [&](unsigned t) {
+            const uint32_t lo = uint32_t(uint64_t(n) * t / T), hi = uint32_t(uint64_t(n) * (t + 1) / T);
+            pieces[t].clear();
+            if (conservation) fgio::format_kmer_conservation(names, lo, hi, res_off.data(), vals.data(), pieces[t]);
+            else fgio::format_kmer_matches(names, lo, hi, off.data(), info.k, res_off.data(), vals.data(), counts.data(), info.num_colors, pieces[t]);
+        });
+        for (unsigned t = 0; t < T; ++t) std::fwrite(pieces[t].data(), 1, pieces[t].size(), out);
         num_reads += n;
         if (a.verbose) std::cout << "processed " << num_reads << " reads" << std::endl;
     }

@@ -55,6 +55,26 @@ int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads
     return 0;
 }
 
+/* the per-k-mer tools' lines for n reads named r<first+i>; which = 0: kmer-conservation (off = triple offsets, vals = triples),
+   which = 1: kmer-matches (read_off, k, off = word offsets, vals = positive words, counts, num_colors); formatted in `pieces` ranges */
+int fxio_format_kmer_tool(const char* path, int which, unsigned n, unsigned first, const unsigned long long* off, const unsigned* vals,
+                          const unsigned long long* read_off, unsigned k, const unsigned* counts, unsigned num_colors, unsigned pieces) {
+    std::vector<std::string> names(n);
+    for (unsigned i = 0; i < n; ++i) names[i] = "r" + std::to_string(first + i);
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return -1;
+    if (pieces < 1) pieces = 1;
+    for (unsigned p = 0; p < pieces; ++p) {
+        const unsigned lo = unsigned((unsigned long long)n * p / pieces), hi = unsigned((unsigned long long)n * (p + 1) / pieces);
+        std::string line;
+        if (which == 0) fgio::format_kmer_conservation(names, lo, hi, reinterpret_cast<const uint64_t*>(off), vals, line);
+        else fgio::format_kmer_matches(names, lo, hi, reinterpret_cast<const uint64_t*>(read_off), k, reinterpret_cast<const uint64_t*>(off), vals, counts, num_colors, line);
+        std::fwrite(line.data(), 1, line.size(), f);
+    }
+    std::fclose(f);
+    return 0;
+}
+
 /* one write_batch call with deduplicated results: record i carries the range of read rep[i] */
 int fxio_format_dedup(const char* path, int fmt, unsigned num_colors, unsigned threads, unsigned n, const unsigned long long* off,
                       const unsigned* colors, const unsigned* rep) {

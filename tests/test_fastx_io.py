@@ -28,6 +28,7 @@ def fx():
     L.fxio_parse.argtypes = [C.c_char_p, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.fxio_free.argtypes = [C.c_void_p]
     L.fxio_format.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint]
+    L.fxio_format_kmer_tool.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
     L.fxio_format_dedup.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
@@ -167,6 +168,41 @@ def test_formatters_fan_out_deduplicated_results(fx, tmp_path, threads):
         assert fx.fxio_format_dedup(path.encode(), fmt, num_colors, threads, n, off.ctypes.data, colors.ctypes.data, rep.ctypes.data) == 0
         got = parse_fn(path)
         assert (got[1] if fmt == 2 else got) == exp
+
+
+@pytest.mark.parametrize("pieces", [1, 4])
+def test_kmer_tool_lines(fx, tmp_path, pieces):
+    """the output lines of kmer-conservation / kmer-matches (tools/kmer_conservation.cpp:27-37, tools/kmer_matches.cpp:28-34) from
+    the C ABI's batch results, whatever the split into formatting ranges"""
+    rng = np.random.default_rng(pieces)
+    n, k, C_ = 700, 31, 7
+    lens = rng.integers(0, 200, n)
+    read_off = np.zeros(n + 1, dtype=np.uint64)
+    read_off[1:] = np.cumsum(lens)
+    nk = np.maximum(0, lens - k + 1)
+    # kmer-conservation
+    ntr = rng.integers(0, 5, n)
+    toff = np.zeros(n + 1, dtype=np.uint64)
+    toff[1:] = np.cumsum(ntr)
+    tr = rng.integers(0, 100000, (int(toff[n]), 3)).astype(np.uint32)
+    path = str(tmp_path / "cons.txt")
+    assert fx.fxio_format_kmer_tool(path.encode(), 0, n, 5, toff.ctypes.data, tr.ctypes.data, None, k, None, 0, pieces) == 0
+    want = ["\t".join(["r%d" % (5 + i), str(int(ntr[i]))] + ["(%d %d %d)" % tuple(t) for t in tr[int(toff[i]):int(toff[i + 1])]]) for i in range(n)]
+    assert open(path).read().split("\n")[:-1] == want
+    # kmer-matches
+    woff = np.zeros(n + 1, dtype=np.uint64)
+    woff[1:] = np.cumsum((nk + 31) // 32)
+    bits = [rng.integers(0, 2, int(x)).astype(np.uint8) for x in nk]
+    words = np.zeros(int(woff[n]) + 1, dtype=np.uint32)
+    for i in range(n):
+        for j, b in enumerate(bits[i]):
+            if b:
+                words[int(woff[i]) + j // 32] |= np.uint32(1 << (j % 32))
+    counts = rng.integers(0, 300, (n, C_)).astype(np.uint32)
+    path = str(tmp_path / "match.txt")
+    assert fx.fxio_format_kmer_tool(path.encode(), 1, n, 0, woff.ctypes.data, words.ctypes.data, read_off.ctypes.data, k, counts.ctypes.data, C_, pieces) == 0
+    want = ["\t".join(["r%d" % i, str(int(nk[i]))] + [str(int(b)) for b in bits[i]] + [str(int(c)) for c in counts[i]]) for i in range(n)]
+    assert open(path).read().split("\n")[:-1] == want
 
 
 def compressed_records_prefix(path, limit):
