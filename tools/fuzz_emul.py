@@ -19,6 +19,7 @@ seed0 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 E = C.CDLL(os.path.join(ROOT, "build", "libfg_simt_emul.so"))
 E.emul_pseudoalign.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int, C.c_int]
 E.emul_fetch_color_set_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint, C.c_int]
+E.emul_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int]
 E.emul_kmer_tool.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint, C.c_int]
 path = ck.index_path(index)
 img, o = fg.build_image(path), ck.Oracle(path)
@@ -79,6 +80,21 @@ for rd in range(rounds):
     assert E.emul_kmer_tool(img.ctypes.data, 0, bases.ctypes.data, off.ctypes.data, nr, to.ctypes.data, tr.ctypes.data, cap, None, grid, generic) == 0
     e3 = o.kmer_conservation(reads)
     ok = ok and np.array_equal(to, e3[0]) and np.array_equal(tr[: 3 * int(to[nr])].reshape(-1, 3), e3[1])
+    # kmer-matches (decoded table)
+    wo, ww, cc = np.zeros(nr + 1, dtype=np.uint64), np.zeros(cap, dtype=np.uint32), np.zeros((nr, o.num_colors), dtype=np.uint32)
+    assert E.emul_kmer_tool(img.ctypes.data, 1, bases.ctypes.data, off.ctypes.data, nr, wo.ctypes.data, ww.ctypes.data, cap, cc.ctypes.data, grid, 0) == 0
+    koff, pos, ecounts = o.kmer_matches(reads)
+    ok = ok and np.array_equal(ck.unpack_positive_words(wo, ww, koff), pos) and np.array_equal(cc, ecounts)
+    # deduplicated full intersection: the batch twice over, so every list has at least two reads
+    twice = ck.reads_from_list(seqs + seqs)
+    b2, f2 = twice
+    n2 = len(f2) - 1
+    rep, do, dv = np.zeros(n2, dtype=np.uint32), np.zeros(n2 + 1, dtype=np.uint64), np.zeros(2 * cap, dtype=np.uint32)
+    assert E.emul_pseudoalign_dedup(img.ctypes.data, b2.ctypes.data, f2.ctypes.data, n2, rep.ctypes.data, do.ctypes.data, dv.ctypes.data, 2 * cap, grid, 1) == 0
+    try:
+        ck.check_dedup(rep, do, dv, o.pseudoalign(twice, 0), o.fetch_color_set_ids(twice))
+    except AssertionError:
+        ok = False
     print(f"round {rd}: {nr} reads, grid {grid}, generic {generic}: {'ok' if ok else 'MISMATCH'}", flush=True)
     bad += not ok
 print("mismatching rounds:", bad)
