@@ -11,7 +11,32 @@ import pytest
 
 import _checkers as ck
 
-CLI = os.path.join(ck.ROOT, "fulgor_b200", "fulgor_b200_pseudoalign")
+GPU_CLI = os.path.join(ck.ROOT, "fulgor_b200", "fulgor_b200_pseudoalign")
+HOST_CLI = os.path.join(ck.ROOT, "build", "fulgor_cli_hosttest")
+
+
+def _build_host_cli():
+    """build/fulgor_cli_hosttest = the tool's host code (fulgor_b200/csrc/pseudoalign_cli.cpp) linked against
+    tests/fake_gpu_lib.cpp, a test double of the C ABI answered by the oracle"""
+    ck.build_checkers()
+    srcs = [os.path.join(ck.ROOT, "fulgor_b200", "csrc", "pseudoalign_cli.cpp"), os.path.join(ck.ROOT, "tests", "fake_gpu_lib.cpp")]
+    deps = srcs + [os.path.join(ck.ROOT, "fulgor_b200", "csrc", "fastx_io.h"), os.path.join(ck.ROOT, "include", "fulgor_gpu.h"), ck.ORACLE_SO]
+    if not os.path.exists(HOST_CLI) or any(os.path.getmtime(d) > os.path.getmtime(HOST_CLI) for d in deps):
+        os.makedirs(os.path.dirname(HOST_CLI), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-w", "-o", HOST_CLI] + srcs +
+                              ["-L" + os.path.dirname(ck.ORACLE_SO), "-lfulgor_oracle", "-Wl,-rpath," + os.path.dirname(ck.ORACLE_SO), "-lz"])
+    return HOST_CLI
+
+
+@pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "host"])
+def cli(request, built_lib):
+    """the tool under test: "gpu" = the shipped binary on a B200 (GPU tier); "host" = the SAME host code linked against the
+    oracle-backed test double of the C ABI, so that the CPU tier covers the tool's host logic: arguments, feeder, batch
+    pipeline, multi-device split and splice, de-duplication fan-out, output formats, the per-k-mer tools' lines.
+    Returns (path, scale of the read counts: the oracle behind the double is single-threaded)."""
+    if request.param == "gpu":
+        return GPU_CLI, 1.0
+    return _build_host_cli(), 0.3
 
 
 def write_fastq(path, reads, gz=False, fasta=False):
@@ -112,14 +137,14 @@ def csr_records(csr):
     return {i: vals[int(off[i]):int(off[i + 1])].tolist() for i in range(len(off) - 1)}
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("index,algo_args", [("salmonella_10.fur", []), ("salmonella_10.fur", ["-r", "0.8"]), ("salmonella_10.mfur", []),
                                              ("synth_200.fur", []), ("synth_200.mfur", ["-r", "0.6"]),
                                              ("salmonella_10.dfur", ["-r", "0.7"]), ("salmonella_10.mdfur", []),
                                              ("synth_200.dfur", []), ("synth_200.mdfur", ["-r", "0.5"])])
-def test_cli_matches_oracle_and_reference(index, algo_args, built_lib, tmp_path):
+def test_cli_matches_oracle_and_reference(index, algo_args, cli, tmp_path):
+    CLI, scale = cli
     genomes = index.split(".")[0]
-    reads = ck.gen_reads(3000, 75, 300, seed=31, genomes=genomes)
+    reads = ck.gen_reads(int(3000 * scale), 75, 300, seed=31, genomes=genomes)
     fq = str(tmp_path / "reads.fq")
     write_fastq(fq, reads)
     path = ck.index_path(index)
@@ -129,7 +154,7 @@ def test_cli_matches_oracle_and_reference(index, algo_args, built_lib, tmp_path)
     outs = {}
     for fmt in ("ascii", "binary", "compressed"):
         out = str(tmp_path / f"out.{fmt}")
-        subprocess.check_call([CLI, "-i", path, "-q", fq, "-o", out, "--format", fmt, "--batch-reads", "1000"] + algo_args)
+        subprocess.check_call([CLI, "-i", path, "-q", fq, "-o", out, "--format", fmt, "--batch-reads", str(int(1000 * scale))] + algo_args)
         outs[fmt] = out
     assert ascii_records(outs["ascii"]) == exp
     assert binary_records(outs["binary"]) == exp
@@ -150,22 +175,22 @@ def test_cli_matches_oracle_and_reference(index, algo_args, built_lib, tmp_path)
         assert compressed_records(ref_out) == (C, recs)
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_200.mfur", "synth_200.dfur"])
-def test_cli_deduplicate(index, built_lib, tmp_path):
+def test_cli_deduplicate(index, cli, tmp_path):
     """--deduplicate (tools/pseudoalign.cpp:92-226): same records as without it, and as the reference's own --deduplicate run"""
+    CLI, scale = cli
     genomes = index.split(".")[0]
     base = ck.gen_reads(500, 75, 300, seed=41, genomes=genomes)
     seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(500)]
     rng = np.random.default_rng(9)
-    reads = ck.reads_from_list([seqs[j] for j in rng.integers(0, 500, 4000)] + [b"ACGT", b"N" * 100])
+    reads = ck.reads_from_list([seqs[j] for j in rng.integers(0, 500, int(4000 * scale))] + [b"ACGT", b"N" * 100])
     fq = str(tmp_path / "reads.fq")
     write_fastq(fq, reads)
     path = ck.index_path(index)
     exp = csr_records(ck.Oracle(path).pseudoalign(reads, 0))
     for fmt, parse in (("ascii", ascii_records), ("binary", binary_records)):
         out = str(tmp_path / f"out.{fmt}")
-        subprocess.check_call([CLI, "-i", path, "-q", fq, "-o", out, "--format", fmt, "--batch-reads", "1500", "--deduplicate"])
+        subprocess.check_call([CLI, "-i", path, "-q", fq, "-o", out, "--format", fmt, "--batch-reads", str(int(1500 * scale)), "--deduplicate"])
         assert parse(out) == exp
     if os.path.exists(ck.REF_CLI):
         ref_out = str(tmp_path / "ref.ascii")
@@ -186,12 +211,12 @@ def test_cli_deduplicate(index, built_lib, tmp_path):
     assert r.returncode == 1 and "Deduplication not available" in r.stderr
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_200.mdfur"])
-def test_cli_kmer_tools(index, built_lib, tmp_path):
+def test_cli_kmer_tools(index, cli, tmp_path):
     """`kmer-conservation` / `kmer-matches` front-ends: the reference's output lines (tools/kmer_conservation.cpp:27-37,
     tools/kmer_matches.cpp:28-34), checked against the oracle and, where it was built, against the reference's own tools
     (their line order depends on thread scheduling: compared as sorted lines)"""
+    CLI, scale = cli
     genomes = index.split(".")[0]
     reads = ck.gen_reads(600, 75, 300, seed=51, genomes=genomes)
     fq = str(tmp_path / "reads.fq")
@@ -202,6 +227,11 @@ def test_cli_kmer_tools(index, built_lib, tmp_path):
     out_c, out_m = str(tmp_path / "cons.txt"), str(tmp_path / "match.txt")
     subprocess.check_call([CLI, "kmer-conservation", "-i", path, "-q", fq, "-o", out_c, "--batch-reads", "250"])
     subprocess.check_call([CLI, "kmer-matches", "-i", path, "-q", fq, "-o", out_m, "--batch-reads", "250"])
+    if scale < 1:  # host tier: also the multi-threaded formatting of one large batch
+        for tool, first in (("kmer-conservation", out_c), ("kmer-matches", out_m)):
+            again = str(tmp_path / (tool + ".t6"))
+            subprocess.check_call([CLI, tool, "-i", path, "-q", fq, "-o", again, "-t", "6"])
+            assert open(again, "rb").read() == open(first, "rb").read()
     toff, tr = o.kmer_conservation(reads)
     want = []
     for i in range(n):
@@ -240,8 +270,8 @@ def test_cli_kmer_tools(index, built_lib, tmp_path):
                 assert all(x == y or (x == "1" and y == "0") for x, y in zip(fa[2:2 + nk], fb[2:2 + nk]))
 
 
-@pytest.mark.gpu
-def test_cli_gz_fasta_and_verbose_summary(built_lib, tmp_path):
+def test_cli_gz_fasta_and_verbose_summary(cli, tmp_path):
+    CLI, scale = cli
     reads = ck.gen_reads(2000, seed=5)
     fa = str(tmp_path / "reads.fa.gz")
     write_fastq(fa, reads, gz=True, fasta=True)
@@ -255,7 +285,28 @@ def test_cli_gz_fasta_and_verbose_summary(built_lib, tmp_path):
     assert f"num_mapped_reads {mapped}/2000" in p.stdout
 
 
+def test_cli_multi_device_split_and_splice(tmp_path):
+    """host tier only (the double offers two "devices"): --gpus 2 cuts every batch by cumulative k-mer count, runs the halves on
+    two handles from two threads and splices the CSR results back in read order; with --deduplicate the representatives'
+    indexes are rebased onto the batch"""
+    _build_host_cli()
+    reads = ck.gen_reads(900, 75, 300, seed=61, genomes="synth_200")
+    base = [reads[0][int(reads[1][i]):int(reads[1][i + 1])].tobytes() for i in range(900)]
+    reads = ck.reads_from_list(base + base[:300] + [b"", b"ACGT"])
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path("synth_200.mfur")
+    o = ck.Oracle(path)
+    for args, algo, thr in ((["--gpus", "2"], 0, 1.0), (["--gpus", "2", "-r", "0.6"], 1, 0.6), (["--gpus", "2", "--deduplicate", "-t", "6"], 0, 1.0)):
+        out = str(tmp_path / "out.txt")
+        subprocess.check_call([HOST_CLI, "-i", path, "-q", fq, "-o", out, "--batch-reads", "500"] + args)
+        assert ascii_records(out) == csr_records(o.pseudoalign(reads, algo, thr))
+    r = subprocess.run([HOST_CLI, "-i", path, "-q", fq, "-o", str(tmp_path / "x"), "--gpus", "3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--gpus must be in [1,2]" in r.stderr
+
+
 def test_cli_flag_errors(built_lib, tmp_path):
+    CLI = GPU_CLI
     """flag validation mirrors tools/pseudoalign.cpp:272-321 and needs no GPU"""
     if not os.path.exists(CLI):
         pytest.skip("CLI not built")
