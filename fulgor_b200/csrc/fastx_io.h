@@ -54,6 +54,10 @@ struct read_batch {
     uint64_t bases_cap = 0, reads_cap = 0;
     uint32_t n = 0;
     std::function<void(read_batch&, uint64_t /*bases*/, uint64_t /*reads*/)> grow;
+    /* record names (first word of the header), only filled when the source was opened with want_names: read i is
+       names[name_off[i] .. name_off[i+1]) */
+    std::vector<char> names;
+    std::vector<uint64_t> name_off;
     void reserve(uint64_t nbases, uint64_t nreads) {
         if (nbases > bases_cap || nreads > reads_cap) grow(*this, nbases, nreads);
     }
@@ -159,7 +163,8 @@ public:
         if (fd_ >= 0) close(fd_);
     }
     /* threads = tokenising threads for memory-mapped input; span = bytes of file per batch */
-    bool open(const char* path, unsigned threads, uint64_t span_bytes, uint64_t max_reads_serial) {
+    bool open(const char* path, unsigned threads, uint64_t span_bytes, uint64_t max_reads_serial, bool want_names = false) {
+        want_names_ = want_names;
         if (const char* e = std::getenv("FULGOR_SLAB_KB")) slab_bytes_ = std::max<size_t>(64, std::strtoull(e, nullptr, 10)) << 10;
         threads_ = std::max(1u, threads);
         span_ = std::max<uint64_t>(span_bytes, 1 << 16);
@@ -208,6 +213,8 @@ public:
     /* fills b with the next reads; returns false when the input is exhausted and b is empty */
     bool next_batch(read_batch& b) {
         b.n = 0;
+        b.names.clear();
+        b.name_off.assign(1, 0);
         if (mapped_) {
             while (b.n == 0 && pos_ < size_) {
                 if (!next_mapped(b)) mapped_ = false; /* a record the slab tokeniser does not handle (multi-line FASTQ): serial from here on */
@@ -249,6 +256,8 @@ private:
         std::vector<char> raw;   /* the slab's bytes (pread scales across threads where first-touch faults of one mapping do not) */
         std::vector<char> bases;
         std::vector<uint32_t> lens;
+        std::vector<char> names; /* want_names_: the reads' names, concatenated, and their lengths */
+        std::vector<uint32_t> name_lens;
         bool ok = true;
     };
 
@@ -261,6 +270,8 @@ private:
     void tokenise(const char* d, size_t n, slab_out& o) const {
         o.bases.clear(); /* the slabs' buffers persist across batches: no reallocation, no fresh pages after the first batch */
         o.lens.clear();
+        o.names.clear();
+        o.name_lens.clear();
         o.ok = true;
         o.bases.reserve(n / (fastq_ ? 2 : 1) + 64);
         o.lens.reserve(n / (fastq_ ? 64 : 32) + 64);
@@ -270,12 +281,24 @@ private:
             if (p >= n) break;
             const size_t l1 = line_after(d, n, p); /* header */
             const size_t start = o.bases.size();
+            if (want_names_) { /* the first word after '@' / '>' (klibpp: up to the first white space) */
+                size_t e = p + 1;
+                while (e < l1 && !std::isspace(static_cast<unsigned char>(d[e]))) ++e;
+                o.names.insert(o.names.end(), d + p + 1, d + e);
+                o.name_lens.push_back(uint32_t(e - (p + 1)));
+            }
             if (fastq_) {
                 if (d[p] != '@') {
                     o.ok = false;
                     return;
                 }
-                if (l1 >= n) return; /* a header without a sequence line ends the input, like the serial reader */
+                if (l1 >= n) { /* a header without a sequence line ends the input, like the serial reader */
+                    if (want_names_) {
+                        o.names.resize(o.names.size() - o.name_lens.back());
+                        o.name_lens.pop_back();
+                    }
+                    return;
+                }
                 const size_t l2 = line_after(d, n, l1);
                 size_t s_end = l2 - (l2 > l1 && d[l2 - 1] == '\n' ? 1 : 0);
                 if (s_end > l1 && d[s_end - 1] == '\r') --s_end;
@@ -375,6 +398,11 @@ private:
                     o += len;
                 }
             });
+            if (want_names_)
+                for (unsigned t = 0; t < T; ++t) {
+                    b.names.insert(b.names.end(), out[t].names.begin(), out[t].names.end());
+                    for (uint32_t len : out[t].name_lens) b.name_off.push_back(b.name_off.back() + len);
+                }
             reads_done_ += read_at[T] - nreads;
             nbases = base_at[T];
             nreads = read_at[T];
@@ -401,9 +429,14 @@ private:
         std::vector<char>& bases = serial_bases_;
         bases.clear();
         serial_off_.assign(1, 0);
+        std::string name;
         while (serial_off_.size() - 1 < max_reads_serial_ && bases.size() < (1ull << 31)) {
-            if (!serial_.next(bases)) break;
+            if (!serial_.next(bases, want_names_ ? &name : nullptr)) break;
             serial_off_.push_back(bases.size());
+            if (want_names_) {
+                b.names.insert(b.names.end(), name.begin(), name.end());
+                b.name_off.push_back(b.names.size());
+            }
         }
         const uint64_t n = serial_off_.size() - 1;
         if (n == 0) return false;
@@ -418,7 +451,7 @@ private:
     int fd_ = -1;
     const char* map_ = nullptr;
     size_t size_ = 0, pos_ = 0;
-    bool mapped_ = false, fastq_ = true, serial_open_ = false;
+    bool mapped_ = false, fastq_ = true, serial_open_ = false, want_names_ = false;
     unsigned threads_ = 1;
     uint64_t span_ = 1ull << 28, max_reads_serial_ = 1u << 22, reads_done_ = 0;
     size_t slab_bytes_ = 2u << 20;
@@ -481,10 +514,10 @@ inline void append_u32(std::string& line, uint64_t v) {
     char num[16];
     line.append(num, size_t(put_u32(num, uint32_t(v)) - num));
 }
-inline void format_kmer_conservation(const std::vector<std::string>& names, uint32_t lo, uint32_t hi, const uint64_t* triple_off,
+inline void format_kmer_conservation(const char* names, const uint64_t* name_off, uint32_t lo, uint32_t hi, const uint64_t* triple_off,
                                      const uint32_t* triples, std::string& line) {
     for (uint32_t i = lo; i < hi; ++i) {
-        line += names[i];
+        line.append(names + name_off[i], size_t(name_off[i + 1] - name_off[i]));
         line += '\t';
         append_u32(line, triple_off[i + 1] - triple_off[i]);
         for (uint64_t t = triple_off[i]; t < triple_off[i + 1]; ++t) {
@@ -499,11 +532,11 @@ inline void format_kmer_conservation(const std::vector<std::string>& names, uint
         line += '\n';
     }
 }
-inline void format_kmer_matches(const std::vector<std::string>& names, uint32_t lo, uint32_t hi, const uint64_t* read_off, uint32_t k,
+inline void format_kmer_matches(const char* names, const uint64_t* name_off, uint32_t lo, uint32_t hi, const uint64_t* read_off, uint32_t k,
                                 const uint64_t* word_off, const uint32_t* words, const uint32_t* counts, uint32_t num_colors, std::string& line) {
     for (uint32_t i = lo; i < hi; ++i) {
         const uint64_t len = read_off[i + 1] - read_off[i], nk = len >= k ? len - k + 1 : 0;
-        line += names[i];
+        line.append(names + name_off[i], size_t(name_off[i + 1] - name_off[i]));
         line += '\t';
         append_u32(line, nk);
         const uint32_t* w = words + word_off[i];

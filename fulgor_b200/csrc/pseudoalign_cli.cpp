@@ -112,8 +112,8 @@ struct pinned {
    same output lines, written in input order:
        kmer-conservation:  name \t n [\t (start_pos_in_query num_kmers color_set_id)]*      (tools/kmer_conservation.cpp:27-37)
        kmer-matches:       "num_colors=C" once, then  name \t num_kmers [\t 0|1]* [\t count]*C  (tools/kmer_matches.cpp:98, 28-34)
-   These tools print the read NAMES, so the records come from the serial reader (one thread). A read shorter than k is a line
-   without k-mers (and, for kmer-matches, zero counts). */
+   These tools print the read NAMES: the feeder keeps the first word of every header (fastx_io.h, want_names). A read shorter
+   than k is a line without k-mers (and, for kmer-matches, zero counts). */
 int kmer_tool_main(bool conservation, int argc, char** argv) {
     args_t a;
     if (!parse(argc, argv, a)) {
@@ -137,8 +137,12 @@ int kmer_tool_main(bool conservation, int argc, char** argv) {
     }
     fulgor_gpu_info info;
     fulgor_gpu_index_info(gpu, &info);
-    fgio::serial_fastx_reader reader;
-    if (!reader.open(a.query.c_str())) {
+    /* kmer-matches returns num_colors counts per read: one C-ABI call takes at most `slice` reads (~64 MB of counts) */
+    const uint64_t slice = conservation ? std::min<uint64_t>(a.batch_reads, 1u << 18)
+                                        : std::max<uint64_t>(64, std::min<uint64_t>(a.batch_reads, (64ull << 20) / std::max<uint32_t>(1, info.num_colors)));
+    const unsigned host_threads = unsigned(std::max<uint64_t>(1, a.threads));
+    fgio::fastx_source reader; /* the same feeder as pseudoalign, keeping the record names */
+    if (!reader.open(a.query.c_str(), host_threads, std::min<uint64_t>(1ull << 28, slice * 320), slice, /*want_names=*/true)) {
         std::cerr << "error in opening the file '" << a.query << "'" << std::endl;
         return 1;
     }
@@ -149,57 +153,57 @@ int kmer_tool_main(bool conservation, int argc, char** argv) {
     }
     if (!conservation) std::fprintf(out, "num_colors=%u\n", info.num_colors); /* tools/kmer_matches.cpp:98 */
     const auto t0 = std::chrono::high_resolution_clock::now();
-    /* kmer-matches returns num_colors counts per read: keep a batch's counts within ~256 MB */
-    const uint64_t batch = conservation ? std::min<uint64_t>(a.batch_reads, 1u << 18)
-                                        : std::max<uint64_t>(64, std::min<uint64_t>(a.batch_reads, (64ull << 20) / std::max<uint32_t>(1, info.num_colors)));
-    std::vector<char> bases;
-    std::vector<uint64_t> off, res_off;
-    std::vector<std::string> names;
+    std::vector<char> bases_buf;
+    std::vector<uint64_t> off_buf, res_off;
+    fgio::read_batch rb;
+    rb.grow = [&](fgio::read_batch& r, uint64_t nb, uint64_t nr) { /* std::vector::resize keeps what the batch already holds */
+        if (nb > r.bases_cap) {
+            bases_buf.resize(std::max<uint64_t>(nb + nb / 4 + 64, 2 * r.bases_cap));
+            r.bases = bases_buf.data();
+            r.bases_cap = bases_buf.size();
+        }
+        if (nr > r.reads_cap) {
+            off_buf.resize(std::max<uint64_t>(nr + nr / 4 + 64, 2 * r.reads_cap));
+            r.off = off_buf.data();
+            r.reads_cap = off_buf.size();
+        }
+    };
     std::vector<uint32_t> vals, counts;
     std::vector<std::string> pieces;
     uint64_t num_reads = 0;
-    for (bool more = true; more;) {
-        bases.clear();
-        off.assign(1, 0);
-        names.clear();
-        std::string name;
-        while (names.size() < batch && bases.size() < (256ull << 20)) {
-            if (!reader.next(bases, &name)) {
-                more = false;
-                break;
+    while (reader.next_batch(rb)) {
+        for (uint32_t first = 0; first < rb.n; first += uint32_t(slice)) { /* a batch may hold more reads than one call should take */
+            const uint32_t n = uint32_t(std::min<uint64_t>(slice, rb.n - first));
+            const uint64_t* off = rb.off + first; /* absolute offsets into rb.bases, like the C ABI wants them */
+            const uint64_t* name_off = rb.name_off.data() + first;
+            res_off.assign(uint64_t(n) + 1, 0);
+            int rc;
+            if (conservation) {
+                if (vals.size() < 3 * (uint64_t(n) * 4 + 64)) vals.resize(3 * (uint64_t(n) * 4 + 64));
+                while ((rc = fulgor_gpu_kmer_conservation(gpu, rb.bases, off, n, res_off.data(), vals.data(), vals.size() / 3)) == FULGOR_GPU_E2BIG)
+                    vals.resize(3 * res_off[n]);
+            } else {
+                const uint64_t words = (off[n] - off[0]) / 32 + n + 1;
+                if (vals.size() < words) vals.resize(words);
+                counts.resize(uint64_t(n) * info.num_colors);
+                rc = fulgor_gpu_kmer_matches(gpu, rb.bases, off, n, res_off.data(), vals.data(), vals.size(), counts.data());
             }
-            off.push_back(bases.size());
-            names.push_back(name);
+            if (rc) {
+                std::cerr << fulgor_gpu_last_error() << std::endl;
+                return 1;
+            }
+            /* the lines of the slice, formatted by up to T threads over contiguous read ranges and written in input order */
+            const unsigned T = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(host_threads, n / 256)));
+            pieces.resize(T);
+            fgio::parallel_for(T, [&](unsigned t) {
+                const uint32_t lo = uint32_t(uint64_t(n) * t / T), hi = uint32_t(uint64_t(n) * (t + 1) / T);
+                pieces[t].clear();
+                if (conservation) fgio::format_kmer_conservation(rb.names.data(), name_off, lo, hi, res_off.data(), vals.data(), pieces[t]);
+                else fgio::format_kmer_matches(rb.names.data(), name_off, lo, hi, off, info.k, res_off.data(), vals.data(), counts.data(), info.num_colors, pieces[t]);
+            });
+            for (unsigned t = 0; t < T; ++t) std::fwrite(pieces[t].data(), 1, pieces[t].size(), out);
+            num_reads += n;
         }
-        const uint32_t n = uint32_t(names.size());
-        if (n == 0) break;
-        res_off.assign(uint64_t(n) + 1, 0);
-        int rc;
-        if (conservation) {
-            if (vals.size() < 3 * (uint64_t(n) * 4 + 64)) vals.resize(3 * (uint64_t(n) * 4 + 64));
-            while ((rc = fulgor_gpu_kmer_conservation(gpu, bases.data(), off.data(), n, res_off.data(), vals.data(), vals.size() / 3)) == FULGOR_GPU_E2BIG)
-                vals.resize(3 * res_off[n]);
-        } else {
-            const uint64_t words = bases.size() / 32 + n + 1;
-            if (vals.size() < words) vals.resize(words);
-            counts.resize(uint64_t(n) * info.num_colors);
-            rc = fulgor_gpu_kmer_matches(gpu, bases.data(), off.data(), n, res_off.data(), vals.data(), vals.size(), counts.data());
-        }
-        if (rc) {
-            std::cerr << fulgor_gpu_last_error() << std::endl;
-            return 1;
-        }
-        /* the lines of the batch, formatted by up to T threads over contiguous read ranges and written in input order */
-        const unsigned T = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(a.threads, n / 256)));
-        pieces.resize(T);
-        fgio::parallel_for(T, [&](unsigned t) {
-            const uint32_t lo = uint32_t(uint64_t(n) * t / T), hi = uint32_t(uint64_t(n) * (t + 1) / T);
-            pieces[t].clear();
-            if (conservation) fgio::format_kmer_conservation(names, lo, hi, res_off.data(), vals.data(), pieces[t]);
-            else fgio::format_kmer_matches(names, lo, hi, off.data(), info.k, res_off.data(), vals.data(), counts.data(), info.num_colors, pieces[t]);
-        });
-        for (unsigned t = 0; t < T; ++t) std::fwrite(pieces[t].data(), 1, pieces[t].size(), out);
-        num_reads += n;
         if (a.verbose) std::cout << "processed " << num_reads << " reads" << std::endl;
     }
     std::fclose(out);

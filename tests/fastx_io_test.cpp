@@ -39,6 +39,36 @@ long long fxio_parse(const char* path, unsigned threads, unsigned long long span
 }
 void fxio_free(void* p) { std::free(p); }
 
+/* like fxio_parse with want_names: *names = the reads' names joined by '\n' (malloc'ed, NUL-terminated); returns the number of reads */
+long long fxio_parse_names(const char* path, unsigned threads, unsigned long long span, unsigned long long max_reads_serial, char** names) {
+    fgio::fastx_source src;
+    if (!src.open(path, threads, span, max_reads_serial, true)) return -1;
+    fgio::read_batch b;
+    std::vector<char> bb;
+    std::vector<uint64_t> bo;
+    b.grow = [&](fgio::read_batch& x, uint64_t nb, uint64_t nr) {
+        bb.resize(nb + 16);
+        bo.resize(nr + 16);
+        x.bases = bb.data();
+        x.off = bo.data();
+        x.bases_cap = bb.size();
+        x.reads_cap = bo.size();
+    };
+    std::string all;
+    long long total = 0;
+    while (src.next_batch(b)) {
+        if (b.name_off.size() != size_t(b.n) + 1 || b.name_off.back() != b.names.size()) return -2;
+        for (uint32_t i = 0; i < b.n; ++i) {
+            all.append(b.names.data() + b.name_off[i], size_t(b.name_off[i + 1] - b.name_off[i]));
+            all += '\n';
+        }
+        total += b.n;
+    }
+    *names = static_cast<char*>(std::malloc(all.size() + 1));
+    std::memcpy(*names, all.c_str(), all.size() + 1);
+    return total;
+}
+
 /* formats one CSR batch to a file, in `pieces` calls of write_batch */
 int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads, unsigned n, const unsigned long long* off, const unsigned* colors,
                 unsigned pieces) {
@@ -59,16 +89,20 @@ int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads
    which = 1: kmer-matches (read_off, k, off = word offsets, vals = positive words, counts, num_colors); formatted in `pieces` ranges */
 int fxio_format_kmer_tool(const char* path, int which, unsigned n, unsigned first, const unsigned long long* off, const unsigned* vals,
                           const unsigned long long* read_off, unsigned k, const unsigned* counts, unsigned num_colors, unsigned pieces) {
-    std::vector<std::string> names(n);
-    for (unsigned i = 0; i < n; ++i) names[i] = "r" + std::to_string(first + i);
+    std::string names;
+    std::vector<uint64_t> name_off(1, 0);
+    for (unsigned i = 0; i < n; ++i) {
+        names += "r" + std::to_string(first + i);
+        name_off.push_back(names.size());
+    }
     FILE* f = std::fopen(path, "wb");
     if (!f) return -1;
     if (pieces < 1) pieces = 1;
     for (unsigned p = 0; p < pieces; ++p) {
         const unsigned lo = unsigned((unsigned long long)n * p / pieces), hi = unsigned((unsigned long long)n * (p + 1) / pieces);
         std::string line;
-        if (which == 0) fgio::format_kmer_conservation(names, lo, hi, reinterpret_cast<const uint64_t*>(off), vals, line);
-        else fgio::format_kmer_matches(names, lo, hi, reinterpret_cast<const uint64_t*>(read_off), k, reinterpret_cast<const uint64_t*>(off), vals, counts, num_colors, line);
+        if (which == 0) fgio::format_kmer_conservation(names.data(), name_off.data(), lo, hi, reinterpret_cast<const uint64_t*>(off), vals, line);
+        else fgio::format_kmer_matches(names.data(), name_off.data(), lo, hi, reinterpret_cast<const uint64_t*>(read_off), k, reinterpret_cast<const uint64_t*>(off), vals, counts, num_colors, line);
         std::fwrite(line.data(), 1, line.size(), f);
     }
     std::fclose(f);

@@ -28,6 +28,8 @@ def fx():
     L.fxio_parse.argtypes = [C.c_char_p, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.fxio_free.argtypes = [C.c_void_p]
     L.fxio_format.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint]
+    L.fxio_parse_names.argtypes = [C.c_char_p, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_void_p)]
+    L.fxio_parse_names.restype = C.c_longlong
     L.fxio_format_kmer_tool.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
     L.fxio_format_dedup.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
@@ -108,6 +110,46 @@ def test_fasta_multiline(fx, tmp_path, threads, span):
                 f.write(s[j:j + 60] + b"\n")
     got, mapped = parse(fx, p, threads, span)
     assert mapped and got == seqs
+
+
+@pytest.mark.parametrize("threads,span", [(1, 1 << 16), (4, 1 << 16), (7, 1 << 30)])
+def test_record_names(fx, tmp_path, threads, span):
+    """want_names: the first word of every header (klibpp's rule, FQFeeder/include/kseq++.hpp:598), in record order, from the slab
+    tokeniser (plain FASTQ / FASTA) and from the serial reader (gzip, multi-line FASTQ)"""
+    import gzip
+
+    rng = np.random.default_rng(threads)
+    seqs = random_seqs(3000, rng, 1, 300)
+    names = [b"read_%d/%d" % (i, i % 3) for i in range(len(seqs))]
+
+    def check(path, mapped_expected=None):
+        out = C.c_void_p()
+        n = fx.fxio_parse_names(str(path).encode(), threads, span, 700, C.byref(out))
+        got = C.string_at(out).split(b"\n")[:-1]
+        fx.fxio_free(out)
+        assert n == len(names) and got == names
+
+    p = tmp_path / "n.fq"
+    with open(p, "wb") as f:
+        for nm, s in zip(names, seqs):
+            f.write(b"@%s some comment\tx\n%s\n+\n%s\n" % (nm, s, b"I" * len(s)))
+    check(p)
+    p = tmp_path / "n.fa"
+    with open(p, "wb") as f:
+        for nm, s in zip(names, seqs):
+            f.write(b">%s\n" % nm + b"".join(s[j:j + 60] + b"\n" for j in range(0, len(s), 60)))
+    check(p)
+    p = tmp_path / "n.fq.gz"
+    with gzip.open(p, "wb") as f:
+        for nm, s in zip(names, seqs):
+            f.write(b"@%s\tc\r\n%s\r\n+\r\n%s\r\n" % (nm, s, b"I" * len(s)))
+    check(p)
+    p = tmp_path / "multi.fq"  # multi-line FASTQ: the slab tokeniser hands over to the serial reader
+    with open(p, "wb") as f:
+        for nm, s in zip(names, seqs):
+            h = len(s) // 2
+            f.write(b"@%s\n%s\n%s\n+\n%s\n%s\n" % (nm, s[:h], s[h:], b"I" * h, b"I" * (len(s) - h)))
+    check(p)
 
 
 def test_empty_and_missing_input(fx, tmp_path):
