@@ -60,7 +60,7 @@ typedef struct fulgor_gpu_info {
 /* ---- index image: host side, no GPU needed -------------------------------------------------- */
 
 /* Replaces essentials::load(index, path) (reference tools/pseudoalign.cpp:340): parses a
-   reference-built .fur / .mfur (type by file suffix, tools/util.cpp:5-19) and flattens it into one
+   reference-built .fur / .mfur / .dfur / .mdfur (type by file suffix, tools/util.cpp:5-19) and flattens it into one
    position-independent byte image. *image is malloc'ed by the library; release it with
    fulgor_gpu_image_free. Load errors mirror the reference's std::runtime_error texts. */
 int fulgor_gpu_image_build(const char* index_path, uint8_t** image, uint64_t* image_bytes);
@@ -86,7 +86,8 @@ int fulgor_gpu_index_info(const fulgor_gpu_index*, fulgor_gpu_info* out);
 /* Stage 1. Replaces index::fetch_color_set_ids for a batch: per read, the ascending distinct
    color-set ids of its positive k-mers; num_positive[i] (nullable) = number of positive k-mers
    (what pseudoalign_threshold_union counts, src/ps_threshold_union.cpp:327-347).
-   bases: concatenated read characters; read i = bases[read_off[i] .. read_off[i+1]). */
+   bases: concatenated read characters; read i = bases[read_off[i] .. read_off[i+1]) -- read_off[0] need not be 0, so a
+   slice of a larger batch is passed as (bases, read_off + first, n). The same holds for every entry point below. */
 int fulgor_gpu_fetch_color_set_ids(fulgor_gpu_index*, const char* bases, const uint64_t* read_off, uint32_t n_reads,
                                    uint64_t* cid_off /* n_reads+1 */, uint32_t* cids, uint64_t cids_cap,
                                    uint32_t* num_positive /* n_reads, nullable */);
