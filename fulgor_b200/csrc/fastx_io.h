@@ -312,7 +312,10 @@ private:
                     o.ok = false;
                     return;
                 }
-                const size_t l3 = line_after(d, n, l2), l4 = l3 < n ? line_after(d, n, l3) : n;
+                const size_t l3 = line_after(d, n, l2);
+                /* the quality line normally is exactly as long as the sequence: look for its newline there before scanning */
+                const size_t q_guess = l3 + (s_end - l1);
+                const size_t l4 = (q_guess < n && d[q_guess] == '\n') ? q_guess + 1 : (l3 < n ? line_after(d, n, l3) : n);
                 size_t q_end = l4 - (l4 > l3 && d[l4 - 1] == '\n' ? 1 : 0);
                 if (q_end > l3 && d[q_end - 1] == '\r') --q_end;
                 if (q_end - l3 < s_end - l1 && l4 < n) { /* quality shorter than the sequence: multi-line record */
