@@ -559,6 +559,31 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
         throw std::runtime_error("dictionary too large for 32-bit super-k-mer ids / 31-bit string offsets");
     if (H.k - H.m + 1 > 31) throw std::runtime_error("k - m + 1 > 31 is not supported");
 
+    /* structural checks the kernels rely on (a reference-built file passes all of them; the reference itself does not look) */
+    if (2 * pieces.back() > strings.num_bits || strings.words.size() * 64 < strings.num_bits)
+        throw std::runtime_error("unitig end-points run past the strings");
+    if (u2c.words.size() * 64 < u2c.num_bits) throw std::runtime_error("u2c bit vector shorter than its size");
+    for (size_t i = 0; i < F.hybrids.size(); ++i) { /* color-set bit offsets: ascending, inside the container's stream */
+        const fgi_hybrid& h = F.hybrids[i];
+        const uint64_t stream_bits = ((i + 1 < F.hybrids.size() ? F.hybrids[i + 1].word_base : F.color_words.size()) - h.word_base - 2) * 64;
+        const uint64_t* so = F.set_bit_off.data() + h.set_off_base;
+        for (uint64_t j = 0; j <= h.num_sets; ++j)
+            if (so[j] > stream_bits || (j && so[j] < so[j - 1])) throw std::runtime_error("color-set offsets are not ascending inside their bit stream");
+        if (h.kind == FGI_SETS_DIFFERENTIAL)
+            for (uint64_t j = 0; j < h.num_sets; ++j)
+                if (so[h.num_sets + 1 + j] >= stream_bits) throw std::runtime_error("representative offset outside the color-set bit stream");
+    }
+    if (type == 1 || type == 3) { /* meta lists: [n, meta color 1..n] records, meta colors inside the partial sets */
+        if (meta_off.empty() || meta_off.back() != meta_vals.size()) throw std::runtime_error("meta color lists do not fill their vector");
+        const uint64_t total_partial = part_sets_before.empty() ? 0 : part_sets_before.back();
+        for (uint64_t c = 0; c + 1 < meta_off.size(); ++c) {
+            const uint64_t b = meta_off[c], e = meta_off[c + 1];
+            if (b >= e || e > meta_vals.size() || meta_vals[b] != e - b - 1) throw std::runtime_error("malformed meta color list");
+            for (uint64_t j = b + 1; j < e; ++j)
+                if (meta_vals[j] >= total_partial) throw std::runtime_error("meta color out of range");
+        }
+    }
+
     /* buckets::locate_bucket (sshash/buckets.hpp:62-67): begin(b) = EF[b] + b */
     std::vector<uint32_t> bucket_begin(nskb.size());
     for (uint64_t b = 0; b < nskb.size(); ++b) bucket_begin[b] = uint32_t(nskb[b] + b);
@@ -573,6 +598,7 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
             rank += uint32_t((u2c.words[u >> 6] >> (u & 63)) & 1);
         }
     }
+    if (H.num_unitigs && unitig_cid.back() >= H.num_color_sets) throw std::runtime_error("u2c marks more color sets than the index holds");
     /* per super-k-mer: offset, window = min(k-m+1, contig_end - offset - k + 1) (buckets.hpp:133-160), the color-set id
        of the unitig that contains it (buckets.hpp:13-40 + u2c), and the position of the canonical minimizer */
     std::vector<uint64_t> sk_records(H.num_super_kmers);
