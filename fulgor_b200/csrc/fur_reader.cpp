@@ -56,6 +56,7 @@ struct bit_vector {
     void read(byte_reader& r) {
         num_bits = r.pod<uint64_t>();
         words = r.vec<uint64_t>();
+        if (num_bits > words.size() * 64) throw std::runtime_error("malformed bit vector");
     }
 };
 
@@ -68,8 +69,10 @@ struct compact_vector {
         width = r.pod<uint64_t>();
         mask = r.pod<uint64_t>();
         words = r.vec<uint64_t>();
+        if (width > 64 || (width && size > (words.size() * 64) / width)) throw std::runtime_error("malformed compact vector");
     }
     uint64_t operator[](uint64_t i) const {
+        if (i >= size) throw std::runtime_error("compact vector index out of range (damaged index file)");
         if (width == 0) return 0;
         const uint64_t pos = i * width, w = pos >> 6, s = pos & 63;
         uint64_t v = words[w] >> s;

@@ -273,6 +273,35 @@ def test_c_abi_exports_every_declared_symbol(built_lib):
     assert set(names) <= exported
 
 
+@pytest.mark.parametrize("index", ["synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"])
+def test_loader_survives_damaged_files(index, built_lib, tmp_path):
+    """truncated and bit-flipped index files either load or are rejected with a message -- never a crash (the loader runs in
+    the caller's process); every truncation must be rejected"""
+    import fulgor_b200 as fg
+
+    raw = open(ck.index_path(index), "rb").read()
+    ext = index.split(".")[1]
+    rng = np.random.default_rng(len(raw))
+    for i, cut in enumerate((3, 10, 1000, len(raw) // 3, len(raw) // 2, len(raw) - 100, len(raw) - 1)):
+        p = tmp_path / f"t{i}.{ext}"
+        p.write_bytes(raw[:cut])
+        with pytest.raises(fg.FulgorGpuError):
+            fg.build_image(str(p))
+    loaded = 0
+    for i in range(25):
+        b = bytearray(raw)
+        for _ in range(3):
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        p = tmp_path / f"f{i}.{ext}"
+        p.write_bytes(bytes(b))
+        try:
+            fg.build_image(str(p))
+            loaded += 1
+        except fg.FulgorGpuError as e:
+            assert str(e)
+    assert loaded <= 25
+
+
 def test_no_cpu_fallback_without_a_gpu(built_lib):
     """on a box without a GPU the compute entry points must fail loudly (ENODEV), never compute on the CPU"""
     import fulgor_b200 as fg
