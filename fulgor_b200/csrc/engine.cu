@@ -212,9 +212,9 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
         FG_CUDA(cudaGetDeviceProperties(&prop, device));
         x->sm_count = prop.multiProcessorCount;
         FG_CUDA(cudaMalloc(&x->d_carry, 8));
-        build_color_set_table(x);
+        for (auto& s : x->slots) FG_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        build_color_set_table(x); /* on slots[0].stream */
         for (auto& s : x->slots) {
-            FG_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             FG_CUDA(cudaEventCreateWithFlags(&s.scanned, cudaEventDisableTiming));
             FG_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             FG_CUDA(cudaEventCreateWithFlags(&s.info_ready, cudaEventDisableTiming));
@@ -475,9 +475,12 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         FG_CUDA(cudaEventRecord(s.done, s.stream));
     };
 
-    /* chunks are cut and validated on the fly, so the host-side O(n) work overlaps the GPU work of earlier chunks */
+    /* chunks are cut and validated on the fly, so the host-side O(n) work overlaps the GPU work of earlier chunks. Whatever
+       goes wrong after the first chunk has been enqueued (a bad offset further down, an allocation, a CUDA error), the copies
+       already queued into the caller's buffers must have landed before this call returns: drain every slot, then rethrow. */
     std::deque<pending> inflight;
     uint32_t ci = 0;
+    try {
     for (uint32_t first = 0; first < n_reads; ++ci) {
         uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
         uint32_t chunk_max_len = 1;
@@ -542,6 +545,13 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         first += n;
     }
     for (auto const& c : inflight) finalize(c);
+    } catch (...) {
+        for (auto& s : x->slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream); /* best effort: the first error is the one reported */
+            s.busy = false;
+        }
+        throw;
+    }
     for (auto& s : x->slots) {
         FG_CUDA(cudaStreamSynchronize(s.stream));
         s.busy = false;

@@ -221,6 +221,11 @@ public:
                 if (!mapped_) break;
             }
             if (mapped_) return b.n != 0;
+            /* the failed round may follow successful rounds of this batch: the serial reader starts the batch over, so what those
+               rounds appended (names in particular) must go */
+            b.n = 0;
+            b.names.clear();
+            b.name_off.assign(1, 0);
         }
         return next_serial(b);
     }

@@ -107,6 +107,7 @@ struct elias_fano {
         std::vector<uint64_t> out(size());
         uint64_t i = 0;
         const uint64_t l = low.width;
+        if (l >= 64) throw std::runtime_error("malformed Elias-Fano sequence (low-bits width)");
         for (uint64_t w = 0; w < high.words.size() && i < out.size(); ++w) {
             uint64_t x = high.words[w];
             while (x && i < out.size()) {
@@ -222,7 +223,8 @@ struct flattener {
         r.pod<uint64_t>();
         auto inverse = [](uint64_t d) -> uint64_t {
             if (d >= (1ULL << 32)) throw std::runtime_error("MPHF partition with a modulus >= 2^32 is not supported");
-            if (d <= 1) return UINT64_MAX;
+            if (d == 0) return 0; /* never used: mod_by_inverse answers 0 for a zero modulus (kernels.cuh) */
+            if (d == 1) return UINT64_MAX;
             return uint64_t((u128(1) << 64) / d);
         };
         P.inv_table = inverse(P.table_size);
@@ -245,7 +247,15 @@ struct flattener {
         for (uint64_t i = 0; i < back_ranks.size; ++i)
             hashed_pilots.push_back(murmur2_64(back_dict[back_ranks[i]], P.seed));
         if (P.num_keys >= (1ULL << 32)) throw std::runtime_error("MPHF partition with >= 2^32 keys is not supported");
-        for (uint64_t v : fs.decode()) free_slots.push_back(uint32_t(v));
+        /* what phf_position dereferences on the GPU: one pilot per PTHash bucket, one free slot per table position beyond the
+           keys, every free slot a valid key position */
+        if (front_ranks.size + back_ranks.size != P.num_dense + P.num_sparse) throw std::runtime_error("damaged index: MPHF pilot count differs from its bucket count");
+        if (P.table_size < P.num_keys || P.table_size == 0) throw std::runtime_error("damaged index: MPHF table smaller than its key set");
+        if (fs.size() != P.table_size - P.num_keys) throw std::runtime_error("damaged index: MPHF free-slot count differs from table_size - num_keys");
+        for (uint64_t v : fs.decode()) {
+            if (v >= P.num_keys) throw std::runtime_error("damaged index: MPHF free slot outside the key range");
+            free_slots.push_back(uint32_t(v));
+        }
         parts.push_back(P);
     }
 
@@ -531,6 +541,7 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
             meta_vals.push_back(uint32_t(parts_of_group.size()));
             host_bit_cursor rc{relative_colors, rco[i]};
             for (uint32_t pid : parts_of_group) {
+                if (eps[pid].num_color_sets == 0) throw std::runtime_error("meta-differential color sets: partition without color sets");
                 const uint64_t width = 64 - uint64_t(__builtin_clzll(eps[pid].num_color_sets));
                 const uint64_t rel = rc.take(width);
                 if (rel >= eps[pid].num_color_sets) throw std::runtime_error("meta-differential color sets: relative id out of range");
@@ -589,8 +600,27 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
 
     /* buckets::locate_bucket (sshash/buckets.hpp:62-67): begin(b) = EF[b] + b */
     std::vector<uint32_t> bucket_begin(nskb.size());
-    for (uint64_t b = 0; b < nskb.size(); ++b) bucket_begin[b] = uint32_t(nskb[b] + b);
-    if (bucket_begin.back() != H.num_super_kmers) throw std::runtime_error("bucket sizes do not add up to the number of super-k-mers");
+    for (uint64_t b = 0; b < nskb.size(); ++b) {
+        if (b && nskb[b] < nskb[b - 1]) throw std::runtime_error("damaged index: bucket sizes are not ascending");
+        bucket_begin[b] = uint32_t(nskb[b] + b);
+    }
+    if (nskb.back() + nskb.size() - 1 != H.num_super_kmers) throw std::runtime_error("bucket sizes do not add up to the number of super-k-mers");
+    /* what the MPHF lookups index on the GPU: the minimizer MPHF answers in [0, num_minimizers), skew MPHF i in
+       [0, its positions table), and every partition's key range lies inside its function's */
+    for (size_t f = 0; f < F.phfs.size(); ++f) {
+        const fgi_phf& P = F.phfs[f];
+        uint64_t limit = H.num_minimizers;
+        if (f > 0) {
+            limit = 0;
+            for (uint32_t i = 0; i < H.num_skew; ++i)
+                if (H.skew_phf[i] == f) limit = (i + 1 < H.num_skew ? H.skew_pos_base[i + 1] : F.skew_positions.size()) - H.skew_pos_base[i];
+        }
+        if (P.num_keys > limit) throw std::runtime_error("damaged index: MPHF with more keys than the table it indexes");
+        for (uint64_t j = 0; j < P.num_partitions; ++j) {
+            const fgi_phf_part& part = F.parts[P.first_part + j];
+            if (part.offset > P.num_keys || part.num_keys > P.num_keys - part.offset) throw std::runtime_error("damaged index: MPHF partition outside its function's key range");
+        }
+    }
 
     /* index::u2c (include/index.hpp:37): color-set id of unitig u = number of ones in u2c[0, u) */
     std::vector<uint32_t> unitig_cid(H.num_unitigs);

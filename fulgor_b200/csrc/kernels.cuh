@@ -128,6 +128,7 @@ FG_HD uint64_t murmur2_64(uint64_t key, uint64_t seed) {
    conditional subtraction gives the exact remainder -- the value the reference's fastmod_u64
    (pthash/external/fastmod/fastmod.h:159-162) returns. */
 FG_HD uint64_t mod_by_inverse(uint64_t a, uint64_t inv, uint64_t d) {
+    if (d == 0) return 0; /* a PTHash partition of <= 15 keys has no dense buckets (0.3 * num_buckets == 0): everything maps to bucket 0 */
     const uint64_t q = fg_mulhi64(a, inv);
     uint64_t r = a - q * d;
     if (r >= d) r -= d;

@@ -248,6 +248,35 @@ def gen_reads(n, min_len=150, max_len=150, seed=42, first=0, sub_rate=0.01, geno
     return bases[:-1], off
 
 
+def tile_genomes(name, read_len=400, k=31, every=1):
+    """Every contig of the packed genomes `name` (tools/mkdump .gpk) cut into reads of read_len bases that overlap by k-1, so
+    that EVERY k-mer of every genome is a k-mer of exactly one read: a walk over the whole dictionary the index was built
+    from (each of these k-mers is in the index). `every` keeps one genome in `every`. Returns (bases, read_off)."""
+    gpk = load_gpk(name)
+    assert gpk[:5].tobytes() == b"FGPK1"
+    nc, total = (int(v) for v in gpk[8:24].view(np.uint64))
+    rec = np.frombuffer(gpk[24:24 + 12 * nc].tobytes(), dtype=np.dtype([("genome", "<u4"), ("len", "<u8")]))
+    packed = gpk[24 + 12 * nc: 24 + 12 * nc + (total + 3) // 4]
+    codes = np.empty(packed.size * 4, dtype=np.uint8)
+    for j in range(4):
+        codes[j::4] = (packed >> (2 * j)) & 3
+    ascii_ = np.frombuffer(b"ACGT", dtype=np.uint8)[codes[:total]]
+    pieces, lens = [], []
+    start = 0
+    step = read_len - k + 1
+    for c in range(nc):
+        n = int(rec["len"][c])
+        if int(rec["genome"][c]) % every == 0:
+            for a in range(0, max(1, n - k + 1), step):
+                b = min(n, a + read_len)
+                pieces.append(ascii_[start + a:start + b])
+                lens.append(b - a)
+        start += n
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(np.array(lens, dtype=np.uint64))
+    return np.concatenate(pieces), off
+
+
 def reads_from_list(seqs):
     """Pack a list of bytes objects into (bases, read_off)."""
     off = np.zeros(len(seqs) + 1, dtype=np.uint64)

@@ -7,7 +7,7 @@ import _checkers as ck
 
 pytestmark = pytest.mark.gpu
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]  # 10 colors (fused kernel) and 200 colors (general kernels)
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur", "synth_skew.fur"]  # 10 colors (fused kernel) and 200 colors (general kernels)
 
 
 @pytest.fixture(scope="module", params=INDEXES)
@@ -132,7 +132,8 @@ def test_long_reads_many_color_sets(pair):
         assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
 
 
-BIG = ["synth_4546.fur", "synth_4546.mfur", "synth_4546.dfur", "synth_4546.mdfur", "synth_4546_dense.fur", "synth_4546_dense.mfur"]
+BIG = ["synth_4546_big.fur", "synth_4546_big.mfur", "synth_4546_big.dfur", "synth_4546_big.mdfur", "synth_4546.fur", "synth_4546.mfur",
+       "synth_4546.dfur", "synth_4546.mdfur", "synth_4546_dense.fur", "synth_4546_dense.mfur"]
 
 
 @pytest.mark.parametrize("index", BIG)
@@ -146,7 +147,7 @@ def test_4546_color_standin(index, built_lib):
     except FileNotFoundError:
         pytest.skip("fixtures_big fixture not generated on this machine")
     genomes = index.split(".")[0]
-    reads = ck.gen_reads(3000, 75, 300, seed=21, genomes=genomes)
+    reads = ck.gen_reads(3000 if "big" not in index else 1500, 75, 300, seed=21, genomes=genomes)
     o = ck.Oracle(path)
     with fg.Index.open(path, 0) as gpu:
         got = gpu.fetch_color_set_ids(reads, want_positive=True)
@@ -226,3 +227,57 @@ def test_kmer_conservation_and_matches(pair):
         koff, pos, ecounts = o.kmer_matches(reads)
         assert np.array_equal(ck.unpack_positive_words(woff, words, koff), pos)
         assert np.array_equal(counts, ecounts)
+
+
+def test_whole_dictionary_walk_multi_partition_and_skew(built_lib):
+    """synth_skew.fur on the GPU: reads tile the genomes the index was built from, so EVERY k-mer of the dictionary is looked up --
+    through each of the 8 minimizer-MPHF partitions (partitioned_phf.hpp:155-159) and, for the ~10 % of the k-mers that live in
+    buckets of more than 64 super-k-mers, through every non-empty skew partition including the absorbing, itself partitioned,
+    last one (skew_index.hpp:40-52; a k-mer of such a bucket can only be found that way). All positive, ids == the oracle's."""
+    import fulgor_b200 as fg
+
+    path = ck.index_path("synth_skew.fur")
+    o = ck.Oracle(path)
+    reads = ck.tile_genomes("synth_skew")
+    with fg.Index.open(path, 0) as gpu:
+        got = gpu.fetch_color_set_ids(reads, want_positive=True)
+        exp = o.fetch_color_set_ids(reads, want_positive=True)
+        assert _same(got, exp) and np.array_equal(got[2], exp[2])
+        assert np.array_equal(got[2], np.maximum(0, np.diff(reads[1].astype(np.int64)) - (o.k - 1)))
+        toff, tr = gpu.kmer_conservation(reads)  # the per-k-mer view: runs cover every k-mer of every read
+        eoff, etr = o.kmer_conservation(reads)
+        assert np.array_equal(toff, eoff) and np.array_equal(tr, etr)
+        for algo, thr in ((0, 1.0), (1, 0.8)):
+            assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+    o.close()
+
+
+def test_salmonella_4546_scale_standin_walk(built_lib):
+    """synth_4546_big.fur, the salmonella_4546-SCALE stand-in (tools/make_standin_4546.sh with SYNTH_EXTRA, built by the
+    reference's own `load -m 20`): ~47 M k-mers, 3 minimizer-MPHF partitions, 7 skew size classes up to buckets of > 2^13
+    super-k-mers, dictionary image and decoded color-set table larger than the L2. Reads tile every 20th genome (the part of
+    the collection that travels with the repo): every one of their ~45 M k-mers must be positive (a size-independent
+    property), and on a slice of the walk the per-read ids equal the oracle's."""
+    import fulgor_b200 as fg
+    from fulgor_b200 import imageview as iv
+
+    try:
+        path = ck.index_path("synth_4546_big.fur")
+    except FileNotFoundError:
+        pytest.skip("fixtures_big/synth_4546_big.fur not generated on this machine")
+    img = fg.build_image(path)
+    h = iv.header(img)
+    phfs = iv.section(img, h.off_phfs, "<u8", 4 * h.num_phfs).reshape(-1, 4)
+    assert phfs[0][1] >= 2 and h.num_skew >= 3 and h.num_kmers >= 40_000_000
+    assert h.off_hybrids > 126 << 20, "the SSHash part of the image must not fit the L2"
+    reads = ck.tile_genomes("synth_4546_big", read_len=1000)
+    n = len(reads[1]) - 1
+    o = ck.Oracle(path)
+    with fg.Index.from_image(img, 0) as gpu:
+        off, vals, npos = gpu.fetch_color_set_ids(reads, want_positive=True, cap=64 * n)
+        assert np.array_equal(npos, np.maximum(0, np.diff(reads[1].astype(np.int64)) - (o.k - 1))), "a dictionary k-mer was not found"
+        lo, hi = n // 3, n // 3 + 4000
+        sub = (reads[0][int(reads[1][lo]):int(reads[1][hi])], reads[1][lo:hi + 1] - reads[1][lo])
+        eoff, evals, enpos = o.fetch_color_set_ids(sub, want_positive=True)
+        assert np.array_equal(off[lo:hi + 1] - off[lo], eoff) and np.array_equal(vals[int(off[lo]):int(off[hi])], evals)
+    o.close()

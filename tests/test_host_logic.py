@@ -13,7 +13,7 @@ import _checkers as ck
 
 ROOT = ck.ROOT
 EMUL_SO = os.path.join(ROOT, "build", "libfg_simt_emul.so")
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur", "synth_skew.fur"]
 
 
 @pytest.fixture(scope="module")
@@ -339,3 +339,29 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "fulgor_oracle" not in text and "oracle/" not in text and "_checkers" not in text, os.path.join(dirpath, f)
+
+
+def test_emulated_kernels_walk_the_multi_partition_skew_dictionary(emul, built_lib):
+    """synth_skew.fur: 8 minimizer-MPHF partitions (minimizer_bucket's load_part branch), 7 skew size classes, one of them
+    empty, the last one absorbing buckets beyond 2^max_l and itself a 3-partition MPHF (lookup_in_bucket / phf_lookup). Reads
+    tile the genomes the index was built from, so every k-mer is positive; the image header must show what the test is for."""
+    import fulgor_b200 as fg
+    from fulgor_b200 import imageview as iv
+
+    path = ck.index_path("synth_skew.fur")
+    img, o = fg.build_image(path), ck.Oracle(path)
+    h = iv.header(img)
+    phfs = iv.section(img, h.off_phfs, "<u8", 4 * h.num_phfs).reshape(-1, 4)  # seed, num_partitions, first_part, num_keys
+    assert phfs[0][1] >= 2, "the minimizer MPHF must have several partitions"
+    assert h.num_skew >= 3 and h.skew_log2_max_bucket > h.skew_max_log2, "skew index with the absorbing last partition"
+    assert any(phfs[h.skew_phf[i]][1] == 0 for i in range(h.num_skew)), "an empty skew partition"
+    assert phfs[h.skew_phf[h.num_skew - 1]][1] >= 2, "a partitioned skew MPHF"
+    sizes = iv.bucket_sizes(img)
+    assert sizes.max() > 4096 and len({int(np.ceil(np.log2(s))) for s in sizes[sizes > 64]}) >= 5
+    reads = ck.tile_genomes("synth_skew", every=4)
+    got = emul_fetch(emul, img, reads, grid=4)
+    exp = o.fetch_color_set_ids(reads, want_positive=True)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[2], np.maximum(0, np.diff(reads[1].astype(np.int64)) - (o.k - 1)))
+    o.close()

@@ -9,7 +9,7 @@ import _checkers as ck
 
 pytestmark = pytest.mark.skipif(not ck.reference_available(), reason="oracle/_ref/libfulgor_ref.so not built (needs /root/reference)")
 
-INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur"]
+INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur", "synth_skew.fur"]
 
 
 @pytest.fixture(scope="module", params=INDEXES)
@@ -109,3 +109,23 @@ def test_reference_self_checks_run_clean(index):
         assert _same(r.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
     r.close()
     o.close()
+
+
+def test_whole_dictionary_walk_multi_partition_and_skew():
+    """synth_skew.fur (tools/make_skew_fixture.sh): 8 minimizer-MPHF partitions (partitioned_phf.hpp:155-159), a skew index
+    with 7 size classes of which one is EMPTY and the last one absorbs buckets beyond 2^max_l and is itself a 3-partition
+    MPHF (skew_index.hpp:40-52, dictionary.cpp:61-73). Every k-mer of every genome the index was built from is looked up
+    (reads tile the genomes): all positive, and the oracle == the reference on every read."""
+    path = ck.index_path("synth_skew.fur")
+    o, r = ck.Oracle(path), ck.Reference(path)
+    reads = ck.tile_genomes("synth_skew")
+    a = o.fetch_color_set_ids(reads, want_positive=True)
+    assert _same(a, r.fetch_color_set_ids(reads, threads=4))
+    assert np.array_equal(a[2], np.maximum(0, np.diff(reads[1].astype(np.int64)) - (o.k - 1)))
+    assert _same(o.pseudoalign(reads, 0), r.pseudoalign(reads, 0, threads=4))
+    bases, off = reads
+    for i in range(0, len(off) - 1, 97):  # per-k-mer streaming answers on a sample of the tiles
+        seq = bases[int(off[i]):int(off[i + 1])].tobytes()
+        assert np.array_equal(o.lookup_read(seq), r.lookup_read(seq)), i
+    o.close()
+    r.close()

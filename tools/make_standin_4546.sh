@@ -5,6 +5,11 @@
 # genuine .fur / .mfur / .dfur / .mdfur by the REFERENCE's own tools (oracle/_ref/fulgor_ref load -m 20, color --meta / --diff / --meta --diff), like README.md:158-160.
 # Needs oracle/_ref (i.e. /root/reference at build time). Output: fixtures_big/NAME.{fur,mfur,dfur,mdfur,gpk} (git-ignored).
 #   tools/make_standin_4546.sh [GENOME_LEN=200000] [N=4546] [SUB=0.00003] [NAME=synth_N]
+# SYNTH_EXTRA (environment) is passed on to tools/synthgen.py. The salmonella_4546-SCALE stand-in (as many k-mers as the real
+# index: ~46 M, several minimizer-MPHF partitions, a skew index with every size class, dictionary and decoded color-set table
+# both larger than the 126 MB L2) is
+#   SYNTH_EXTRA="--novel 4000 6000 --plant 20 --plant-scale 1.6" tools/make_standin_4546.sh 200000 4546 0.00003 synth_4546_big
+# (about an hour on 8 cores, ~25 GB of RAM in mkdump).
 # The default substitution rate gives ~0.4 unitigs per genome position, like the real collection (1.88 M unitigs over ~5 Mbp
 # genomes, reference README.md:158-160); SUB=0.0005 with GENOME_LEN=100000 gives a much more fragmented stress case
 # (fixtures_big/synth_4546_dense: ~7 unitigs per position, ~74 distinct color sets per 150 bp read).
@@ -14,7 +19,7 @@ LEN=${1:-200000}; N=${2:-4546}; SUB=${3:-0.00003}; NAME=${4:-synth_$N}
 OUT=fixtures_big; TMP=${TMPDIR:-/tmp}/fg_standin_$NAME
 mkdir -p "$OUT" "$TMP" build
 [ -x build/mkdump ] && [ build/mkdump -nt tools/mkdump.cpp ] || g++ -O2 -std=c++17 tools/mkdump.cpp -o build/mkdump -lz
-python tools/synthgen.py "$TMP/genomes" "$N" "$LEN" --seed 4546 --sub "$SUB" --indel 0.10 --hgt 0.5
+python tools/synthgen.py "$TMP/genomes" "$N" "$LEN" --seed 4546 --sub "$SUB" --indel 0.10 --hgt 0.5 ${SYNTH_EXTRA:-}
 build/mkdump "$TMP/$NAME" "@$TMP/genomes/list.txt"
 oracle/_ref/fulgor_ref load -i "$TMP/$NAME" -o "$TMP/$NAME" -m 20 -d "$TMP" -t 8 --verbose
 oracle/_ref/fulgor_ref color -i "$TMP/$NAME.fur" -d "$TMP" -t 8 --meta --verbose
