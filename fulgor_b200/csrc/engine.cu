@@ -24,6 +24,7 @@
 
 #include "../../include/fulgor_gpu.h"
 #include "fur_reader.h"
+#include "pack_reads.h"
 #include "pipeline_kernels.cuh"
 
 namespace fgb {
@@ -71,6 +72,8 @@ struct slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t scanned = nullptr, done = nullptr, info_ready = nullptr;
     dev_buffer bases, read_off, per_read /* masks or counts */, stage, pool, npos, res_bits, res_counts, tile_sums, tile_off, off, out, group_slots, rep, rep_counts, kmer_off, per_kmer, word_off;
+    dev_buffer read_len, invalid, pk_word_off; /* packed reads: lengths, invalid positions, first word of every read (device scan) */
+    uint64_t* pk_scan = nullptr;           /* device: {carry, chunk base, chunk total} of the word-offset scan */
     uint64_t* chunk_info = nullptr;        /* device: {base, total} */
     uint64_t* h_info = nullptr;            /* pinned host: {base, total, pool exhausted} */
     uint32_t* exhausted = nullptr;         /* device flag: the entry pool was too small */
@@ -222,6 +225,7 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
             FG_CUDA(cudaMalloc(&s.exhausted, 4));
             FG_CUDA(cudaMalloc(&s.max_positive, 4));
             FG_CUDA(cudaMalloc(&s.pool_used, 8));
+            FG_CUDA(cudaMalloc(&s.pk_scan, 24));
             FG_CUDA(cudaHostAlloc(&s.h_info, 32, cudaHostAllocDefault));
             std::memset(s.h_info, 0, 32);
         }
@@ -257,10 +261,24 @@ struct chunk_args {
     uint64_t read_off_base;
     uint32_t n;
     uint32_t max_len; /* longest read of the chunk when the host knows it, else 0 */
+    /* packed reads (d_words != nullptr) instead of d_bases / d_read_off */
+    const uint32_t* d_words = nullptr;
+    const uint64_t* d_word_off = nullptr;
+    const uint32_t* d_read_len = nullptr;
+    const uint64_t* d_invalid = nullptr;
+    uint32_t n_invalid = 0;
+    uint64_t pos_base = 0;
 };
 
+/* calls f with the chunk's reads in the form the lookup kernels are templated on */
+template <typename F>
+static void with_reads(const chunk_args& a, F&& f) {
+    if (a.d_words) f(packed_reads{a.d_words, a.d_word_off, a.d_read_len, a.d_invalid, a.n_invalid, a.pos_base});
+    else f(ascii_reads{a.d_bases, a.d_read_off, a.read_off_base});
+}
+
 /* enqueue scan (counts -> CSR offsets with the cross-chunk carry) */
-template <bool POPC>
+template <int POPC>
 static int enqueue_scan(fulgor_gpu_index* x, slot& s, const uint32_t* d_counts, uint32_t n, uint64_t* d_off) {
     const uint32_t tiles = (n + FG_SCAN_TILE - 1) / FG_SCAN_TILE;
     s.tile_sums.reserve(size_t(tiles) * 4);
@@ -309,9 +327,11 @@ static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool wa
     entry_pool pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted};
     const uint32_t grid = read_grid(x, a.n);
     dispatch_window(x->H, [&](auto w) {
-        k_fetch_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, s.stage.as<uint2>(),
-                                                                                  s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr, pool,
-                                                                                  a.max_len ? nullptr : s.max_positive);
+        with_reads(a, [&](auto in) {
+            k_fetch_color_sets<decltype(w)::value, decltype(in)><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, s.stage.as<uint2>(), s.per_read.as<uint32_t>(),
+                                                                                                    want_npos ? s.npos.as<uint32_t>() : nullptr, pool,
+                                                                                                    a.max_len ? nullptr : s.max_positive);
+        });
     });
     FG_CUDA(cudaGetLastError());
     return 1;
@@ -330,15 +350,16 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
         s.per_read.reserve(size_t(a.n) * 4);
         const uint32_t grid = read_grid(x, a.n);
         dispatch_window(x->H, [&](auto w) {
-            k_pseudoalign_small<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, a.n, algo, threshold,
-                                                                                       s.per_read.as<uint32_t>());
+            with_reads(a, [&](auto in) {
+                k_pseudoalign_small<decltype(w)::value, decltype(in)><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, algo, threshold, s.per_read.as<uint32_t>());
+            });
         });
         FG_CUDA(cudaGetLastError());
         *launches += 1;
         if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
         if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
-        *launches += enqueue_scan<true>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
         e.kind = emit_plan::MASKS;
+        if (d_off) *launches += enqueue_scan<FG_SCAN_POPC>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
         return e;
     }
     *launches += enqueue_k1(x, s, a, true);
@@ -393,8 +414,8 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
     FG_CUDA(cudaGetLastError());
     *launches += 1;
     if (after_k2) FG_CUDA(cudaEventRecord(after_k2, s.stream));
-    *launches += enqueue_scan<false>(x, s, s.res_counts.as<uint32_t>(), a.n, d_off);
     e.kind = emit_plan::BITS;
+    if (d_off) *launches += enqueue_scan<FG_SCAN_PLAIN>(x, s, s.res_counts.as<uint32_t>(), a.n, d_off); /* no offsets: the caller takes the bitmap rows */
     return e;
 }
 
@@ -403,7 +424,7 @@ static emit_plan enqueue_fetch(fulgor_gpu_index* x, slot& s, const chunk_args& a
     e.n = a.n;
     e.kind = emit_plan::ENTRIES;
     *launches += enqueue_k1(x, s, a, want_npos);
-    *launches += enqueue_scan<false>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
+    *launches += enqueue_scan<FG_SCAN_PLAIN>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
     return e;
 }
 
@@ -443,17 +464,37 @@ static const int RC_RETRY_LARGER_POOL = 1;
 
 enum class op_kind { FETCH, PSEUDOALIGN, DEDUP };
 
-static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
-                               uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* per_read_out) {
-    /* per_read_out (n_reads entries, nullable): FETCH -> the reads' positive k-mer counts; DEDUP -> their representatives */
-    uint32_t* const num_positive = op == op_kind::FETCH ? per_read_out : nullptr;
+/* the caller's reads: ASCII (bases + read_off) or packed (words + read_len + invalid positions, include/fulgor_gpu.h) */
+struct host_reads {
+    const char* bases = nullptr;
+    const uint64_t* read_off = nullptr;
+    const uint32_t* words = nullptr;
+    const uint32_t* read_len = nullptr;
+    const uint64_t* invalid = nullptr;
+    uint64_t n_invalid = 0;
+    bool packed() const { return read_len != nullptr; }
+};
+/* the caller's result buffers: CSR lists (off + vals, cap entries) or one bitmap row of ceil(num_colors / 32) words per read */
+struct host_results {
+    uint64_t* off = nullptr;
+    uint32_t* vals = nullptr;
+    uint64_t cap = 0;
+    uint32_t* bitmaps = nullptr;
+    uint32_t* per_read = nullptr; /* n_reads entries, nullable: FETCH -> positive k-mer counts; DEDUP -> representatives */
+    bool lists() const { return bitmaps == nullptr; }
+};
+
+static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const host_reads& in, uint32_t n_reads,
+                               const host_results& out) {
+    uint32_t* const num_positive = op == op_kind::FETCH ? out.per_read : nullptr;
     FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, x->slots[0].stream));
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
     const bool small = x->H.num_colors <= 32 && op != op_kind::DEDUP;
+    const uint32_t words_per_read = (x->H.num_colors + 31) / 32;
     uint64_t max_reads = chunk_max_reads(op == op_kind::DEDUP);
     if (op != op_kind::FETCH && !small)
-        max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (((x->H.num_colors + 31) / 32) * 4)));
+        max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (uint64_t(words_per_read) * 4)));
     struct pending { uint32_t first, n; int slot; emit_plan plan; };
     bool too_big = false, exhausted = false;
     cudaEvent_t prev_scanned = nullptr;
@@ -461,16 +502,18 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     auto finalize = [&](const pending& c) {
         slot& s = x->slots[c.slot];
         FG_CUDA(cudaEventSynchronize(s.info_ready));
-        const uint64_t base = s.h_info[0], total = s.h_info[1];
         if (uint32_t(s.h_info[2])) exhausted = true;
-        if (base + total > cap) too_big = true;
-        if (!too_big && !exhausted && total) {
-            if (total * 4 > s.out.cap) { /* the first emit ran into the end of the buffer: grow and repeat it */
-                FG_CUDA(cudaStreamSynchronize(s.stream));
-                s.out.reserve(size_t(total) * 4);
-                enqueue_emit(s, c.plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
+        if (out.lists()) {
+            const uint64_t base = s.h_info[0], total = s.h_info[1];
+            if (base + total > out.cap) too_big = true;
+            if (!too_big && !exhausted && total) {
+                if (total * 4 > s.out.cap) { /* the first emit ran into the end of the buffer: grow and repeat it */
+                    FG_CUDA(cudaStreamSynchronize(s.stream));
+                    s.out.reserve(size_t(total) * 4);
+                    enqueue_emit(s, c.plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
+                }
+                FG_CUDA(cudaMemcpyAsync(out.vals + base, s.out.p, total * 4, cudaMemcpyDeviceToHost, s.stream));
             }
-            FG_CUDA(cudaMemcpyAsync(out_vals + base, s.out.p, total * 4, cudaMemcpyDeviceToHost, s.stream));
         }
         FG_CUDA(cudaEventRecord(s.done, s.stream));
     };
@@ -480,20 +523,34 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
        already queued into the caller's buffers must have landed before this call returns: drain every slot, then rethrow. */
     std::deque<pending> inflight;
     uint32_t ci = 0;
+    uint64_t word_first = 0, inv_first = 0; /* packed: first word / first invalid-position entry of the next chunk */
     try {
     for (uint32_t first = 0; first < n_reads; ++ci) {
         uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
         uint32_t chunk_max_len = 1;
-        if (read_off[first + n] - read_off[first] > CHUNK_MAX_BASES) { /* largest n >= 1 within the byte budget */
-            uint32_t lo = 1, hi = n;
-            while (lo < hi) {
-                const uint32_t mid = lo + (hi - lo + 1) / 2;
-                if (read_off[first + mid] - read_off[first] <= CHUNK_MAX_BASES) lo = mid; else hi = mid - 1;
+        uint64_t chunk_words = 0;
+        if (in.packed()) { /* lengths, not offsets: one pass finds the chunk's end, its longest read and its words */
+            const uint32_t* rl = in.read_len + first;
+            uint32_t longest = 1, i = 0;
+            for (; i < n; ++i) {
+                const uint32_t len = rl[i] & 0x7fffffffu;
+                const uint64_t w = (uint64_t(len) + 15) >> 4;
+                if (i && (chunk_words + w) * 4 > CHUNK_MAX_BASES / 4) break; /* the same number of bases per chunk as the ASCII path */
+                chunk_words += w;
+                longest = std::max(longest, len);
             }
-            n = lo;
-        }
-        {
-            const uint64_t* ro = read_off + first;
+            n = i;
+            chunk_max_len = longest;
+        } else {
+            if (in.read_off[first + n] - in.read_off[first] > CHUNK_MAX_BASES) { /* largest n >= 1 within the byte budget */
+                uint32_t lo = 1, hi = n;
+                while (lo < hi) {
+                    const uint32_t mid = lo + (hi - lo + 1) / 2;
+                    if (in.read_off[first + mid] - in.read_off[first] <= CHUNK_MAX_BASES) lo = mid; else hi = mid - 1;
+                }
+                n = lo;
+            }
+            const uint64_t* ro = in.read_off + first;
             uint64_t bad = 0, longest = 0;
             for (uint32_t i = 0; i < n; ++i) {
                 const uint64_t len = ro[i + 1] - ro[i];
@@ -507,34 +564,85 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         slot& s = x->slots[c.slot];
         if (s.busy) FG_CUDA(cudaEventSynchronize(s.done));
         s.busy = true;
-        const uint64_t b0 = read_off[c.first], b1 = read_off[c.first + c.n];
-        s.bases.reserve(size_t(b1 - b0) + 64);
-        s.read_off.reserve(size_t(c.n + 1) * 8);
-        s.off.reserve(size_t(c.n + 1) * 8);
-        /* values buffer: exact upper bound when it is small, otherwise a guess that finalize() corrects */
-        const uint64_t per_read_guess = (op == op_kind::PSEUDOALIGN && small) ? x->H.num_colors : 64;
-        s.out.reserve(size_t(c.n) * per_read_guess * 4);
-        if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
-        FG_CUDA(cudaMemcpyAsync(s.read_off.p, read_off + c.first, size_t(c.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-        if (prev_scanned) FG_CUDA(cudaStreamWaitEvent(s.stream, prev_scanned, 0));
-        chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, c.n, chunk_max_len};
+        chunk_args a{};
+        a.n = c.n;
+        a.max_len = chunk_max_len;
         int launches = 0;
-        if (op == op_kind::FETCH) {
-            c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, s.off.as<uint64_t>(), &launches);
-        } else if (op == op_kind::DEDUP) {
-            c.plan = enqueue_dedup(x, s, a, c.first, s.off.as<uint64_t>(), &launches);
-            FG_CUDA(cudaMemcpyAsync(per_read_out + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (in.packed()) {
+            uint64_t inv_end = inv_first;
+            const uint64_t pos_end = 16 * (word_first + chunk_words);
+            while (inv_end < in.n_invalid && in.invalid[inv_end] < pos_end) ++inv_end;
+            if (inv_end - inv_first > 0xffffffffull) throw std::invalid_argument("too many invalid characters in one chunk of reads");
+            s.bases.reserve(size_t(chunk_words) * 4 + 64);
+            s.read_len.reserve(size_t(c.n) * 4);
+            s.pk_word_off.reserve(size_t(c.n + 1) * 8);
+            s.invalid.reserve(size_t(inv_end - inv_first) * 8 + 8);
+            if (chunk_words) FG_CUDA(cudaMemcpyAsync(s.bases.p, in.words + word_first, chunk_words * 4, cudaMemcpyHostToDevice, s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.read_len.p, in.read_len + c.first, size_t(c.n) * 4, cudaMemcpyHostToDevice, s.stream));
+            if (inv_end > inv_first)
+                FG_CUDA(cudaMemcpyAsync(s.invalid.p, in.invalid + inv_first, (inv_end - inv_first) * 8, cudaMemcpyHostToDevice, s.stream));
+            /* first word of every read: exclusive scan of the reads' word counts (chunk-local, its own carry) */
+            FG_CUDA(cudaMemsetAsync(s.pk_scan, 0, 8, s.stream));
+            const uint32_t tiles = (c.n + FG_SCAN_TILE - 1) / FG_SCAN_TILE;
+            s.tile_sums.reserve(size_t(tiles) * 4);
+            s.tile_off.reserve(size_t(tiles) * 8);
+            k_scan_tile_sums<FG_SCAN_PACKED_WORDS><<<tiles, FG_SCAN_BLOCK, 0, s.stream>>>(s.read_len.as<uint32_t>(), c.n, s.tile_sums.as<uint32_t>());
+            k_scan_tile_offsets<<<1, FG_SCAN_BLOCK, 0, s.stream>>>(s.tile_sums.as<uint32_t>(), tiles, s.tile_off.as<uint64_t>(), s.pk_scan, s.pk_scan + 1,
+                                                                  s.pk_word_off.as<uint64_t>() + c.n);
+            k_scan_write<FG_SCAN_PACKED_WORDS><<<tiles, FG_SCAN_BLOCK, 0, s.stream>>>(s.read_len.as<uint32_t>(), c.n, s.tile_off.as<uint64_t>(), s.pk_scan + 1,
+                                                                                     s.pk_word_off.as<uint64_t>());
+            FG_CUDA(cudaGetLastError());
+            launches += 3;
+            a.d_words = s.bases.as<uint32_t>();
+            a.d_word_off = s.pk_word_off.as<uint64_t>();
+            a.d_read_len = s.read_len.as<uint32_t>();
+            a.d_invalid = s.invalid.as<uint64_t>();
+            a.n_invalid = uint32_t(inv_end - inv_first);
+            a.pos_base = 16 * word_first;
+            word_first += chunk_words;
+            inv_first = inv_end;
         } else {
-            c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, s.off.as<uint64_t>(), nullptr, nullptr, &launches);
+            const uint64_t b0 = in.read_off[c.first], b1 = in.read_off[c.first + c.n];
+            s.bases.reserve(size_t(b1 - b0) + 64);
+            s.read_off.reserve(size_t(c.n + 1) * 8);
+            if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, in.bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.read_off.p, in.read_off + c.first, size_t(c.n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            a.d_bases = s.bases.as<uint8_t>();
+            a.d_read_off = s.read_off.as<uint64_t>();
+            a.read_off_base = b0;
         }
-        FG_CUDA(cudaEventRecord(s.scanned, s.stream));
-        prev_scanned = s.scanned;
-        enqueue_emit(s, c.plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
-        FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+        uint64_t* d_off = nullptr;
+        if (out.lists()) {
+            s.off.reserve(size_t(c.n + 1) * 8);
+            d_off = s.off.as<uint64_t>();
+            /* values buffer: exact upper bound when it is small, otherwise a guess that finalize() corrects */
+            const uint64_t per_read_guess = (op == op_kind::PSEUDOALIGN && small) ? x->H.num_colors : 64;
+            s.out.reserve(size_t(c.n) * per_read_guess * 4);
+            if (prev_scanned) FG_CUDA(cudaStreamWaitEvent(s.stream, prev_scanned, 0)); /* the running CSR offset */
+        }
+        if (op == op_kind::FETCH) {
+            c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, d_off, &launches);
+        } else if (op == op_kind::DEDUP) {
+            c.plan = enqueue_dedup(x, s, a, c.first, d_off, &launches);
+            FG_CUDA(cudaMemcpyAsync(out.per_read + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, d_off, nullptr, nullptr, &launches);
+        }
+        if (out.lists()) {
+            FG_CUDA(cudaEventRecord(s.scanned, s.stream));
+            prev_scanned = s.scanned;
+            enqueue_emit(s, c.plan, d_off, s.out.as<uint32_t>(), s.out.cap / 4);
+            FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+        }
         FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
         FG_CUDA(cudaEventRecord(s.info_ready, s.stream));
-        /* offsets of reads [first, first+n) and the running total at [first+n] (the next chunk rewrites that entry with the same value) */
-        FG_CUDA(cudaMemcpyAsync(out_off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (out.lists()) {
+            /* offsets of reads [first, first+n) and the running total at [first+n] (the next chunk rewrites that entry with the same value) */
+            FG_CUDA(cudaMemcpyAsync(out.off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+        } else { /* bitmap rows: one mask per read (<= 32 colors, the fused kernel's result) or the color-set kernel's rows, as they are */
+            const void* rows = c.plan.kind == emit_plan::MASKS ? s.per_read.p : s.res_bits.p;
+            FG_CUDA(cudaMemcpyAsync(out.bitmaps + uint64_t(c.first) * words_per_read, rows, size_t(c.n) * words_per_read * 4, cudaMemcpyDeviceToHost, s.stream));
+        }
         if (op == op_kind::FETCH && num_positive)
             FG_CUDA(cudaMemcpyAsync(num_positive + c.first, s.npos.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
         inflight.push_back(c);
@@ -560,13 +668,12 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     return too_big ? FULGOR_GPU_E2BIG : 0;
 }
 
-static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const char* bases, const uint64_t* read_off,
-                          uint32_t n_reads, uint64_t* out_off, uint32_t* out_vals, uint64_t cap, uint32_t* per_read_out) {
+static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const host_reads& in, uint32_t n_reads, const host_results& out) {
     FG_CUDA(cudaSetDevice(x->device));
-    out_off[0] = 0;
+    if (out.off) out.off[0] = 0;
     if (n_reads == 0) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
-        const int rc = run_host_batch_once(x, op, algo, threshold, bases, read_off, n_reads, out_off, out_vals, cap, per_read_out);
+        const int rc = run_host_batch_once(x, op, algo, threshold, in, n_reads, out);
         if (rc != RC_RETRY_LARGER_POOL) return rc;
         x->pool_per_read *= 4; /* reads with many distinct color sets: rerun with a larger entry pool (kept for later calls) */
     }
@@ -622,8 +729,8 @@ static int run_kmer_tool(fulgor_gpu_index* x, kmer_tool tool, const char* bases,
         chunk_args a{s.bases.as<uint8_t>(), s.read_off.as<uint64_t>(), b0, n, uint32_t(longest)};
         const uint32_t grid = read_grid(x, n);
         dispatch_window(x->H, [&](auto w) {
-            k_kmer_color_sets<decltype(w)::value><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, a.d_bases, a.d_read_off, a.read_off_base, n, s.kmer_off.as<uint64_t>(),
-                                                                                     s.per_kmer.as<uint32_t>());
+            k_kmer_color_sets<decltype(w)::value, ascii_reads><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, ascii_reads{a.d_bases, a.d_read_off, a.read_off_base}, n,
+                                                                                                  s.kmer_off.as<uint64_t>(), s.per_kmer.as<uint32_t>());
         });
         FG_CUDA(cudaGetLastError());
         const uint32_t warp_grid = uint32_t((uint64_t(n) * 32 + 255) / 256);
@@ -633,7 +740,7 @@ static int run_kmer_tool(fulgor_gpu_index* x, kmer_tool tool, const char* bases,
             k_kmer_runs<false><<<warp_grid, 256, 0, s.stream>>>(s.per_kmer.as<uint32_t>(), s.kmer_off.as<uint64_t>(), n, s.per_read.as<uint32_t>(), nullptr,
                                                                  nullptr, nullptr, 0);
             FG_CUDA(cudaGetLastError());
-            enqueue_scan<false>(x, s, s.per_read.as<uint32_t>(), n, s.off.as<uint64_t>());
+            enqueue_scan<FG_SCAN_PLAIN>(x, s, s.per_read.as<uint32_t>(), n, s.off.as<uint64_t>());
             FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
             FG_CUDA(cudaMemcpyAsync(out_off + first, s.off.p, size_t(n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
             FG_CUDA(cudaStreamSynchronize(s.stream));
@@ -677,6 +784,13 @@ static int run_kmer_tool(fulgor_gpu_index* x, kmer_tool tool, const char* bases,
         first += n;
     }
     return too_big ? FULGOR_GPU_E2BIG : 0;
+}
+
+static void check_algo(int algo, double threshold) {
+    if (algo != FULGOR_GPU_FULL_INTERSECTION && algo != FULGOR_GPU_THRESHOLD_UNION) throw std::invalid_argument("unknown algorithm");
+    /* same domain check as the reference CLI (tools/pseudoalign.cpp:272-281) */
+    if (algo == FULGOR_GPU_THRESHOLD_UNION && !(threshold > 0.0 && threshold <= 1.0))
+        throw std::invalid_argument("threshold must be a float in (0.0,1.0]");
 }
 
 template <typename F>
@@ -859,12 +973,14 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
     for (auto& s : x->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (dev_buffer* b : {&s.bases, &s.read_off, &s.per_read, &s.stage, &s.pool, &s.npos, &s.res_bits, &s.res_counts, &s.tile_sums, &s.tile_off,
-                              &s.off, &s.out, &s.group_slots, &s.rep, &s.rep_counts, &s.kmer_off, &s.per_kmer, &s.word_off})
+                              &s.off, &s.out, &s.group_slots, &s.rep, &s.rep_counts, &s.kmer_off, &s.per_kmer, &s.word_off, &s.read_len, &s.invalid,
+                              &s.pk_word_off})
             b->release();
         if (s.chunk_info) cudaFree(s.chunk_info);
         if (s.exhausted) cudaFree(s.exhausted);
         if (s.max_positive) cudaFree(s.max_positive);
         if (s.pool_used) cudaFree(s.pool_used);
+        if (s.pk_scan) cudaFree(s.pk_scan);
         if (s.h_info) cudaFreeHost(s.h_info);
         if (s.scanned) cudaEventDestroy(s.scanned);
         if (s.done) cudaEventDestroy(s.done);
@@ -890,7 +1006,15 @@ int fulgor_gpu_fetch_color_set_ids(fulgor_gpu_index* x, const char* bases, const
     return guarded([&]() -> int {
         if (!x || !read_off || !cid_off || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!cids && cids_cap))
             throw std::invalid_argument("null argument");
-        int rc = run_host_batch(x, op_kind::FETCH, 0, 0.0, bases, read_off, n_reads, cid_off, cids, cids_cap, num_positive);
+        host_reads in;
+        in.bases = bases;
+        in.read_off = read_off;
+        host_results out;
+        out.off = cid_off;
+        out.vals = cids;
+        out.cap = cids_cap;
+        out.per_read = num_positive;
+        int rc = run_host_batch(x, op_kind::FETCH, 0, 0.0, in, n_reads, out);
         if (rc == FULGOR_GPU_E2BIG) return fail(rc, "cids_cap too small; cid_off[n_reads] holds the required capacity");
         return rc;
     });
@@ -901,11 +1025,15 @@ int fulgor_gpu_pseudoalign(fulgor_gpu_index* x, int algo, double threshold, cons
     return guarded([&]() -> int {
         if (!x || !read_off || !color_off || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!colors && colors_cap))
             throw std::invalid_argument("null argument");
-        if (algo != FULGOR_GPU_FULL_INTERSECTION && algo != FULGOR_GPU_THRESHOLD_UNION) throw std::invalid_argument("unknown algorithm");
-        /* same domain check as the reference CLI (tools/pseudoalign.cpp:272-281) */
-        if (algo == FULGOR_GPU_THRESHOLD_UNION && !(threshold > 0.0 && threshold <= 1.0))
-            throw std::invalid_argument("threshold must be a float in (0.0,1.0]");
-        int rc = run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, bases, read_off, n_reads, color_off, colors, colors_cap, nullptr);
+        check_algo(algo, threshold);
+        host_reads in;
+        in.bases = bases;
+        in.read_off = read_off;
+        host_results out;
+        out.off = color_off;
+        out.vals = colors;
+        out.cap = colors_cap;
+        int rc = run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, in, n_reads, out);
         if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
         return rc;
     });
@@ -916,10 +1044,95 @@ int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index* x, const char* bases, const u
     return guarded([&]() -> int {
         if (!x || !read_off || !color_off || !rep_of_read || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!colors && colors_cap))
             throw std::invalid_argument("null argument");
-        int rc = run_host_batch(x, op_kind::DEDUP, FULGOR_GPU_FULL_INTERSECTION, 1.0, bases, read_off, n_reads, color_off, colors, colors_cap,
-                                rep_of_read);
+        host_reads in;
+        in.bases = bases;
+        in.read_off = read_off;
+        host_results out;
+        out.off = color_off;
+        out.vals = colors;
+        out.cap = colors_cap;
+        out.per_read = rep_of_read;
+        int rc = run_host_batch(x, op_kind::DEDUP, FULGOR_GPU_FULL_INTERSECTION, 1.0, in, n_reads, out);
         if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
         return rc;
+    });
+}
+
+int fulgor_gpu_pack_reads(const char* bases, const uint64_t* read_off, uint32_t n_reads, uint32_t* words, uint64_t words_cap, uint32_t* read_len,
+                          uint64_t* invalid_pos, uint64_t invalid_cap, uint64_t* n_words, uint64_t* n_invalid, int threads) {
+    return guarded([&]() -> int {
+        if (!read_off || !n_words || !n_invalid || (n_reads && (!read_len || (!bases && read_off[n_reads] > read_off[0]))) || (!words && words_cap) ||
+            (!invalid_pos && invalid_cap))
+            throw std::invalid_argument("null argument");
+        for (uint32_t i = 0; i < n_reads; ++i)
+            if ((read_off[i + 1] - read_off[i]) >> 31) throw std::invalid_argument("read_off must be non-decreasing and reads shorter than 2^31 characters");
+        *n_words = packed_words_of(read_off, n_reads);
+        *n_invalid = 0;
+        if (*n_words > words_cap) return fail(FULGOR_GPU_E2BIG, "words_cap too small; *n_words holds the required capacity");
+        std::vector<uint64_t> inv;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        pack_reads(bases, read_off, n_reads, words, read_len, inv, threads > 0 ? unsigned(threads) : hw);
+        *n_invalid = inv.size();
+        if (inv.size() > invalid_cap) return fail(FULGOR_GPU_E2BIG, "invalid_cap too small; *n_invalid holds the required capacity");
+        if (!inv.empty()) std::memcpy(invalid_pos, inv.data(), inv.size() * 8);
+        return 0;
+    });
+}
+
+static host_reads packed_input(const uint32_t* words, const uint32_t* read_len, uint32_t n_reads, const uint64_t* invalid_pos, uint64_t n_invalid) {
+    if (!read_len || (!invalid_pos && n_invalid)) throw std::invalid_argument("null argument");
+    if (!words)
+        for (uint32_t i = 0; i < n_reads; ++i)
+            if (read_len[i] & 0x7fffffffu) throw std::invalid_argument("null argument");
+    for (uint64_t i = 1; i < n_invalid; ++i)
+        if (invalid_pos[i] <= invalid_pos[i - 1]) throw std::invalid_argument("invalid_pos must be ascending");
+    host_reads in;
+    in.words = words;
+    in.read_len = read_len;
+    in.invalid = invalid_pos;
+    in.n_invalid = n_invalid;
+    return in;
+}
+
+int fulgor_gpu_pseudoalign_packed(fulgor_gpu_index* x, int algo, double threshold, const uint32_t* words, const uint32_t* read_len, uint32_t n_reads,
+                                  const uint64_t* invalid_pos, uint64_t n_invalid, uint64_t* color_off, uint32_t* colors, uint64_t colors_cap) {
+    return guarded([&]() -> int {
+        if (!x || !color_off || (!colors && colors_cap)) throw std::invalid_argument("null argument");
+        check_algo(algo, threshold);
+        const host_reads in = packed_input(words, read_len, n_reads, invalid_pos, n_invalid);
+        host_results out;
+        out.off = color_off;
+        out.vals = colors;
+        out.cap = colors_cap;
+        int rc = run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, in, n_reads, out);
+        if (rc == FULGOR_GPU_E2BIG) return fail(rc, "colors_cap too small; color_off[n_reads] holds the required capacity");
+        return rc;
+    });
+}
+
+int fulgor_gpu_pseudoalign_bitmaps(fulgor_gpu_index* x, int algo, double threshold, const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                                   uint32_t* bitmaps) {
+    return guarded([&]() -> int {
+        if (!x || !read_off || (!bases && n_reads && read_off[n_reads] > read_off[0]) || (!bitmaps && n_reads)) throw std::invalid_argument("null argument");
+        check_algo(algo, threshold);
+        host_reads in;
+        in.bases = bases;
+        in.read_off = read_off;
+        host_results out;
+        out.bitmaps = bitmaps;
+        return run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, in, n_reads, out);
+    });
+}
+
+int fulgor_gpu_pseudoalign_packed_bitmaps(fulgor_gpu_index* x, int algo, double threshold, const uint32_t* words, const uint32_t* read_len,
+                                          uint32_t n_reads, const uint64_t* invalid_pos, uint64_t n_invalid, uint32_t* bitmaps) {
+    return guarded([&]() -> int {
+        if (!x || (!bitmaps && n_reads)) throw std::invalid_argument("null argument");
+        check_algo(algo, threshold);
+        const host_reads in = packed_input(words, read_len, n_reads, invalid_pos, n_invalid);
+        host_results out;
+        out.bitmaps = bitmaps;
+        return run_host_batch(x, op_kind::PSEUDOALIGN, algo, threshold, in, n_reads, out);
     });
 }
 
@@ -950,9 +1163,7 @@ int fulgor_gpu_pseudoalign_device(fulgor_gpu_index* x, int algo, double threshol
                                   uint64_t* total_out) {
     return guarded([&]() -> int {
         if (!x || !d_read_off || !d_color_off || !total_out) throw std::invalid_argument("null argument");
-        if (algo != FULGOR_GPU_FULL_INTERSECTION && algo != FULGOR_GPU_THRESHOLD_UNION) throw std::invalid_argument("unknown algorithm");
-        if (algo == FULGOR_GPU_THRESHOLD_UNION && !(threshold > 0.0 && threshold <= 1.0))
-            throw std::invalid_argument("threshold must be a float in (0.0,1.0]");
+        check_algo(algo, threshold);
         FG_CUDA(cudaSetDevice(x->device));
         slot& s = x->slots[0];
         FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
@@ -980,6 +1191,77 @@ int fulgor_gpu_pseudoalign_device(fulgor_gpu_index* x, int algo, double threshol
             x->pool_per_read *= 4;
         }
         for (int i = 0; i < 3; ++i) FG_CUDA(cudaEventElapsedTime(&x->last_ms[i], x->ev[i], x->ev[i + 1]));
+        *total_out = s.h_info[1];
+        if (s.h_info[1] > colors_cap) return fail(FULGOR_GPU_E2BIG, "colors_cap too small; *total_out holds the required capacity");
+        return 0;
+    });
+}
+
+int fulgor_gpu_pseudoalign_packed_device(fulgor_gpu_index* x, int algo, double threshold, const uint32_t* d_words, const uint32_t* d_read_len,
+                                         uint32_t n_reads, const uint64_t* d_invalid_pos, uint32_t n_invalid, int result_bitmaps,
+                                         uint64_t* d_color_off, uint32_t* d_colors, uint64_t colors_cap, uint64_t* total_out) {
+    return guarded([&]() -> int {
+        if (!x || !total_out || (n_reads && !d_read_len) || (!result_bitmaps && !d_color_off) || (n_invalid && !d_invalid_pos))
+            throw std::invalid_argument("null argument");
+        check_algo(algo, threshold);
+        FG_CUDA(cudaSetDevice(x->device));
+        slot& s = x->slots[0];
+        const uint32_t words_per_read = (x->H.num_colors + 31) / 32;
+        *total_out = 0;
+        x->last_launches = 0;
+        if (n_reads == 0) {
+            if (!result_bitmaps) FG_CUDA(cudaMemsetAsync(d_color_off, 0, 8, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            return 0;
+        }
+        if (result_bitmaps && uint64_t(n_reads) * words_per_read > colors_cap) {
+            *total_out = uint64_t(n_reads) * words_per_read;
+            return fail(FULGOR_GPU_E2BIG, "colors_cap too small; *total_out holds the required capacity");
+        }
+        s.pk_word_off.reserve(size_t(n_reads + 1) * 8);
+        const uint32_t tiles = (n_reads + FG_SCAN_TILE - 1) / FG_SCAN_TILE;
+        s.tile_sums.reserve(size_t(tiles) * 4);
+        s.tile_off.reserve(size_t(tiles) * 8);
+        chunk_args a{};
+        a.n = n_reads;
+        a.d_words = d_words;
+        a.d_word_off = s.pk_word_off.as<uint64_t>();
+        a.d_read_len = d_read_len;
+        a.d_invalid = d_invalid_pos;
+        a.n_invalid = n_invalid;
+        uint64_t* d_off = result_bitmaps ? nullptr : d_color_off;
+        for (int attempt = 0;; ++attempt) {
+            FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
+            FG_CUDA(cudaMemsetAsync(s.pk_scan, 0, 8, s.stream));
+            FG_CUDA(cudaEventRecord(x->ev[0], s.stream));
+            x->last_launches = 3;
+            k_scan_tile_sums<FG_SCAN_PACKED_WORDS><<<tiles, FG_SCAN_BLOCK, 0, s.stream>>>(d_read_len, n_reads, s.tile_sums.as<uint32_t>());
+            k_scan_tile_offsets<<<1, FG_SCAN_BLOCK, 0, s.stream>>>(s.tile_sums.as<uint32_t>(), tiles, s.tile_off.as<uint64_t>(), s.pk_scan, s.pk_scan + 1,
+                                                                  s.pk_word_off.as<uint64_t>() + n_reads);
+            k_scan_write<FG_SCAN_PACKED_WORDS><<<tiles, FG_SCAN_BLOCK, 0, s.stream>>>(d_read_len, n_reads, s.tile_off.as<uint64_t>(), s.pk_scan + 1,
+                                                                                     s.pk_word_off.as<uint64_t>());
+            FG_CUDA(cudaGetLastError());
+            const emit_plan plan = enqueue_pseudoalign(x, s, a, algo, threshold, d_off, x->ev[1], x->ev[2], &x->last_launches);
+            if (result_bitmaps) { /* the rows as the kernels left them: masks (<= 32 colors) or the color-set kernel's bitmaps */
+                const void* rows = plan.kind == emit_plan::MASKS ? s.per_read.p : s.res_bits.p;
+                FG_CUDA(cudaMemcpyAsync(d_colors, rows, size_t(n_reads) * words_per_read * 4, cudaMemcpyDeviceToDevice, s.stream));
+            } else {
+                enqueue_emit(s, plan, d_off, d_colors, colors_cap);
+                x->last_launches += 1;
+                FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+            }
+            FG_CUDA(cudaEventRecord(x->ev[3], s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            if (!uint32_t(s.h_info[2])) break;
+            if (attempt >= 12) throw std::runtime_error("entry pool kept overflowing");
+            x->pool_per_read *= 4;
+        }
+        for (int i = 0; i < 3; ++i) FG_CUDA(cudaEventElapsedTime(&x->last_ms[i], x->ev[i], x->ev[i + 1]));
+        if (result_bitmaps) {
+            *total_out = uint64_t(n_reads) * words_per_read;
+            return 0;
+        }
         *total_out = s.h_info[1];
         if (s.h_info[1] > colors_cap) return fail(FULGOR_GPU_E2BIG, "colors_cap too small; *total_out holds the required capacity");
         return 0;

@@ -1,14 +1,12 @@
 /*
  * kernels.cuh -- sm_100a device code of the pseudoalignment hot path.
  *
- * Mapping: ONE WARP PER READ. Lanes own consecutive k-mer start positions (tiles of 32 k-mers);
- * every lane resolves its own k-mer independently -- canonical minimizer -> minimizer MPHF ->
- * bucket range -> super-k-mer record -> 2-bit string window compare. A lookup answer is a pure
- * function of the k-mer (the reference asserts this itself: external/sshash/include/
- * streaming_query.hpp:107 compares every streamed answer with a from-scratch lookup), so the
- * reference's sequential seed-and-extend state machine is NOT reproduced: neighbouring lanes that
- * share a minimizer issue identical addresses, which the LSU coalesces into one sector request,
- * and that is the device analogue of "extension".
+ * Mapping: ONE WARP PER READ, a read handled in segments of 128 k-mers (kmer_tiles below). The reference's sequential
+ * seed-and-extend state machine (external/sshash/include/streaming_query.hpp:50-190) is not reproduced step by step; its
+ * effect is: the k-mers of a segment are cut into runs that share one minimizer occurrence, the first k-mer of a run is
+ * looked up through the minimizer MPHF (one seed per lane), and one comparison of the stored super-k-mer string with the
+ * read, aligned on the minimizer, answers every k-mer of the run at once ("extension"). A lookup answer is a pure function of
+ * the k-mer (the reference asserts this itself, streaming_query.hpp:107), so the answers are the reference's.
  *
  * Citations: "sshash/" = reference external/sshash/include/, "pthash/" =
  * external/sshash/external/pthash/include/, "bits/" = .../pthash/external/bits/include/.
@@ -23,8 +21,8 @@
 
 #include "image.h"
 
-/* The per-lane functions (hashing, MPHF, string compare, color-set decode) are FG_HD so that
-   tests/host_emul.cu can run the SAME source on the host against the oracle when no GPU is around.
+/* The per-lane functions (hashing, MPHF, string compare, color-set decode) are FG_HD so that the CPU test tier can call them,
+   and the kernels themselves compile for the host on the lock-step warp emulator tests/simt_emul.{h,cpp} (FG_SIMT_EMUL).
    That harness is test infrastructure; the library itself has no CPU path. */
 #define FG_HD __host__ __device__ __forceinline__
 #ifdef __CUDA_ARCH__
@@ -461,11 +459,24 @@ __device__ __forceinline__ void mask_below(uint32_t nb, uint64_t& lo, uint64_t& 
    k-mer can only be stored in the bucket of its own minimizer, so a run needs no other bucket.
    Runs whose bucket is served by the skew index and k-mers whose minimizer value appears on both strands take the
    per-k-mer path (lookup_in_bucket); super-k-mers without a single minimizer position are scanned k-mer by k-mer. */
-template <int W, bool PERK = false>
+/* A read in PACKED form (include/fulgor_gpu.h, fulgor_gpu_pack_reads): 2-bit codes, 16 per 32-bit word, the read starting on a
+   word; the characters that are not ACGTacgt are listed apart (ascending positions, in bases from the start of the packed
+   buffer) and only looked at when the read is flagged. A quarter of the ASCII bytes over PCIe, and no packing in the kernel. */
+struct packed_read {
+    const uint32_t* words;  /* first word of the read */
+    uint32_t len;           /* bases */
+    bool flagged;           /* some character is not one of ACGTacgt */
+    const uint64_t* invalid; /* ascending positions of such characters (all reads of the launch) */
+    uint32_t n_invalid;
+    uint64_t pos;           /* position of the read's first base in the coordinates of `invalid` */
+};
+
+template <int W, bool PERK = false, bool PACKED = false>
 struct kmer_tiles {
     const dev_index& I;
     const uint8_t* __restrict__ seq;
     const uint8_t *buf_begin, *buf_end; /* the bases buffer the read lives in: aligned 4-byte loads stay inside it */
+    packed_read pr;                     /* PACKED: the read */
     warp_stage& S;
     uint32_t len, lane, nk, seg_end, nitems, cursor;
     uint32_t shift; /* the packed stream starts at the 4-byte aligned address at or below the segment: base j sits at stream position j + shift */
@@ -480,6 +491,13 @@ struct kmer_tiles {
     __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, const uint8_t* buf_begin_, const uint8_t* buf_end_,
                                           uint32_t lane_, warp_stage& S_)
         : I(I_), seq(seq_), buf_begin(buf_begin_), buf_end(buf_end_), S(S_), len(len_), lane(lane_) {
+        init();
+    }
+    __device__ __forceinline__ kmer_tiles(const dev_index& I_, const packed_read& pr_, uint32_t lane_, warp_stage& S_)
+        : I(I_), seq(nullptr), buf_begin(nullptr), buf_end(nullptr), pr(pr_), S(S_), len(pr_.len), lane(lane_) {
+        init();
+    }
+    __device__ __forceinline__ void init() {
         const uint32_t k = I.k;
         nk = len >= k ? len - k + 1 : 0; /* src/ps_full_intersection.cpp:337: shorter reads have no k-mers */
         seg_end = 0;
@@ -597,9 +615,38 @@ struct kmer_tiles {
         /* 0. bases. Lane l loads the l-th aligned 4-byte word at or after the segment's aligned floor, packs its four
               characters to one byte (2 bits each) and stores it: the packed stream is the byte array over S.words. */
         const uint8_t* p0 = seq + seg0;
-        shift = uint32_t(reinterpret_cast<uintptr_t>(p0) & 3u);
+        shift = PACKED ? 0u : uint32_t(reinterpret_cast<uintptr_t>(p0) & 3u);
         const uint32_t nstream = nchars + shift;
         const uint32_t nwords = (nstream + 31) >> 5;
+        bool all_valid;
+        if (PACKED) {
+            /* the segment starts on a word (FG_SEG_KMERS is a multiple of 16): lane l copies 32-bit word l, bits past the
+               segment's last character cleared like the 'A' padding of the ASCII path */
+            const uint32_t n32 = (nchars + 15) >> 4;
+            if (lane < 2 * nwords) {
+                uint32_t x = lane < n32 ? __ldg(pr.words + (seg0 >> 4) + lane) : 0u;
+                if (lane + 1 == n32 && (nchars & 15u)) x &= (1u << (2 * (nchars & 15u))) - 1u;
+                reinterpret_cast<uint32_t*>(S.words + FG_WORDS_PAD_BEFORE)[lane] = x;
+            }
+            all_valid = !pr.flagged;
+            if (!all_valid) { /* rare: validity bits from the list of invalid positions that fall into this segment */
+                const uint32_t nvw = (nchars + 32 + 31) >> 5;
+                if (lane < nvw) S.valid[lane] = nchars >= 32 * lane + 32 ? ~0u : (nchars > 32 * lane ? (1u << (nchars - 32 * lane)) - 1u : 0u);
+                __syncwarp();
+                const uint64_t lo_pos = pr.pos + seg0, hi_pos = lo_pos + nchars;
+                uint32_t lo = 0, hi = pr.n_invalid; /* first entry >= lo_pos */
+                while (lo < hi) {
+                    const uint32_t mid = lo + ((hi - lo) >> 1);
+                    if (__ldg(pr.invalid + mid) < lo_pos) lo = mid + 1; else hi = mid;
+                }
+                for (uint32_t i = lo + lane; i < pr.n_invalid; i += 32) {
+                    const uint64_t at = __ldg(pr.invalid + i);
+                    if (at >= hi_pos) break;
+                    const uint32_t j = uint32_t(at - lo_pos);
+                    atomicAnd(&S.valid[j >> 5], ~(1u << (j & 31)));
+                }
+            }
+        } else {
         bool bad = false;
         for (uint32_t w0 = 0; w0 < 8 * nwords; w0 += 32) {
             const uint32_t wi = w0 + lane;
@@ -627,13 +674,14 @@ struct kmer_tiles {
             bad |= __byte_perm(0x47544341u, 0u, sel) != (x & 0xdfdfdfdfu);
             if (wi < 8 * nwords) reinterpret_cast<uint8_t*>(S.words + FG_WORDS_PAD_BEFORE)[wi] = uint8_t(packed);
         }
-        const bool all_valid = __ballot_sync(FG_FULL, bad) == 0;
+        all_valid = __ballot_sync(FG_FULL, bad) == 0;
         if (!all_valid) { /* rare: per-character validity bits (segment coordinates) */
             for (uint32_t c = 0; 32 * c < nchars + 32; ++c) {
                 const uint32_t j = 32 * c + lane;
                 const uint32_t v = __ballot_sync(FG_FULL, j < nchars && base_valid(p0[j < nchars ? j : 0]));
                 if (lane == 0) S.valid[c] = v;
             }
+        }
         }
         __syncwarp();
         if (lane < nwords) S.rcw[FG_WORDS_PAD_BEFORE + nwords - 1 - lane] = revcomp(S.words[FG_WORDS_PAD_BEFORE + lane], 32);
@@ -972,10 +1020,8 @@ __device__ __noinline__ bool table_reserve(read_hits& R, uint32_t extra, uint32_
    32-entry register table (one entry per lane) across tiles; a read with more distinct color sets moves to
    an append-only list in `scratch` (shared memory, scratch_cap entries, a power of two, >= 64) and then in
    the pool, sorted and merged by table_compact() when it fills up and at the end. */
-template <int W>
-__device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, const uint8_t* __restrict__ seq, uint32_t len, const uint8_t* buf_begin,
-                                                           const uint8_t* buf_end, uint32_t lane,
-                                                           warp_stage& stage, uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
+template <class TILES>
+__device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_t lane, uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
     read_hits R;
     R.cid = FG_NOT_FOUND;
     R.cnt = 0;
@@ -984,7 +1030,6 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(const dev_index& I, c
     R.tab = nullptr;
     R.cap = 0;
     R.failed = false;
-    kmer_tiles<W> tiles(I, seq, len, buf_begin, buf_end, lane, stage);
     uint32_t cid, cnt;
     while (tiles.next(cid, cnt)) {
         const bool found = cnt != 0;

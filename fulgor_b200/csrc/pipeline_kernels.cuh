@@ -24,23 +24,62 @@ namespace fgb {
 #endif
 #define FG_STAGE_STRIDE FG_MAX_ENTRIES
 
+/* The reads of one launch, in one of two forms. ASCII: the caller's characters as they are (include/fulgor_gpu.h: bases +
+   read_off). PACKED: 2-bit codes, every read starting on a 32-bit word, lengths instead of offsets (word_off is their prefix
+   sum, computed on the device), invalid characters listed apart. The lookup kernels are templated on the form. */
+struct ascii_reads {
+    const uint8_t* bases;
+    const uint64_t* read_off; /* n + 1 */
+    uint64_t read_off_base;   /* bases[0] is character read_off_base of the caller's buffer */
+    static constexpr bool packed = false;
+    __device__ __forceinline__ uint32_t length(uint32_t r) const { return uint32_t(__ldg(read_off + r + 1) - __ldg(read_off + r)); }
+};
+struct packed_reads {
+    const uint32_t* words;
+    const uint64_t* word_off; /* n + 1, first word of every read (chunk-local) */
+    const uint32_t* read_len; /* n: bases | FG_READ_FLAGGED */
+    const uint64_t* invalid;  /* ascending base positions (16 * word index + base in word, caller's coordinates) */
+    uint32_t n_invalid;
+    uint64_t pos_base;        /* position of words[0] in those coordinates */
+    static constexpr bool packed = true;
+    __device__ __forceinline__ uint32_t length(uint32_t r) const { return __ldg(read_len + r) & 0x7fffffffu; }
+};
+#define FG_READ_FLAGGED 0x80000000u
+
+template <int W, bool PERK>
+__device__ __forceinline__ kmer_tiles<W, PERK, false> make_tiles(const dev_index& I, const ascii_reads& in, uint32_t r, uint32_t n_reads, uint32_t lane, warp_stage& S) {
+    const uint64_t beg = __ldg(in.read_off + r), end = __ldg(in.read_off + r + 1);
+    return kmer_tiles<W, PERK, false>(I, in.bases + (beg - in.read_off_base), uint32_t(end - beg), in.bases,
+                                      in.bases + (__ldg(in.read_off + n_reads) - in.read_off_base), lane, S);
+}
+template <int W, bool PERK>
+__device__ __forceinline__ kmer_tiles<W, PERK, true> make_tiles(const dev_index& I, const packed_reads& in, uint32_t r, uint32_t n_reads, uint32_t lane, warp_stage& S) {
+    const uint32_t l = __ldg(in.read_len + r);
+    const uint64_t w = __ldg(in.word_off + r);
+    packed_read pr;
+    pr.words = in.words + w;
+    pr.len = l & 0x7fffffffu;
+    pr.flagged = (l & FG_READ_FLAGGED) != 0;
+    pr.invalid = in.invalid;
+    pr.n_invalid = in.n_invalid;
+    pr.pos = in.pos_base + 16 * w;
+    return kmer_tiles<W, PERK, true>(I, pr, lane, S);
+}
+
 /* K1 + fused K2 for indexes with at most 32 colors: each read's result is one 32-bit color mask,
    accumulated item by item (no per-read table: AND is idempotent and scores are sums over k-mers).
    Full intersection (src/ps_full_intersection.cpp:377-400 -> intersect :33-127): AND of the hit sets.
    Threshold union (src/ps_threshold_union.cpp:389 + merge :17-40 / merge_meta :43-120): color c is
    reported iff sum over positive k-mers of [c in set(k-mer)] >= uint64(double(npos) * threshold). */
-template <int W>
-__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
-                                                               const uint64_t* __restrict__ read_off, uint64_t read_off_base,
+template <int W, class READS>
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_pseudoalign_small(const __grid_constant__ dev_index I, const READS in,
                                                                uint32_t n_reads, int algo, double threshold,
                                                                uint32_t* __restrict__ masks) {
     __shared__ warp_stage stage[FG_WARPS_PER_BLOCK];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + (threadIdx.x >> 5); r < n_reads; r += warps) {
-        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        kmer_tiles<W> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base), lane,
-                            stage[threadIdx.x >> 5]);
+        auto tiles = make_tiles<W, false>(I, in, r, n_reads, lane, stage[threadIdx.x >> 5]);
         uint32_t acc = ~0u, score = 0, npos = 0;
         uint32_t cid, cnt;
         while (tiles.next(cid, cnt)) { /* items {color-set id, number of k-mers}: every lane decodes its own set */
@@ -94,9 +133,8 @@ __device__ __forceinline__ const uint2* entries_of(uint32_t r, uint32_t n, const
 }
 
 /* K1 alone: per read, ascending distinct color-set ids with multiplicities */
-template <int W>
-__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
-                                                              const uint64_t* __restrict__ read_off, uint64_t read_off_base,
+template <int W, class READS>
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const READS in,
                                                               uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
                                                               uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool,
                                                               uint32_t* __restrict__ max_positive /* nullable: running maximum of num_positive */) {
@@ -105,9 +143,8 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(co
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
-        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        read_hits R = warp_fetch_color_sets<W>(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base),
-                                               lane, wstage[wib], scratch[wib], FG_SCRATCH_ENTRIES, pool);
+        auto tiles = make_tiles<W, false>(I, in, r, n_reads, lane, wstage[wib]);
+        read_hits R = warp_fetch_color_sets(tiles, lane, scratch[wib], FG_SCRATCH_ENTRIES, pool);
         uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
         if (R.tab == nullptr) {
             if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);
@@ -644,18 +681,15 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
    color-set id of every k-mer of every read, FG_NOT_FOUND for negative and invalid k-mers -- what the loops around
    streaming_query::lookup_advanced + u2c see (src/kmer_conservation.cpp:31-36, src/kmer_matches.cpp:20-24).
    kmer_off (n_reads + 1, chunk-local) = first k-mer slot of every read. */
-template <int W>
-__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_kmer_color_sets(const __grid_constant__ dev_index I, const uint8_t* __restrict__ bases,
-                                                                            const uint64_t* __restrict__ read_off, uint64_t read_off_base,
+template <int W, class READS>
+__global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_kmer_color_sets(const __grid_constant__ dev_index I, const READS in,
                                                                             uint32_t n_reads, const uint64_t* __restrict__ kmer_off,
                                                                             uint32_t* __restrict__ per_kmer) {
     __shared__ warp_stage wstage[FG_WARPS_PER_BLOCK];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
-        const uint64_t beg = __ldg(read_off + r), end = __ldg(read_off + r + 1);
-        kmer_tiles<W, true> tiles(I, bases + (beg - read_off_base), uint32_t(end - beg), bases, bases + (__ldg(read_off + n_reads) - read_off_base), lane,
-                                  wstage[wib]);
+        auto tiles = make_tiles<W, true>(I, in, r, n_reads, lane, wstage[wib]);
         tiles.per_kmer = per_kmer + __ldg(kmer_off + r);
         uint32_t cid, cnt;
         while (tiles.next(cid, cnt)) {}
@@ -828,10 +862,15 @@ static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {
 #define FG_SCAN_BLOCK 256
 #define FG_SCAN_TILE (FG_SCAN_ITEMS * FG_SCAN_BLOCK)
 
-template <bool POPC>
+/* MODE 0: the values themselves; 1: their popcounts (color masks -> list lengths); 2: 32-bit words of a packed read of that
+   many bases (16 per word, flag bit ignored) */
+#define FG_SCAN_PLAIN 0
+#define FG_SCAN_POPC 1
+#define FG_SCAN_PACKED_WORDS 2
+template <int MODE>
 __device__ __forceinline__ uint32_t count_of(const uint32_t* __restrict__ in, uint32_t i) {
     const uint32_t v = __ldg(in + i);
-    return POPC ? uint32_t(__popc(v)) : v;
+    return MODE == FG_SCAN_POPC ? uint32_t(__popc(v)) : (MODE == FG_SCAN_PACKED_WORDS ? ((v & 0x7fffffffu) + 15u) >> 4 : v);
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
@@ -861,7 +900,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return before + x - v;
 }
 
-template <bool POPC>
+template <int POPC>
 __global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
     const uint32_t base = blockIdx.x * FG_SCAN_TILE + threadIdx.x * FG_SCAN_ITEMS;
     uint32_t s = 0;
@@ -900,7 +939,7 @@ __global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_tile_offsets(const uint3
     }
 }
 
-template <bool POPC>
+template <int POPC>
 __global__ void __launch_bounds__(FG_SCAN_BLOCK) k_scan_write(const uint32_t* __restrict__ in, uint32_t n, const uint64_t* __restrict__ tile_off,
                                                              const uint64_t* __restrict__ chunk_info, uint64_t* __restrict__ off) {
     const uint32_t base = blockIdx.x * FG_SCAN_TILE + threadIdx.x * FG_SCAN_ITEMS;

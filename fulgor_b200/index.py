@@ -76,6 +76,14 @@ def lib():
         L.fulgor_gpu_pseudoalign_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                                     C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
         L.fulgor_gpu_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
+        L.fulgor_gpu_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, _u64p, _u64p, C.c_int]
+        L.fulgor_gpu_pseudoalign_packed.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                    C.c_void_p, C.c_void_p, C.c_uint64]
+        L.fulgor_gpu_pseudoalign_bitmaps.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.fulgor_gpu_pseudoalign_packed_bitmaps.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                                            C.c_void_p]
+        L.fulgor_gpu_pseudoalign_packed_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                           C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
         _lib = L
     return _lib
 
@@ -102,6 +110,41 @@ def image_info(image):
     info = Info()
     _check(lib().fulgor_gpu_image_info(image.ctypes.data, image.size, C.byref(info)))
     return info
+
+
+def pack_reads(reads, threads=0):
+    """(bases, read_off) -> (words uint32, read_len uint32 with FULGOR_GPU_READ_HAS_INVALID flags, invalid_pos uint64): the packed
+    read form of include/fulgor_gpu.h, produced on host threads (no GPU needed)"""
+    bases, off = reads
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = off.size - 1
+    L = lib()
+    lens = np.zeros(max(1, n), dtype=np.uint32)
+    nw, ni = C.c_uint64(0), C.c_uint64(0)
+    wcap = int((int(off[n]) - int(off[0])) // 16 + n + 1) if n else 1
+    words = np.zeros(wcap, dtype=np.uint32)
+    inv = np.zeros(64, dtype=np.uint64)
+    while True:
+        rc = L.fulgor_gpu_pack_reads(bases.ctypes.data, off.ctypes.data, n, words.ctypes.data, words.size, lens.ctypes.data, inv.ctypes.data, inv.size,
+                                     C.byref(nw), C.byref(ni), int(threads))
+        if rc == E2BIG:
+            if nw.value > words.size:
+                words = np.zeros(nw.value, dtype=np.uint32)
+            if ni.value > inv.size:
+                inv = np.zeros(ni.value, dtype=np.uint64)
+            continue
+        _check(rc)
+        return words[: nw.value], lens[:n], inv[: ni.value]
+
+
+def unpack_bitmaps(bitmaps, num_colors):
+    """bitmap rows (n x ceil(num_colors / 32) uint32) -> CSR (off uint64[n+1], colors uint32): the lists fulgor_gpu_pseudoalign returns"""
+    rows = np.ascontiguousarray(bitmaps, dtype=np.uint32)
+    bits = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")[:, :num_colors]
+    off = np.zeros(rows.shape[0] + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(bits.sum(axis=1, dtype=np.uint64))
+    return off, np.nonzero(bits)[1].astype(np.uint32)
 
 
 def bind_host_thread(device):
@@ -267,6 +310,34 @@ class Index:
         words = np.zeros(max(1, cap), dtype=np.uint32)
         _check(L.fulgor_gpu_kmer_matches(self._h, bases.ctypes.data, off.ctypes.data, n, woff.ctypes.data, words.ctypes.data, cap, counts.ctypes.data))
         return woff, words[: int(woff[n])], counts
+
+    def pseudoalign_packed(self, packed, algo=FULL_INTERSECTION, threshold=1.0, cap=None):
+        """fulgor_gpu_pseudoalign_packed: packed = (words, read_len, invalid_pos) from pack_reads"""
+        words, lens, inv = packed
+        n = lens.size
+        L = lib()
+
+        def fn(o, v, c):
+            return L.fulgor_gpu_pseudoalign_packed(self._h, algo, float(threshold), words.ctypes.data, lens.ctypes.data, n, inv.ctypes.data if inv.size else None,
+                                                   inv.size, o.ctypes.data, v.ctypes.data, c)
+
+        return self._csr_call(fn, n, cap if cap is not None else 8 * n + 64)
+
+    def pseudoalign_bitmaps(self, reads, algo=FULL_INTERSECTION, threshold=1.0, packed=False):
+        """bitmap rows instead of lists: uint32[n, ceil(num_colors / 32)]; reads = (bases, read_off), or pack_reads' triple with packed=True"""
+        wpr = (self.num_colors + 31) // 32
+        L = lib()
+        if packed:
+            words, lens, inv = reads
+            n = lens.size
+            out = np.zeros((n, wpr), dtype=np.uint32)
+            _check(L.fulgor_gpu_pseudoalign_packed_bitmaps(self._h, algo, float(threshold), words.ctypes.data, lens.ctypes.data, n,
+                                                           inv.ctypes.data if inv.size else None, inv.size, out.ctypes.data))
+            return out
+        bases, off, n = self._reads(reads)
+        out = np.zeros((n, wpr), dtype=np.uint32)
+        _check(L.fulgor_gpu_pseudoalign_bitmaps(self._h, algo, float(threshold), bases.ctypes.data, off.ctypes.data, n, out.ctypes.data))
+        return out
 
     def pseudoalign_full_intersection(self, reads, cap=None):
         return self.pseudoalign(reads, FULL_INTERSECTION, 1.0, cap)

@@ -114,6 +114,43 @@ int fulgor_gpu_pseudoalign_dedup(fulgor_gpu_index*, const char* bases, const uin
                                  uint32_t* rep_of_read /* n_reads */,
                                  uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
 
+/* ---- compact forms of the same path: fewer bytes over PCIe per read --------------------------------------------------
+   The reference's worker owns std::string reads and std::vector<uint32_t> results (tools/pseudoalign.cpp:22-52); a GPU worker is
+   bound by the copies of exactly those, so both have a compact form here. Results are identical to fulgor_gpu_pseudoalign's.
+
+   PACKED READS: what the reference's own k-mer type holds (external/sshash/include/kmer.hpp:199: 2 bits per base,
+   code = (c >> 1) & 3, i.e. A 0, C 1, T 2, G 3, either case), 16 bases per 32-bit word, base p of a read in bits [2 (p % 16), +2) of
+   its word p / 16; EVERY READ STARTS ON A WORD: read i occupies words [W_i, W_i + ceil(len_i / 16)), W_i = sum of the earlier
+   reads' word counts; unused bits of a read's last word are ignored.
+     read_len[i]    = len_i (< 2^31), with FULGOR_GPU_READ_HAS_INVALID set when the read holds a character other than ACGTacgt
+                      (such characters invalidate every k-mer over them, kmer.hpp:214-224,258-260; their codes are ignored);
+     invalid_pos[]  = ascending positions 16 * W_i + p of those characters, n_invalid of them (NULL / 0 when there are none).
+   fulgor_gpu_pack_reads produces this form from ASCII (host threads; what a FASTQ tokeniser would emit directly).
+
+   BITMAP RESULTS: instead of CSR lists, one row of ceil(num_colors / 32) 32-bit words per read, bit c % 32 of word c / 32 set
+   iff color c is in the read's result -- the set the reference writes as a list (src/ps_utils.cpp:127-135). 4 bytes per read
+   for up to 32 colors, 572 bytes for 4,546 colors (a full-intersection list there averages kilobytes). */
+#define FULGOR_GPU_READ_HAS_INVALID 0x80000000u
+
+/* ASCII reads -> packed reads with up to `threads` host threads (<= 0: all). Returns FULGOR_GPU_E2BIG when words_cap or
+   invalid_cap is too small; *n_words / *n_invalid then hold the required capacities. No GPU needed. */
+int fulgor_gpu_pack_reads(const char* bases, const uint64_t* read_off, uint32_t n_reads,
+                          uint32_t* words, uint64_t words_cap, uint32_t* read_len /* n_reads */,
+                          uint64_t* invalid_pos, uint64_t invalid_cap, uint64_t* n_words, uint64_t* n_invalid, int threads);
+
+/* fulgor_gpu_pseudoalign on packed reads, CSR lists out */
+int fulgor_gpu_pseudoalign_packed(fulgor_gpu_index*, int algo, double threshold,
+                                  const uint32_t* words, const uint32_t* read_len, uint32_t n_reads,
+                                  const uint64_t* invalid_pos, uint64_t n_invalid,
+                                  uint64_t* color_off /* n_reads+1 */, uint32_t* colors, uint64_t colors_cap);
+/* fulgor_gpu_pseudoalign with bitmap rows out: bitmaps = n_reads * ceil(num_colors / 32) words */
+int fulgor_gpu_pseudoalign_bitmaps(fulgor_gpu_index*, int algo, double threshold,
+                                   const char* bases, const uint64_t* read_off, uint32_t n_reads, uint32_t* bitmaps);
+/* packed reads in, bitmap rows out */
+int fulgor_gpu_pseudoalign_packed_bitmaps(fulgor_gpu_index*, int algo, double threshold,
+                                          const uint32_t* words, const uint32_t* read_len, uint32_t n_reads,
+                                          const uint64_t* invalid_pos, uint64_t n_invalid, uint32_t* bitmaps);
+
 /* ---- the per-k-mer tools that share the lookup kernel (reference tools/kmer_conservation.cpp, tools/kmer_matches.cpp) ---- */
 
 /* Replaces index::kmer_conservation (src/kmer_conservation.cpp:7-54, called tools/kmer_conservation.cpp:26) for a batch: per
@@ -139,6 +176,14 @@ int fulgor_gpu_kmer_matches(fulgor_gpu_index*, const char* bases, const uint64_t
 int fulgor_gpu_pseudoalign_device(fulgor_gpu_index*, int algo, double threshold,
                                   const char* d_bases, const uint64_t* d_read_off, uint32_t n_reads, uint64_t read_off_base,
                                   uint64_t* d_color_off, uint32_t* d_colors, uint64_t colors_cap, uint64_t* total_out);
+
+/* the same on packed reads resident on the device (d_words, d_read_len, d_invalid_pos: device pointers; positions relative
+   to d_words[0]). result_bitmaps != 0: d_colors receives n_reads bitmap rows (colors_cap counts 32-bit words, d_color_off is
+   not written, *total_out = words written); else CSR lists like fulgor_gpu_pseudoalign_device. */
+int fulgor_gpu_pseudoalign_packed_device(fulgor_gpu_index*, int algo, double threshold,
+                                         const uint32_t* d_words, const uint32_t* d_read_len, uint32_t n_reads,
+                                         const uint64_t* d_invalid_pos, uint32_t n_invalid, int result_bitmaps,
+                                         uint64_t* d_color_off, uint32_t* d_colors, uint64_t colors_cap, uint64_t* total_out);
 
 /* device time (ms, CUDA events on the handle's stream) of the kernels of the last *_device call:
    [0] k-mer lookup (+ fused small-color-count intersect/union), [1] color-set kernel (0 when fused),

@@ -6,9 +6,38 @@
  */
 #include "simt_emul.h"
 
+#include "../fulgor_b200/csrc/pack_reads.h"
 #include "../fulgor_b200/csrc/pipeline_kernels.cuh"
 
 using namespace fgb;
+
+/* emul_set_packed(1): every entry point below first packs its ASCII reads (pack_reads.h, the host half of the packed form) and
+   runs the lookup kernels on packed_reads, word offsets from the scan kernels like engine.cu; 0: ascii_reads */
+static int g_packed = 0;
+
+template <int MODE>
+static void run_scan_into(const uint32_t* counts, uint32_t n, uint64_t* off);
+
+struct emul_reads {
+    const uint8_t* bases;
+    const uint64_t* read_off;
+    uint32_t n;
+    std::vector<uint32_t> words, read_len;
+    std::vector<uint64_t> invalid, word_off;
+    emul_reads(const uint8_t* b, const uint64_t* ro, uint32_t n_) : bases(b), read_off(ro), n(n_) {
+        if (!g_packed || n == 0) return;
+        words.assign(packed_words_of(ro, n) + 1, 0xdeadbeefu);
+        read_len.assign(n, 0);
+        pack_reads(reinterpret_cast<const char*>(b), ro, n, words.data(), read_len.data(), invalid, 3);
+        word_off.assign(size_t(n) + 1, 0);
+        run_scan_into<FG_SCAN_PACKED_WORDS>(read_len.data(), n, word_off.data());
+    }
+    template <typename F>
+    void with(F&& f) const {
+        if (g_packed) f(packed_reads{words.data(), word_off.data(), read_len.data(), invalid.data(), uint32_t(invalid.size()), 0});
+        else f(ascii_reads{bases, read_off, read_off[0]});
+    }
+};
 
 static dev_index view_of(const uint8_t* base) {
     fgi_header H;
@@ -64,8 +93,8 @@ static void dispatch_window(const dev_index& I, int force_generic, F&& f) {
     }
 }
 
-template <bool POPC>
-static void run_scan(const uint32_t* counts, uint32_t n, uint64_t* off) {
+template <int POPC>
+static void run_scan_into(const uint32_t* counts, uint32_t n, uint64_t* off) {
     const uint32_t tiles = (n + FG_SCAN_TILE - 1) / FG_SCAN_TILE;
     std::vector<uint32_t> tile_sums(tiles);
     std::vector<uint64_t> tile_off(tiles);
@@ -75,13 +104,17 @@ static void run_scan(const uint32_t* counts, uint32_t n, uint64_t* off) {
     simt::launch(tiles, FG_SCAN_BLOCK, 0, [&] { k_scan_write<POPC>(counts, n, tile_off.data(), chunk_info, off); });
 }
 
+template <bool POPC>
+static void run_scan(const uint32_t* counts, uint32_t n, uint64_t* off) {
+    run_scan_into<POPC ? FG_SCAN_POPC : FG_SCAN_PLAIN>(counts, n, off);
+}
+
 struct k1_out {
     std::vector<uint2> stage, pool;
     std::vector<uint32_t> counts, npos;
 };
 
-static int run_k1(const dev_index& I, const uint8_t* bases, const uint64_t* read_off, uint32_t n, unsigned grid, int force_generic,
-                  uint64_t pool_entries, k1_out& o) {
+static int run_k1(const dev_index& I, const emul_reads& rd, uint32_t n, unsigned grid, int force_generic, uint64_t pool_entries, k1_out& o) {
     o.stage.assign(size_t(n) * FG_STAGE_STRIDE, uint2{0, 0});
     o.pool.assign(pool_entries, uint2{0, 0});
     o.counts.assign(n, 0);
@@ -90,14 +123,18 @@ static int run_k1(const dev_index& I, const uint8_t* bases, const uint64_t* read
     uint32_t exhausted = 0;
     entry_pool pool{o.pool.data(), &used, pool_entries, &exhausted};
     dispatch_window(I, force_generic, [&](auto w) {
-        simt::launch(grid, FG_BLOCK, 0, [&] {
-            k_fetch_color_sets<decltype(w)::value>(I, bases, read_off, read_off[0], n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
+        rd.with([&](auto in) {
+            simt::launch(grid, FG_BLOCK, 0, [&] {
+                k_fetch_color_sets<decltype(w)::value, decltype(in)>(I, in, n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
+            });
         });
     });
     return int(exhausted);
 }
 
 extern "C" {
+
+void emul_set_packed(int on) { g_packed = on; }
 
 /* color-set id of every k-mer of one read (0xffffffff = negative / invalid), each k-mer looked up independently with the
    per-lane functions (the specification the warp pipeline must agree with) */
@@ -148,12 +185,14 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     }
     out_off[0] = 0;
     if (n == 0) return 0;
+    const emul_reads rd(bases, read_off, n);
     uint64_t chunk_info[2] = {0, 0};
     if (I.num_colors <= 32) {
         std::vector<uint32_t> masks(n, 0xdeadbeefu);
         dispatch_window(I, force_generic, [&](auto w) {
-            simt::launch(grid, FG_BLOCK, 0,
-                         [&] { k_pseudoalign_small<decltype(w)::value>(I, bases, read_off, read_off[0], n, algo, threshold, masks.data()); });
+            rd.with([&](auto in) {
+                simt::launch(grid, FG_BLOCK, 0, [&] { k_pseudoalign_small<decltype(w)::value, decltype(in)>(I, in, n, algo, threshold, masks.data()); });
+            });
         });
         run_scan<true>(masks.data(), n, out_off);
         if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
@@ -162,7 +201,7 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     }
     k1_out k1;
     uint64_t pool_entries = 1u << 12; /* small on purpose: exercises the grow-and-rerun path */
-    while (run_k1(I, bases, read_off, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
+    while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
     uint32_t max_kmers = 1;
     for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
     const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
@@ -208,7 +247,8 @@ int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uin
     uint64_t chunk_info[2] = {0, 0};
     k1_out k1;
     uint64_t pool_entries = 1u << 12;
-    while (run_k1(I, bases, read_off, n, grid, 0, pool_entries, k1)) pool_entries *= 4;
+    const emul_reads rd(bases, read_off, n);
+    while (run_k1(I, rd, n, grid, 0, pool_entries, k1)) pool_entries *= 4;
     uint32_t log2_slots = 4; /* small on purpose: long probe sequences */
     while ((1ull << log2_slots) < 2ull * n) ++log2_slots;
     std::vector<uint32_t> slots(size_t(1) << log2_slots, 0xffffffffu), rep_counts(n, 0xdeadbeefu);
@@ -255,8 +295,11 @@ int emul_kmer_tool(const uint8_t* image, int which, const uint8_t* bases, const 
         koff[i + 1] = koff[i] + (len >= I.k ? len - I.k + 1 : 0);
     }
     std::vector<uint32_t> per_kmer(koff[n] + 1, 0xdeadbeefu);
+    const emul_reads rd(bases, read_off, n);
     dispatch_window(I, force_generic, [&](auto w) {
-        simt::launch(grid, FG_BLOCK, 0, [&] { k_kmer_color_sets<decltype(w)::value>(I, bases, read_off, read_off[0], n, koff.data(), per_kmer.data()); });
+        rd.with([&](auto in) {
+            simt::launch(grid, FG_BLOCK, 0, [&] { k_kmer_color_sets<decltype(w)::value, decltype(in)>(I, in, n, koff.data(), per_kmer.data()); });
+        });
     });
     const uint32_t warp_grid = uint32_t((uint64_t(n) * 32 + 255) / 256);
     uint64_t chunk_info[2] = {0, 0};
@@ -279,7 +322,7 @@ int emul_kmer_tool(const uint8_t* image, int which, const uint8_t* bases, const 
     if (out_off[n] > cap) return FULGOR_GPU_E2BIG;
     k1_out k1;
     uint64_t pool_entries = 1u << 12;
-    while (run_k1(I, bases, read_off, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
+    while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
     simt::launch(warp_grid, 256, 0, [&] { k_kmer_positive_bits(per_kmer.data(), koff.data(), out_off, n, out_vals); });
     simt::launch(grid, FG_BLOCK, 0, [&] { k_kmer_match_counts(I, k1.counts.data(), k1.stage.data(), k1.pool.data(), n, counts); });
     return 0;
@@ -293,7 +336,8 @@ int emul_fetch_color_set_ids(const uint8_t* image, const uint8_t* bases, const u
     if (n == 0) return 0;
     k1_out k1;
     uint64_t pool_entries = 1u << 12;
-    while (run_k1(I, bases, read_off, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
+    const emul_reads rd(bases, read_off, n);
+    while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
     uint64_t chunk_info[2] = {0, 0};
     run_scan<false>(k1.counts.data(), n, out_off);
     if (num_positive) std::memcpy(num_positive, k1.npos.data(), size_t(n) * 4);

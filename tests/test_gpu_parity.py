@@ -281,3 +281,45 @@ def test_salmonella_4546_scale_standin_walk(built_lib):
         eoff, evals, enpos = o.fetch_color_set_ids(sub, want_positive=True)
         assert np.array_equal(off[lo:hi + 1] - off[lo], eoff) and np.array_equal(vals[int(off[lo]):int(off[hi])], evals)
     o.close()
+
+
+def _nasty_reads(genomes):
+    """invalid characters at word boundaries (the packed form has 16 bases per word), at the ends, in runs; lengths around 16 / 32"""
+    g = ck.gen_reads(24, 150, 150, seed=31, genomes=genomes)
+    s = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(24)]
+    out = [s[0][:15] + b"N" + s[0][16:], s[1][:16] + b"n" + s[1][17:], b"N" + s[2][1:], s[3][:149] + b"N", s[4][:31] + b"N" * 18 + s[4][49:],
+           s[5][:47] + b"." + s[5][48:100] + b"R" + s[5][101:], s[6] + s[7][:10] + b"N" + s[7][11:], (s[8] + s[9])[:159] + b"N" + s[10],
+           s[11][:16], s[12][:32], s[13][:33], s[14].lower(), b"N" * 33, b"", b"ACGTN", s[15] + s[16] + s[17][:17]]
+    return out
+
+
+@pytest.mark.parametrize("chunk", [0, 700])
+def test_packed_reads_and_bitmap_results(pair, chunk, monkeypatch):
+    """the compact forms of include/fulgor_gpu.h: packed reads in (fulgor_gpu_pack_reads -> fulgor_gpu_pseudoalign_packed) and
+    bitmap rows out (fulgor_gpu_pseudoalign_bitmaps / _packed_bitmaps) give exactly the lists of fulgor_gpu_pseudoalign == the
+    oracle's; chunk = 700 cuts the batch into many pipeline chunks (the invalid-position list is sliced per chunk)"""
+    import fulgor_b200 as fg
+
+    gpu, o = pair
+    if chunk:
+        monkeypatch.setenv("FULGOR_GPU_CHUNK_READS", str(chunk))
+    g = ck.gen_reads(_sized(gpu, 6000), 75, 300, seed=77, genomes=gpu.genomes)
+    seqs = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(len(g[1]) - 1)]
+    nasty = _nasty_reads(gpu.genomes)
+    for i, s in enumerate(nasty):  # spread the reads with invalid characters over the batch (and over the chunks)
+        seqs.insert((i * 397) % len(seqs), s)
+    e = edge_reads(gpu.genomes)
+    seqs += [e[0][int(e[1][i]):int(e[1][i + 1])].tobytes() for i in range(len(e[1]) - 1)]
+    reads = ck.reads_from_list(seqs)
+    packed = fg.pack_reads(reads)
+    assert packed[2].size > 30
+    for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.3)):
+        exp = o.pseudoalign(reads, algo, thr)
+        assert _same(gpu.pseudoalign_packed(packed, algo, thr), exp)
+        assert _same(gpu.pseudoalign_packed(packed, algo, thr, cap=1), exp)  # E2BIG protocol
+        assert _same(fg.unpack_bitmaps(gpu.pseudoalign_bitmaps(reads, algo, thr), gpu.num_colors), exp)
+        assert _same(fg.unpack_bitmaps(gpu.pseudoalign_bitmaps(packed, algo, thr, packed=True), gpu.num_colors), exp)
+    empty = ck.reads_from_list([])
+    assert gpu.pseudoalign_bitmaps(empty).shape[0] == 0
+    off, vals = gpu.pseudoalign_packed(fg.pack_reads(empty))
+    assert off.tolist() == [0] and vals.size == 0

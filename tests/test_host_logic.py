@@ -365,3 +365,86 @@ def test_emulated_kernels_walk_the_multi_partition_skew_dictionary(emul, built_l
         assert np.array_equal(a, b)
     assert np.array_equal(got[2], np.maximum(0, np.diff(reads[1].astype(np.int64)) - (o.k - 1)))
     o.close()
+
+
+@pytest.fixture
+def packed_emul(emul):
+    """the emulator with its lookup kernels fed PACKED reads (pack_reads.h + packed_reads, the scan kernels for the word offsets)"""
+    emul.emul_set_packed.argtypes = [C.c_int]
+    emul.emul_set_packed(1)
+    yield emul
+    emul.emul_set_packed(0)
+
+
+def _nasty_reads(genomes):
+    """edge reads plus reads with invalid characters at word boundaries, first / last positions and in runs"""
+    g = ck.gen_reads(24, 150, 150, seed=31, genomes=genomes)
+    s = [g[0][int(g[1][i]):int(g[1][i + 1])].tobytes() for i in range(24)]
+    out = [s[0][:15] + b"N" + s[0][16:], s[1][:16] + b"n" + s[1][17:], b"N" + s[2][1:], s[3][:149] + b"N", s[4][:31] + b"NNNNNNNNNNNNNNNNNN" + s[4][49:],
+           s[5][:47] + b"." + s[5][48:100] + b"R" + s[5][101:], s[6] + s[7][:10] + b"N" + s[7][11:], (s[8] + s[9])[:159] + b"N" + s[10],
+           s[11][:16], s[12][:32], s[13][:33], s[14].lower(), b"N" * 33, b"", b"ACGTN", s[15] + s[16] + s[17][:17]]
+    e = _edge_reads(genomes)
+    seqs = [e[0][int(e[1][i]):int(e[1][i + 1])].tobytes() for i in range(len(e[1]) - 1)]
+    return ck.reads_from_list(out + seqs)
+
+
+@pytest.mark.parametrize("index", ["salmonella_10.fur", "salmonella_10.mdfur", "synth_200.mfur", "synth_skew.fur"])
+def test_emulated_kernels_on_packed_reads(index, packed_emul, built_lib):
+    """the lookup kernels on PACKED reads (2-bit codes + list of invalid positions) == the oracle on the ASCII reads they were
+    packed from: stage 1, full intersection / threshold union, the per-k-mer view; both minimizer-window code paths"""
+    import fulgor_b200 as fg
+
+    path = ck.index_path(index)
+    img, o = fg.build_image(path), ck.Oracle(path)
+    genomes = index.split(".")[0]
+    for reads in (ck.gen_reads(200 if o.num_colors <= 32 else 80, 75, 300, seed=17, genomes=genomes), _nasty_reads(genomes)):
+        for generic in (0, 1):
+            got = emul_fetch(packed_emul, img, reads, grid=2, generic=generic)
+            exp = o.fetch_color_set_ids(reads, want_positive=True)
+            for a, b in zip(got, exp):
+                assert np.array_equal(a, b)
+        for algo, thr in ((0, 1.0), (1, 0.6)):
+            got = emul_pseudoalign(packed_emul, img, reads, algo, thr, o.num_colors, table=1)
+            exp = o.pseudoalign(reads, algo, thr)
+            assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+        bases, off = reads
+        nr = len(off) - 1
+        cap = int(off[nr]) + 1
+        toff, tr = np.zeros(nr + 1, dtype=np.uint64), np.zeros(3 * cap, dtype=np.uint32)
+        assert packed_emul.emul_kmer_tool(img.ctypes.data, 0, bases.ctypes.data, off.ctypes.data, nr, toff.ctypes.data, tr.ctypes.data, cap, None, 2, 0) == 0
+        exp_off, exp_tr = o.kmer_conservation(reads)
+        assert np.array_equal(toff, exp_off) and np.array_equal(tr[: 3 * int(toff[nr])].reshape(-1, 3), exp_tr)
+    o.close()
+
+
+def test_pack_reads_host_function(built_lib):
+    """fulgor_gpu_pack_reads: 2-bit codes (c >> 1) & 3 at 16 bases per word, every read on a word boundary, invalid characters
+    listed by position and flagged in read_len, E2BIG with the required capacities"""
+    import fulgor_b200 as fg
+
+    seqs = [b"ACGTacgt", b"", b"N", b"ACGTACGTACGTACGTA", b"TTTTTTTTTTTTTTTTGGGGGGGGGGGGGGGG", b"ACNNGT" * 7, b"A" * 16 + b"x"]
+    reads = ck.reads_from_list(seqs)
+    words, lens, inv = fg.pack_reads(reads, threads=3)
+    exp_words, exp_inv, w = [], [], 0
+    for s in seqs:
+        nw = (len(s) + 15) // 16
+        for j in range(nw):
+            x = 0
+            for t, c in enumerate(s[16 * j:16 * j + 16]):
+                x |= ((c >> 1) & 3) << (2 * t)
+            exp_words.append(x)
+        exp_inv += [16 * w + p for p, c in enumerate(s) if chr(c) not in "ACGTacgt"]
+        w += nw
+    assert words.tolist() == exp_words and inv.tolist() == exp_inv
+    assert [int(x) & 0x7fffffff for x in lens] == [len(s) for s in seqs]
+    assert [bool(int(x) >> 31) for x in lens] == [any(chr(c) not in "ACGTacgt" for c in s) for s in seqs]
+    big = ck.gen_reads(20000, 75, 300, seed=5)
+    w1, l1, i1 = fg.pack_reads(big, threads=1)
+    w8, l8, i8 = fg.pack_reads(big, threads=8)
+    assert np.array_equal(w1, w8) and np.array_equal(l1, l8) and np.array_equal(i1, i8)
+    L = fg.lib()
+    bases, off = reads
+    nw, ni = C.c_uint64(0), C.c_uint64(0)
+    lens2 = np.zeros(len(seqs), dtype=np.uint32)
+    rc = L.fulgor_gpu_pack_reads(bases.ctypes.data, off.ctypes.data, len(seqs), None, 0, lens2.ctypes.data, None, 0, C.byref(nw), C.byref(ni), 1)
+    assert rc == fg.index.E2BIG and nw.value == len(exp_words)
