@@ -1,15 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- pseudoalign reads/s on synthetic 150 bp reads against the salmonella_10 index (BASELINE.json configs[1]:
-full-intersection, 10 M reads per GPU), one JSON line on stdout.
+"""bench.py -- pseudoalign reads/s on synthetic reads, one JSON line on stdout.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through libfulgor_gpu.so)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation on the host cores
 
-A "step" is one pass of the hot path (k-mer lookup -> color-set ids -> full intersection -> CSR color lists) over one
-batch of synthetic reads. `value` = reads/s with the batch already resident in HBM (CUDA events on the library's
-launch stream); `e2e` = the same through the host-buffer C-ABI call (pinned host memory, H2D + kernels + D2H inside
-the timed region). Multi-GPU: one process per GPU (torchrun), the index image is broadcast once with NCCL, every rank
-pseudoaligns its own shard of reads, no data-path collective ("scaling": "weak").
+The headline fields are BASELINE.json configs[1] (salmonella_10.fur, full intersection, 10 M x 150 bp per GPU). The same line
+carries, under "configs", every other BASELINE.json config measured the same way in the same run: configs[2] (threshold union
+tau = 0.8), configs[3] (4,546-color index, full intersection) and configs[4] (its meta-colored form, threshold union,
+75-300 bp reads) -- the last two on the salmonella_4546-SCALE synthetic stand-in (fixtures_big/, tools/make_standin_4546.sh;
+the real collection is a download).
+
+A "step" is one pass of the hot path (k-mer lookup -> color-set ids -> full intersection / threshold union -> results) over one
+batch of synthetic reads. Per workload:
+    value      reads/s with the batch resident in HBM, CUDA events on the library's launch stream; packed reads in, CSR color
+               lists out (lookup + color-set kernel + offsets scan + emit)
+    e2e        the same through the host-buffer C ABI, pinned host memory, H2D + kernels + D2H inside the timed region, in the
+               COMPACT forms of include/fulgor_gpu.h (packed reads in, bitmap rows out); e2e_lists = packed reads in, CSR lists
+               out; e2e_ascii = ASCII reads in, CSR lists out (round 1's e2e)
+Multi-GPU: one process per GPU (torchrun), the index image is broadcast once with NCCL, every rank pseudoaligns its own shard of
+reads, no data-path collective ("scaling": "weak").
 """
 import argparse
 import json
@@ -26,9 +35,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 INDEX = "salmonella_10.fur"
+BIG = "synth_4546_big"
 READ_LEN = 150
 METRIC = "pseudoalign_reads_per_sec_150bp_full_intersection"
 UNIT = "reads/s"
+STANDIN = ("salmonella_4546-scale SYNTHETIC stand-in (4,546 genomes, ~47 M k-mers, 3 minimizer-MPHF partitions, 7 skew classes; "
+           "tools/make_standin_4546.sh) -- the real collection cannot be downloaded here")
 
 
 def parse_args():
@@ -45,11 +57,14 @@ def parse_args():
     ap.add_argument("--index", default=INDEX)
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-primary", action="store_true", help="skip the other BASELINE.json configs")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="profiling runs: device-resident steps only, fixed launch sequence (no capacity probe, no end-to-end legs, no checks)")
     return ap.parse_args()
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed regions (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -72,18 +87,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, windows):
+    def stats(self, windows):
         """statistics over the samples that fell inside the timed windows [(t0, t1), ...] (perf_counter seconds)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)]
+        inside = [r for t, r in list(self.rows) if any(a <= t <= b for a, b in windows)]
         for r in inside:
             if len(r) < 9:
                 continue
@@ -98,37 +108,124 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
+    def stop(self):
+        if not self.proc:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
 
-def algorithmic_bytes(image, reads, cid_csr, res_csr, k):
-    """bytes(read) = L + 160*v + sum_{c in hit sets}(8 + ceil(bits(c)/8)) + 8 + 4*|R|, summed over the batch.
-    v = valid k-mers: the synthetic reads are pure ACGT, so v = L - k + 1."""
+
+# ---------------------------------------------------------------------------------------------- workloads
+
+def workloads_of(args):
+    """the primary workload (from the flags; default BASELINE.json configs[1]) followed by the other BASELINE.json configs"""
+    def wl(name, index, algo, lo, hi, reads, label):
+        return {"name": name, "index": index, "algo": algo, "threshold": args.threshold if algo == "tu" else 1.0, "min_len": lo, "max_len": hi,
+                "reads": reads, "label": label, "genomes": index.split(".")[0]}
+
+    small = args.index.startswith("salmonella_10")
+    n = args.reads or (10_000_000 if small else 1_000_000)
+    label = {("salmonella_10.fur", "fi", 150, 150): "BASELINE.json configs[1]", ("salmonella_10.fur", "tu", 150, 150): "BASELINE.json configs[2]"}.get(
+        (args.index, args.algo, args.min_len, args.max_len), "")
+    if args.index.startswith("synth_4546"):
+        label = "stand-in for BASELINE.json configs[3]/[4]: " + STANDIN
+    out = [wl("primary", args.index, args.algo, args.min_len, args.max_len, n, label)]
+    default_primary = (args.index, args.algo, args.min_len, args.max_len, args.reads) == (INDEX, "fi", READ_LEN, READ_LEN, 0)
+    if default_primary and not args.only_primary and not args.kernel_only:
+        out[0]["name"] = "configs[1]"
+        out.append(wl("configs[2]", INDEX, "tu", 150, 150, 10_000_000, "BASELINE.json configs[2]"))
+        out.append(wl("configs[3]", BIG + ".fur", "fi", 150, 150, 1_000_000, "BASELINE.json configs[3] on the " + STANDIN))
+        out.append(wl("configs[4]", BIG + ".mfur", "tu", 75, 300, 1_000_000, "BASELINE.json configs[4] on the " + STANDIN))
+    return out
+
+
+def metric_name(w):
+    m = METRIC if w["algo"] == "fi" else METRIC.replace("full_intersection", "threshold_union")
+    if not (w["min_len"] == w["max_len"] == READ_LEN):
+        m = m.replace("150bp", f"{w['min_len']}_{w['max_len']}bp")
+    return m
+
+
+def describe(w, n=None):
+    lens = f"{w['min_len']} bp" if w["min_len"] == w["max_len"] else f"{w['min_len']}-{w['max_len']} bp"
+    what = "full-intersection" if w["algo"] == "fi" else f"threshold-union tau={w['threshold']}"
+    return f"{w['index']}, {what}, {n or w['reads']} synthetic {lens} reads per GPU per step" + (f" ({w['label']})" if w["label"] else "")
+
+
+# ---------------------------------------------------------------------------------------------- byte models
+
+def seeds_per_read(reads, k, m, magic, sample=4000):
+    """Independent numpy count of the lookup kernel's SEEDS: maximal runs of consecutive k-mers that share one canonical-minimizer
+    occurrence (same value, same read position, same strand; sshash util::compute_minimizer, streaming_query.hpp:76-83). The
+    synthetic reads are pure ACGT apart from the genomes' own N's, which this estimate ignores."""
+    bases, off = reads
+    n = min(sample, len(off) - 1)
+    lut = np.zeros(256, dtype=np.uint64)
+    for c in b"ACGTacgt":
+        lut[c] = (c >> 1) & 3
+    mul, mask = np.uint64(0x517cc1b727220a95), np.uint64((1 << (2 * m)) - 1)
+    w = k - m + 1
+    total = 0
+    for i in range(n):
+        s = lut[bases[int(off[i]):int(off[i + 1])]]
+        L = s.size
+        if L < k:
+            continue
+        npos = L - m + 1
+        f = np.zeros(npos, dtype=np.uint64)
+        r = np.zeros(npos, dtype=np.uint64)
+        for j in range(m):
+            f |= s[j:j + npos] << np.uint64(2 * j)
+            r |= (s[j:j + npos] ^ np.uint64(2)) << np.uint64(2 * (m - 1 - j))
+        hf, hr = (f * mul) ^ np.uint64(magic), (r * mul) ^ np.uint64(magic)
+        nk = L - k + 1
+        win = np.lib.stride_tricks.sliding_window_view
+        pf = np.argmin(win(hf, w), axis=1) + np.arange(nk)                       # leftmost minimum on the forward strand
+        pr = (w - 1 - np.argmin(win(hr, w)[:, ::-1], axis=1)) + np.arange(nk)    # rightmost in forward coordinates on the reverse strand
+        vf, vr = f[pf], r[pr]
+        fw = vf <= vr
+        val, pos = np.where(fw, vf, vr), np.where(fw, pf, pr)
+        same = (val[1:] == val[:-1]) & (pos[1:] == pos[:-1]) & (fw[1:] == fw[:-1]) & (vf[1:] != vr[1:]) & (vf[:-1] != vr[:-1])
+        total += 1 + int((~same).sum())
+    return total / max(1, n)
+
+
+def byte_models(image, reads, cid_csr, res_csr, k, seeds):
+    """per read: SURVEY.md 8(d)'s algorithmic bytes (independent lookups: L + 160 v + hit color sets + output) and its
+    seed-and-extend variant (160 per seed lookup + 0.25 per extended k-mer instead of 160 per k-mer)"""
     import fulgor_b200.imageview as iv
 
     bits = iv.color_set_bits(image)
     bases, off = reads
+    n = len(off) - 1
     L = np.diff(off.astype(np.int64))
     v = np.maximum(L - k + 1, 0)
-    cid_off, cids = cid_csr
-    set_bytes = 8 + (bits[cids] + 7) // 8
-    total = int(L.sum()) + 160 * int(v.sum()) + int(set_bytes.sum()) + 8 * (len(off) - 1) + 4 * int(res_csr[1].size)
-    return total
+    set_bytes = int((8 + (bits[cid_csr[1]] + 7) // 8).sum())
+    fixed = int(L.sum()) + set_bytes + 8 * n + 4 * int(res_csr[1].size)
+    return (fixed + 160 * int(v.sum())) / n, (fixed + 160 * seeds * n + 0.25 * max(0.0, float(v.sum()) - seeds * n)) / n
 
 
-def workload_of(args, ck):
-    """reads per GPU per step, genome pack to draw reads from, and the label of the workload"""
-    small = args.index.startswith("salmonella_10")
-    n = args.reads or (10_000_000 if small else 1_000_000)
-    genomes = args.index.split(".")[0]
-    lens = f"{args.min_len} bp" if args.min_len == args.max_len else f"{args.min_len}-{args.max_len} bp"
-    which = {("salmonella_10.fur", "fi", 150, 150): "BASELINE.json configs[1]", ("salmonella_10.fur", "tu", 150, 150): "BASELINE.json configs[2]"}.get(
-        (args.index, args.algo, args.min_len, args.max_len), "")
-    if args.index.startswith("synth_4546"):
-        which = ("stand-in for BASELINE.json configs[3]/[4]: 4,546 SYNTHETIC genomes (tools/make_standin_4546.sh), the real salmonella_4546 "
-                 "collection cannot be downloaded here")
-    return n, genomes, lens, which
+def ncu_view(kname, index):
+    """what the committed ncu capture of this kernel on this index says (profiles/kernels.json)"""
+    path = os.path.join(ROOT, "profiles", "kernels.json")
+    try:
+        return json.load(open(path)).get(f"{kname}@{index}")
+    except (OSError, ValueError):
+        return None
 
 
-def run_reference(args, rank, world):
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def open_cpu_impl(ck, path):
+    if ck.reference_available():
+        return ck.Reference(path), "reference", os.cpu_count() or 1
+    return ck.Oracle(path), "port", 1
+
+
+def run_reference(args, rank):
     """the reference's own CPU implementation of the path (oracle/_ref, unmodified reference sources; else the oracle port)
     on all host threads, each step a bounded sample of the workload"""
     if rank != 0:
@@ -136,43 +233,307 @@ def run_reference(args, rank, world):
     import _checkers as ck
 
     cores = os.cpu_count() or 1
-    algo = 0 if args.algo == "fi" else 1
-    path = ck.index_path(args.index)
-    n, genomes, lens, which = workload_of(args, ck)
-    if ck.reference_available():
-        impl, kind, threads = ck.Reference(path), "reference", cores
-    else:
-        impl, kind, threads = ck.Oracle(path), "port", 1
-    per_thread = (100_000 if kind == "reference" else 30_000) if impl.num_colors <= 32 else 4_000
-    sample = args.cpu_sample or min(n, per_thread * threads)
-    reads = ck.gen_reads(sample, args.min_len, args.max_len, seed=42, threads=min(cores, 32), genomes=genomes)
-    call = (lambda: impl.pseudoalign(reads, algo, args.threshold, threads=threads)) if kind == "reference" else (
-        lambda: impl.pseudoalign(reads, algo, args.threshold))
-    for _ in range(args.warmup):
-        call()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        call()
-    dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    out = []
+    for w in workloads_of(args):
+        try:
+            path = ck.index_path(w["index"])
+        except FileNotFoundError:
+            out.append({"name": w["name"], "unavailable": f"{w['index']} not present (generated fixture)"})
+            continue
+        impl, kind, threads = open_cpu_impl(ck, path)
+        algo = 0 if w["algo"] == "fi" else 1
+        per_thread = (100_000 if kind == "reference" else 30_000) if impl.num_colors <= 32 else 1_000
+        sample = args.cpu_sample or min(w["reads"], per_thread * threads)
+        reads = ck.gen_reads(sample, w["min_len"], w["max_len"], seed=42, threads=min(cores, 32), genomes=w["genomes"])
+        call = (lambda: impl.pseudoalign(reads, algo, w["threshold"], threads=threads)) if kind == "reference" else (
+            lambda: impl.pseudoalign(reads, algo, w["threshold"]))
+        primary = w is not None and len(out) == 0
+        steps, warm = (args.steps, args.warmup) if primary else (min(args.steps, 3), 1)
+        for _ in range(warm):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        dt = time.perf_counter() - t0
+        value = sample * steps / dt
+        out.append({"name": w["name"], "metric": metric_name(w), "value": value, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps,
+                    "workload": describe(w) + f"; this arm: a bounded sample of {sample} reads per step on the host CPU",
+                    "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                                     "sample": f"{sample} reads x {steps} steps, library-level fetch_color_set_ids + pseudoalign, {threads} threads"}})
+        impl.close()
+    p = out[0]
     print(json.dumps({
-        "impl": "reference", "metric": metric_name(args), "value": value,
-        "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{args.index}, {'full-intersection' if algo == 0 else f'threshold-union tau={args.threshold}'}, synthetic {lens} reads "
-                               f"({which}; our arm runs {n} reads per GPU per step; this arm: a bounded sample of {sample} reads per step on the host CPU)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{sample} reads x {args.steps} steps, library-level fetch_color_set_ids + pseudoalign, {threads} threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": p["metric"], "value": p["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": p["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": p["workload"]}, "cpu_baseline": p["cpu_baseline"],
+        "e2e": {"value": p["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "configs": out,
     }))
 
 
-def metric_name(args):
-    m = METRIC if args.algo == "fi" else METRIC.replace("full_intersection", "threshold_union")
-    if not (args.min_len == args.max_len == READ_LEN):
-        m = m.replace("150bp", f"{args.min_len}_{args.max_len}bp")
-    return m
+# ---------------------------------------------------------------------------------------------- our arm
+
+class Ctx:
+    pass
+
+
+def run_workload(cx, w, steps, warmup, first):
+    """one workload on this rank's GPU; returns the rank-0 summary dict (None on other ranks)"""
+    import torch
+
+    ck, fg, args = cx.ck, cx.fg, cx.args
+    algo = fg.FULL_INTERSECTION if w["algo"] == "fi" else fg.THRESHOLD_UNION
+    thr = w["threshold"]
+    try:
+        path = ck.index_path(w["index"])
+    except FileNotFoundError:
+        return {"name": w["name"], "unavailable": f"{w['index']} not present (generated fixture, tools/make_standin_4546.sh)"} if cx.rank == 0 else None
+    if w["index"] not in cx.indexes:
+        if cx.world > 1:
+            idx, d_image = cx.replicate.open_replica(path, cx.local_rank)
+            image = d_image.cpu().numpy() if cx.rank == 0 else None
+        else:
+            image = fg.build_image(path)
+            idx = fg.Index.from_image(image, cx.local_rank)
+        cx.indexes[w["index"]] = (idx, image)
+    idx, image = cx.indexes[w["index"]]
+    dev = cx.dev
+    n = w["reads"]
+    wpr = (idx.num_colors + 31) // 32
+    fused = idx.num_colors <= 32
+
+    # ---- this rank's shard of synthetic reads (weak scaling: n per GPU), ASCII and packed, in pinned host memory
+    key = (w["genomes"], w["min_len"], w["max_len"], n)
+    if cx.reads_key != key:
+        for b in cx.pinned:
+            b.free()
+        cx.pinned = []
+        bases_np, off_np = ck.gen_reads(n, w["min_len"], w["max_len"], seed=42, first=cx.rank * n, threads=cx.gen_threads, genomes=w["genomes"])
+        words_np, lens_np, inv_np = fg.pack_reads((bases_np, off_np), threads=cx.gen_threads)
+        nbases = int(off_np[n])
+
+        def pin(arr):
+            b = fg.PinnedBuffer(max(64, arr.nbytes))
+            b.view(arr.dtype, arr.size)[:] = arr
+            cx.pinned.append(b)
+            return b
+
+        cx.r = Ctx()
+        cx.r.nbases, cx.r.off_np = nbases, off_np
+        cx.r.pin_bases, cx.r.pin_off = pin(bases_np[:nbases]), pin(off_np)
+        cx.r.pin_words, cx.r.pin_lens, cx.r.pin_inv = pin(words_np), pin(lens_np), pin(inv_np)
+        cx.r.nwords, cx.r.ninv = words_np.size, inv_np.size
+        cx.r.d_words = torch.from_numpy(cx.r.pin_words.view(np.int32, cx.r.nwords)).to(dev)
+        cx.r.d_lens = torch.from_numpy(cx.r.pin_lens.view(np.int32, n)).to(dev)
+        cx.r.d_inv = torch.from_numpy(cx.r.pin_inv.view(np.int64, max(1, cx.r.ninv))).to(dev)
+        cx.reads_key = key
+        del bases_np, words_np
+    r = cx.r
+    nbases, off_np = r.nbases, r.off_np
+
+    # output capacity: exact bound when it is small, else measured on a sample of the batch (+25 %); a step that overflows fails loudly
+    if fused:
+        cap = n * idx.num_colors
+    elif args.kernel_only:
+        cap = n * (idx.num_colors // (2 if w["algo"] == "fi" else 1) + 1)
+    else:
+        ns = min(n, 20_000)
+        so, _ = idx.pseudoalign((r.pin_bases.view(np.uint8, int(off_np[ns])), off_np[: ns + 1]), algo, thr, cap=ns * idx.num_colors)
+        cap = int(int(so[ns]) / ns * n * 1.25) + (1 << 20)
+    d_coff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_colors = torch.empty(cap, dtype=torch.int32, device=dev)
+    L = fg.lib()
+    import ctypes as C
+
+    def step_device():
+        total = C.c_uint64(0)
+        rc = L.fulgor_gpu_pseudoalign_packed_device(idx._h, algo, float(thr), r.d_words.data_ptr(), r.d_lens.data_ptr(), n,
+                                                    r.d_inv.data_ptr() if r.ninv else None, r.ninv, 0, d_coff.data_ptr(), d_colors.data_ptr(), cap,
+                                                    C.byref(total))
+        if rc != 0:
+            raise RuntimeError(f"fulgor_gpu_pseudoalign_packed_device rc={rc}: {L.fulgor_gpu_last_error().decode()}")
+        return total.value
+
+    def barrier():
+        if cx.world > 1:
+            cx.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if cx.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-only: inputs resident in HBM. Device time from CUDA events recorded by the library on its launch stream.
+    for _ in range(warmup):
+        total = step_device()
+    barrier()
+    dev_ms, k_ms, launches = 0.0, [0.0, 0.0, 0.0], 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        total = step_device()
+        l, ms = idx.last_kernel_times()
+        dev_ms += sum(ms)
+        k_ms = [a + b for a, b in zip(k_ms, ms)]
+        launches += l
+    barrier()
+    t1 = time.perf_counter()
+    cx.windows.append((t0, t1))
+    wall_ms = max_over_ranks((t1 - t0) * 1e3)
+    ms_per_step = max_over_ranks(dev_ms) / steps
+    value = cx.world * n / (ms_per_step / 1e3)
+    if args.kernel_only:
+        return {"name": w["name"], "metric": metric_name(w), "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+                "gpu_launches": launches, "workload": describe(w), "kernel_ms": {"lookup": k_ms[0] / steps, "color_sets": k_ms[1] / steps, "scan_emit": k_ms[2] / steps}}
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory; H2D + kernels + D2H inside the timed region)
+    pin_coff = fg.PinnedBuffer(8 * (n + 1))
+    pin_colors = fg.PinnedBuffer(4 * cap)
+    pin_rows = fg.PinnedBuffer(4 * n * wpr)
+
+    def check(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} rc={rc}: {L.fulgor_gpu_last_error().decode()}")
+
+    def host_compact():
+        check(L.fulgor_gpu_pseudoalign_packed_bitmaps(idx._h, algo, float(thr), r.pin_words.ptr, r.pin_lens.ptr, n, r.pin_inv.ptr if r.ninv else None,
+                                                      r.ninv, pin_rows.ptr), "fulgor_gpu_pseudoalign_packed_bitmaps")
+
+    def host_lists():
+        check(L.fulgor_gpu_pseudoalign_packed(idx._h, algo, float(thr), r.pin_words.ptr, r.pin_lens.ptr, n, r.pin_inv.ptr if r.ninv else None, r.ninv,
+                                              pin_coff.ptr, pin_colors.ptr, cap), "fulgor_gpu_pseudoalign_packed")
+
+    def host_ascii():
+        check(idx.pseudoalign_raw(algo, thr, r.pin_bases.ptr, r.pin_off.ptr, n, pin_coff.ptr, pin_colors.ptr, cap), "fulgor_gpu_pseudoalign")
+
+    def timed(fn, k, wu):
+        for _ in range(wu):
+            fn()
+        barrier()
+        a = time.perf_counter()
+        for _ in range(k):
+            fn()
+        barrier()
+        b = time.perf_counter()
+        cx.windows.append((a, b))
+        return max_over_ranks(b - a) / k
+
+    in_packed = 4 * r.nwords + 4 * n + 8 * r.ninv
+    s_compact = timed(host_compact, steps, warmup)
+    e2e = {"value": cx.world * n / s_compact, "unit": UNIT, "ms_per_step": s_compact * 1e3, "h2d_bytes_per_step": in_packed,
+           "d2h_bytes_per_step": 4 * n * wpr + 8 * ((n + (1 << 18) - 1) >> 18),
+           "api": "fulgor_gpu_pseudoalign_packed_bitmaps (packed reads in, one bitmap row of ceil(num_colors/32) words per read out)"}
+    few = max(2, min(steps, 5))
+    s_lists = timed(host_lists, few, 1)
+    total_colors = int(pin_coff.view(np.uint64, n + 1)[n])
+    e2e_lists = {"value": cx.world * n / s_lists, "unit": UNIT, "ms_per_step": s_lists * 1e3, "h2d_bytes_per_step": in_packed,
+                 "d2h_bytes_per_step": 8 * (n + 1) + 4 * total_colors + 24 * ((n + (1 << 18) - 1) >> 18), "steps": few,
+                 "api": "fulgor_gpu_pseudoalign_packed (packed reads in, CSR color lists out)"}
+    lists_coff = pin_coff.view(np.uint64, n + 1).copy()
+    lists_head = pin_colors.view(np.uint32, total_colors)[: 1 << 22].copy()
+    s_ascii = timed(host_ascii, few, 1)
+    e2e_ascii = {"value": cx.world * n / s_ascii, "unit": UNIT, "ms_per_step": s_ascii * 1e3, "h2d_bytes_per_step": nbases + 8 * (n + 1),
+                 "d2h_bytes_per_step": e2e_lists["d2h_bytes_per_step"], "steps": few,
+                 "api": "fulgor_gpu_pseudoalign (ASCII reads in, CSR color lists out)"}
+
+    # every path must give the same answer: device-resident lists == host lists (packed) == host lists (ASCII) == the bitmap rows
+    res_off = pin_coff.view(np.uint64, n + 1)
+    res_vals = pin_colors.view(np.uint32, total_colors)
+    same = bool(np.array_equal(d_coff.cpu().numpy().view(np.uint64), res_off) and np.array_equal(lists_coff, res_off) and
+                np.array_equal(lists_head, res_vals[: 1 << 22]) and
+                np.array_equal(d_colors[:total_colors].cpu().numpy().view(np.uint32), res_vals))
+    nb = min(n, 200_000)
+    boff, bvals = fg.unpack_bitmaps(pin_rows.view(np.uint32, n * wpr).reshape(n, wpr)[:nb], idx.num_colors)
+    same = same and bool(np.array_equal(boff, res_off[: nb + 1]) and np.array_equal(bvals, res_vals[: int(res_off[nb])]))
+    rows_pop = int(np.bitwise_count(pin_rows.view(np.uint32, n * wpr)).sum(dtype=np.uint64))  # every row, against the lists' total
+    same = same and rows_pop == total_colors
+    if not same:
+        raise SystemExit(f"bench.py: {w['name']}: the device-resident, packed, ASCII and bitmap paths disagree")
+
+    out = None
+    if cx.rank == 0:
+        # ---- rooflines of the lookup kernel (binding resource: instruction issue) and of the byte models
+        sub = min(n, 1_000_000 if fused else 100_000)  # per-read figures are measured on the first `sub` reads (i.i.d. synthetic reads)
+        reads_sub = (r.pin_bases.view(np.uint8, int(off_np[sub])), off_np[: sub + 1])
+        cid_csr = idx.fetch_color_set_ids(reads_sub, cap=64 * sub)
+        sub_res = (res_off[: sub + 1], res_vals[: int(res_off[sub])])
+        h = cx.iv.header(image)
+        seeds = seeds_per_read(reads_sub, idx.k, idx.m, h.hash_magic)
+        b_indep, b_seed = byte_models(image, reads_sub, cid_csr, sub_res, idx.k, seeds)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        table_off = os.environ.get("FULGOR_GPU_TABLE_MAX_MB", "") == "0"
+        k1 = "k_pseudoalign_small" if fused else "k_fetch_color_sets"
+        k2 = None if fused else ("k_color_sets_general" if table_off else "k_color_sets_table")
+        path_s = sum(k_ms) / steps / 1e3  # every stage that moves the counted bytes: lookup, color sets, scan + emit
+        clocks_now = cx.sampler.stats(cx.windows[-4:])
+        sm_mhz = clocks_now.get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions/s: 4 schedulers per SM, one warp instruction per cycle each
+        kernels = []
+        for kname, ms in ((k1, k_ms[0] / steps), (k2, k_ms[1] / steps), ("k_scan_* + k_emit_*", k_ms[2] / steps)):
+            if kname is None:
+                continue
+            v = ncu_view(kname, w["index"]) or {}
+            wi = v.get("warp_instructions_per_read")
+            kernels.append({"kernel": kname, "ms_per_launch": ms, "share_of_step": ms / (sum(k_ms) / steps),
+                            "warp_instructions_per_read": wi,
+                            "issue_frac": (wi * n / (ms / 1e3) / 1e9 / issue_peak) if (wi and ms > 0) else None,
+                            "dram_bytes_per_launch": (v["dram_bytes_per_read"] * n) if v.get("dram_bytes_per_read") else None,
+                            "ncu": v or None})
+        top = max(kernels[:2], key=lambda x: x["ms_per_launch"]) if len(kernels) > 1 else kernels[0]
+        hbm = {"algorithmic_model": {"bytes_per_read": b_indep, "achieved_gbs": b_indep * n / path_s / 1e9, "frac": b_indep * n / path_s / 1e9 / peak,
+                                     "what": "SURVEY.md 8(d): L + 160 per valid k-mer (independent lookups) + hit color sets + output"},
+               "seed_extend_model": {"bytes_per_read": b_seed, "seeds_per_read": seeds, "achieved_gbs": b_seed * n / path_s / 1e9,
+                                     "frac": b_seed * n / path_s / 1e9 / peak,
+                                     "what": "the same with 160 per SEED lookup + 0.25 per extended k-mer: what seed-and-extend (the reference's and this "
+                                             "kernel's strategy) has to touch"},
+               "peak_gbs": peak, "peak_source": peak_src, "over": "lookup + color-set + scan/emit kernels"}
+        if top["issue_frac"] is not None:
+            roofline = {"bound": "issue", "achieved": top["warp_instructions_per_read"] * n / (top["ms_per_launch"] / 1e3) / 1e9, "peak": issue_peak,
+                        "unit": "G warp-instr/s", "frac": top["issue_frac"], "traffic": top["dram_bytes_per_launch"],
+                        "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed regions)"}
+        else:  # no committed capture of this kernel on this index: fall back to the byte model
+            roofline = {"bound": "hbm", "achieved": hbm["seed_extend_model"]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": hbm["seed_extend_model"]["frac"], "traffic": None, "peak_source": peak_src}
+        roofline.update({"kernel": top["kernel"], "kernel_ms_per_launch": top["ms_per_launch"], "kernel_share_of_step": top["share_of_step"],
+                         "kernels": kernels, "hbm": hbm,
+                         "note": "the dominant kernel is bound by instruction issue / the integer pipe, not by DRAM (profiles/): frac = warp "
+                                 "instructions per read (committed ncu capture, profiles/kernels.json) x reads/s over the SMs' issue rate; "
+                                 "`hbm` holds SURVEY.md 8(d)'s byte model and its seed-and-extend variant over ALL stages' time"})
+
+        cpu_baseline = None
+        if not args.no_cpu_baseline and cx.world == 1:
+            os.sched_setaffinity(0, cx.all_cpus)  # the reference gets every core of the box
+            ref, kind, threads = open_cpu_impl(ck, path)
+            per_thread = (250_000 if kind == "reference" else 200_000) if fused else 1_000
+            if not first:
+                per_thread //= 4
+            sample = args.cpu_sample or min(n, per_thread * threads)
+            sreads = (r.pin_bases.view(np.uint8, int(off_np[sample])), off_np[: sample + 1])
+            tc = time.perf_counter()
+            cpu_out = ref.pseudoalign(sreads, algo, thr, threads=threads) if kind == "reference" else ref.pseudoalign(sreads, algo, thr)
+            cdt = time.perf_counter() - tc
+            ok = bool(np.array_equal(cpu_out[0], res_off[: sample + 1]) and np.array_equal(cpu_out[1], res_vals[: int(res_off[sample])]))
+            ref.close()
+            cpu_baseline = {"value": sample / cdt, "unit": UNIT, "cores": threads, "kind": kind,
+                            "sample": f"first {sample} reads of the GPU batch, one pass, library-level (no parsing/formatting)",
+                            "matches_gpu_output": ok}
+        out = {"name": w["name"], "metric": metric_name(w), "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+               "workload": describe(w), "index": w["index"], "reads_per_gpu": n, "read_len": [w["min_len"], w["max_len"]],
+               "e2e": e2e, "e2e_lists": e2e_lists, "e2e_ascii": e2e_ascii, "gpu_launches": launches,
+               "kernel_ms": {"lookup": k_ms[0] / steps, "color_sets": k_ms[1] / steps, "scan_emit": k_ms[2] / steps},
+               "roofline": roofline, "cpu_baseline": cpu_baseline, "wall_ms_per_step": wall_ms / steps, "results_total_colors": total_colors,
+               "image_mb": image.size / 1e6, "paths_agree": same,
+               "input_bytes_per_read": {"packed": in_packed / n, "ascii": (nbases + 8 * (n + 1)) / n}}
+    for b in (pin_coff, pin_colors, pin_rows):
+        b.free()
+    del d_coff, d_colors
+    return out
 
 
 def main():
@@ -181,7 +542,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
@@ -189,195 +550,54 @@ def main():
 
     import _checkers as ck  # read generator (+ the cpu_baseline leg); never on the measured GPU path
     import fulgor_b200 as fg
+    from fulgor_b200 import imageview, replicate
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cx = Ctx()
+    cx.args, cx.ck, cx.fg, cx.iv, cx.replicate, cx.dist = args, ck, fg, imageview, replicate, dist
+    cx.rank, cx.world, cx.local_rank = rank, world, local_rank
+    cx.dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=cx.dev)
     # one process per GPU: keep this rank's pinned buffers and copy threads on the GPU's NUMA node (the cpu_baseline leg gets all cores back)
-    all_cpus = os.sched_getaffinity(0)
+    cx.all_cpus = os.sched_getaffinity(0)
     numa_cpus = fg.bind_host_thread(local_rank)
-
-    # ---- index: rank 0 parses + flattens the .fur; one NCCL broadcast replicates the image; no other collective on the data path
-    algo = fg.FULL_INTERSECTION if args.algo == "fi" else fg.THRESHOLD_UNION
-    from fulgor_b200 import replicate
-
-    if world > 1:
-        idx, d_image = replicate.open_replica(ck.index_path(args.index), local_rank)
-        image = d_image.cpu().numpy()
-    else:
-        image = fg.build_image(ck.index_path(args.index))
-        idx = fg.Index.from_image(image, local_rank)
-
-    # ---- this rank's shard of synthetic reads (weak scaling: n per GPU), in pinned host memory
-    n, genomes, lens, which = workload_of(args, ck)
     cores = os.cpu_count() or 1
-    gen_threads = max(1, min(32, cores // max(1, world)))
-    bases_np, off_np = ck.gen_reads(n, args.min_len, args.max_len, seed=42, first=rank * n, threads=gen_threads, genomes=genomes)
-    nbases = int(off_np[n])
-    # output capacity: exact bound when it is small, else measured on a sample of the batch (+25 %); a step that still overflows fails loudly
-    if idx.num_colors <= 32:
-        cap = n * idx.num_colors
-    else:
-        ns = min(n, 20_000)
-        so, _ = idx.pseudoalign((bases_np[: int(off_np[ns])], off_np[: ns + 1]), algo, args.threshold)
-        cap = int(int(so[ns]) / ns * n * 1.25) + (1 << 20)
-    pin_bases = fg.PinnedBuffer(nbases + 64)
-    pin_off = fg.PinnedBuffer(8 * (n + 1))
-    pin_coff = fg.PinnedBuffer(8 * (n + 1))
-    pin_colors = fg.PinnedBuffer(4 * cap)
-    pin_bases.view(np.uint8, nbases)[:] = bases_np
-    pin_off.view(np.uint64, n + 1)[:] = off_np
-    del bases_np
+    cx.gen_threads = max(1, min(32, cores // max(1, world)))
+    cx.indexes, cx.pinned, cx.reads_key, cx.windows = {}, [], None, []
+    cx.sampler = ClockSampler(local_rank)
+    cx.sampler.start()  # nvidia-smi needs a moment to start: it runs through the warm-up, only samples inside the timed windows count
 
-    # device-resident copy for the kernel-only number
-    d_bases = torch.from_numpy(pin_bases.view(np.uint8, nbases)).to(dev)
-    d_off = torch.from_numpy(pin_off.view(np.int64, n + 1)).to(dev)
-    d_coff = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    d_colors = torch.empty(cap, dtype=torch.int32, device=dev)
-
-    def step_device():
-        return idx.pseudoalign_device(algo, args.threshold, d_bases.data_ptr(), d_off.data_ptr(), n, 0, d_coff.data_ptr(), d_colors.data_ptr(), cap)
-
-    def step_host():
-        rc = idx.pseudoalign_raw(algo, args.threshold, pin_bases.ptr, pin_off.ptr, n, pin_coff.ptr, pin_colors.ptr, cap)
-        if rc != 0:
-            raise RuntimeError(f"fulgor_gpu_pseudoalign rc={rc}: {fg.lib().fulgor_gpu_last_error().decode()}")
-
-    def barrier():
+    results = []
+    for i, w in enumerate(workloads_of(args)):
+        steps, warmup = (args.steps, args.warmup) if i == 0 else (max(2, min(args.steps, 5)), max(3, min(args.warmup, 3)))
+        results.append(run_workload(cx, w, steps, warmup, first=(i == 0)))
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()  # nvidia-smi needs a moment to start: it runs through the warm-up, only samples inside the timed windows count
-
-    # ---- kernel-only: inputs resident in HBM. Device time from CUDA events recorded by the library on its launch stream.
-    for _ in range(args.warmup):
-        total = step_device()
-    barrier()
-    dev_ms, k_ms, launches = 0.0, [0.0, 0.0, 0.0], 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        total = step_device()
-        l, ms = idx.last_kernel_times()
-        dev_ms += sum(ms)
-        k_ms = [a + b for a, b in zip(k_ms, ms)]
-        launches += l
-    barrier()
-    t1 = time.perf_counter()
-    wall_ms = (t1 - t0) * 1e3
-    dev_ms = max_over_ranks(dev_ms)
-    wall_ms = max_over_ranks(wall_ms)
-    ms_per_step = dev_ms / args.steps
-    value = world * n / (ms_per_step / 1e3)
-
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory; H2D + kernels + D2H inside the timed region)
-    for _ in range(args.warmup):
-        step_host()
-    barrier()
-    t2 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    t3 = time.perf_counter()
-    clocks = sampler.stop([(t0, t1), (t2, t3)])
-    e2e_s = max_over_ranks(t3 - t2)
-    total_colors = int(pin_coff.view(np.uint64, n + 1)[n])
-    e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
-           "h2d_bytes_per_step": nbases + 8 * (n + 1), "d2h_bytes_per_step": 8 * (n + 1) + 4 * total_colors + 24 * ((n + (1 << 20) - 1) >> 20)}
-
-    # the device-resident and the host-buffer path must agree (same CSR)
-    same = bool(np.array_equal(d_coff.cpu().numpy().view(np.uint64), pin_coff.view(np.uint64, n + 1)) and
-                np.array_equal(d_colors[:total_colors].cpu().numpy().view(np.uint32), pin_colors.view(np.uint32, total_colors)))
-    if not same:
-        raise SystemExit("bench.py: device-resident and host-buffer results differ")
+    clocks = cx.sampler.stats(cx.windows)
+    cx.sampler.stop()
 
     if rank == 0:
-        # ---- roofline of the dominant kernel: algorithmic bytes / its mean launch time
-        fused = idx.num_colors <= 32
-        res_csr = (pin_coff.view(np.uint64, n + 1), pin_colors.view(np.uint32, total_colors))
-        sub = min(n, 1_000_000 if fused else 100_000)  # per-read algorithmic bytes are measured on the first `sub` reads and scaled (i.i.d. synthetic reads)
-        reads_sub = (pin_bases.view(np.uint8, int(off_np[sub])), off_np[: sub + 1])
-        cid_csr = idx.fetch_color_set_ids(reads_sub)
-        sub_res = (res_csr[0][: sub + 1], res_csr[1][: int(res_csr[0][sub])])
-        bytes_per_read = algorithmic_bytes(image, reads_sub, cid_csr, sub_res, idx.k) / sub
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        top = 0 if (fused or k_ms[0] >= k_ms[1]) else 1
-        table_off = os.environ.get("FULGOR_GPU_TABLE_MAX_MB", "") == "0"  # the decoded color-set table is built unless disabled / over budget
-        kname = ("k_pseudoalign_small" if fused else "k_fetch_color_sets") if top == 0 else ("k_color_sets_general" if table_off else "k_color_sets_table")
-        top_ms_per_launch = k_ms[top] / args.steps
-        path_ms_per_step = (k_ms[0] + k_ms[1]) / args.steps
-        achieved = bytes_per_read * n / (path_ms_per_step / 1e3) / 1e9
-        traffic, ncu_view = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                per_read = tj.get(f"{kname}_dram_bytes_per_read@{args.index}")
-                traffic = per_read * n if per_read else None  # ncu DRAM bytes per read of the same kernel x reads per launch
-                ncu_view = tj.get(f"{kname}_ncu@{args.index}")  # what actually bounds the kernel (pipe utilisation from the committed capture)
-            except (ValueError, OSError):
-                pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": kname, "kernel_ms_per_launch": top_ms_per_launch,
-                    "kernel_share_of_step": (k_ms[top] / sum(k_ms)) if world == 1 else None,
-                    "lookup_ms": k_ms[0] / args.steps, "color_sets_ms": k_ms[1] / args.steps, "scan_emit_ms": k_ms[2] / args.steps,
-                    "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src, "ncu": ncu_view,
-                    "note": "algorithmic bytes = SURVEY.md 8(d) (independent lookups: 160 B per valid k-mer + hit color sets + output) over the "
-                            "lookup + color-set kernels' time. The kernels use SEED-AND-EXTEND (one MPHF lookup and ~1.2 string comparisons per run "
-                            "of ~5 k-mers), i.e. do less work than independent lookups, so frac may exceed 1; the index is L2-resident and the "
-                            "kernels are bound by the integer pipes, not by DRAM (see profiles/)"}
-
-        cpu_baseline = None
-        if not args.no_cpu_baseline and world == 1:
-            os.sched_setaffinity(0, all_cpus)  # the reference gets every core of the box
-            if ck.reference_available():
-                ref, kind, threads = ck.Reference(ck.index_path(args.index)), "reference", cores
-            else:
-                ref, kind, threads = ck.Oracle(ck.index_path(args.index)), "port", 1
-            per_thread = (250_000 if kind == "reference" else 200_000) if fused else 8_000
-            sample = args.cpu_sample or min(n, per_thread * threads)
-            sreads = (pin_bases.view(np.uint8, int(off_np[sample])), off_np[: sample + 1])
-            tc = time.perf_counter()
-            cpu_out = ref.pseudoalign(sreads, algo, args.threshold, threads=threads) if kind == "reference" else ref.pseudoalign(sreads, algo, args.threshold)
-            cdt = time.perf_counter() - tc
-            ok = bool(np.array_equal(cpu_out[0], res_csr[0][: sample + 1]) and np.array_equal(cpu_out[1], res_csr[1][: int(res_csr[0][sample])]))
-            cpu_baseline = {"value": sample / cdt, "unit": UNIT, "cores": threads, "kind": kind,
-                            "sample": f"first {sample} reads of the GPU batch, one pass, library-level (no parsing/formatting)",
-                            "matches_gpu_output": ok}
-
-        print(json.dumps({
-            "metric": metric_name(args), "value": value, "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.index} (k={idx.k}, m={idx.m}, {idx.num_colors} colors), "
-                                   f"{'full-intersection' if algo == 0 else f'threshold-union tau={args.threshold}'}, {n} synthetic {lens} reads per GPU"
-                                   + (f" ({which})" if which else ""),
-                       "reads_per_gpu": n, "read_len": [args.min_len, args.max_len], "index": args.index,
-                       "l2": f"inputs ({nbases / 1e9:.2f} GB of reads per step) are larger than L2; the {image.size / 1e6:.0f} MB index image is L2-resident "
-                             "by nature of the workload",
-                       "parallelism": f"reads sharded over {world} GPU(s), index replicated by one NCCL broadcast, no data-path collective",
-                       "host_numa_binding": f"{numa_cpus} CPUs next to the GPU" if numa_cpus else "none (single node or unknown topology)"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "wall_ms_per_step": wall_ms / args.steps, "results_total_colors": total_colors,
-        }))
-    barrier()
-    idx.close()
+        p = results[0]
+        line = {"metric": p["metric"], "value": p["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": p["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": p["workload"],
+                           "l2": "inputs are larger than L2 for every workload (0.4-1.5 GB of reads per step); the salmonella_10 image (20 MB) is "
+                                 "L2-resident by nature of the workload, the 4,546-color stand-in's image (189 MB) and decoded table are not",
+                           "parallelism": f"reads sharded over {world} GPU(s), index replicated by one NCCL broadcast, no data-path collective",
+                           "host_numa_binding": f"{numa_cpus} CPUs next to the GPU" if numa_cpus else "none (single node or unknown topology)"},
+                "gpu_launches": p["gpu_launches"], "clocks": clocks}
+        for key in ("e2e", "e2e_lists", "e2e_ascii", "roofline", "cpu_baseline", "kernel_ms", "wall_ms_per_step", "results_total_colors"):
+            if key in p:
+                line[key] = p[key]
+        line["configs"] = results
+        print(json.dumps(line))
+    for idx, _ in cx.indexes.values():
+        idx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
