@@ -375,7 +375,7 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
     e.n = a.n;
     /* the counters of the color-set kernels must hold the largest score: at most the k-mers of the longest read. Chunks that
        come from host buffers know that length; for device-resident reads K1 reports the largest number of positive k-mers. */
-    uint32_t max_kmers = a.max_len;
+    uint32_t max_kmers = a.max_len ? (a.max_len >= x->H.k ? a.max_len - x->H.k + 1 : 1u) : 0u;
     if (max_kmers == 0 && algo != FULGOR_GPU_FULL_INTERSECTION) {
         FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
         FG_CUDA(cudaStreamSynchronize(s.stream));

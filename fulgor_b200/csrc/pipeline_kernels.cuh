@@ -634,12 +634,19 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
 #pragma unroll
             for (int t = 0; t < T; ++t) acc[t] = ~0u;
             if (!FI) cs.clear();
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint2 e = ents[j];
+            /* the rows are fetched one entry AHEAD of the arithmetic (and the entry list two ahead): a warp keeps 2 T row
+               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops */
+            auto load_row = [&](const uint2& e, uint32_t (&x)[T]) {
                 const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
-                uint32_t x[T];
 #pragma unroll
                 for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
+            };
+            uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
+            uint32_t x[T], x_next[T];
+            load_row(e, x);
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
+                if (j + 1 < n) load_row(e_next, x_next);
                 if (FI) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[t] &= x[t];
@@ -651,6 +658,10 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
                         cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
                 }
+                e = e_next;
+                e_next = e_after;
+#pragma unroll
+                for (int t = 0; t < T; ++t) x[t] = x_next[t];
             }
             if (!FI) cs.finish();
 #pragma unroll

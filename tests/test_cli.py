@@ -305,6 +305,25 @@ def test_cli_multi_device_split_and_splice(tmp_path):
     assert r.returncode == 1 and "--gpus must be in [1,2]" in r.stderr
 
 
+@pytest.mark.gpu
+def test_cli_two_real_gpus(built_lib, tmp_path):
+    """the shipped tool with --gpus 2 on two REAL devices (skipped on a one-GPU box): image on both, every batch split by
+    cumulative k-mer count, results spliced back in read order == the oracle; also with --deduplicate"""
+    import fulgor_b200 as fg
+
+    if fg.lib().fulgor_gpu_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    reads = ck.gen_reads(30000, 75, 300, seed=63, genomes="synth_200")
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path("synth_200.mfur")
+    o = ck.Oracle(path)
+    for args, algo, thr in ((["--gpus", "2"], 0, 1.0), (["--gpus", "2", "-r", "0.6"], 1, 0.6), (["--gpus", "2", "--deduplicate", "-t", "6"], 0, 1.0)):
+        out = str(tmp_path / "out.txt")
+        subprocess.check_call([GPU_CLI, "-i", path, "-q", fq, "-o", out, "--batch-reads", "7000"] + args)
+        assert ascii_records(out) == csr_records(o.pseudoalign(reads, algo, thr))
+
+
 def test_cli_flag_errors(built_lib, tmp_path):
     CLI = GPU_CLI
     """flag validation mirrors tools/pseudoalign.cpp:272-321 and needs no GPU"""
@@ -318,3 +337,37 @@ def test_cli_flag_errors(built_lib, tmp_path):
     assert r.returncode == 1 and "Unknown output format" in r.stdout
     r = subprocess.run([CLI, "-q", "q.fq", "-o", "o"], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+REF_GPU_CLI = os.path.join(ck.ROOT, "oracle", "_ref", "fulgor_ref_gpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("index,algo_args", [("salmonella_10.fur", []), ("salmonella_10.mfur", ["-r", "0.8"]), ("synth_200.dfur", []),
+                                             ("synth_skew.fur", ["-r", "0.6"])])
+def test_reference_tool_with_the_gpu_worker(index, algo_args, tmp_path, built_lib):
+    """the drop-in claim as a test: oracle/_ref/fulgor_ref_gpu is the REFERENCE's pseudoalign tool (its parser, FQFeeder, formatters,
+    counters, compiled from /root/reference) with pseudoalign_worker replaced by one fulgor_gpu_pseudoalign call per chunk
+    (oracle/ref/ref_gpu_cli.cpp = INTEGRATION.md compiled). Its output must equal the unmodified reference binary's, record
+    for record, in all three formats (sorted by read id: both write in thread order)."""
+    if not (os.path.exists(REF_GPU_CLI) and os.path.exists(ck.REF_CLI)):
+        pytest.skip("oracle/_ref/fulgor_ref_gpu not built (make -C oracle ref_gpu; needs /root/reference at build time)")
+    genomes = index.split(".")[0]
+    reads = ck.gen_reads(20000, 75, 300, seed=51, genomes=genomes)
+    bases, off = reads
+    seqs = [bases[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
+    seqs[7] = seqs[7][:40] + b"N" + seqs[7][41:]
+    seqs[11] = b"ACGT" * 5
+    reads = ck.reads_from_list(seqs)
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path(index)
+    for fmt, parse in (("ascii", ascii_records), ("binary", binary_records), ("compressed", compressed_records)):
+        a, b = str(tmp_path / f"gpu.{fmt}"), str(tmp_path / f"ref.{fmt}")
+        subprocess.check_call([REF_GPU_CLI, "pseudoalign", "-i", path, "-q", fq, "-o", a, "-t", "4", "--format", fmt] + algo_args,
+                              stdout=subprocess.DEVNULL)
+        subprocess.check_call([ck.REF_CLI, "pseudoalign", "-i", path, "-q", fq, "-o", b, "-t", "4", "--format", fmt] + algo_args,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ra, rb = parse(a), parse(b)
+        assert ra == rb
+        assert len(ra if fmt != "compressed" else ra[1]) == len(seqs)
