@@ -97,6 +97,8 @@ struct fulgor_gpu_index {
     int sm_count = 0;
     uint64_t pool_per_read = 8; /* entry-pool size per read of a chunk; grows (x4) when a launch exhausts it */
     uint32_t* d_table = nullptr; /* decoded color-set table (dev_index::set_table), owned */
+    /* deduplication keeps the lists of EVERY read of a call resident until the groups are known (call-wide arrays) */
+    fgb::dev_buffer dd_stage, dd_counts, dd_npos, dd_pool, dd_rep, dd_rep_counts, dd_slots;
     /* timing of the last *_device call */
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[3] = {0, 0, 0};
@@ -306,12 +308,39 @@ static void enqueue_emit(slot& s, const emit_plan& e, const uint64_t* d_off, uin
             k_emit_entries<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.stage.as<uint2>(), s.pool.as<uint2>(), s.per_read.as<uint32_t>(),
                                                                                           d_off, s.chunk_info, e.n, d_out, out_cap);
             break;
-        case emit_plan::BITS:
-            k_emit_bits<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(),
-                                                                                       d_off, s.chunk_info, e.n, d_out, out_cap);
+        case emit_plan::BITS: {
+            static const bool v1 = std::getenv("FULGOR_GPU_EMIT") && std::atoi(std::getenv("FULGOR_GPU_EMIT")) == 1; /* A/B runs */
+            const uint32_t grid = uint32_t((uint64_t(e.n) * 32 + 255) / 256);
+            if (v1)
+                k_emit_bits_v1<<<grid, 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(), d_off, s.chunk_info, e.n,
+                                                           d_out, out_cap);
+            else
+                k_emit_bits<<<grid, 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(), d_off, s.chunk_info, e.n, d_out,
+                                                        out_cap);
             break;
+        }
     }
     FG_CUDA(cudaGetLastError());
+}
+
+/* where K1 leaves a chunk's per-read lists: the chunk's own slot buffers, or slices of call-wide arrays (deduplication) */
+struct k1_target {
+    uint2* stage;
+    uint32_t* counts;
+    uint32_t* npos; /* nullable */
+    entry_pool pool;
+};
+
+static int launch_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, const k1_target& t) {
+    const uint32_t grid = read_grid(x, a.n);
+    dispatch_window(x->H, [&](auto w) {
+        with_reads(a, [&](auto in) {
+            k_fetch_color_sets<decltype(w)::value, decltype(in)><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, t.stage, t.counts, t.npos, t.pool,
+                                                                                                    a.max_len ? nullptr : s.max_positive);
+        });
+    });
+    FG_CUDA(cudaGetLastError());
+    return 1;
 }
 
 /* K1 alone into stage/pool + counts (+ npos) */
@@ -324,20 +353,18 @@ static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool wa
     FG_CUDA(cudaMemsetAsync(s.exhausted, 0, 4, s.stream));
     FG_CUDA(cudaMemsetAsync(s.pool_used, 0, 8, s.stream));
     FG_CUDA(cudaMemsetAsync(s.max_positive, 0, 4, s.stream));
-    entry_pool pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted};
-    const uint32_t grid = read_grid(x, a.n);
-    dispatch_window(x->H, [&](auto w) {
-        with_reads(a, [&](auto in) {
-            k_fetch_color_sets<decltype(w)::value, decltype(in)><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, s.stage.as<uint2>(), s.per_read.as<uint32_t>(),
-                                                                                                    want_npos ? s.npos.as<uint32_t>() : nullptr, pool,
-                                                                                                    a.max_len ? nullptr : s.max_positive);
-        });
-    });
-    FG_CUDA(cudaGetLastError());
-    return 1;
+    return launch_k1(x, s, a, k1_target{s.stage.as<uint2>(), s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr,
+                                        entry_pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted}});
 }
 
-static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const uint32_t* counts, int algo, double threshold,
+/* the per-read {color-set id, multiplicity} lists the color-set kernel reads */
+struct list_source {
+    const uint32_t* counts;
+    const uint2* stage;
+    const uint2* pool;
+    const uint32_t* npos;
+};
+static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const list_source& ls, int algo, double threshold,
                                     uint64_t* d_off, cudaEvent_t after_k2, int* launches);
 
 /* whole path for a device-resident chunk, up to the CSR offsets (d_off, n+1 entries); returns how to emit the values */
@@ -364,12 +391,13 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
     }
     *launches += enqueue_k1(x, s, a, true);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
-    return enqueue_color_sets(x, s, a, s.per_read.as<uint32_t>(), algo, threshold, d_off, after_k2, launches);
+    return enqueue_color_sets(x, s, a, list_source{s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>()}, algo, threshold,
+                              d_off, after_k2, launches);
 }
 
 /* the color-set kernel (K2) over the per-read {color-set id, multiplicity} lists K1 left in stage/pool, then the CSR offsets.
    `counts` = entries per read (K1's, or the deduplicated ones where only a group's representative keeps its list). */
-static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const uint32_t* counts, int algo, double threshold,
+static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_args& a, const list_source& ls, int algo, double threshold,
                                     uint64_t* d_off, cudaEvent_t after_k2, int* launches) {
     emit_plan e;
     e.n = a.n;
@@ -387,9 +415,8 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
     if (x->I.set_table) { /* decoded table: registers only */
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, 0, s.stream>>>(
-                x->I, counts, s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(), a.n, threshold, e.words_per_read,
-                s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
+            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, table_kernel_smem(decltype(t)::value), s.stream>>>(
+                x->I, ls.counts, ls.stage, ls.pool, ls.npos, a.n, threshold, e.words_per_read, s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */
         if (x->I.diff)
@@ -407,9 +434,8 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
         FG_CUDA(cudaFuncSetAttribute(k_color_sets_general, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem, 48 * 1024))));
         const uint64_t blocks_needed = (uint64_t(a.n) + wpb - 1) / wpb;
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(blocks_needed, uint64_t(x->sm_count) * 8)));
-        k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, counts, s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>(),
-                                                               a.n, algo, threshold, e.words_per_read, g.planes, ints, s.res_bits.as<uint32_t>(),
-                                                               s.res_counts.as<uint32_t>());
+        k_color_sets_general<<<grid, wpb * 32, smem, s.stream>>>(x->I, ls.counts, ls.stage, ls.pool, ls.npos, a.n, algo, threshold, e.words_per_read, g.planes,
+                                                               ints, s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
     }
     FG_CUDA(cudaGetLastError());
     *launches += 1;
@@ -426,25 +452,6 @@ static emit_plan enqueue_fetch(fulgor_gpu_index* x, slot& s, const chunk_args& a
     *launches += enqueue_k1(x, s, a, want_npos);
     *launches += enqueue_scan<FG_SCAN_PLAIN>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
     return e;
-}
-
-/* full intersection computed once per distinct color-set-id list of the chunk (k_group_reads): K1 -> group -> K2 on the
-   representatives -> scan -> emit. Reads that are not representatives get an empty CSR range; rep (device, a.n entries)
-   receives the global index of every read's representative. */
-static emit_plan enqueue_dedup(fulgor_gpu_index* x, slot& s, const chunk_args& a, uint32_t read_base, uint64_t* d_off, int* launches) {
-    *launches += enqueue_k1(x, s, a, true);
-    uint32_t log2_slots = 10;
-    while ((1ull << log2_slots) < 2ull * a.n) ++log2_slots;
-    s.group_slots.reserve(size_t(4) << log2_slots);
-    s.rep.reserve(size_t(a.n) * 4);
-    s.rep_counts.reserve(size_t(a.n) * 4);
-    FG_CUDA(cudaMemsetAsync(s.group_slots.p, 0xff, size_t(4) << log2_slots, s.stream));
-    const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
-    k_group_reads<<<grid, FG_BLOCK, 0, s.stream>>>(s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), a.n, read_base,
-                                                   s.group_slots.as<uint32_t>(), log2_slots, s.rep.as<uint32_t>(), s.rep_counts.as<uint32_t>());
-    FG_CUDA(cudaGetLastError());
-    *launches += 1;
-    return enqueue_color_sets(x, s, a, s.rep_counts.as<uint32_t>(), FULGOR_GPU_FULL_INTERSECTION, 1.0, d_off, nullptr, launches);
 }
 
 /* ---- the chunked host pipeline ---- */
@@ -490,9 +497,9 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, x->slots[0].stream));
     FG_CUDA(cudaStreamSynchronize(x->slots[0].stream));
 
-    const bool small = x->H.num_colors <= 32 && op != op_kind::DEDUP;
+    const bool small = x->H.num_colors <= 32;
     const uint32_t words_per_read = (x->H.num_colors + 31) / 32;
-    uint64_t max_reads = chunk_max_reads(op == op_kind::DEDUP);
+    uint64_t max_reads = chunk_max_reads(false);
     if (op != op_kind::FETCH && !small)
         max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (uint64_t(words_per_read) * 4)));
     struct pending { uint32_t first, n; int slot; emit_plan plan; };
@@ -622,9 +629,6 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
         }
         if (op == op_kind::FETCH) {
             c.plan = enqueue_fetch(x, s, a, num_positive != nullptr, d_off, &launches);
-        } else if (op == op_kind::DEDUP) {
-            c.plan = enqueue_dedup(x, s, a, c.first, d_off, &launches);
-            FG_CUDA(cudaMemcpyAsync(out.per_read + c.first, s.rep.p, size_t(c.n) * 4, cudaMemcpyDeviceToHost, s.stream));
         } else {
             c.plan = enqueue_pseudoalign(x, s, a, algo, threshold, d_off, nullptr, nullptr, &launches);
         }
@@ -668,12 +672,109 @@ static int run_host_batch_once(fulgor_gpu_index* x, op_kind op, int algo, double
     return too_big ? FULGOR_GPU_E2BIG : 0;
 }
 
+/* Full intersection computed once per distinct color-set-id list of the WHOLE call (the reference deduplicates the whole query
+   file, tools/pseudoalign.cpp:92-226). Two passes over the chunks on slot 0:
+     1. lookup kernel per chunk, the per-read lists kept in call-wide arrays (256 bytes of list head per read + one entry pool);
+     2. k_group_reads over all reads of the call: reads with the same list share a representative, the first one found;
+     3. color-set kernel, scan, emit and the copy back per chunk, on the representatives only (the others own an empty range).
+   The gain of deduplication is the work and the bytes NOT spent on repeated lists, so this path is not software-pipelined. */
+static int run_host_dedup_once(fulgor_gpu_index* x, const host_reads& in, uint32_t n_reads, const host_results& out) {
+    slot& s = x->slots[0];
+    const uint32_t words_per_read = (x->H.num_colors + 31) / 32;
+    uint64_t max_reads = chunk_max_reads(true);
+    max_reads = std::max<uint64_t>(1024, std::min<uint64_t>(max_reads, CHUNK_MAX_RESULT_BITS_BYTES / (uint64_t(words_per_read) * 4)));
+    x->dd_stage.reserve(size_t(n_reads) * FG_STAGE_STRIDE * sizeof(uint2));
+    x->dd_counts.reserve(size_t(n_reads) * 4);
+    x->dd_npos.reserve(size_t(n_reads) * 4);
+    x->dd_rep.reserve(size_t(n_reads) * 4);
+    x->dd_rep_counts.reserve(size_t(n_reads) * 4);
+    const uint64_t pool_entries = std::max<uint64_t>(1u << 16, uint64_t(n_reads) * x->pool_per_read);
+    x->dd_pool.reserve(size_t(pool_entries) * sizeof(uint2));
+    uint32_t log2_slots = 10;
+    while ((1ull << log2_slots) < 2ull * n_reads) ++log2_slots;
+    x->dd_slots.reserve(size_t(4) << log2_slots);
+    FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
+    FG_CUDA(cudaMemsetAsync(s.exhausted, 0, 4, s.stream));
+    FG_CUDA(cudaMemsetAsync(s.pool_used, 0, 8, s.stream));
+    FG_CUDA(cudaMemsetAsync(x->dd_slots.p, 0xff, size_t(4) << log2_slots, s.stream));
+    const entry_pool pool{x->dd_pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted};
+    struct piece { uint32_t first, n, max_len; };
+    std::vector<piece> pieces;
+    try {
+        /* 1. the lists of every read */
+        for (uint32_t first = 0; first < n_reads;) {
+            uint32_t n = uint32_t(std::min<uint64_t>(max_reads, n_reads - first));
+            while (n > 1 && in.read_off[first + n] - in.read_off[first] > CHUNK_MAX_BASES) n = (n + 1) / 2;
+            uint64_t longest = 1;
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint64_t len = in.read_off[first + i + 1] - in.read_off[first + i];
+                if (len >> 31) throw std::invalid_argument("read_off must be non-decreasing and reads shorter than 2^31 characters");
+                longest = std::max(longest, len);
+            }
+            const uint64_t b0 = in.read_off[first], b1 = in.read_off[first + n];
+            s.bases.reserve(size_t(b1 - b0) + 64);
+            s.read_off.reserve(size_t(n + 1) * 8);
+            if (b1 > b0) FG_CUDA(cudaMemcpyAsync(s.bases.p, in.bases + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
+            FG_CUDA(cudaMemcpyAsync(s.read_off.p, in.read_off + first, size_t(n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            chunk_args a{};
+            a.d_bases = s.bases.as<uint8_t>();
+            a.d_read_off = s.read_off.as<uint64_t>();
+            a.read_off_base = b0;
+            a.n = n;
+            a.max_len = uint32_t(longest);
+            launch_k1(x, s, a, k1_target{x->dd_stage.as<uint2>() + uint64_t(first) * FG_STAGE_STRIDE, x->dd_counts.as<uint32_t>() + first,
+                                         x->dd_npos.as<uint32_t>() + first, pool});
+            FG_CUDA(cudaStreamSynchronize(s.stream)); /* the next chunk reuses the input buffers */
+            pieces.push_back({first, n, uint32_t(longest)});
+            first += n;
+        }
+        FG_CUDA(cudaMemcpyAsync(s.h_info + 2, s.exhausted, 4, cudaMemcpyDeviceToHost, s.stream));
+        FG_CUDA(cudaStreamSynchronize(s.stream));
+        if (uint32_t(s.h_info[2])) return RC_RETRY_LARGER_POOL;
+        /* 2. groups over the whole call */
+        const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(n_reads) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
+        k_group_reads<<<grid, FG_BLOCK, 0, s.stream>>>(x->dd_counts.as<uint32_t>(), x->dd_stage.as<uint2>(), x->dd_pool.as<uint2>(), n_reads, 0,
+                                                       x->dd_slots.as<uint32_t>(), log2_slots, x->dd_rep.as<uint32_t>(), x->dd_rep_counts.as<uint32_t>());
+        FG_CUDA(cudaGetLastError());
+        FG_CUDA(cudaMemcpyAsync(out.per_read, x->dd_rep.p, size_t(n_reads) * 4, cudaMemcpyDeviceToHost, s.stream));
+        /* 3. the representatives' intersections, chunk by chunk */
+        bool too_big = false;
+        for (const piece& c : pieces) {
+            chunk_args a{};
+            a.n = c.n;
+            a.max_len = c.max_len;
+            s.off.reserve(size_t(c.n + 1) * 8);
+            s.out.reserve(size_t(c.n) * 64 * 4);
+            int launches = 0;
+            const list_source ls{x->dd_rep_counts.as<uint32_t>() + c.first, x->dd_stage.as<uint2>() + uint64_t(c.first) * FG_STAGE_STRIDE, x->dd_pool.as<uint2>(),
+                                 x->dd_npos.as<uint32_t>() + c.first};
+            const emit_plan plan = enqueue_color_sets(x, s, a, ls, FULGOR_GPU_FULL_INTERSECTION, 1.0, s.off.as<uint64_t>(), nullptr, &launches);
+            FG_CUDA(cudaMemcpyAsync(s.h_info, s.chunk_info, 16, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaMemcpyAsync(out.off + c.first, s.off.p, size_t(c.n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            const uint64_t base = s.h_info[0], total = s.h_info[1];
+            if (base + total > out.cap) too_big = true;
+            if (!too_big && total) {
+                s.out.reserve(size_t(total) * 4);
+                enqueue_emit(s, plan, s.off.as<uint64_t>(), s.out.as<uint32_t>(), s.out.cap / 4);
+                FG_CUDA(cudaMemcpyAsync(out.vals + base, s.out.p, total * 4, cudaMemcpyDeviceToHost, s.stream));
+                FG_CUDA(cudaStreamSynchronize(s.stream));
+            }
+        }
+        FG_CUDA(cudaStreamSynchronize(s.stream));
+        return too_big ? FULGOR_GPU_E2BIG : 0;
+    } catch (...) {
+        cudaStreamSynchronize(s.stream);
+        throw;
+    }
+}
+
 static int run_host_batch(fulgor_gpu_index* x, op_kind op, int algo, double threshold, const host_reads& in, uint32_t n_reads, const host_results& out) {
     FG_CUDA(cudaSetDevice(x->device));
     if (out.off) out.off[0] = 0;
     if (n_reads == 0) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
-        const int rc = run_host_batch_once(x, op, algo, threshold, in, n_reads, out);
+        const int rc = op == op_kind::DEDUP ? run_host_dedup_once(x, in, n_reads, out) : run_host_batch_once(x, op, algo, threshold, in, n_reads, out);
         if (rc != RC_RETRY_LARGER_POOL) return rc;
         x->pool_per_read *= 4; /* reads with many distinct color sets: rerun with a larger entry pool (kept for later calls) */
     }
@@ -991,6 +1092,7 @@ void fulgor_gpu_index_close(fulgor_gpu_index* x) {
         if (e) cudaEventDestroy(e);
     if (x->d_carry) cudaFree(x->d_carry);
     if (x->d_table) cudaFree(x->d_table);
+    for (fgb::dev_buffer* b : {&x->dd_stage, &x->dd_counts, &x->dd_npos, &x->dd_pool, &x->dd_rep, &x->dd_rep_counts, &x->dd_slots}) b->release();
     if (x->owns_image && x->d_image) cudaFree(x->d_image);
     delete x;
 }
@@ -1230,6 +1332,14 @@ int fulgor_gpu_pseudoalign_packed_device(fulgor_gpu_index* x, int algo, double t
         a.d_invalid = d_invalid_pos;
         a.n_invalid = n_invalid;
         uint64_t* d_off = result_bitmaps ? nullptr : d_color_off;
+        if (x->H.num_colors > 32) { /* the color-set kernel's counters are sized by the longest read: learn it before the pipeline starts */
+            FG_CUDA(cudaMemsetAsync(s.max_positive, 0, 4, s.stream));
+            k_max_read_len<<<std::min<uint32_t>((n_reads + 255) / 256, 1024), 256, 0, s.stream>>>(d_read_len, n_reads, s.max_positive);
+            FG_CUDA(cudaGetLastError());
+            FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
+            FG_CUDA(cudaStreamSynchronize(s.stream));
+            a.max_len = std::max<uint32_t>(1, uint32_t(s.h_info[3]));
+        }
         for (int attempt = 0;; ++attempt) {
             FG_CUDA(cudaMemsetAsync(x->d_carry, 0, 8, s.stream));
             FG_CUDA(cudaMemsetAsync(s.pk_scan, 0, 8, s.stream));

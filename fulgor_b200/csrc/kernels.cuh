@@ -65,6 +65,22 @@ FG_HD uint32_t fg_clz32(uint32_t x) {
 #endif
 }
 
+/* 16-byte asynchronous global -> shared copies (LDGSTS): the data bypasses the registers, so a warp can keep several table rows
+   in flight without holding them. The emulator copies synchronously. */
+#ifdef FG_SIMT_EMUL
+static inline void fg_cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }
+static inline void fg_cp_async_commit() {}
+template <int N>
+static inline void fg_cp_async_wait() {}
+#else
+__device__ __forceinline__ void fg_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 #define FG_FULL 0xffffffffu
 #define FG_NOT_FOUND 0xffffffffu
 #define FG_MAX_ENTRIES 32 /* distinct color sets per read held in registers (one per lane) */

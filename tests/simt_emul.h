@@ -344,6 +344,14 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
         for (int l = 0; l < 32; ++l) w.out[l] = r & 0xffffffffu;
     }));
 }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    fg_emul_check_mask(mask);
+    return unsigned(simt::collective(21, v, 0, [](simt::warp_state& w) {
+        uint64_t r = 0;
+        for (int l = 0; l < 32; ++l) r = w.vals[l] > r ? w.vals[l] : r;
+        for (int l = 0; l < 32; ++l) w.out[l] = r;
+    }));
+}
 static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
     fg_emul_check_mask(mask);
     return unsigned(simt::collective(8, v, 0, [](simt::warp_state& w) {

@@ -178,11 +178,15 @@ def test_without_the_decoded_table(index, built_lib, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_deduplicated_full_intersection(pair):
+@pytest.mark.parametrize("chunk", [0, 1500])
+def test_deduplicated_full_intersection(pair, chunk, monkeypatch):
     """fulgor_gpu_pseudoalign_dedup (the reference's --deduplicate, tools/pseudoalign.cpp:92-226): reads drawn WITH repeats;
     every read's colors through its representative == pseudoalign_full_intersection, the groups are exactly the distinct
-    color-set-id lists, only representatives own values (so the intersection ran once per group)"""
+    color-set-id lists, only representatives own values (so the intersection ran once per group). chunk = 1500: the call is
+    processed in several chunks and the groups must still span the WHOLE call, like the reference's whole-file deduplication"""
     gpu, o = pair
+    if chunk:
+        monkeypatch.setenv("FULGOR_GPU_CHUNK_READS", str(chunk))
     base = ck.gen_reads(800, 100, 250, seed=77, genomes=gpu.genomes)
     seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(800)]
     rng = np.random.default_rng(3)
