@@ -308,17 +308,10 @@ static void enqueue_emit(slot& s, const emit_plan& e, const uint64_t* d_off, uin
             k_emit_entries<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.stage.as<uint2>(), s.pool.as<uint2>(), s.per_read.as<uint32_t>(),
                                                                                           d_off, s.chunk_info, e.n, d_out, out_cap);
             break;
-        case emit_plan::BITS: {
-            static const bool v1 = std::getenv("FULGOR_GPU_EMIT") && std::atoi(std::getenv("FULGOR_GPU_EMIT")) == 1; /* A/B runs */
-            const uint32_t grid = uint32_t((uint64_t(e.n) * 32 + 255) / 256);
-            if (v1)
-                k_emit_bits_v1<<<grid, 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(), d_off, s.chunk_info, e.n,
-                                                           d_out, out_cap);
-            else
-                k_emit_bits<<<grid, 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(), d_off, s.chunk_info, e.n, d_out,
-                                                        out_cap);
+        case emit_plan::BITS:
+            k_emit_bits<<<uint32_t((uint64_t(e.n) * 32 + 255) / 256), 256, 0, s.stream>>>(s.res_bits.as<uint32_t>(), e.words_per_read, s.res_counts.as<uint32_t>(),
+                                                                                       d_off, s.chunk_info, e.n, d_out, out_cap);
             break;
-        }
     }
     FG_CUDA(cudaGetLastError());
 }
@@ -331,12 +324,17 @@ struct k1_target {
     entry_pool pool;
 };
 
-static int launch_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, const k1_target& t) {
+/* sorted: the lists come out ascending by id (stage 1 results, deduplication); the color-set kernels do not need that */
+static int launch_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, const k1_target& t, bool sorted) {
     const uint32_t grid = read_grid(x, a.n);
     dispatch_window(x->H, [&](auto w) {
         with_reads(a, [&](auto in) {
-            k_fetch_color_sets<decltype(w)::value, decltype(in)><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, t.stage, t.counts, t.npos, t.pool,
-                                                                                                    a.max_len ? nullptr : s.max_positive);
+            if (sorted)
+                k_fetch_color_sets<decltype(w)::value, decltype(in), true><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, t.stage, t.counts, t.npos, t.pool,
+                                                                                                              a.max_len ? nullptr : s.max_positive);
+            else
+                k_fetch_color_sets<decltype(w)::value, decltype(in), false><<<grid, FG_BLOCK, 0, s.stream>>>(x->I, in, a.n, t.stage, t.counts, t.npos, t.pool,
+                                                                                                               a.max_len ? nullptr : s.max_positive);
         });
     });
     FG_CUDA(cudaGetLastError());
@@ -344,7 +342,7 @@ static int launch_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, const k1
 }
 
 /* K1 alone into stage/pool + counts (+ npos) */
-static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool want_npos) {
+static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool want_npos, bool sorted = true) {
     s.per_read.reserve(size_t(a.n) * 4);
     s.stage.reserve(size_t(a.n) * FG_STAGE_STRIDE * sizeof(uint2));
     if (want_npos) s.npos.reserve(size_t(a.n) * 4);
@@ -354,7 +352,7 @@ static int enqueue_k1(fulgor_gpu_index* x, slot& s, const chunk_args& a, bool wa
     FG_CUDA(cudaMemsetAsync(s.pool_used, 0, 8, s.stream));
     FG_CUDA(cudaMemsetAsync(s.max_positive, 0, 4, s.stream));
     return launch_k1(x, s, a, k1_target{s.stage.as<uint2>(), s.per_read.as<uint32_t>(), want_npos ? s.npos.as<uint32_t>() : nullptr,
-                                        entry_pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted}});
+                                        entry_pool{s.pool.as<uint2>(), s.pool_used, pool_entries, s.exhausted}}, sorted);
 }
 
 /* the per-read {color-set id, multiplicity} lists the color-set kernel reads */
@@ -389,7 +387,7 @@ static emit_plan enqueue_pseudoalign(fulgor_gpu_index* x, slot& s, const chunk_a
         if (d_off) *launches += enqueue_scan<FG_SCAN_POPC>(x, s, s.per_read.as<uint32_t>(), a.n, d_off);
         return e;
     }
-    *launches += enqueue_k1(x, s, a, true);
+    *launches += enqueue_k1(x, s, a, true, /*sorted=*/false);
     if (after_k1) FG_CUDA(cudaEventRecord(after_k1, s.stream));
     return enqueue_color_sets(x, s, a, list_source{s.per_read.as<uint32_t>(), s.stage.as<uint2>(), s.pool.as<uint2>(), s.npos.as<uint32_t>()}, algo, threshold,
                               d_off, after_k2, launches);
@@ -415,7 +413,7 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
     if (x->I.set_table) { /* decoded table: registers only */
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, table_kernel_smem(decltype(t)::value), s.stream>>>(
+            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, 0, s.stream>>>(
                 x->I, ls.counts, ls.stage, ls.pool, ls.npos, a.n, threshold, e.words_per_read, s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */
@@ -723,7 +721,7 @@ static int run_host_dedup_once(fulgor_gpu_index* x, const host_reads& in, uint32
             a.n = n;
             a.max_len = uint32_t(longest);
             launch_k1(x, s, a, k1_target{x->dd_stage.as<uint2>() + uint64_t(first) * FG_STAGE_STRIDE, x->dd_counts.as<uint32_t>() + first,
-                                         x->dd_npos.as<uint32_t>() + first, pool});
+                                         x->dd_npos.as<uint32_t>() + first, pool}, /*sorted=*/true);
             FG_CUDA(cudaStreamSynchronize(s.stream)); /* the next chunk reuses the input buffers */
             pieces.push_back({first, n, uint32_t(longest)});
             first += n;

@@ -65,22 +65,6 @@ FG_HD uint32_t fg_clz32(uint32_t x) {
 #endif
 }
 
-/* 16-byte asynchronous global -> shared copies (LDGSTS): the data bypasses the registers, so a warp can keep several table rows
-   in flight without holding them. The emulator copies synchronously. */
-#ifdef FG_SIMT_EMUL
-static inline void fg_cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }
-static inline void fg_cp_async_commit() {}
-template <int N>
-static inline void fg_cp_async_wait() {}
-#else
-__device__ __forceinline__ void fg_cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void fg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void fg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
-
 #define FG_FULL 0xffffffffu
 #define FG_NOT_FOUND 0xffffffffu
 #define FG_MAX_ENTRIES 32 /* distinct color sets per read held in registers (one per lane) */
@@ -838,9 +822,14 @@ struct kmer_tiles {
             uint32_t n = 0;
             if (g0 + lane < nseeds) {
                 seed_slot& slot = seeds()[g0 + lane];
-                const uint64_t b = minimizer_bucket(I, uint64_t(slot.begin) | (uint64_t(slot.n) << 32));
+                const uint64_t mini = uint64_t(slot.begin) | (uint64_t(slot.n) << 32);
+                const uint64_t b = minimizer_bucket(I, mini);
                 const uint32_t begin = FG_LDG(I.bucket_begin + b), size = FG_LDG(I.bucket_begin + b + 1) - begin;
                 if (size > I.skew_threshold) slot.key |= FG_SEED_SLOW; /* skew index: per-k-mer path */
+                /* A minimizer that is its own reverse complement (possible for even m only) reads the same off both strands, so how
+                   it reads says nothing about the orientation of the stored string against the read -- which the pair pass relies
+                   on. The per-k-mer path compares both orientations. */
+                if (!(I.m & 1u) && revcomp(mini, I.m) == mini) slot.key |= FG_SEED_SLOW;
                 n = (slot.key & FG_SEED_SLOW) ? 0u : size;
                 any_slow |= (slot.key & FG_SEED_SLOW) != 0;
                 slot.begin = begin;
@@ -1030,13 +1019,69 @@ __device__ __noinline__ bool table_reserve(read_hits& R, uint32_t extra, uint32_
     return true;
 }
 
+/* The per-read table beyond the registers, first stage: an open-addressing HASH TABLE of {color-set id, multiplicity} over the
+   warp's scratch entries (shared memory, a power of two). A batch of items costs a few probes per lane (atomicCAS on the key,
+   atomicAdd on the count) whatever the number of distinct ids, and nothing is sorted on the way. */
+#define FG_HASH_EMPTY FG_NOT_FOUND
+
+__device__ __forceinline__ void hash_clear(uint2* tab, uint32_t cap, uint32_t lane) {
+    for (uint32_t i = lane; i < cap; i += 32) tab[i] = make_uint2(FG_HASH_EMPTY, 0);
+    __syncwarp();
+}
+
+/* inserts {cid, cnt} of every lane with have = true; returns how many NEW ids the batch brought (warp-uniform) */
+__device__ __forceinline__ uint32_t hash_insert(uint2* tab, uint32_t cap, bool have, uint32_t cid, uint32_t cnt) {
+    uint32_t slot = (cid * 0x9E3779B1u) >> 7 & (cap - 1);
+    uint32_t fresh = 0;
+    bool pending = have;
+    while (__ballot_sync(FG_FULL, pending) != 0) {
+        if (pending) {
+            const uint32_t old = atomicCAS(&tab[slot].x, FG_HASH_EMPTY, cid);
+            if (old == FG_HASH_EMPTY || old == cid) {
+                atomicAdd(&tab[slot].y, cnt);
+                fresh += old == FG_HASH_EMPTY;
+                pending = false;
+            } else {
+                slot = (slot + 1) & (cap - 1);
+            }
+        }
+    }
+    __syncwarp();
+    return __reduce_add_sync(FG_FULL, fresh);
+}
+
+/* packs the occupied slots of the hash table (cap <= 128 entries, at most 4 per lane) into dst[0, n), in slot order; dst may be
+   the table itself. Returns n. */
+__device__ __forceinline__ uint32_t hash_pack(const uint2* tab, uint32_t cap, uint2* dst, uint32_t lane) {
+    uint2 e[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) e[g] = uint32_t(32 * g) + lane < cap ? tab[32 * g + lane] : make_uint2(FG_HASH_EMPTY, 0);
+    __syncwarp(); /* every slot has been read before dst (possibly the table) is written */
+    uint32_t n = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const bool have = e[g].x != FG_HASH_EMPTY;
+        const uint32_t b = __ballot_sync(FG_FULL, have);
+        if (have) dst[n + __popc(b & ((1u << lane) - 1u))] = e[g];
+        n += __popc(b);
+    }
+    __syncwarp();
+    return n;
+}
+
 /* index::fetch_color_set_ids (src/ps_full_intersection.cpp:335-374) and the counting half of
-   index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read.
-   The reference's two sort+unique passes become: warp match on the color-set id inside a tile, a
-   32-entry register table (one entry per lane) across tiles; a read with more distinct color sets moves to
-   an append-only list in `scratch` (shared memory, scratch_cap entries, a power of two, >= 64) and then in
-   the pool, sorted and merged by table_compact() when it fills up and at the end. */
-template <class TILES>
+   index::pseudoalign_threshold_union (src/ps_threshold_union.cpp:327-387) for one read: its DISTINCT color-set ids with the
+   number of positive k-mers of each. The reference's two sort+unique passes become three stages, by how many distinct sets
+   the read turns out to have:
+     1. a 32-entry register table (one entry per lane), fed by a warp match on the ids of each batch of items;
+     2. from the first batch with >= FG_DIVERSE_BATCH different ids (or when the registers are full): the hash table above in
+        `scratch` (shared memory, scratch_cap entries, a power of two in [64, 128]);
+     3. beyond 3/4 of its slots (long reads): an append-only list in the pool, sorted and merged by table_compact() when it
+        fills up and at the end.
+   SORTED: the list comes out ascending by id, the order index::fetch_color_set_ids returns and the one the deduplication
+   compares lists in. The color-set kernels take the ids in any order (an intersection and a sum of multiplicities do not
+   care), so the pseudoalignment path skips every sort. */
+template <bool SORTED, class TILES>
 __device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_t lane, uint2* scratch, uint32_t scratch_cap, const entry_pool& pool) {
     read_hits R;
     R.cid = FG_NOT_FOUND;
@@ -1046,24 +1091,42 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_
     R.tab = nullptr;
     R.cap = 0;
     R.failed = false;
+    bool hashed = false;   /* stage 2: scratch is the hash table, R.n = ids in it */
+    /* stage 1 -> 2: the register entries move into the (cleared) hash table */
+    auto to_hash = [&]() {
+        hash_clear(scratch, scratch_cap, lane);
+        hash_insert(scratch, scratch_cap, lane < R.n, R.cid, R.cnt);
+        hashed = true;
+    };
+    /* stage 2 -> 3: the table's entries become the head of a list in the pool (table_reserve sizes it for the whole read) */
+    auto to_list = [&]() {
+        hashed = false;
+        R.n = hash_pack(scratch, scratch_cap, scratch, lane);
+        R.tab = scratch;
+        R.cap = scratch_cap;
+        table_reserve(R, scratch_cap, tiles.nk, pool, lane); /* sorts the (distinct) entries, then moves them: no room for a batch here */
+    };
     uint32_t cid, cnt;
     while (tiles.next(cid, cnt)) {
         const bool found = cnt != 0;
         R.npos += __reduce_add_sync(FG_FULL, cnt);
-        if (R.tab != nullptr) { /* the read already has more than 32 distinct color sets: append, merge later */
+        if (R.tab != nullptr) { /* stage 3: append, merge later */
             table_append(R, found, cid, cnt, tiles.nk, pool, lane);
+            continue;
+        }
+        if (hashed) {
+            R.n += hash_insert(scratch, scratch_cap, found, cid, cnt);
+            if (4 * R.n > 3 * scratch_cap) to_list();
             continue;
         }
         const uint32_t grp = __match_any_sync(FG_FULL, cid);
         const bool leader = found && (uint32_t(__ffs(int(grp))) - 1 == lane);
         uint32_t leaders = __ballot_sync(FG_FULL, leader);
         if (__popc(leaders) >= FG_DIVERSE_BATCH) { /* a batch with many different ids: the register table would be walked once per
-                                                     id and overflow soon anyway -- go to the list now, with the batch as it is */
-            if (lane < R.n) scratch[lane] = make_uint2(R.cid, R.cnt);
-            R.tab = scratch;
-            R.cap = scratch_cap;
-            __syncwarp();
-            table_append(R, found, cid, cnt, tiles.nk, pool, lane);
+                                                     id and overflow soon anyway */
+            to_hash();
+            R.n += hash_insert(scratch, scratch_cap, found, cid, cnt);
+            if (4 * R.n > 3 * scratch_cap) to_list();
             continue;
         }
         while (leaders) {
@@ -1071,7 +1134,7 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_
             leaders &= leaders - 1;
             const uint32_t kk = __shfl_sync(FG_FULL, cid, src);
             const uint32_t cc = __reduce_add_sync(FG_FULL, cid == kk ? cnt : 0u);
-            if (R.tab == nullptr) {
+            if (!hashed) {
                 const uint32_t hit = __ballot_sync(FG_FULL, R.cid == kk);
                 if (hit) {
                     if (R.cid == kk) R.cnt += cc;
@@ -1085,15 +1148,24 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_
                     R.n += 1;
                     continue;
                 }
-                scratch[lane] = make_uint2(R.cid, R.cnt); /* registers are full: move to the list */
-                R.tab = scratch;
-                R.cap = scratch_cap;
-                __syncwarp();
+                to_hash(); /* registers are full */
             }
-            table_append(R, lane == 0, kk, cc, tiles.nk, pool, lane); /* the rest of this batch: one merged entry per id */
+            R.n += hash_insert(scratch, scratch_cap, lane == 0, kk, cc); /* the rest of this batch: one merged entry per id */
         }
     }
-    if (R.tab != nullptr) {
+    if (hashed) { /* out of the table: into the registers when few, else a list in scratch */
+        R.n = hash_pack(scratch, scratch_cap, scratch, lane);
+        if (R.n <= FG_MAX_ENTRIES) {
+            const uint2 e = lane < R.n ? scratch[lane] : make_uint2(FG_NOT_FOUND, 0);
+            R.cid = e.x;
+            R.cnt = e.y;
+        } else {
+            R.tab = scratch;
+            R.cap = scratch_cap;
+            if (SORTED) table_sort(R.tab, R.n, lane);
+            return R;
+        }
+    } else if (R.tab != nullptr) {
         if (!R.failed) {
             table_compact(R, lane);
             if (R.n <= FG_MAX_ENTRIES) { /* few distinct ids after all: back to one entry per lane (already sorted) */
@@ -1104,7 +1176,9 @@ __device__ __forceinline__ read_hits warp_fetch_color_sets(TILES& tiles, uint32_
                 R.cap = 0;
             }
         }
-    } else if (R.n > 1) { /* bitonic sort across lanes; unused lanes hold FG_NOT_FOUND and sink to the end */
+        return R;
+    }
+    if (SORTED && R.n > 1) { /* bitonic sort across lanes; unused lanes hold FG_NOT_FOUND and sink to the end */
 #pragma unroll
         for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll

@@ -132,8 +132,9 @@ __device__ __forceinline__ const uint2* entries_of(uint32_t r, uint32_t n, const
     return pool + (uint64_t(o.x) | (uint64_t(o.y) << 32));
 }
 
-/* K1 alone: per read, ascending distinct color-set ids with multiplicities */
-template <int W, class READS>
+/* K1 alone: per read, distinct color-set ids with multiplicities -- ascending when SORTED (index::fetch_color_set_ids' order, which
+   the deduplication also relies on), in no particular order otherwise (all the color-set kernels need) */
+template <int W, class READS, bool SORTED>
 __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(const __grid_constant__ dev_index I, const READS in,
                                                               uint32_t n_reads, uint2* __restrict__ stage, uint32_t* __restrict__ counts,
                                                               uint32_t* __restrict__ num_positive /* nullable */, entry_pool pool,
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(FG_BLOCK, FG_MIN_BLOCKS) k_fetch_color_sets(co
     const uint32_t warps = gridDim.x * FG_WARPS_PER_BLOCK;
     for (uint32_t r = blockIdx.x * FG_WARPS_PER_BLOCK + wib; r < n_reads; r += warps) {
         auto tiles = make_tiles<W, false>(I, in, r, n_reads, lane, wstage[wib]);
-        read_hits R = warp_fetch_color_sets(tiles, lane, scratch[wib], FG_SCRATCH_ENTRIES, pool);
+        read_hits R = warp_fetch_color_sets<SORTED>(tiles, lane, scratch[wib], FG_SCRATCH_ENTRIES, pool);
         uint2* s = stage + uint64_t(r) * FG_STAGE_STRIDE;
         if (R.tab == nullptr) {
             if (lane < R.n) s[lane] = make_uint2(R.cid, R.cnt);
@@ -607,27 +608,16 @@ struct carry_save_counters {
     __device__ __forceinline__ void finish() { finish_from<0>(); }
 };
 
-#define FG_TABLE_RING 4 /* table rows a warp keeps in flight (shared-memory ring filled by asynchronous copies) */
-
-/* dynamic shared memory of k_color_sets_table: a ring of FG_TABLE_RING row pieces of 32 T words per warp */
-static inline size_t table_kernel_smem(int T) { return size_t(FG_WARPS_PER_BLOCK) * FG_TABLE_RING * 32 * size_t(T) * 4; }
-
 template <bool FI, int NP, int T>
 __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
                                                               const uint2* __restrict__ stage, const uint2* __restrict__ pool,
                                                               const uint32_t* __restrict__ num_positive, uint32_t n_reads, double threshold,
                                                               uint32_t words_per_read, uint32_t* __restrict__ res_bits,
                                                               uint32_t* __restrict__ res_counts) {
-#ifdef FG_SIMT_EMUL
-    uint32_t* smem = static_cast<uint32_t*>(fg_emul_dynamic_smem());
-#else
-    extern __shared__ __align__(16) uint32_t smem[];
-#endif
     const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const uint32_t C = I.num_colors, W = words_per_read;
     const uint32_t* __restrict__ table = I.set_table;
     const uint64_t stride = I.table_stride;
-    uint32_t* ring = smem + size_t(threadIdx.x >> 5) * (FG_TABLE_RING * 32 * T);
     for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * wpb) {
         const uint32_t n = __ldg(counts + r);
         uint32_t* out = res_bits + uint64_t(r) * W;
@@ -645,44 +635,35 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
 #pragma unroll
             for (int t = 0; t < T; ++t) acc[t] = ~0u;
             if (!FI) cs.clear();
-            /* The rows of the read's hit sets stream through a per-warp ring in shared memory, FG_TABLE_RING rows ahead of the
-               arithmetic: 16-byte asynchronous copies (8 T per row piece, one or two per lane) that bypass the registers. The kernel
-               is bound by the latency of these row fetches (L2 / HBM), not by its logic operations; the ring gives a warp
-               FG_TABLE_RING x T 128-byte lines in flight where register prefetching gave 2 T at the cost of T registers. */
-            const uint32_t pieces = min(uint32_t(8 * T), uint32_t((stride - w0) >> 2)); /* 16-byte pieces of this pass inside the row */
-            auto issue = [&](uint32_t j) {
-                if (j < n) {
-                    const uint32_t* row = table + uint64_t(ents[j].x) * stride + w0;
-                    uint32_t* dst = ring + (j % FG_TABLE_RING) * (32 * T);
-                    for (uint32_t p = lane; p < pieces; p += 32) fg_cp_async16(dst + 4 * p, row + 4 * p);
-                }
-                fg_cp_async_commit(); /* one group per entry, empty past the end: the wait below counts groups */
-            };
-            for (uint32_t j = 0; j < FG_TABLE_RING; ++j) issue(j);
-            for (uint32_t j = 0; j < n; ++j) {
-                fg_cp_async_wait<FG_TABLE_RING - 1>(); /* this lane's pieces of row j have landed ... */
-                __syncwarp();                          /* ... and so have the other lanes' */
-                const uint32_t* src = ring + (j % FG_TABLE_RING) * (32 * T) + lane;
-                uint32_t x[T];
+            /* the rows are fetched one entry AHEAD of the arithmetic (and the entry list two ahead): a warp keeps 2 T row
+               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops */
+            auto load_row = [&](const uint2& e, uint32_t (&x)[T]) {
+                const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
 #pragma unroll
-                for (int t = 0; t < T; ++t) x[t] = uint32_t(32 * t) < 4 * pieces ? src[32 * t] : 0u;
-                const uint32_t wt_all = ents[j].y;
-                __syncwarp(); /* every lane has read the slot before it is refilled */
-                issue(j + FG_TABLE_RING);
+                for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
+            };
+            uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
+            uint32_t x[T], x_next[T];
+            load_row(e, x);
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
+                if (j + 1 < n) load_row(e_next, x_next);
                 if (FI) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[t] &= x[t];
                 } else { /* score += multiplicity for every member: the bitmap enters at the plane of every set bit of the multiplicity */
-                    for (uint32_t wt = wt_all; wt; wt &= wt - 1) {
+                    for (uint32_t wt = e.y; wt; wt &= wt - 1) {
                         uint32_t v[FI ? 1 : T];
 #pragma unroll
                         for (int t = 0; t < (FI ? 1 : T); ++t) v[t] = x[t];
                         cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
                 }
+                e = e_next;
+                e_next = e_after;
+#pragma unroll
+                for (int t = 0; t < T; ++t) x[t] = x_next[t];
             }
-            fg_cp_async_wait<0>();
-            __syncwarp();
             if (!FI) cs.finish();
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -1032,43 +1013,10 @@ __global__ void __launch_bounds__(256) k_emit_entries(const uint2* __restrict__ 
         if (o + i < out_cap) out[o + i] = e[i].x;
 }
 
-/* per-read color bitmaps -> ascending color lists at their CSR positions. One warp per read, 32 words at a time: every lane
-   takes ONE word, a warp scan of the popcounts places it, and the lane writes its own run of up to 32 consecutive colors
-   (its loop runs popcount(word) times -- about a third of the instructions of testing one bit per lane and word). */
+/* per-read color bitmaps -> ascending color lists at their CSR positions */
 __global__ void __launch_bounds__(256) k_emit_bits(const uint32_t* __restrict__ res_bits, uint32_t words_per_read, const uint32_t* __restrict__ counts,
                                                   const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
                                                   uint32_t* __restrict__ out, uint64_t out_cap) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n) return;
-    if (__ldg(counts + r) == 0) return;
-    uint64_t o = __ldg(off + r) - chunk_info[0];
-    const uint32_t* bits = res_bits + uint64_t(r) * words_per_read;
-    for (uint32_t w0 = 0; w0 < words_per_read; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        uint32_t word = w < words_per_read ? __ldg(bits + w) : 0u;
-        const uint32_t pc = uint32_t(__popc(word));
-        uint32_t incl = pc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(FG_FULL, incl, d);
-            if (lane >= uint32_t(d)) incl += y;
-        }
-        uint64_t at = o + incl - pc;
-        const uint32_t c0 = w * 32;
-        while (word) {
-            if (at < out_cap) out[at] = c0 + uint32_t(__ffs(int(word))) - 1u;
-            ++at;
-            word &= word - 1;
-        }
-        o += __shfl_sync(FG_FULL, incl, 31);
-    }
-}
-
-/* the previous form (one bit per lane and word), kept for A/B runs: FULGOR_GPU_EMIT=1 */
-__global__ void __launch_bounds__(256) k_emit_bits_v1(const uint32_t* __restrict__ res_bits, uint32_t words_per_read, const uint32_t* __restrict__ counts,
-                                                     const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
-                                                     uint32_t* __restrict__ out, uint64_t out_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;

@@ -26,6 +26,7 @@ CASES = [  # name, index, n, min_len, max_len, seed
     ("s10_mdfur_mixed", "salmonella_10.mdfur", 4000, 75, 300, 45),
     ("synth200_dfur_mixed", "synth_200.dfur", 3000, 75, 300, 46),
     ("synth200_mdfur_mixed", "synth_200.mdfur", 3000, 75, 300, 46),
+    ("synthskew_fur_mixed", "synth_skew.fur", 4000, 75, 300, 47),  # multi-partition MPHF, every skew class, palindromic minimizers
 ]
 THRESHOLDS = [0.8, 1.0, 0.3]
 

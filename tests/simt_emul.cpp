@@ -114,7 +114,7 @@ struct k1_out {
     std::vector<uint32_t> counts, npos;
 };
 
-static int run_k1(const dev_index& I, const emul_reads& rd, uint32_t n, unsigned grid, int force_generic, uint64_t pool_entries, k1_out& o) {
+static int run_k1(const dev_index& I, const emul_reads& rd, uint32_t n, unsigned grid, int force_generic, uint64_t pool_entries, k1_out& o, bool sorted = true) {
     o.stage.assign(size_t(n) * FG_STAGE_STRIDE, uint2{0, 0});
     o.pool.assign(pool_entries, uint2{0, 0});
     o.counts.assign(n, 0);
@@ -125,7 +125,8 @@ static int run_k1(const dev_index& I, const emul_reads& rd, uint32_t n, unsigned
     dispatch_window(I, force_generic, [&](auto w) {
         rd.with([&](auto in) {
             simt::launch(grid, FG_BLOCK, 0, [&] {
-                k_fetch_color_sets<decltype(w)::value, decltype(in)>(I, in, n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
+                if (sorted) k_fetch_color_sets<decltype(w)::value, decltype(in), true>(I, in, n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
+                else k_fetch_color_sets<decltype(w)::value, decltype(in), false>(I, in, n, o.stage.data(), o.counts.data(), o.npos.data(), pool, nullptr);
             });
         });
     });
@@ -201,7 +202,7 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     }
     k1_out k1;
     uint64_t pool_entries = 1u << 12; /* small on purpose: exercises the grow-and-rerun path */
-    while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1)) pool_entries *= 4;
+    while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1, /*sorted=*/false)) pool_entries *= 4; /* like engine.cu: the color-set kernels take any order */
     uint32_t max_kmers = 1;
     for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
     const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
@@ -209,7 +210,7 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            simt::launch(grid, FG_BLOCK, table_kernel_smem(decltype(t)::value), [&] {
+            simt::launch(grid, FG_BLOCK, 0, [&] {
                 k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
                     I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, threshold, g.words_per_read, res_bits.data(), res_counts.data());
             });
@@ -263,7 +264,7 @@ int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uin
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            simt::launch(grid, FG_BLOCK, table_kernel_smem(decltype(t)::value), [&] {
+            simt::launch(grid, FG_BLOCK, 0, [&] {
                 k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
                     I, rep_counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, 1.0, g.words_per_read, res_bits.data(), res_counts.data());
             });

@@ -43,17 +43,63 @@ def skew_motifs(m, rng, targets=SKEW_TARGETS):
     return out
 
 
+def palindrome_traps(m, k, rng, count=48):
+    """(k + m - 1)-base stretches around an m-mer P that is its OWN reverse complement (even m) such that some k-mer of the
+    stretch has P as canonical minimizer read off ONE strand only: the other strand holds P too (same hash) but has an m-mer
+    with a smaller hash whose value is larger than P's. How the minimizer reads then says nothing about the orientation of the
+    indexed string against a query -- a lookup that infers the orientation from the minimizer must try both."""
+    if m % 2:
+        return []
+    sscode = [0, 1, 3, 2]  # this tool's A0 C1 G2 T3 -> sshash A0 C1 T2 G3
+    mask = (1 << 64) - 1
+
+    def value(b):
+        v = 0
+        for i, c in enumerate(b):
+            v |= sscode[c] << (2 * i)
+        return v
+
+    def strand_min(b):  # (value, hash) of the first m-mer with the smallest hash (util::compute_minimizer)
+        best = None
+        for j in range(len(b) - m + 1):
+            v = value(b[j:j + m])
+            h = ((v * MIX_MUL) & mask) ^ MIX_MAGIC_SEED1
+            if best is None or h < best[1]:
+                best = (v, h)
+        return best[0]
+
+    out = []
+    while len(out) < count:
+        x = [3, 3, 3] + [int(c) for c in rng.integers(0, 4, m // 2 - 3)]  # TTT...: P ends in ...AAA, a small value
+        p = x + [3 - c for c in reversed(x)]
+        s = [int(c) for c in rng.integers(0, 4, k - m)] + p + [int(c) for c in rng.integers(0, 4, k - m)]
+        pv = value(p)
+        for i in range(len(s) - k + 1):
+            kmer = s[i:i + k]
+            vf, vr = strand_min(kmer), strand_min([3 - c for c in reversed(kmer)])
+            if vf != vr and min(vf, vr) == pv:
+                out.append(np.array(s, dtype=np.uint8))
+                break
+    return out
+
+
 def novel_stretch(rng, n, plant):
     """n random bases; with --plant, motifs in fresh random contexts at a rate that reaches the targets over all lineages"""
     s = rng.integers(0, 4, n, dtype=np.uint8)
     if plant is not None:
-        motifs, weights, rate = plant
+        motifs, weights, rate = plant[:3]
         m = motifs[0].size
         for _ in range(int(rng.poisson(n * rate))):
             r = motifs[int(rng.choice(len(motifs), p=weights))]
             at = int(rng.integers(16, max(17, n - m - 16)))
             if at + m + 16 <= n:
                 s[at:at + m] = r
+        traps = plant[3] if len(plant) > 3 else []
+        if traps and n > 200:
+            for _ in range(2):
+                t = traps[int(rng.integers(0, len(traps)))]
+                at = int(rng.integers(0, n - t.size))
+                s[at:at + t.size] = t
     return s
 
 
@@ -110,6 +156,8 @@ def main():
     ap.add_argument("--novel", type=int, nargs=2, metavar=("LO", "HI"), help="open pangenome: novel bases gained (and lost) per new lineage")
     ap.add_argument("--plant", type=int, metavar="M", help="plant skew-bucket motifs for minimizer length M (needs --novel)")
     ap.add_argument("--plant-scale", type=float, default=1.0, help="scale of the planted bucket sizes")
+    ap.add_argument("--plant-palindromes", action="store_true",
+                    help="also plant stretches around reverse-complement-palindromic minimizers (see palindrome_traps)")
     ap.add_argument("--plant-targets", type=str, default=None, help="comma-separated contexts per motif (default: one per skew size class)")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
@@ -122,7 +170,7 @@ def main():
         motifs = skew_motifs(a.plant, rng, targets)
         w = np.array(targets, dtype=np.float64)
         novel_total = 2 * (a.n - 1) * (a.novel[0] + a.novel[1]) / 2
-        plant = (motifs, w / w.sum(), 1.15 * w.sum() / novel_total)
+        plant = (motifs, w / w.sum(), 1.15 * w.sum() / novel_total, palindrome_traps(a.plant, 31, rng) if a.plant_palindromes else [])
     while len(pool) < a.n:  # split a random lineage into two children (Yule tree)
         i = int(rng.integers(0, len(pool)))
         parent = pool.pop(i)
