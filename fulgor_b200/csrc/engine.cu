@@ -413,7 +413,10 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
     if (x->I.set_table) { /* decoded table: registers only */
         const uint32_t grid = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((uint64_t(a.n) + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK, uint64_t(x->sm_count) * 16)));
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value><<<grid, FG_BLOCK, 0, s.stream>>>(
+            auto kernel = k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>;
+            const size_t smem = table_kernel_smem(decltype(fi)::value, decltype(np)::value, decltype(t)::value);
+            if (smem > 48 * 1024) FG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            kernel<<<grid, FG_BLOCK, smem, s.stream>>>(
                 x->I, ls.counts, ls.stage, ls.pool, ls.npos, a.n, threshold, e.words_per_read, s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */

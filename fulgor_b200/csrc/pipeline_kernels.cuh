@@ -546,7 +546,10 @@ __global__ void __launch_bounds__(FG_BLOCK) k_expand_color_sets(const __grid_con
    many planes the counters have -- the ripple-carry adder this replaces paid a full adder per plane and word for every set. */
 template <int NP, int T>
 struct carry_save_counters {
-    uint32_t acc[NP][T], pend[NP][T];
+    uint32_t acc[NP][T];
+    uint32_t* pend;   /* the pending vectors live in SHARED memory (word (K, t) of this lane at pend[(K * T + t) * 32]): they are touched once
+                         per visit of their plane, and keeping them out of the registers halves the kernel's register count -- a third
+                         resident block per SM and one pass over the row where the registers allowed only a part of it */
     uint32_t pending; /* bit k: plane k holds a pending vector (warp-uniform) */
 
     __device__ __forceinline__ void clear() {
@@ -566,7 +569,7 @@ struct carry_save_counters {
             if ((pending >> K) & 1u) {
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    const uint32_t a = acc[K][t], p = pend[K][t], x = v[t];
+                    const uint32_t a = acc[K][t], p = pend[(K * T + t) * 32], x = v[t];
                     acc[K][t] = a ^ p ^ x;
                     v[t] = (a & p) | (a & x) | (p & x);
                 }
@@ -574,7 +577,7 @@ struct carry_save_counters {
                 add_from<K + 1>(v);
             } else {
 #pragma unroll
-                for (int t = 0; t < T; ++t) pend[K][t] = v[t];
+                for (int t = 0; t < T; ++t) pend[(K * T + t) * 32] = v[t];
                 pending |= 1u << K;
             }
         }
@@ -596,8 +599,9 @@ struct carry_save_counters {
                 uint32_t c[T];
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    c[t] = acc[K][t] & pend[K][t];
-                    acc[K][t] ^= pend[K][t];
+                    const uint32_t p = pend[(K * T + t) * 32];
+                    c[t] = acc[K][t] & p;
+                    acc[K][t] ^= p;
                 }
                 pending &= ~(1u << K);
                 add_from<K + 1>(c);
@@ -608,12 +612,20 @@ struct carry_save_counters {
     __device__ __forceinline__ void finish() { finish_from<0>(); }
 };
 
+/* dynamic shared memory of k_color_sets_table: the pending vectors of every warp's counters (none for full intersection) */
+static inline size_t table_kernel_smem(bool fi, int NP, int T) { return fi ? 0 : size_t(FG_WARPS_PER_BLOCK) * NP * T * 32 * 4; }
+
 template <bool FI, int NP, int T>
-__global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
                                                               const uint2* __restrict__ stage, const uint2* __restrict__ pool,
                                                               const uint32_t* __restrict__ num_positive, uint32_t n_reads, double threshold,
                                                               uint32_t words_per_read, uint32_t* __restrict__ res_bits,
                                                               uint32_t* __restrict__ res_counts) {
+#ifdef FG_SIMT_EMUL
+    uint32_t* smem = static_cast<uint32_t*>(fg_emul_dynamic_smem());
+#else
+    extern __shared__ uint32_t smem[];
+#endif
     const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const uint32_t C = I.num_colors, W = words_per_read;
     const uint32_t* __restrict__ table = I.set_table;
@@ -634,20 +646,19 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
             carry_save_counters<FI ? 1 : NP, FI ? 1 : T> cs;   /* TU: the colors' scores, bit-sliced */
 #pragma unroll
             for (int t = 0; t < T; ++t) acc[t] = ~0u;
-            if (!FI) cs.clear();
+            if (!FI) {
+                cs.pend = smem + size_t(threadIdx.x >> 5) * ((FI ? 1 : NP) * (FI ? 1 : T) * 32) + lane;
+                cs.clear();
+            }
             /* the rows are fetched one entry AHEAD of the arithmetic (and the entry list two ahead): a warp keeps 2 T row
-               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops */
+               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops. Two row
+               buffers take turns (the loop is unrolled by two), so no row is ever copied between registers. */
             auto load_row = [&](const uint2& e, uint32_t (&x)[T]) {
                 const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
 #pragma unroll
                 for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
             };
-            uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
-            uint32_t x[T], x_next[T];
-            load_row(e, x);
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
-                if (j + 1 < n) load_row(e_next, x_next);
+            auto consume = [&](const uint2& e, uint32_t (&x)[T]) {
                 if (FI) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[t] &= x[t];
@@ -659,10 +670,20 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_table(const __grid_cons
                         cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
                 }
-                e = e_next;
-                e_next = e_after;
-#pragma unroll
-                for (int t = 0; t < T; ++t) x[t] = x_next[t];
+            };
+            uint2 ea = ents[0], eb = n > 1 ? ents[1] : ea;
+            uint32_t xa[T], xb[T];
+            load_row(ea, xa);
+            for (uint32_t j = 0; j < n; j += 2) {
+                const uint2 e2 = j + 2 < n ? ents[j + 2] : ea, e3 = j + 3 < n ? ents[j + 3] : ea;
+                if (j + 1 < n) load_row(eb, xb);
+                consume(ea, xa);
+                if (j + 1 < n) {
+                    if (j + 2 < n) load_row(e2, xa);
+                    consume(eb, xb);
+                }
+                ea = e2;
+                eb = e3;
             }
             if (!FI) cs.finish();
 #pragma unroll
@@ -864,8 +885,8 @@ template <typename F>
 static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {
     if (algo == FULGOR_GPU_FULL_INTERSECTION) f(std::true_type(), std::integral_constant<int, 1>(), std::integral_constant<int, 5>());
     else if (max_kmers < (1u << 7)) f(std::false_type(), std::integral_constant<int, 7>(), std::integral_constant<int, 5>());
-    else if (max_kmers < (1u << 10)) f(std::false_type(), std::integral_constant<int, 10>(), std::integral_constant<int, 4>());
-    else if (max_kmers < (1u << 16)) f(std::false_type(), std::integral_constant<int, 16>(), std::integral_constant<int, 2>());
+    else if (max_kmers < (1u << 10)) f(std::false_type(), std::integral_constant<int, 10>(), std::integral_constant<int, 5>());
+    else if (max_kmers < (1u << 16)) f(std::false_type(), std::integral_constant<int, 16>(), std::integral_constant<int, 5>());
     else f(std::false_type(), std::integral_constant<int, 32>(), std::integral_constant<int, 1>());
 }
 

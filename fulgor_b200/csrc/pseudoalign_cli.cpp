@@ -42,6 +42,7 @@ struct args_t {
     bool has_threshold = false, verbose = false, deduplicate = false;
     int gpus = 1;
     uint64_t batch_reads = 1u << 20;
+    bool batch_given = false;
 };
 
 void usage() {
@@ -65,7 +66,7 @@ bool parse(int argc, char** argv, args_t& a) {
         else if (k == "-r") { if (!val(v)) return false; a.threshold = std::strtod(v.c_str(), nullptr); a.has_threshold = true; }
         else if (k == "--format") { if (!val(a.format)) return false; }
         else if (k == "--gpus") { if (!val(v)) return false; a.gpus = std::atoi(v.c_str()); }
-        else if (k == "--batch-reads") { if (!val(v)) return false; a.batch_reads = std::strtoull(v.c_str(), nullptr, 10); }
+        else if (k == "--batch-reads") { if (!val(v)) return false; a.batch_reads = std::strtoull(v.c_str(), nullptr, 10); a.batch_given = true; }
         else if (k == "--verbose") a.verbose = true;
         else if (k == "--deduplicate") a.deduplicate = true;
         else if (k == "-h" || k == "--help") return false;
@@ -244,6 +245,9 @@ int main(int argc, char** argv) {
         std::cerr << "Deduplication not available for threshold < 1.0. Remove --deduplicate flag." << std::endl;
         return 1;
     }
+    /* the library deduplicates over a whole call, the reference over the whole file (tools/pseudoalign.cpp:92-226): larger batches
+       bring the two closer (8 M reads = 1.2 GB of 150 bp reads per batch buffer, three batches in flight) */
+    if (a.deduplicate && !a.batch_given) a.batch_reads = 1u << 23;
     if (!(ends_with(a.index, ".fur") || ends_with(a.index, ".mfur") || ends_with(a.index, ".dfur") || ends_with(a.index, ".mdfur"))) { /* tools/util.cpp:5-19 */
         std::cerr << "Wrong index filename supplied." << std::endl;
         return 1;

@@ -101,9 +101,9 @@ int fulgor_gpu_pseudoalign(fulgor_gpu_index*, int algo, double threshold,
 /* Full intersection with cross-read deduplication of the color-set-id lists. Replaces the reference's `--deduplicate` mode:
    fetch_and_deduplicate_sets (tools/pseudoalign.cpp:92-226: fetch every read's list, sort the lists, keep one copy of each)
    followed by pseudoalign_worker over preprocessed_query_reader (tools/pseudoalign.cpp:39-44, src/ps_utils.cpp:307-415: one
-   intersection per distinct list, written once per read id that has it). Here reads with the same list form a group inside
-   each chunk of reads (up to 2^20); the first one found is the group's representative and the only one whose intersection is
-   computed, emitted and copied back:
+   intersection per distinct list, written once per read id that has it). Here reads with the same list form a group over the
+   WHOLE call (the per-read lists of all n_reads stay in device memory, 256 bytes per read, until the groups are known); the
+   first one found is the group's representative and the only one whose intersection is computed, emitted and copied back:
      rep_of_read[i] = index of the read that represents read i (== i for a representative, and for every read without a
                       positive k-mer);
      colors of read i = colors[color_off[rep_of_read[i]] .. color_off[rep_of_read[i] + 1])  (reads that are not

@@ -210,7 +210,7 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            simt::launch(grid, FG_BLOCK, 0, [&] {
+            simt::launch(grid, FG_BLOCK, table_kernel_smem(decltype(fi)::value, decltype(np)::value, decltype(t)::value), [&] {
                 k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
                     I, k1.counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, threshold, g.words_per_read, res_bits.data(), res_counts.data());
             });
@@ -264,7 +264,7 @@ int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uin
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {
         dispatch_table_kernel(algo, max_kmers, [&](auto fi, auto np, auto t) {
-            simt::launch(grid, FG_BLOCK, 0, [&] {
+            simt::launch(grid, FG_BLOCK, table_kernel_smem(decltype(fi)::value, decltype(np)::value, decltype(t)::value), [&] {
                 k_color_sets_table<decltype(fi)::value, decltype(np)::value, decltype(t)::value>(
                     I, rep_counts.data(), k1.stage.data(), k1.pool.data(), k1.npos.data(), n, 1.0, g.words_per_read, res_bits.data(), res_counts.data());
             });

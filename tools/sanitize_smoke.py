@@ -11,7 +11,7 @@ import _checkers as ck
 import fulgor_b200 as fg
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-for name in ("salmonella_10.fur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur"):
+for name in ("salmonella_10.fur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_skew.fur"):
     genomes = name.split(".")[0]
     reads = ck.gen_reads(n, 75, 300, seed=5, genomes=genomes)
     long_reads = ck.gen_reads(20, 2000, 4000, seed=6, genomes=genomes)
@@ -28,6 +28,11 @@ for name in ("salmonella_10.fur", "salmonella_10.mdfur", "synth_200.fur", "synth
                 assert all(np.array_equal(a, b) for a, b in zip(idx.fetch_color_set_ids(r), o.fetch_color_set_ids(r)))
                 for algo, thr in ((0, 1.0), (1, 0.7)):
                     assert all(np.array_equal(a, b) for a, b in zip(idx.pseudoalign(r, algo, thr), o.pseudoalign(r, algo, thr)))
+            packed = fg.pack_reads(reads)  # the compact forms: packed reads in, bitmap rows out
+            for algo, thr in ((0, 1.0), (1, 0.7)):
+                exp = o.pseudoalign(reads, algo, thr)
+                assert all(np.array_equal(a, b) for a, b in zip(idx.pseudoalign_packed(packed, algo, thr), exp))
+                assert all(np.array_equal(a, b) for a, b in zip(fg.unpack_bitmaps(idx.pseudoalign_bitmaps(packed, algo, thr, packed=True), idx.num_colors), exp))
             if not (table == "0" and name.endswith("dfur")):
                 rep, off, vals = idx.pseudoalign_dedup(reads)
                 ck.check_dedup(rep, off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
