@@ -420,15 +420,12 @@ static emit_plan enqueue_color_sets(fulgor_gpu_index* x, slot& s, const chunk_ar
                 x->I, ls.counts, ls.stage, ls.pool, ls.npos, a.n, threshold, e.words_per_read, s.res_bits.as<uint32_t>(), s.res_counts.as<uint32_t>());
         });
     } else { /* compressed sets decoded per read */
-        if (x->I.diff)
-            throw std::runtime_error("differential indexes (.dfur/.mdfur) need the decoded color-set table for this operation "
-                                     "(it did not fit FULGOR_GPU_TABLE_MAX_MB / the free device memory)");
         if (max_kmers == 0) { /* full intersection counts sets, at most as many as positive k-mers */
             FG_CUDA(cudaMemcpyAsync(s.h_info + 3, s.max_positive, 4, cudaMemcpyDeviceToHost, s.stream));
             FG_CUDA(cudaStreamSynchronize(s.stream));
             max_kmers = std::max<uint32_t>(1, uint32_t(s.h_info[3]));
         }
-        const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions, algo, max_kmers);
+        const general_plan g = plan_color_sets_general(x->H.num_colors, x->H.num_partitions, algo, max_kmers, x->I.diff != 0);
         if (!g.ok) throw std::runtime_error("indexes with more than ~50,000 colors are not supported yet");
         const uint32_t wpb = g.warps_per_block, ints = g.ints_per_warp;
         const size_t smem = g.smem_bytes;

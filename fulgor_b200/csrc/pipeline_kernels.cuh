@@ -188,13 +188,14 @@ struct general_plan {
     size_t smem_bytes;
     bool ok;
 };
-static inline general_plan plan_color_sets_general(uint32_t num_colors, uint32_t num_partitions, int algo, uint32_t max_kmers) {
+static inline general_plan plan_color_sets_general(uint32_t num_colors, uint32_t num_partitions, int algo, uint32_t max_kmers, bool differential = false) {
     general_plan g;
     g.words_per_read = (num_colors + 31) / 32;
     g.planes = 1;
     while (g.planes < 32 && (uint64_t(1) << g.planes) <= max_kmers) g.planes += 1;
     const uint32_t counters = algo == FULGOR_GPU_FULL_INTERSECTION ? 1u : 2u;
     g.ints_per_warp = g.words_per_read * (1 + counters * g.planes) + 2 * num_partitions + (FG_K2_SETS_PER_ROUND + 1) + FG_K2_SETS_PER_ROUND / 2 + 4;
+    if (differential) g.ints_per_warp += g.words_per_read; /* one decoded (partial) set at a time */
     g.ints_per_warp = (g.ints_per_warp + 3) & ~3u;
     g.ok = size_t(g.ints_per_warp) * 4 <= 200 * 1024;
     size_t w = (72 * 1024) / (size_t(g.ints_per_warp) * 4); /* ~3 blocks per SM */
@@ -269,7 +270,72 @@ __global__ void __launch_bounds__(FG_BLOCK) k_color_sets_general(const __grid_co
         for (uint32_t p = lane; p < 2 * P; p += 32) pa[p] = 0;
         __syncwarp();
 
-        for (uint32_t j0 = 0; j0 < n; j0 += FG_K2_SETS_PER_ROUND) {
+        if (I.diff) {
+            /* Differential containers (.dfur / .mdfur, include/color_sets/differential.hpp:256-287): a (partial) set is the symmetric
+               difference of its cluster's representative and its own difference list, so it cannot be folded into the result list
+               by list; the reference merges the two on the fly (diff_intersect, src/ps_full_intersection.cpp:130-240; merge_diff /
+               merge_metadiff, src/ps_threshold_union.cpp:123-318). Here each one is decoded into a scratch bitmap (lane 0 the
+               representative, lane 1 the differences, atomic XOR) and then treated as a bitmap. One set at a time: this is the path for
+               indexes whose decoded table does not fit the device, not the fast one. */
+            uint32_t* tmp = ctl + 4;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e = ents[j];
+                const uint32_t weight = fi ? 1u : e.y;
+                uint64_t list = 0;
+                uint32_t units = 1;
+                if (I.type != 0) {
+                    list = __ldg(I.meta_off + e.x);
+                    units = __ldg(I.meta_vals + list);
+                }
+                for (uint32_t u = 0; u < units; ++u) {
+                    uint32_t part = 0, color_base = 0;
+                    uint64_t local_id = e.x;
+                    if (I.type != 0) { /* meta.hpp:227-235 */
+                        const uint32_t mc = __ldg(I.meta_vals + list + 1 + u);
+                        uint32_t plo = 0, phi = P;
+                        while (phi - plo > 1) {
+                            const uint32_t mid = (plo + phi) >> 1;
+                            if (__ldg(I.part_sets_before + mid) <= mc) plo = mid; else phi = mid;
+                        }
+                        part = plo;
+                        local_id = mc - __ldg(I.part_sets_before + plo);
+                        color_base = __ldg(I.part_min_color + plo);
+                    }
+                    const fgi_hybrid* h = I.hybrids + part;
+                    const uint32_t nc = __ldg(&h->num_colors);
+                    const uint32_t w_lo = color_base >> 5, w_hi = (color_base + nc + 31) >> 5; /* words the partition's colors touch */
+                    for (uint32_t w = w_lo + lane; w < w_hi; w += 32) tmp[w] = 0;
+                    __syncwarp();
+                    if (lane < 2) {
+                        const uint64_t* words = I.color_words + __ldg(&h->word_base);
+                        const uint64_t base = __ldg(&h->set_off_base);
+                        bit_cursor cur;
+                        cur.open(words, __ldg(I.set_bit_off + base + (lane ? 0 : __ldg(&h->num_sets) + 1) + local_id));
+                        const uint32_t cnt = cur.delta();
+                        if (lane) cur.delta(); /* the difference list carries the size of the decoded set */
+                        uint32_t v = 0;
+                        for (uint32_t i = 0; i < cnt; ++i) {
+                            const uint32_t d = cur.delta();
+                            v = i ? v + d + 1 : d;
+                            const uint32_t c = color_base + v;
+                            atomicXor(tmp + (c >> 5), 1u << (c & 31));
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t w = w_lo + lane; w < w_hi; w += 32) {
+                        const int lo = int(32 * w) - int(color_base);
+                        const int first = lo < 0 ? -lo : 0, last = min(32, int(nc) - lo);
+                        const uint32_t gmask = (last >= 32 ? ~0u : ((1u << last) - 1u)) & ~((1u << first) - 1u);
+                        const uint32_t bits = tmp[w] & gmask;
+                        if (fi) atomicAnd(acc + w, bits | ~gmask); /* edge words are shared with the neighbouring partitions' lanes */
+                        else if (bits) A.add_word(w, bits, weight);
+                    }
+                    if (fi && lane == 0) pa[part] += 1;
+                    __syncwarp();
+                }
+            }
+        }
+        for (uint32_t j0 = 0; !I.diff && j0 < n; j0 += FG_K2_SETS_PER_ROUND) {
             const uint32_t nb = min(uint32_t(FG_K2_SETS_PER_ROUND), n - j0);
             /* units of this round: prefix of the sets' partial-set counts */
             uint32_t carry = 0;
@@ -651,14 +717,18 @@ __global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color
                 cs.clear();
             }
             /* the rows are fetched one entry AHEAD of the arithmetic (and the entry list two ahead): a warp keeps 2 T row
-               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops. Two row
-               buffers take turns (the loop is unrolled by two), so no row is ever copied between registers. */
+               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops */
             auto load_row = [&](const uint2& e, uint32_t (&x)[T]) {
                 const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
 #pragma unroll
                 for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
             };
-            auto consume = [&](const uint2& e, uint32_t (&x)[T]) {
+            uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
+            uint32_t x[T], x_next[T];
+            load_row(e, x);
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
+                if (j + 1 < n) load_row(e_next, x_next);
                 if (FI) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[t] &= x[t];
@@ -670,20 +740,10 @@ __global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color
                         cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
                 }
-            };
-            uint2 ea = ents[0], eb = n > 1 ? ents[1] : ea;
-            uint32_t xa[T], xb[T];
-            load_row(ea, xa);
-            for (uint32_t j = 0; j < n; j += 2) {
-                const uint2 e2 = j + 2 < n ? ents[j + 2] : ea, e3 = j + 3 < n ? ents[j + 3] : ea;
-                if (j + 1 < n) load_row(eb, xb);
-                consume(ea, xa);
-                if (j + 1 < n) {
-                    if (j + 2 < n) load_row(e2, xa);
-                    consume(eb, xb);
-                }
-                ea = e2;
-                eb = e3;
+                e = e_next;
+                e_next = e_after;
+#pragma unroll
+                for (int t = 0; t < T; ++t) x[t] = x_next[t];
             }
             if (!FI) cs.finish();
 #pragma unroll

@@ -205,7 +205,7 @@ int emul_pseudoalign(const uint8_t* image, int algo, double threshold, const uin
     while (run_k1(I, rd, n, grid, force_generic, pool_entries, k1, /*sorted=*/false)) pool_entries *= 4; /* like engine.cu: the color-set kernels take any order */
     uint32_t max_kmers = 1;
     for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
-    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
+    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers, I.diff != 0);
     if (!g.ok) return FULGOR_GPU_EINVAL;
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {
@@ -259,7 +259,7 @@ int emul_pseudoalign_dedup(const uint8_t* image, const uint8_t* bases, const uin
     const int algo = FULGOR_GPU_FULL_INTERSECTION;
     uint32_t max_kmers = 1;
     for (uint32_t i = 0; i < n; ++i) max_kmers = std::max<uint32_t>(max_kmers, uint32_t(read_off[i + 1] - read_off[i]));
-    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers);
+    const general_plan g = plan_color_sets_general(I.num_colors, I.num_partitions, algo, max_kmers, I.diff != 0);
     if (!g.ok) return FULGOR_GPU_EINVAL;
     std::vector<uint32_t> res_bits(size_t(n) * g.words_per_read), res_counts(n);
     if (use_table) {

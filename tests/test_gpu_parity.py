@@ -200,17 +200,23 @@ def test_deduplicated_full_intersection(pair, chunk, monkeypatch):
     ck.check_dedup(rep2, off2, vals2, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
 
 
-def test_differential_sets_need_the_table_beyond_32_colors(built_lib, monkeypatch):
-    """no silent wrong answer: without the decoded table a differential index of more than 32 colors is refused loudly"""
+def test_differential_sets_without_the_table(built_lib, monkeypatch):
+    """differential containers of more than 32 colors queried WITHOUT the decoded table (k_color_sets_general decodes representative
+    XOR differences per read): diff_intersect / merge_diff / merge_metadiff of the reference (src/ps_full_intersection.cpp:130-240,
+    src/ps_threshold_union.cpp:123-318)"""
     import fulgor_b200 as fg
 
     monkeypatch.setenv("FULGOR_GPU_TABLE_MAX_MB", "0")
-    reads = ck.gen_reads(100, 150, 150, seed=1, genomes="synth_200")
-    with fg.Index.open(ck.index_path("synth_200.dfur"), 0) as gpu:
-        with pytest.raises(fg.FulgorGpuError) as e:
-            gpu.pseudoalign(reads, 0)
-        assert "decoded color-set table" in str(e.value)
-        gpu.fetch_color_set_ids(reads)  # stage 1 does not touch the color sets
+    for index in ("synth_200.dfur", "synth_200.mdfur"):
+        reads = ck.gen_reads(3000, 75, 300, seed=29, genomes="synth_200")
+        path = ck.index_path(index)
+        o = ck.Oracle(path)
+        with fg.Index.open(path, 0) as gpu:
+            for algo, thr in ((0, 1.0), (1, 0.8), (1, 0.2)):
+                assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+            rep, off, vals = gpu.pseudoalign_dedup(reads)
+            ck.check_dedup(rep, off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
+        o.close()
 
 
 def test_kmer_conservation_and_matches(pair):

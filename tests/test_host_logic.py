@@ -154,8 +154,6 @@ def test_emulated_kernels_pseudoalign_like_the_oracle(loaded, emul, algo, thr, t
     pseudoalign_full_intersection / pseudoalign_threshold_union; table = with the decoded color-set table
     (k_expand_color_sets + k_color_sets_table) or decoding the compressed sets per read (k_color_sets_general)"""
     fg, img, o = loaded
-    if not table and o.type >= 2 and o.num_colors > 32:
-        pytest.skip("differential sets of more than 32 colors are only queried through the decoded table (the engine refuses otherwise)")
     n = 400 if o.num_colors <= 32 else 120
     for reads in (ck.gen_reads(n, 150, 150, seed=12, genomes=o.name.split(".")[0]), _edge_reads(o.name.split(".")[0])):
         got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors, table=table)
@@ -189,8 +187,6 @@ def test_emulated_kernels_deduplicate_like_the_reference(loaded, emul, table):
     result (through its representative) == pseudoalign_full_intersection, and the groups are exactly the distinct
     color-set-id lists (tools/pseudoalign.cpp:92-226). The reads are drawn with repeats so that groups have several members."""
     fg, img, o = loaded
-    if not table and o.type >= 2:
-        pytest.skip("the unfused color-set kernel reads differential sets only through the decoded table")
     base = ck.gen_reads(60, 100, 200, seed=21, genomes=o.name.split(".")[0])
     seqs = [base[0][int(base[1][i]):int(base[1][i + 1])].tobytes() for i in range(60)]
     rng = np.random.default_rng(5)

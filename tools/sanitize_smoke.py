@@ -16,8 +16,6 @@ for name in ("salmonella_10.fur", "salmonella_10.mdfur", "synth_200.fur", "synth
     reads = ck.gen_reads(n, 75, 300, seed=5, genomes=genomes)
     long_reads = ck.gen_reads(20, 2000, 4000, seed=6, genomes=genomes)
     for table in ("", "0"):
-        if table == "0" and name.endswith("dfur") and genomes == "synth_200":
-            continue
         if table:
             os.environ["FULGOR_GPU_TABLE_MAX_MB"] = table
         else:
@@ -33,9 +31,8 @@ for name in ("salmonella_10.fur", "salmonella_10.mdfur", "synth_200.fur", "synth
                 exp = o.pseudoalign(reads, algo, thr)
                 assert all(np.array_equal(a, b) for a, b in zip(idx.pseudoalign_packed(packed, algo, thr), exp))
                 assert all(np.array_equal(a, b) for a, b in zip(fg.unpack_bitmaps(idx.pseudoalign_bitmaps(packed, algo, thr, packed=True), idx.num_colors), exp))
-            if not (table == "0" and name.endswith("dfur")):
-                rep, off, vals = idx.pseudoalign_dedup(reads)
-                ck.check_dedup(rep, off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
+            rep, off, vals = idx.pseudoalign_dedup(reads)
+            ck.check_dedup(rep, off, vals, o.pseudoalign(reads, 0), o.fetch_color_set_ids(reads))
             toff, tr = idx.kmer_conservation(reads)
             eoff, etr = o.kmer_conservation(reads)
             assert np.array_equal(toff, eoff) and np.array_equal(tr, etr)
