@@ -268,7 +268,7 @@ def run_reference(args, rank):
         "config": {"workload": p["workload"]}, "cpu_baseline": p["cpu_baseline"],
         "e2e": {"value": p["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "configs": out,
-    }))
+    }), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- tool level
@@ -650,7 +650,7 @@ def main():
                 line[key] = p[key]
         line["e2e_tool"] = e2e_tool
         line["configs"] = results
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     for idx, _ in cx.indexes.values():
         idx.close()
     if world > 1:

@@ -318,6 +318,42 @@ FG_HD uint32_t lookup_in_bucket(const dev_index& I, uint32_t begin, uint32_t n, 
     return FG_NOT_FOUND;
 }
 
+#ifndef FG_SIMT_EMUL
+/* out-of-line copies for the warp pipeline's RARE paths (skew-index buckets, ambiguous or palindromic minimizers, super-k-mers
+   without a single minimizer position): the lookup kernels are ~100 KB of code against a 32 KB instruction cache, so what is
+   seldom executed is kept out of the instruction stream of what always is */
+__device__ __noinline__ uint32_t lookup_in_bucket_rare(const dev_index& I, uint32_t begin, uint32_t n, uint64_t fwd, uint64_t rc, uint32_t cpos, bool ambiguous,
+                                                       uint64_t kmask) {
+    minimizer_t mz;
+    mz.value = 0;
+    mz.cpos = cpos;
+    mz.ambiguous = ambiguous;
+    return lookup_in_bucket(I, begin, n, fwd, rc, mz, kmask);
+}
+__device__ __noinline__ bool scan_super_kmer_rare(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t kmask) {
+    minimizer_t mz;
+    mz.value = 0;
+    mz.cpos = 0;
+    mz.ambiguous = true;
+    return scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+}
+#else
+static inline uint32_t lookup_in_bucket_rare(const dev_index& I, uint32_t begin, uint32_t n, uint64_t fwd, uint64_t rc, uint32_t cpos, bool ambiguous, uint64_t kmask) {
+    minimizer_t mz;
+    mz.value = 0;
+    mz.cpos = cpos;
+    mz.ambiguous = ambiguous;
+    return lookup_in_bucket(I, begin, n, fwd, rc, mz, kmask);
+}
+static inline bool scan_super_kmer_rare(const dev_index& I, uint32_t sk, uint64_t fwd, uint64_t kmask) {
+    minimizer_t mz;
+    mz.value = 0;
+    mz.cpos = 0;
+    mz.ambiguous = true;
+    return scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+}
+#endif
+
 /* dictionary::lookup_uint_canonical (sshash/../src/dictionary.cpp:47-77): minimizer -> bucket (minimizers.hpp:36-39,
    buckets::locate_bucket buckets.hpp:62-67) -> lookup inside the bucket */
 FG_HD uint32_t lookup_color_set(const dev_index& I, uint64_t fwd, uint64_t rc, const minimizer_t& mz, uint64_t kmask) {
@@ -548,14 +584,10 @@ struct kmer_tiles {
         const int win = int((rec.y >> FGI_SK_WINDOW_SHIFT) & 31u), pm = int((rec.y >> FGI_SK_PM_SHIFT) & 31u);
         if (!(rec.y >> FGI_SK_PINNED_SHIFT)) { /* no single minimizer position: every k-mer of the run against every stored k-mer */
             uint32_t cnt = 0;
-            minimizer_t mz;
-            mz.value = 0;
-            mz.cpos = 0;
-            mz.ambiguous = true;
             for (uint32_t i = i_first; i <= i_last; ++i) {
                 if (!((S.vk[i >> 5] >> (i & 31)) & 1u)) continue;
                 const uint64_t fwd = bases_at(i) & kmask;
-                const bool found = scan_super_kmer(I, sk, fwd, revcomp(fwd, I.k), kmask, mz) != FG_NOT_FOUND;
+                const bool found = scan_super_kmer_rare(I, sk, fwd, kmask);
                 cnt += found;
                 if (PERK && found) per_kmer[seg_base + i] = cid;
             }
@@ -871,7 +903,7 @@ struct kmer_tiles {
         }
         /* per-k-mer path: ambiguous k-mers and runs behind the skew index */
         if (__ballot_sync(FG_FULL, any_slow)) {
-#pragma unroll
+#pragma unroll 1
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
                 uint32_t cid = FG_NOT_FOUND;
                 const uint32_t note = notes()[tt * 32 + lane];
@@ -879,11 +911,7 @@ struct kmer_tiles {
                     const seed_slot slot = seeds()[note & 0xffu];
                     if (slot.key & FG_SEED_SLOW) {
                         const uint64_t fwd = bases_at(FG_SEG_B * lane + tt) & kmask;
-                        minimizer_t mz;
-                        mz.value = 0;
-                        mz.cpos = (note >> 16) & 31u;
-                        mz.ambiguous = (note >> 13) & 1u;
-                        cid = lookup_in_bucket(I, slot.begin, slot.size, fwd, revcomp(fwd, I.k), mz, kmask);
+                        cid = lookup_in_bucket_rare(I, slot.begin, slot.size, fwd, revcomp(fwd, I.k), (note >> 16) & 31u, (note >> 13) & 1u, kmask);
                         if (PERK && cid != FG_NOT_FOUND) per_kmer[seg_base + FG_SEG_B * lane + tt] = cid;
                     }
                 }
@@ -1030,7 +1058,7 @@ __device__ __forceinline__ void hash_clear(uint2* tab, uint32_t cap, uint32_t la
 }
 
 /* inserts {cid, cnt} of every lane with have = true; returns how many NEW ids the batch brought (warp-uniform) */
-__device__ __forceinline__ uint32_t hash_insert(uint2* tab, uint32_t cap, bool have, uint32_t cid, uint32_t cnt) {
+__device__ __noinline__ uint32_t hash_insert(uint2* tab, uint32_t cap, bool have, uint32_t cid, uint32_t cnt) {
     uint32_t slot = (cid * 0x9E3779B1u) >> 7 & (cap - 1);
     uint32_t fresh = 0;
     bool pending = have;
@@ -1052,7 +1080,7 @@ __device__ __forceinline__ uint32_t hash_insert(uint2* tab, uint32_t cap, bool h
 
 /* packs the occupied slots of the hash table (cap <= 128 entries, at most 4 per lane) into dst[0, n), in slot order; dst may be
    the table itself. Returns n. */
-__device__ __forceinline__ uint32_t hash_pack(const uint2* tab, uint32_t cap, uint2* dst, uint32_t lane) {
+__device__ __noinline__ uint32_t hash_pack(const uint2* tab, uint32_t cap, uint2* dst, uint32_t lane) {
     uint2 e[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) e[g] = uint32_t(32 * g) + lane < cap ? tab[32 * g + lane] : make_uint2(FG_HASH_EMPTY, 0);
