@@ -1,6 +1,6 @@
 """dev helper: one-screen summary of a bench.py JSON line (and of the reference arm's)"""
 import json, sys
-j = json.load(open(sys.argv[1]))
+j = json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])  # (an NCCL banner may precede the line)
 if j.get("impl") == "reference":
     for c in j["configs"]:
         print(c["name"], round(c.get("value", 0)), c.get("unavailable", ""), c.get("cpu_baseline", {}).get("cores"))
