@@ -416,42 +416,45 @@ struct warp_stage {
 
 FG_HD constexpr uint32_t fg_hslot(uint32_t p) { return p + (p >> 2); }
 
-/* Minimum of every window of W consecutive hashes among the W + 3 that start at a lane's base slot, for the lane's four
-   k-mers: h[j] for j in [t, t + W). One suffix scan over the first window (its suffix minima are the left parts of the
-   other three windows) plus a running prefix over the three extra positions: W + 4 comparisons for four k-mers.
-   Ties: util::compute_minimizer (sshash/util.hpp:220-239) keeps the FIRST minimum of the strand it scans. For the forward
-   strand that is the leftmost position; the reverse strand's m-mers come in the opposite order, so there (REV) the
-   rightmost position in forward coordinates wins. mh = hash, mp = position relative to the lane's base. */
-template <int W, bool REV>
-__device__ __forceinline__ void window_minima(const uint64_t* __restrict__ h, uint64_t (&mh)[FG_SEG_B], uint32_t (&mp)[FG_SEG_B]) {
-    uint64_t sh[FG_SEG_B];
-    uint32_t sp[FG_SEG_B];
-    uint64_t ch = h[fg_hslot(W - 1)];
-    uint32_t cp = W - 1;
+/* Minimum of every window of W consecutive m-mer hashes among the W + 3 that start at a lane's base slot, for the lane's four
+   k-mers -- on 32-BIT KEYS. The hashing step stores, per position p of the segment and per strand, the pair
+       x = top 24 bits of the 64-bit hash | p        y = top 24 bits of the 64-bit hash | (255 - p)
+   so min(x) is the smallest hash with the LEFTMOST position among equal top bits and min(y) the same with the RIGHTMOST one:
+   one VIMNMX (two positions per VIMNMX3) per comparison instead of the 64-bit compare-and-select chain (2 ISETP + 3 SEL).
+   Both minima are taken over every window (one suffix scan over the first window, whose suffix minima are the left parts of
+   the other three windows, plus a running prefix over the three extra positions). When they name the same position, exactly
+   one position of the window carries the smallest top bits: it IS the minimum under the full 64-bit order, whatever the low
+   bits are. When they differ -- the window holds its minimizer twice, or two different m-mers agree on 24 hash bits (4.6e-6
+   per window) -- the caller recomputes that window exactly (exact_window_minimizer). Ties of the full hash are ties of the
+   m-mer (mixer_64 is a bijection): util::compute_minimizer (sshash/util.hpp:220-239) keeps the FIRST minimum of the strand
+   it scans, the leftmost position on the forward strand; the reverse strand's m-mers come in the opposite order, so there
+   the rightmost position in forward coordinates wins. */
+#ifndef FG_KEY_HASH_MASK /* the CPU test tier also runs the kernels with 3 hash bits, so that most windows take the exact path */
+#define FG_KEY_HASH_MASK 0xffffff00u
+#endif
+template <int W>
+__device__ __forceinline__ void window_minima32(const uint2* __restrict__ e, uint32_t (&mx)[FG_SEG_B], uint32_t (&my)[FG_SEG_B]) {
+    uint2 c = e[fg_hslot(W - 1)];
 #pragma unroll
     for (int j = W - 2; j >= 0; --j) {
-        const uint64_t x = h[fg_hslot(j)];
-        const bool take = REV ? (x < ch) : (x <= ch);
-        ch = take ? x : ch;
-        cp = take ? uint32_t(j) : cp;
+        const uint2 v = e[fg_hslot(j)];
+        c.x = min(c.x, v.x);
+        c.y = min(c.y, v.y);
         if (j < FG_SEG_B) {
-            sh[j] = ch;
-            sp[j] = cp;
+            mx[j] = c.x;
+            my[j] = c.y;
         }
     }
-    mh[0] = sh[0];
-    mp[0] = sp[0];
-    uint64_t ph = 0;
-    uint32_t pp = 0;
+    uint2 p = e[fg_hslot(W)];
+    mx[1] = min(mx[1], p.x);
+    my[1] = min(my[1], p.y);
 #pragma unroll
-    for (int t = 1; t < FG_SEG_B; ++t) {
-        const uint64_t x = h[fg_hslot(W - 1 + t)];
-        const bool take = t == 1 || (REV ? (x <= ph) : (x < ph));
-        ph = take ? x : ph;
-        pp = take ? uint32_t(W - 1 + t) : pp;
-        const bool right = REV ? (ph <= sh[t]) : (ph < sh[t]);
-        mh[t] = right ? ph : sh[t];
-        mp[t] = right ? pp : sp[t];
+    for (int t = 2; t < FG_SEG_B; ++t) {
+        const uint2 v = e[fg_hslot(W - 1 + t)];
+        p.x = min(p.x, v.x);
+        p.y = min(p.y, v.y);
+        mx[t] = min(mx[t], p.x);
+        my[t] = min(my[t], p.y);
     }
 }
 
@@ -462,6 +465,31 @@ __device__ __forceinline__ uint64_t stretch_at(const uint64_t* w, int p) {
     const uint32_t sh = uint32_t(p & 31) * 2;
     const uint64_t a = w[wi];
     return sh ? (a >> sh) | (w[wi + 1] << (64 - sh)) : a;
+}
+
+/* the m-mer (2m <= 64 bits, mask) that starts at base position p >= 0 of a packed base array, read through 32-bit words:
+   three loads and two funnel shifts */
+__device__ __forceinline__ uint64_t mmer_at(const uint64_t* w, uint32_t p, uint64_t mask) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(w);
+    const uint32_t wi = p >> 4, sh = (p & 15u) * 2;
+    const uint32_t a = u[wi], b = u[wi + 1], c = u[wi + 2];
+    return (uint64_t(__funnelshift_r(a, b, sh)) | (uint64_t(__funnelshift_r(b, c, sh)) << 32)) & mask;
+}
+
+/* util::compute_minimizer (sshash/util.hpp:220-239) on both strands of ONE k-mer, straight from the packed bases, under the
+   full 64-bit hash order: the exact answer for the windows where window_minima32's 24-bit keys cannot decide. fw / rc point at
+   the packed stream and its reverse complement, fpos = stream position of the k-mer's first base, rc_len = length of the
+   reverse-complemented stream in bases. pf / pr = offset of the winning m-mer inside the k-mer, forward coordinates. */
+__device__ __noinline__ void exact_window_minimizer(const uint64_t* fw, const uint64_t* rc, uint32_t fpos, uint32_t rc_len, uint32_t window, uint32_t m,
+                                                    uint64_t mmer_mask, uint64_t magic, uint32_t& pf, uint32_t& pr) {
+    uint64_t bf = 0, br = 0;
+    pf = pr = 0;
+    for (uint32_t j = 0; j < window; ++j) {
+        const uint64_t hf = (mmer_at(fw, fpos + j, mmer_mask) * FG_MIX_MUL) ^ magic;
+        const uint64_t hr = (mmer_at(rc, rc_len - (fpos + j) - m, mmer_mask) * FG_MIX_MUL) ^ magic;
+        if (j == 0 || hf < bf) bf = hf, pf = j;
+        if (j == 0 || hr <= br) br = hr, pr = j;
+    }
 }
 
 /* the bits of a 128-bit value {lo, hi} below bit position nb (0 <= nb <= 128) */
@@ -553,6 +581,20 @@ struct kmer_tiles {
     __device__ __forceinline__ uint64_t bases_at(uint32_t p) const { return stretch_at(words(), int(p + shift)); }
     __device__ __forceinline__ uint64_t* hf() const { return S.h; }
     __device__ __forceinline__ uint64_t* hr() const { return S.h + FG_HASH_SLOTS; }
+    __device__ __forceinline__ uint2* kf() const { return reinterpret_cast<uint2*>(S.h); } /* the 32-bit key pairs of window_minima32 */
+    __device__ __forceinline__ uint2* kr() const { return reinterpret_cast<uint2*>(S.h + FG_HASH_SLOTS); }
+    /* position q of the segment: forward m-mer yf, its reverse complement yr */
+    __device__ __forceinline__ void store_hashes(uint32_t q, uint64_t yf, uint64_t yr) const {
+        const uint64_t a = (yf * FG_MIX_MUL) ^ I.hash_magic, b = (yr * FG_MIX_MUL) ^ I.hash_magic;
+        if (W) {
+            const uint32_t ka = (uint32_t(a >> 32) & FG_KEY_HASH_MASK) | q, kb = (uint32_t(b >> 32) & FG_KEY_HASH_MASK) | q;
+            kf()[fg_hslot(q)] = make_uint2(ka, ka ^ 0xffu);
+            kr()[fg_hslot(q)] = make_uint2(kb, kb ^ 0xffu);
+        } else {
+            hf()[fg_hslot(q)] = a;
+            hr()[fg_hslot(q)] = b;
+        }
+    }
     __device__ __forceinline__ seed_slot* seeds() const { return reinterpret_cast<seed_slot*>(S.h); }
     __device__ __forceinline__ uint2* items() const { return reinterpret_cast<uint2*>(seeds() + FG_SEG_KMERS); }
     __device__ __forceinline__ uint32_t* notes() const { return reinterpret_cast<uint32_t*>(items() + FG_SEG_KMERS); } /* per k-mer, for the per-k-mer path */
@@ -728,26 +770,25 @@ struct kmer_tiles {
         }
         __syncwarp();
         /* 1. m-mer hashes. Lane l hashes the m-mers at positions 5l .. 5l+4 out of ONE 32-base window (m + 4 <= 32): the
-              reverse complement of the window holds the five reverse-complemented m-mers too. */
+              reverse complement of the window holds the five reverse-complemented m-mers too. The templated windows keep a
+              pair of 32-bit keys per position and strand (window_minima32), the generic one the 64-bit hashes. */
         const uint32_t m = I.m;
-        if (m <= 28) {
+        if (W || m <= 28) { /* a templated window means m <= k - 10 */
             const uint32_t q0 = 5 * lane;
-            if (q0 < npos) {
+            /* The key pairs are written for all 160 positions the lanes' windows can touch: a key carries its own position,
+               so whatever bases lie past the segment yield in-range positions for the (invalid) k-mers that see them. */
+            if (W || q0 < npos) {
                 const uint64_t x = bases_at(q0) & (m + 4 == 32 ? ~0ULL : ((1ULL << (2 * (m + 4))) - 1));
                 const uint64_t r = revcomp(x, m + 4);
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    if (q0 + j < npos) {
-                        hf()[fg_hslot(q0 + j)] = (((x >> (2 * j)) & mmer_mask) * FG_MIX_MUL) ^ I.hash_magic;
-                        hr()[fg_hslot(q0 + j)] = (((r >> (2 * (4 - j))) & mmer_mask) * FG_MIX_MUL) ^ I.hash_magic;
-                    }
+                    if (W || q0 + j < npos) store_hashes(q0 + j, (x >> (2 * j)) & mmer_mask, (r >> (2 * (4 - j))) & mmer_mask);
                 }
             }
         } else {
             for (uint32_t q = lane; q < npos; q += 32) {
                 const uint64_t y = bases_at(q) & mmer_mask;
-                hf()[fg_hslot(q)] = (y * FG_MIX_MUL) ^ I.hash_magic;
-                hr()[fg_hslot(q)] = (revcomp(y, m) * FG_MIX_MUL) ^ I.hash_magic;
+                store_hashes(q, y, revcomp(y, m));
             }
         }
         __syncwarp();
@@ -757,20 +798,56 @@ struct kmer_tiles {
         uint64_t val[FG_SEG_B];
         uint32_t key[FG_SEG_B]; /* read position of the minimizer | strand << 8 | ambiguous << 13 | valid << 14 | cpos << 16 */
         {
-            uint64_t mhf[FG_SEG_B], mhr[FG_SEG_B];
-            uint32_t pf[FG_SEG_B], pr[FG_SEG_B];
+            uint32_t pf[FG_SEG_B], pr[FG_SEG_B]; /* where the minimizer of each strand starts inside the k-mer, forward coordinates */
+            uint64_t vf[FG_SEG_B], vr[FG_SEG_B]; /* and its value */
+            const uint32_t rc_len = 32 * nwords; /* bases of the reverse-complemented stream */
             if (W) {
-                window_minima<W ? W : 13, false>(hf() + 5 * lane, mhf, pf);
-                window_minima<W ? W : 13, true>(hr() + 5 * lane, mhr, pr);
+                uint32_t fx[FG_SEG_B], fy[FG_SEG_B], rx[FG_SEG_B], ry[FG_SEG_B];
+                window_minima32<W ? W : 13>(kf() + 5 * lane, fx, fy);
+                window_minima32<W ? W : 13>(kr() + 5 * lane, rx, ry);
+                uint32_t undecided = 0;
+#pragma unroll
+                for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                    /* (clamped to the segment's m-mers: k-mers past the segment's end see keys of whatever lies there) */
+                    pf[tt] = min(fx[tt] & 0xffu, npos - 1) - (i0 + tt);           /* leftmost smallest key */
+                    pr[tt] = min((ry[tt] & 0xffu) ^ 0xffu, npos - 1) - (i0 + tt); /* rightmost smallest key */
+                    /* x ^ y == 0xff iff both minima sit on the same position */
+                    if ((((fx[tt] ^ fy[tt]) ^ 0xffu) | ((rx[tt] ^ ry[tt]) ^ 0xffu)) != 0) undecided |= 1u << tt;
+                }
+                undecided &= i0 + FG_SEG_B <= seg_nk ? 0xfu : (i0 < seg_nk ? (1u << (seg_nk - i0)) - 1u : 0u); /* the lane's k-mers inside the segment */
+                if (__ballot_sync(FG_FULL, undecided != 0)) { /* rare */
+#pragma unroll 1
+                    for (uint32_t tt = 0; tt < FG_SEG_B; ++tt) {
+                        if ((undecided >> tt) & 1u) {
+                            uint32_t ef, er;
+                            exact_window_minimizer(words(), rcwords(), i0 + tt + shift, rc_len, window, m, mmer_mask, I.hash_magic, ef, er);
+#pragma unroll
+                            for (int u = 0; u < FG_SEG_B; ++u)
+                                if (uint32_t(u) == tt) pf[u] = ef, pr[u] = er;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int tt = 0; tt < FG_SEG_B; ++tt) {
+                    vf[tt] = mmer_at(words(), i0 + tt + pf[tt] + shift, mmer_mask);
+                    vr[tt] = mmer_at(rcwords(), rc_len - (i0 + tt + pr[tt] + shift) - m, mmer_mask);
+                }
             } else { /* any other (k, m): plain scan of each window */
 #pragma unroll
                 for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                    mhf[tt] = mhr[tt] = UINT64_MAX;
-                    pf[tt] = pr[tt] = tt;
+                    uint64_t mhf = UINT64_MAX, mhr = UINT64_MAX;
+                    pf[tt] = pr[tt] = 0;
                     for (uint32_t j = 0; j < window; ++j) {
                         const uint64_t a = hf()[fg_hslot(i0 + tt + j)], b = hr()[fg_hslot(i0 + tt + j)];
-                        if (a < mhf[tt]) mhf[tt] = a, pf[tt] = tt + j;
-                        if (b <= mhr[tt]) mhr[tt] = b, pr[tt] = tt + j;
+                        if (a < mhf) mhf = a, pf[tt] = j;
+                        if (b <= mhr) mhr = b, pr[tt] = j;
+                    }
+                    vf[tt] = mmer_of_hash(mhf);
+                    vr[tt] = mmer_of_hash(mhr);
+                    if (I.guard_max_hash) { /* compute_minimizer's "nothing below UINT64_MAX" sentinel when that can occur (image.h);
+                                               such indexes are dispatched to this window (engine.cu: dispatch_window) */
+                        if (mhf == UINT64_MAX) vf[tt] = UINT64_MAX;
+                        if (mhr == UINT64_MAX) vr[tt] = UINT64_MAX;
                     }
                 }
             }
@@ -782,15 +859,10 @@ struct kmer_tiles {
                 const uint32_t i = i0 + tt;
                 const uint32_t bits = __funnelshift_r(vw0, vw1, i & 31);
                 const bool valid = i < seg_nk && (bits & kbits) == kbits;
-                uint64_t vf = mmer_of_hash(mhf[tt]), vr = mmer_of_hash(mhr[tt]);
-                if (I.guard_max_hash) { /* compute_minimizer's "nothing below UINT64_MAX" sentinel when that can occur (image.h) */
-                    if (mhf[tt] == UINT64_MAX) vf = UINT64_MAX;
-                    if (mhr[tt] == UINT64_MAX) vr = UINT64_MAX;
-                }
-                const bool fwd_wins = vf <= vr;
-                val[tt] = fwd_wins ? vf : vr;
-                const uint32_t cpos = (fwd_wins ? pf[tt] : pr[tt]) - tt;
-                key[tt] = (i + cpos) | (uint32_t(fwd_wins) << 8) | (uint32_t(vf == vr) << 13) | (uint32_t(valid) << 14) | (cpos << 16);
+                const bool fwd_wins = vf[tt] <= vr[tt];
+                val[tt] = fwd_wins ? vf[tt] : vr[tt];
+                const uint32_t cpos = fwd_wins ? pf[tt] : pr[tt];
+                key[tt] = (i + cpos) | (uint32_t(fwd_wins) << 8) | (uint32_t(vf[tt] == vr[tt]) << 13) | (uint32_t(valid) << 14) | (cpos << 16);
                 nibble |= uint32_t(valid) << tt;
             }
             /* valid-k-mer bitmap in k-mer order: 8 lanes per 32-bit word */
@@ -812,17 +884,15 @@ struct kmer_tiles {
               is a run of its own. Seeds are numbered in k-mer order. */
         uint32_t nseeds;
         {
-            uint64_t prev_val = __shfl_up_sync(FG_FULL, val[FG_SEG_B - 1], 1);
             uint32_t prev_key = __shfl_up_sync(FG_FULL, key[FG_SEG_B - 1], 1);
             if (lane == 0) prev_key = 0;
             uint32_t leaders = 0;
 #pragma unroll
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                /* same run: both valid, neither ambiguous, same position and strand, same value */
-                const bool same = ((key[tt] ^ prev_key) & 0xffffu) == 0 && (key[tt] & 0x6000u) == 0x4000u && prev_val == val[tt];
+                /* same run: both valid, neither ambiguous, same read position and strand (hence the same m-mer) */
+                const bool same = ((key[tt] ^ prev_key) & 0xffffu) == 0 && (key[tt] & 0x6000u) == 0x4000u;
                 if (((key[tt] >> 14) & 1u) && !same) leaders |= 1u << tt;
                 prev_key = key[tt];
-                prev_val = val[tt];
             }
             uint32_t incl = __popc(leaders); /* inclusive prefix sum over the lanes */
 #pragma unroll

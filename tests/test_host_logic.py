@@ -16,15 +16,14 @@ EMUL_SO = os.path.join(ROOT, "build", "libfg_simt_emul.so")
 INDEXES = ["salmonella_10.fur", "salmonella_10.mfur", "salmonella_10.dfur", "salmonella_10.mdfur", "synth_200.fur", "synth_200.mfur", "synth_200.dfur", "synth_200.mdfur", "synth_skew.fur"]
 
 
-@pytest.fixture(scope="module")
-def emul():
+def _load_emul(so, flags=()):
     src = os.path.join(ROOT, "tests", "simt_emul.cpp")
     csrc = os.path.join(ROOT, "fulgor_b200", "csrc")
     deps = [src, os.path.join(ROOT, "tests", "simt_emul.h")] + [os.path.join(csrc, f) for f in ("kernels.cuh", "pipeline_kernels.cuh", "image.h")]
-    if not os.path.exists(EMUL_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMUL_SO) for d in deps):
-        os.makedirs(os.path.dirname(EMUL_SO), exist_ok=True)
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-o", EMUL_SO, src])
-    E = C.CDLL(EMUL_SO)
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", *flags, "-o", so, src])
+    E = C.CDLL(so)
     E.emul_lookup_read.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p]
     E.emul_color_set_mask.restype = C.c_uint32
     E.emul_color_set_mask.argtypes = [C.c_void_p, C.c_uint32]
@@ -35,7 +34,20 @@ def emul():
                                            C.c_uint, C.c_int]
     E.emul_kmer_tool.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint, C.c_int]
     E.emul_pseudoalign_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int]
+    E.emul_set_packed.argtypes = [C.c_int]
     return E
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return _load_emul(EMUL_SO)
+
+
+@pytest.fixture(scope="module")
+def weak_key_emul():
+    """the same kernels with THREE hash bits in the 32-bit minimizer keys (kernels.cuh: window_minima32) instead of 24: different
+    m-mers then share their key bits in most windows, so the `undecided` detection and exact_window_minimizer carry the result"""
+    return _load_emul(os.path.join(ROOT, "build", "libfg_simt_emul_weak.so"), ["-DFG_KEY_HASH_MASK=0xe0000000u"])
 
 
 def emul_pseudoalign(E, img, reads, algo, thr, num_colors, grid=1, generic=0, table=0):
@@ -411,6 +423,36 @@ def test_emulated_kernels_on_packed_reads(index, packed_emul, built_lib):
         exp_off, exp_tr = o.kmer_conservation(reads)
         assert np.array_equal(toff, exp_off) and np.array_equal(tr[: 3 * int(toff[nr])].reshape(-1, 3), exp_tr)
     o.close()
+
+
+@pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_skew.fur"])
+def test_emulated_kernels_with_weak_minimizer_keys(index, weak_key_emul, built_lib):
+    """32-bit window minima: when the key bits cannot tell two m-mers of a window apart the kernel must notice and recompute the
+    window under the full 64-bit hash order -- forced here by keys of 3 hash bits; ASCII and packed reads, lists and per-k-mer view"""
+    import fulgor_b200 as fg
+
+    path = ck.index_path(index)
+    img, o = fg.build_image(path), ck.Oracle(path)
+    genomes = index.split(".")[0]
+    E = weak_key_emul
+    try:
+        for packed in (0, 1):
+            E.emul_set_packed(packed)
+            for reads in (ck.gen_reads(250, 75, 300, seed=23, genomes=genomes), _nasty_reads(genomes)):
+                got = emul_fetch(E, img, reads, grid=2, generic=0)
+                exp = o.fetch_color_set_ids(reads, want_positive=True)
+                for a, b in zip(got, exp):
+                    assert np.array_equal(a, b)
+                bases, off = reads
+                nr = len(off) - 1
+                cap = int(off[nr]) + 1
+                toff, tr = np.zeros(nr + 1, dtype=np.uint64), np.zeros(3 * cap, dtype=np.uint32)
+                assert E.emul_kmer_tool(img.ctypes.data, 0, bases.ctypes.data, off.ctypes.data, nr, toff.ctypes.data, tr.ctypes.data, cap, None, 2, 0) == 0
+                exp_off, exp_tr = o.kmer_conservation(reads)
+                assert np.array_equal(toff, exp_off) and np.array_equal(tr[: 3 * int(toff[nr])].reshape(-1, 3), exp_tr)
+    finally:
+        E.emul_set_packed(0)
+        o.close()
 
 
 def test_pack_reads_host_function(built_lib):
