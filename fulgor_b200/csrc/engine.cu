@@ -244,8 +244,9 @@ static fulgor_gpu_index* make_handle(const fgi_header& H, void* d_image, bool ow
 template <typename F>
 static void dispatch_window(const fgi_header& H, F&& f) {
     /* common (k, m) pairs get unrolled minimizer loops on 32-bit keys; an index in which some m-mer hashes to UINT64_MAX
-       (compute_minimizer's sentinel, image.h: guard_max_hash) takes the generic window, which knows about it */
-    switch (H.guard_max_hash ? 0 : H.k - H.m + 1) {
+       (compute_minimizer's sentinel, image.h: guard_max_hash) takes the generic window, which knows about it, and so do
+       minimizers shorter than 16 bases (the templated code takes the low word of the m-mer mask for all ones) */
+    switch (H.guard_max_hash || H.m < 16 ? 0 : H.k - H.m + 1) {
         case 13: f(std::integral_constant<int, 13>()); break; /* k=31, m=19 */
         case 12: f(std::integral_constant<int, 12>()); break; /* k=31, m=20 */
         case 11: f(std::integral_constant<int, 11>()); break; /* k=31, m=21 */

@@ -40,6 +40,15 @@ FG_HD uint64_t fg_mulhi64(uint64_t a, uint64_t b) {
     return uint64_t((unsigned __int128)a * b >> 64);
 #endif
 }
+/* bits 32..63 of a * b (mod 2^64): one high multiply and two multiply-adds */
+FG_HD uint32_t fg_mul64_hi32(uint64_t a, uint64_t b) {
+    const uint32_t al = uint32_t(a), ah = uint32_t(a >> 32), bl = uint32_t(b), bh = uint32_t(b >> 32);
+#ifdef __CUDA_ARCH__
+    return __umulhi(al, bl) + al * bh + ah * bl;
+#else
+    return uint32_t((uint64_t(al) * bl) >> 32) + al * bh + ah * bl;
+#endif
+}
 FG_HD uint64_t fg_brev64(uint64_t x) {
 #ifdef __CUDA_ARCH__
     return __brevll(x);
@@ -405,7 +414,7 @@ struct seed_slot {
 #define FG_SEED_SLOW 0x80000000u
 static_assert((sizeof(seed_slot) + sizeof(uint2) + sizeof(uint32_t)) * FG_SEG_KMERS <= 2 * 8 * FG_HASH_SLOTS, "seeds + items + per-k-mer notes must fit in the hash arrays");
 
-struct warp_stage {
+struct alignas(16) warp_stage { /* 16-byte stores of seed slots and notes */
     uint64_t h[2 * FG_HASH_SLOTS];    /* [0, FG_HASH_SLOTS): mixer_64 hash of the forward m-mer starting at every position;
                                          [FG_HASH_SLOTS, ..): hash of its reverse complement; afterwards seed slots and items */
     uint64_t words[FG_WORDS_PAD_BEFORE + FG_SEG_WORDS + FG_WORDS_PAD_AFTER];  /* packed bases, base j of the segment at bits 2(j % 32) of word j / 32 */
@@ -551,6 +560,7 @@ struct kmer_tiles {
        index::kmer_matches consume (src/kmer_conservation.cpp:31-47, src/kmer_matches.cpp:20-28). Set by the caller. */
     uint32_t* per_kmer;
     uint32_t seg_base; /* read index of the current segment's first k-mer */
+    bool seg_all_valid; /* every character of the current segment is one of ACGTacgt (warp-uniform) */
 
     __device__ __forceinline__ kmer_tiles(const dev_index& I_, const uint8_t* seq_, uint32_t len_, const uint8_t* buf_begin_, const uint8_t* buf_end_,
                                           uint32_t lane_, warp_stage& S_)
@@ -585,14 +595,14 @@ struct kmer_tiles {
     __device__ __forceinline__ uint2* kr() const { return reinterpret_cast<uint2*>(S.h + FG_HASH_SLOTS); }
     /* position q of the segment: forward m-mer yf, its reverse complement yr */
     __device__ __forceinline__ void store_hashes(uint32_t q, uint64_t yf, uint64_t yr) const {
-        const uint64_t a = (yf * FG_MIX_MUL) ^ I.hash_magic, b = (yr * FG_MIX_MUL) ^ I.hash_magic;
-        if (W) {
-            const uint32_t ka = (uint32_t(a >> 32) & FG_KEY_HASH_MASK) | q, kb = (uint32_t(b >> 32) & FG_KEY_HASH_MASK) | q;
+        if (W) { /* only bits 32..63 of the hashes are needed */
+            const uint32_t ka = ((fg_mul64_hi32(yf, FG_MIX_MUL) ^ uint32_t(I.hash_magic >> 32)) & FG_KEY_HASH_MASK) | q;
+            const uint32_t kb = ((fg_mul64_hi32(yr, FG_MIX_MUL) ^ uint32_t(I.hash_magic >> 32)) & FG_KEY_HASH_MASK) | q;
             kf()[fg_hslot(q)] = make_uint2(ka, ka ^ 0xffu);
             kr()[fg_hslot(q)] = make_uint2(kb, kb ^ 0xffu);
         } else {
-            hf()[fg_hslot(q)] = a;
-            hr()[fg_hslot(q)] = b;
+            hf()[fg_hslot(q)] = (yf * FG_MIX_MUL) ^ I.hash_magic;
+            hr()[fg_hslot(q)] = (yr * FG_MIX_MUL) ^ I.hash_magic;
         }
     }
     __device__ __forceinline__ seed_slot* seeds() const { return reinterpret_cast<seed_slot*>(S.h); }
@@ -602,8 +612,11 @@ struct kmer_tiles {
     /* m-mer behind a window minimum */
     __device__ __forceinline__ uint64_t mmer_of_hash(uint64_t h) const { return (h ^ I.hash_magic) * FG_MIX_INV; }
 
+    /* k-mer i of the segment (i < seg_nk) holds no invalid character; S.vk is only written for segments that have one */
+    __device__ __forceinline__ bool kmer_valid(uint32_t i) const { return seg_all_valid || ((S.vk[i >> 5] >> (i & 31)) & 1u); }
     /* number of valid k-mers with index in [lo, hi], hi - lo < 32 */
     __device__ __forceinline__ uint32_t count_valid(uint32_t lo, uint32_t hi) const {
+        if (seg_all_valid) return hi - lo + 1; /* [lo, hi] lies inside the segment */
         const uint32_t bits = __funnelshift_r(S.vk[lo >> 5], S.vk[(lo >> 5) + 1], lo & 31);
         const uint32_t len = hi - lo + 1;
         return __popc(len >= 32 ? bits : bits & ((1u << len) - 1u));
@@ -627,7 +640,7 @@ struct kmer_tiles {
         if (!(rec.y >> FGI_SK_PINNED_SHIFT)) { /* no single minimizer position: every k-mer of the run against every stored k-mer */
             uint32_t cnt = 0;
             for (uint32_t i = i_first; i <= i_last; ++i) {
-                if (!((S.vk[i >> 5] >> (i & 31)) & 1u)) continue;
+                if (!kmer_valid(i)) continue;
                 const uint64_t fwd = bases_at(i) & kmask;
                 const bool found = scan_super_kmer_rare(I, sk, fwd, kmask);
                 cnt += found;
@@ -773,6 +786,8 @@ struct kmer_tiles {
               reverse complement of the window holds the five reverse-complemented m-mers too. The templated windows keep a
               pair of 32-bit keys per position and strand (window_minima32), the generic one the 64-bit hashes. */
         const uint32_t m = I.m;
+        /* the templated windows are only dispatched for m >= 16 (engine.cu: dispatch_window): the mask's low word is all ones */
+        const uint64_t wmask = W ? (mmer_mask | 0xffffffffULL) : mmer_mask;
         if (W || m <= 28) { /* a templated window means m <= k - 10 */
             const uint32_t q0 = 5 * lane;
             /* The key pairs are written for all 160 positions the lanes' windows can touch: a key carries its own position,
@@ -782,7 +797,7 @@ struct kmer_tiles {
                 const uint64_t r = revcomp(x, m + 4);
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    if (W || q0 + j < npos) store_hashes(q0 + j, (x >> (2 * j)) & mmer_mask, (r >> (2 * (4 - j))) & mmer_mask);
+                    if (W || q0 + j < npos) store_hashes(q0 + j, (x >> (2 * j)) & wmask, (r >> (2 * (4 - j))) & wmask);
                 }
             }
         } else {
@@ -829,8 +844,8 @@ struct kmer_tiles {
                 }
 #pragma unroll
                 for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                    vf[tt] = mmer_at(words(), i0 + tt + pf[tt] + shift, mmer_mask);
-                    vr[tt] = mmer_at(rcwords(), rc_len - (i0 + tt + pr[tt] + shift) - m, mmer_mask);
+                    vf[tt] = mmer_at(words(), i0 + tt + pf[tt] + shift, wmask);
+                    vr[tt] = mmer_at(rcwords(), rc_len - (i0 + tt + pr[tt] + shift) - m, wmask);
                 }
             } else { /* any other (k, m): plain scan of each window */
 #pragma unroll
@@ -866,9 +881,8 @@ struct kmer_tiles {
                 nibble |= uint32_t(valid) << tt;
             }
             /* valid-k-mer bitmap in k-mer order: 8 lanes per 32-bit word */
-            if (all_valid) {
-                if (lane < FG_SEG_B + 2) S.vk[lane] = seg_nk >= 32 * lane + 32 ? ~0u : (seg_nk > 32 * lane ? (1u << (seg_nk - 32 * lane)) - 1u : 0u);
-            } else {
+            seg_all_valid = all_valid;
+            if (!all_valid) {
                 const uint32_t part = nibble << (4 * (lane & 7));
 #pragma unroll
                 for (int w = 0; w < FG_SEG_B; ++w) {
@@ -902,19 +916,19 @@ struct kmer_tiles {
             }
             nseeds = __shfl_sync(FG_FULL, incl, 31);
             uint32_t s = incl - __popc(leaders); /* seeds before this lane */
+            uint32_t note[FG_SEG_B];
 #pragma unroll
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
-                if ((leaders >> tt) & 1u) {
-                    seed_slot& slot = seeds()[s];
-                    slot.begin = uint32_t(val[tt]);
-                    slot.n = uint32_t(val[tt] >> 32);
-                    slot.key = (key[tt] & 0x1ffu) | ((i0 + tt) << 16) | (((key[tt] >> 13) & 1u) ? FG_SEED_SLOW : 0u);
+                if ((leaders >> tt) & 1u) { /* one 16-byte store: {minimizer, key, -} */
+                    *reinterpret_cast<uint4*>(seeds() + s) =
+                        make_uint4(uint32_t(val[tt]), uint32_t(val[tt] >> 32), (key[tt] & 0x1ffu) | ((i0 + tt) << 16) | (((key[tt] >> 13) & 1u) ? FG_SEED_SLOW : 0u), 0u);
                     s += 1;
                 }
                 /* note for the per-k-mer path: run | ambiguous << 13 | valid << 14 | cpos << 16 (the run wraps to 0xff before the
                    first seed: such k-mers are invalid) */
-                notes()[tt * 32 + lane] = ((s - 1) & 0xffu) | (key[tt] & 0x001f6000u);
+                note[tt] = ((s - 1) & 0xffu) | (key[tt] & 0x001f6000u);
             }
+            reinterpret_cast<uint4*>(notes())[lane] = make_uint4(note[0], note[1], note[2], note[3]); /* k-mer i at notes()[i] */
         }
         __syncwarp();
         /* 4. + 5. in groups of 32 seeds */
@@ -966,7 +980,7 @@ struct kmer_tiles {
                     cnt = extend_pair(slot.begin + j, int(slot.key & 0xffu), (slot.key >> 8) & 1u, i_first, i_last, nchars, nwords, cid, found_lo, found_hi);
                     if (PERK && cnt)
                         for (int i = found_lo; i <= found_hi; ++i)
-                            if ((S.vk[i >> 5] >> (i & 31)) & 1u) per_kmer[seg_base + uint32_t(i)] = cid;
+                            if (kmer_valid(uint32_t(i))) per_kmer[seg_base + uint32_t(i)] = cid;
                 }
                 append_items(cnt != 0, cid, cnt);
             }
@@ -976,7 +990,7 @@ struct kmer_tiles {
 #pragma unroll 1
             for (int tt = 0; tt < FG_SEG_B; ++tt) {
                 uint32_t cid = FG_NOT_FOUND;
-                const uint32_t note = notes()[tt * 32 + lane];
+                const uint32_t note = notes()[FG_SEG_B * lane + tt];
                 if ((note >> 14) & 1u) {
                     const seed_slot slot = seeds()[note & 0xffu];
                     if (slot.key & FG_SEED_SLOW) {

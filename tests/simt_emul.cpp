@@ -85,7 +85,7 @@ static dev_index view_of(const uint8_t* base) {
 
 template <typename F>
 static void dispatch_window(const dev_index& I, int force_generic, F&& f) {
-    switch (force_generic ? 0 : int(I.k - I.m + 1)) {
+    switch (force_generic || I.guard_max_hash || I.m < 16 ? 0 : int(I.k - I.m + 1)) { /* like engine.cu */
         case 13: f(std::integral_constant<int, 13>()); break;
         case 12: f(std::integral_constant<int, 12>()); break;
         case 11: f(std::integral_constant<int, 11>()); break;
