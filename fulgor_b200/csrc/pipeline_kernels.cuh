@@ -610,6 +610,21 @@ __global__ void __launch_bounds__(FG_BLOCK) k_expand_color_sets(const __grid_con
    only on the multiplicities, which every lane shares, so the control flow is warp-uniform and the planes stay in registers
    (compile-time indices). A hit set costs about one compressor (two LOP3 per word) per set bit of its multiplicity, however
    many planes the counters have -- the ripple-carry adder this replaces paid a full adder per plane and word for every set. */
+/* one 3:2 compressor step IN PLACE: a <- a ^ p ^ x (the plane's new bit), x <- majority(a, p, x) (the carry). Two LOP3, the
+   second one on the NEW a (0x8e = majority(A ^ B ^ C, B, C) as a function of A, B, C), so no register beyond the three
+   operands is live -- written as two plain expressions the compiler kept the old a for the carry and paid a chain of ~20
+   register moves where the planes' exits meet (profiles/r02_big_mfur_tu_mixed_k2_*: 21 % IMAD, half of them moves). */
+__device__ __forceinline__ void fg_csa(uint32_t& a, uint32_t p, uint32_t& x) {
+#if defined(__CUDA_ARCH__)
+    asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(p), "r"(x));
+    asm("lop3.b32 %0, %1, %2, %0, 0x8e;" : "+r"(x) : "r"(a), "r"(p));
+#else
+    const uint32_t s = a ^ p ^ x;
+    x = (a & p) | (a & x) | (p & x);
+    a = s;
+#endif
+}
+
 template <int NP, int T>
 struct carry_save_counters {
     uint32_t acc[NP][T];
@@ -626,37 +641,42 @@ struct carry_save_counters {
         }
         pending = 0;
     }
-    /* the vector enters at plane K (compile-time): every plane with a pending vector compresses and passes the carry on, the
-       first one without parks it. Only the planes actually visited cost instructions; a carry out of the top plane cannot
-       happen (scores < 2^NP). */
     template <int K>
-    __device__ __forceinline__ void add_from(uint32_t (&v)[T]) {
-        if constexpr (K < NP) {
-            if ((pending >> K) & 1u) {
+    __device__ __forceinline__ void park(const uint32_t (&v)[T]) {
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    const uint32_t a = acc[K][t], p = pend[(K * T + t) * 32], x = v[t];
-                    acc[K][t] = a ^ p ^ x;
-                    v[t] = (a & p) | (a & x) | (p & x);
-                }
-                pending &= ~(1u << K);
-                add_from<K + 1>(v);
-            } else {
-#pragma unroll
-                for (int t = 0; t < T; ++t) pend[(K * T + t) * 32] = v[t];
-                pending |= 1u << K;
-            }
-        }
+        for (int t = 0; t < T; ++t) pend[(K * T + t) * 32] = v[t];
+        pending |= 1u << K;
     }
     template <int K>
-    __device__ __forceinline__ void dispatch(uint32_t (&v)[T], uint32_t b) {
-        if constexpr (K < NP) {
-            if (b == uint32_t(K)) add_from<K>(v);
-            else dispatch<K + 1>(v, b);
-        }
+    __device__ __forceinline__ void compress(uint32_t (&v)[T]) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) fg_csa(acc[K][t], pend[(K * T + t) * 32], v[t]);
+        pending &= ~(1u << K);
     }
-    /* counters[c] += 2^b for every set bit c of v (v is consumed) */
-    __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) { dispatch<0>(v, b); }
+    /* counters[c] += 2^b for every set bit c of v (v is consumed). The vector enters at plane b: every plane with a pending
+       vector compresses and passes the carry on to the next one, the first one without parks it. ONE copy of every plane's
+       code: the entry plane is a jump into a chain of cases that fall through (the recursion this replaces instantiated the
+       chain once per entry plane, NP^2 / 2 plane bodies). A carry out of the top plane cannot happen (scores < 2^NP). */
+    __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) {
+#define FG_CS_PLANE(K)                          \
+    case K:                                     \
+        if constexpr (K < NP) {                 \
+            if (!((pending >> K) & 1u)) {       \
+                park<K>(v);                     \
+                break;                          \
+            }                                   \
+            compress<K>(v);                     \
+        }                                       \
+        [[fallthrough]];
+        switch (b) {
+            FG_CS_PLANE(0) FG_CS_PLANE(1) FG_CS_PLANE(2) FG_CS_PLANE(3) FG_CS_PLANE(4) FG_CS_PLANE(5) FG_CS_PLANE(6) FG_CS_PLANE(7)
+            FG_CS_PLANE(8) FG_CS_PLANE(9) FG_CS_PLANE(10) FG_CS_PLANE(11) FG_CS_PLANE(12) FG_CS_PLANE(13) FG_CS_PLANE(14) FG_CS_PLANE(15)
+            FG_CS_PLANE(16) FG_CS_PLANE(17) FG_CS_PLANE(18) FG_CS_PLANE(19) FG_CS_PLANE(20) FG_CS_PLANE(21) FG_CS_PLANE(22) FG_CS_PLANE(23)
+            FG_CS_PLANE(24) FG_CS_PLANE(25) FG_CS_PLANE(26) FG_CS_PLANE(27) FG_CS_PLANE(28) FG_CS_PLANE(29) FG_CS_PLANE(30) FG_CS_PLANE(31)
+            default: break;
+        }
+#undef FG_CS_PLANE
+    }
     /* folds the pending vectors in, lowest plane first: afterwards acc[k] is bit k of the scores */
     template <int K>
     __device__ __forceinline__ void finish_from() {
@@ -670,7 +690,7 @@ struct carry_save_counters {
                     acc[K][t] ^= p;
                 }
                 pending &= ~(1u << K);
-                add_from<K + 1>(c);
+                add(c, K + 1);
             }
             finish_from<K + 1>();
         }
@@ -681,8 +701,11 @@ struct carry_save_counters {
 /* dynamic shared memory of k_color_sets_table: the pending vectors of every warp's counters (none for full intersection) */
 static inline size_t table_kernel_smem(bool fi, int NP, int T) { return fi ? 0 : size_t(FG_WARPS_PER_BLOCK) * NP * T * 32 * 4; }
 
+/* resident blocks per SM the table kernels are compiled for (register budget 65536 / (blocks * 256)) */
+static constexpr int table_kernel_blocks(bool fi, int NP) { return fi ? 6 : (NP <= 10 ? 3 : 2); }
+
 template <bool FI, int NP, int T>
-__global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(FG_BLOCK, table_kernel_blocks(FI, NP)) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
                                                               const uint2* __restrict__ stage, const uint2* __restrict__ pool,
                                                               const uint32_t* __restrict__ num_positive, uint32_t n_reads, double threshold,
                                                               uint32_t words_per_read, uint32_t* __restrict__ res_bits,
@@ -694,8 +717,8 @@ __global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color
 #endif
     const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const uint32_t C = I.num_colors, W = words_per_read;
-    const uint32_t* __restrict__ table = I.set_table;
-    const uint64_t stride = I.table_stride;
+    const uint32_t stride = uint32_t(I.table_stride); /* words per row, a multiple of 32 (table_stride_words) */
+    const uint32_t row_bytes = stride * 4; /* < 2^32: a row holds num_colors bits */
     for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_reads; r += gridDim.x * wpb) {
         const uint32_t n = __ldg(counts + r);
         uint32_t* out = res_bits + uint64_t(r) * W;
@@ -716,19 +739,28 @@ __global__ void __launch_bounds__(FG_BLOCK, FI ? 6 : (NP <= 10 ? 3 : 2)) k_color
                 cs.pend = smem + size_t(threadIdx.x >> 5) * ((FI ? 1 : NP) * (FI ? 1 : T) * 32) + lane;
                 cs.clear();
             }
-            /* the rows are fetched one entry AHEAD of the arithmetic (and the entry list two ahead): a warp keeps 2 T row
-               loads in flight instead of T -- the kernel is bound by the latency of these loads, not by its logic ops */
-            auto load_row = [&](const uint2& e, uint32_t (&x)[T]) {
-                const uint32_t* row = table + uint64_t(e.x) * stride + w0 + lane;
+            /* A row load is ONE 64-bit multiply-add (row id x row bytes + this lane's base) and T loads at constant offsets;
+               whether the pass needs guards (a last, partial pass over the row) is decided once per pass, not per load -- the
+               guarded form cost ~27 instructions per row around its 5 loads. The rows are fetched one entry AHEAD of the
+               arithmetic (and the entry list two ahead): a warp keeps 2 T row loads in flight instead of T. */
+            const char* lane_base = reinterpret_cast<const char*>(I.set_table + w0 + lane);
+            const bool whole = w0 + 32 * T <= stride; /* warp-uniform */
+            auto load_row = [&](uint32_t id, uint32_t (&x)[T]) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(lane_base + uint64_t(id) * row_bytes); /* one IMAD.WIDE */
+                if (whole) {
 #pragma unroll
-                for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
+                    for (int t = 0; t < T; ++t) x[t] = __ldg(row + 32 * t);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
+                }
             };
             uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
             uint32_t x[T], x_next[T];
-            load_row(e, x);
+            load_row(e.x, x);
             for (uint32_t j = 0; j < n; ++j) {
                 const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
-                if (j + 1 < n) load_row(e_next, x_next);
+                if (j + 1 < n) load_row(e_next.x, x_next);
                 if (FI) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[t] &= x[t];
@@ -1094,23 +1126,36 @@ __global__ void __launch_bounds__(256) k_emit_entries(const uint2* __restrict__ 
         if (o + i < out_cap) out[o + i] = e[i].x;
 }
 
-/* per-read color bitmaps -> ascending color lists at their CSR positions */
+/* per-read color bitmaps -> ascending color lists at their CSR positions. One warp per read; the lanes load 32 words of the row
+   at once (one coalesced 128-byte load) and hand them round with register shuffles; word by word, the lane whose bit is set
+   writes color 32 w + lane at the running offset + the number of set bits below it: the stores of a word are contiguous.
+   Offsets run in 32 bits from the read's base, and the capacity is tested once per read, not per color. */
 __global__ void __launch_bounds__(256) k_emit_bits(const uint32_t* __restrict__ res_bits, uint32_t words_per_read, const uint32_t* __restrict__ counts,
                                                   const uint64_t* __restrict__ off, const uint64_t* __restrict__ chunk_info, uint32_t n,
                                                   uint32_t* __restrict__ out, uint64_t out_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
-    if (__ldg(counts + r) == 0) return;
-    uint64_t o = __ldg(off + r) - chunk_info[0];
+    const uint32_t cnt = __ldg(counts + r);
+    if (cnt == 0) return;
+    const uint64_t o0 = __ldg(off + r) - chunk_info[0];
+    if (o0 >= out_cap) return;
+    const uint32_t room = uint32_t(min(out_cap - o0, uint64_t(cnt))); /* < cnt only when the caller's buffer is too small (E2BIG) */
+    uint32_t* dst = out + o0;
     const uint32_t* bits = res_bits + uint64_t(r) * words_per_read;
-    for (uint32_t w = 0; w < words_per_read; ++w) {
-        const uint32_t word = __ldg(bits + w);
-        if ((word >> lane) & 1u) {
-            const uint64_t at = o + __popc(word & ((1u << lane) - 1u));
-            if (at < out_cap) out[at] = w * 32 + lane;
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t o = 0;
+    for (uint32_t w0 = 0; w0 < words_per_read; w0 += 32) {
+        const uint32_t mine = w0 + lane < words_per_read ? __ldg(bits + w0 + lane) : 0u;
+        if (__ballot_sync(FG_FULL, mine != 0) == 0) continue;
+        const uint32_t color0 = 32 * w0 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t word = __shfl_sync(FG_FULL, mine, j);
+            const uint32_t at = o + __popc(word & below);
+            if (((word >> lane) & 1u) && at < room) dst[at] = color0 + 32 * j;
+            o += __popc(word);
         }
-        o += __popc(word);
     }
 }
 

@@ -7,7 +7,7 @@ for rep in gpurun_out/*.ncu-rep; do
   base=${rep%.ncu-rep}
   ncu -i "$rep" --page raw --csv > "${base}_raw.csv" 2>/dev/null
   ncu -i "$rep" --page source --csv --print-source cuda,sass > "${base}_src.csv" 2>/dev/null
-  python tools/ncu_lines.py "${base}_src.csv" 45 > "${base}_hot_lines.txt" 2>&1
+  python tools/ncu_lines.py "${base}_src.csv" ${HOT_LINES:-45} > "${base}_hot_lines.txt" 2>&1
   python tools/ncu_opmix.py "${base}_src.csv" > "${base}_opmix.txt" 2>&1
   rm -f "$rep" "${base}_src.csv"
 done
