@@ -145,12 +145,10 @@ FG_HD uint64_t mod_by_inverse(uint64_t a, uint64_t inv, uint64_t d) {
 /* single_phf::position (pthash/single_phf.hpp:79-101): skew_bucketer (utils/bucketers.hpp:163-168), pre-hashed pilot,
    xor displacement, minimal (free slots) */
 FG_HD uint64_t phf_position(const dev_index& I, const fgi_phf_part& P, uint64_t first, uint64_t second) {
-    uint64_t bucket;
-    if (first < I.bucketer_T) {
-        bucket = mod_by_inverse(first, P.inv_dense, P.num_dense);
-    } else {
-        bucket = P.num_dense + mod_by_inverse(first, P.inv_sparse, P.num_sparse);
-    }
+    /* one remainder for either side of the skew bucketer: the lanes of a warp fall on both, and two divergent copies of the
+       multiply-high sequence cost more than three selects */
+    const bool dense = first < I.bucketer_T;
+    const uint64_t bucket = (dense ? 0 : P.num_dense) + mod_by_inverse(first, dense ? P.inv_dense : P.inv_sparse, dense ? P.num_dense : P.num_sparse);
     const uint64_t hashed_pilot = FG_LDG(I.hashed_pilots + P.pilot_base + bucket);
     uint64_t pos = mod_by_inverse(second ^ hashed_pilot, P.inv_table, P.table_size);
     if (pos >= P.num_keys) pos = FG_LDG(I.free_slots + P.free_base + (pos - P.num_keys));

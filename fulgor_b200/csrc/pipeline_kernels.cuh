@@ -625,22 +625,38 @@ __device__ __forceinline__ void fg_csa(uint32_t& a, uint32_t p, uint32_t& x) {
 #endif
 }
 
+/* Planes [0, HI) -- the ones nearly every hit set touches -- keep their accumulated bits in registers and a pending vector in
+   shared memory. Planes [HI, NP) live in shared memory altogether, as plain ripple-carry adders without a pending vector: a
+   vector only gets there as the carry out of plane HI - 1 (once per 2^HI units of weight) or with a multiplicity >= 2^HI, and
+   ripples on while any lane still holds a carry bit. That takes NP x T registers down to HI x T -- the 10-plane kernel ran out
+   of registers at 80 (the loads' descriptors were rebuilt from spilled copies around every row, profiles/r02_big_mfur_tu_mixed_k2_*)
+   -- for a fourth resident block per SM; the shared memory per warp stays NP x T x 128 bytes. */
+#ifndef FG_TU_HI
+#define FG_TU_HI 4
+#endif
 template <int NP, int T>
 struct carry_save_counters {
-    uint32_t acc[NP][T];
-    uint32_t* pend;   /* the pending vectors live in SHARED memory (word (K, t) of this lane at pend[(K * T + t) * 32]): they are touched once
-                         per visit of their plane, and keeping them out of the registers halves the kernel's register count -- a third
-                         resident block per SM and one pass over the row where the registers allowed only a part of it */
-    uint32_t pending; /* bit k: plane k holds a pending vector (warp-uniform) */
+    static constexpr int HI = NP < FG_TU_HI ? NP : FG_TU_HI;
+    uint32_t acc[HI][T];
+    uint32_t* pend;   /* this lane's column of the warp's shared memory: word (K, t) at pend[(K * T + t) * 32] -- for K < HI the plane's
+                         pending vector, for K >= HI the plane itself */
+    uint32_t pending; /* bit k: plane k < HI holds a pending vector (warp-uniform) */
 
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
+        for (int k = 0; k < HI; ++k) {
 #pragma unroll
             for (int t = 0; t < T; ++t) acc[k][t] = 0u;
         }
+#pragma unroll
+        for (int k = HI; k < NP; ++k) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) pend[(k * T + t) * 32] = 0u;
+        }
         pending = 0;
     }
+    /* bit k of the scores of this lane's word t (after finish()) */
+    __device__ __forceinline__ uint32_t plane(int k, int t) const { return k < HI ? acc[k < HI ? k : 0][t] : pend[(k * T + t) * 32]; }
     template <int K>
     __device__ __forceinline__ void park(const uint32_t (&v)[T]) {
 #pragma unroll
@@ -650,23 +666,38 @@ struct carry_save_counters {
     template <int K>
     __device__ __forceinline__ void compress(uint32_t (&v)[T]) {
 #pragma unroll
-        for (int t = 0; t < T; ++t) fg_csa(acc[K][t], pend[(K * T + t) * 32], v[t]);
+        for (int t = 0; t < T; ++t) fg_csa(acc[K < HI ? K : 0][t], pend[(K * T + t) * 32], v[t]);
         pending &= ~(1u << K);
+    }
+    /* plane K >= HI += v, v <- the carry; false when no lane of the warp has a carry left */
+    template <int K>
+    __device__ __forceinline__ bool ripple(uint32_t (&v)[T]) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint32_t a = pend[(K * T + t) * 32];
+            pend[(K * T + t) * 32] = a ^ v[t];
+            v[t] &= a;
+            any |= v[t];
+        }
+        return __any_sync(FG_FULL, any != 0);
     }
     /* counters[c] += 2^b for every set bit c of v (v is consumed). The vector enters at plane b: every plane with a pending
        vector compresses and passes the carry on to the next one, the first one without parks it. ONE copy of every plane's
        code: the entry plane is a jump into a chain of cases that fall through (the recursion this replaces instantiated the
        chain once per entry plane, NP^2 / 2 plane bodies). A carry out of the top plane cannot happen (scores < 2^NP). */
     __device__ __forceinline__ void add(uint32_t (&v)[T], uint32_t b) {
-#define FG_CS_PLANE(K)                          \
-    case K:                                     \
-        if constexpr (K < NP) {                 \
-            if (!((pending >> K) & 1u)) {       \
-                park<K>(v);                     \
-                break;                          \
-            }                                   \
-            compress<K>(v);                     \
-        }                                       \
+#define FG_CS_PLANE(K)                              \
+    case K:                                         \
+        if constexpr (K < HI) {                     \
+            if (!((pending >> K) & 1u)) {           \
+                park<K>(v);                         \
+                break;                              \
+            }                                       \
+            compress<K>(v);                         \
+        } else if constexpr (K < NP) {              \
+            if (!ripple<K>(v)) break;               \
+        }                                           \
         [[fallthrough]];
         switch (b) {
             FG_CS_PLANE(0) FG_CS_PLANE(1) FG_CS_PLANE(2) FG_CS_PLANE(3) FG_CS_PLANE(4) FG_CS_PLANE(5) FG_CS_PLANE(6) FG_CS_PLANE(7)
@@ -677,10 +708,10 @@ struct carry_save_counters {
         }
 #undef FG_CS_PLANE
     }
-    /* folds the pending vectors in, lowest plane first: afterwards acc[k] is bit k of the scores */
+    /* folds the pending vectors in, lowest plane first: afterwards plane(k, t) is bit k of the scores */
     template <int K>
     __device__ __forceinline__ void finish_from() {
-        if constexpr (K < NP) {
+        if constexpr (K < HI) {
             if ((pending >> K) & 1u) {
                 uint32_t c[T];
 #pragma unroll
@@ -702,7 +733,16 @@ struct carry_save_counters {
 static inline size_t table_kernel_smem(bool fi, int NP, int T) { return fi ? 0 : size_t(FG_WARPS_PER_BLOCK) * NP * T * 32 * 4; }
 
 /* resident blocks per SM the table kernels are compiled for (register budget 65536 / (blocks * 256)) */
-static constexpr int table_kernel_blocks(bool fi, int NP) { return fi ? 6 : (NP <= 10 ? 3 : 2); }
+#ifndef FG_TU_BLOCKS
+#define FG_TU_BLOCKS 4
+#endif
+#ifndef FG_FI_DEPTH
+#define FG_FI_DEPTH 1 /* rows in flight ahead of the one being ANDed (full intersection) */
+#endif
+#ifndef FG_FI_BLOCKS
+#define FG_FI_BLOCKS 6
+#endif
+static constexpr int table_kernel_blocks(bool fi, int NP) { return fi ? FG_FI_BLOCKS : (NP <= 10 ? (FG_TU_HI <= 4 ? FG_TU_BLOCKS : 3) : 2); }
 
 template <bool FI, int NP, int T>
 __global__ void __launch_bounds__(FG_BLOCK, table_kernel_blocks(FI, NP)) k_color_sets_table(const __grid_constant__ dev_index I, const uint32_t* __restrict__ counts,
@@ -742,7 +782,7 @@ __global__ void __launch_bounds__(FG_BLOCK, table_kernel_blocks(FI, NP)) k_color
             /* A row load is ONE 64-bit multiply-add (row id x row bytes + this lane's base) and T loads at constant offsets;
                whether the pass needs guards (a last, partial pass over the row) is decided once per pass, not per load -- the
                guarded form cost ~27 instructions per row around its 5 loads. The rows are fetched one entry AHEAD of the
-               arithmetic (and the entry list two ahead): a warp keeps 2 T row loads in flight instead of T. */
+               arithmetic: a warp keeps 2 T row loads in flight instead of T. */
             const char* lane_base = reinterpret_cast<const char*>(I.set_table + w0 + lane);
             const bool whole = w0 + 32 * T <= stride; /* warp-uniform */
             auto load_row = [&](uint32_t id, uint32_t (&x)[T]) {
@@ -755,27 +795,57 @@ __global__ void __launch_bounds__(FG_BLOCK, table_kernel_blocks(FI, NP)) k_color
                     for (int t = 0; t < T; ++t) x[t] = w0 + 32 * t < stride ? __ldg(row + 32 * t) : 0u;
                 }
             };
-            uint2 e = ents[0], e_next = n > 1 ? ents[1] : e;
-            uint32_t x[T], x_next[T];
-            load_row(e.x, x);
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint2 e_after = j + 2 < n ? ents[j + 2] : e_next;
-                if (j + 1 < n) load_row(e_next.x, x_next);
-                if (FI) {
+            if constexpr (FI) {
+                /* full intersection: the rows are fetched FG_FI_DEPTH entries ahead of the ANDs (and the entry list one further):
+                   the kernel waits on these loads and on nothing else (long-scoreboard stalls, profiles/r02_big_fi_k2_*) */
+                uint2 e[FG_FI_DEPTH + 1];
+                uint32_t x[FG_FI_DEPTH + 1][T];
 #pragma unroll
-                    for (int t = 0; t < T; ++t) acc[t] &= x[t];
-                } else { /* score += multiplicity for every member: the bitmap enters at the plane of every set bit of the multiplicity */
-                    for (uint32_t wt = e.y; wt; wt &= wt - 1) {
-                        uint32_t v[FI ? 1 : T];
+                for (int d = 0; d <= FG_FI_DEPTH; ++d) e[d] = uint32_t(d) < n ? ents[d] : make_uint2(0u, 0u);
 #pragma unroll
-                        for (int t = 0; t < (FI ? 1 : T); ++t) v[t] = x[t];
+                for (int d = 0; d < FG_FI_DEPTH; ++d)
+                    if (uint32_t(d) < n) load_row(e[d].x, x[d]);
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint2 e_after = j + FG_FI_DEPTH + 1 < n ? ents[j + FG_FI_DEPTH + 1] : make_uint2(0u, 0u);
+                    if (j + FG_FI_DEPTH < n) load_row(e[FG_FI_DEPTH].x, x[FG_FI_DEPTH]);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc[t] &= x[0][t];
+#pragma unroll
+                    for (int d = 0; d < FG_FI_DEPTH; ++d) {
+                        e[d] = e[d + 1];
+#pragma unroll
+                        for (int t = 0; t < T; ++t) x[d][t] = x[d + 1][t];
+                    }
+                    e[FG_FI_DEPTH] = e_after;
+                }
+            } else {
+                /* threshold union: the entry list comes 32 entries at a time, one per lane in ONE coalesced load (the batch after
+                   it is already on its way), and is handed round with shuffles; the row of entry j + 1 is fetched while the
+                   counters take the row of entry j */
+                const uint2 none = make_uint2(0u, 0u);
+                uint2 cur = lane < n ? ents[lane] : none;
+                uint2 nxt = lane + 32 < n ? ents[lane + 32] : none;
+                uint32_t x[T], x_next[T];
+                load_row(__shfl_sync(FG_FULL, cur.x, 0), x);
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint32_t mult = __shfl_sync(FG_FULL, cur.y, j & 31u);
+                    if (j + 1 < n) {
+                        if (((j + 1) & 31u) == 0) { /* next batch of entries */
+                            cur = nxt;
+                            nxt = j + 33 + lane < n ? ents[j + 33 + lane] : none;
+                        }
+                        load_row(__shfl_sync(FG_FULL, cur.x, (j + 1) & 31u), x_next);
+                    }
+                    /* score += multiplicity for every member: the bitmap enters at the plane of every set bit of the multiplicity */
+                    for (uint32_t wt = mult; wt; wt &= wt - 1) {
+                        uint32_t v[T];
+#pragma unroll
+                        for (int t = 0; t < T; ++t) v[t] = x[t];
                         cs.add(v, uint32_t(__ffs(int(wt))) - 1u);
                     }
-                }
-                e = e_next;
-                e_next = e_after;
 #pragma unroll
-                for (int t = 0; t < T; ++t) x[t] = x_next[t];
+                    for (int t = 0; t < T; ++t) x[t] = x_next[t];
+                }
             }
             if (!FI) cs.finish();
 #pragma unroll
@@ -786,7 +856,7 @@ __global__ void __launch_bounds__(FG_BLOCK, table_kernel_blocks(FI, NP)) k_color
                     uint32_t carry = ~0u;
 #pragma unroll
                     for (int k = 0; k < (FI ? 1 : NP); ++k) {
-                        const uint32_t nb = ((min_score >> k) & 1u) ? 0u : ~0u, pk = cs.acc[k][FI ? 0 : t];
+                        const uint32_t nb = ((min_score >> k) & 1u) ? 0u : ~0u, pk = cs.plane(k, FI ? 0 : t);
                         carry = (pk & nb) | (pk & carry) | (nb & carry);
                     }
                     word = (min_score >> NP) ? 0u : carry; /* a threshold beyond the counters' range is never met */
@@ -977,6 +1047,9 @@ template <typename F>
 static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {
     if (algo == FULGOR_GPU_FULL_INTERSECTION) f(std::true_type(), std::integral_constant<int, 1>(), std::integral_constant<int, 5>());
     else if (max_kmers < (1u << 7)) f(std::false_type(), std::integral_constant<int, 7>(), std::integral_constant<int, 5>());
+#ifdef FG_TU_NP9
+    else if (max_kmers < (1u << 9)) f(std::false_type(), std::integral_constant<int, 9>(), std::integral_constant<int, 5>());
+#endif
     else if (max_kmers < (1u << 10)) f(std::false_type(), std::integral_constant<int, 10>(), std::integral_constant<int, 5>());
     else if (max_kmers < (1u << 16)) f(std::false_type(), std::integral_constant<int, 16>(), std::integral_constant<int, 5>());
     else f(std::false_type(), std::integral_constant<int, 32>(), std::integral_constant<int, 1>());

@@ -287,6 +287,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     }));
 }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 template <typename T>
 static inline T __shfl_sync(unsigned mask, T v, int src) {
     fg_emul_check_mask(mask);

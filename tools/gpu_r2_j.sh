@@ -17,10 +17,20 @@ for v in "" $VARIANTS; do
   tag=${v:-new}
   [ -n "$S10" ] && ko s10_fi_$tag -- --reads 10000000
   ko big_fi_$tag -- --index $BIG.fur --reads 500000
-  ko big_tu_$tag -- --index $BIG.fur --reads 500000 --algo tu
-  ko big_mfur_tu_mixed_$tag -- --index $BIG.mfur --reads 500000 --algo tu --min-len 75 --max-len 300
+  [ -z "$FI_ONLY" ] && ko big_tu_$tag -- --index $BIG.fur --reads 500000 --algo tu
+  [ -z "$FI_ONLY" ] && ko big_mfur_tu_mixed_$tag -- --index $BIG.mfur --reads 500000 --algo tu --min-len 75 --max-len 300
+done
+for v in $VARIANTS_FI; do
+  export FULGOR_GPU_LIB=$PWD/fulgor_b200/variants/libfulgor_gpu_$v.so
+  ko big_fi_$v -- --index $BIG.fur --reads 500000
+done
+for v in $VARIANTS_TU; do
+  export FULGOR_GPU_LIB=$PWD/fulgor_b200/variants/libfulgor_gpu_$v.so
+  ko big_tu_$v -- --index $BIG.fur --reads 500000 --algo tu
+  ko big_mfur_tu_mixed_$v -- --index $BIG.mfur --reads 500000 --algo tu --min-len 75 --max-len 300
 done
 unset FULGOR_GPU_LIB
+if [ "$TESTS" = all ]; then timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4; TESTS=""; fi
 if [ -n "$TESTS" ]; then timeout 900 python -m pytest tests -m gpu -x -q -k "$TESTS" 2>&1 | tail -3; fi
 if [ -n "$BENCH" ]; then
   t0=$(date +%s); timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$? wall $(( $(date +%s) - t0 )) s"; tail -3 gpurun_out/bench.err
