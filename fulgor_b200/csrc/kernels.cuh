@@ -499,12 +499,6 @@ __device__ __noinline__ void exact_window_minimizer(const uint64_t* fw, const ui
     }
 }
 
-/* the bits of a 128-bit value {lo, hi} below bit position nb (0 <= nb <= 128) */
-__device__ __forceinline__ void mask_below(uint32_t nb, uint64_t& lo, uint64_t& hi) {
-    lo = nb >= 64 ? ~0ULL : ((1ULL << nb) - 1);
-    hi = nb <= 64 ? 0ULL : (nb >= 128 ? ~0ULL : ((1ULL << (nb - 64)) - 1));
-}
-
 /* Walks one read and reports its positive k-mers as ITEMS {color-set id, number of k-mers}: after next(), lane l holds one
    item (cnt = 0: none). Over the calls until next() returns false every positive k-mer of the read is counted in exactly
    one item; the consumers -- intersection, per-color scores, distinct-set table -- only need that multiset.
@@ -664,19 +658,16 @@ struct kmer_tiles {
         const int j_max = forward ? min(len_s, int(nchars) - d) : min(len_s, e + k);
         const uint64_t x_lo = s_lo ^ stretch_at(src, off), x_hi = s_hi ^ stretch_at(src, off + 32);
         const uint64_t m_lo = (x_lo | (x_lo >> 1)) & 0x5555555555555555ULL, m_hi = (x_hi | (x_hi >> 1)) & 0x5555555555555555ULL;
-        /* a = first stored position after the last mismatch left of the minimizer's end; b = first mismatch at or right of
-           the minimizer's start. A k-mer at stored position t is present iff a <= t and t + k <= b. */
-        uint64_t q_lo, q_hi;
-        mask_below(2 * uint32_t(pm + m), q_lo, q_hi);
-        const uint64_t l_lo = m_lo & q_lo, l_hi = m_hi & q_hi;
-        int a = 0;
-        if (l_hi) a = 32 + ((64 - __clzll((long long)l_hi)) >> 1) + 1;
-        else if (l_lo) a = ((64 - __clzll((long long)l_lo)) >> 1) + 1;
-        mask_below(2 * uint32_t(pm), q_lo, q_hi);
-        const uint64_t g_lo = m_lo & ~q_lo, g_hi = m_hi & ~q_hi;
+        /* a = first stored position after the last mismatch LEFT of the minimizer (pm < 32: the low word only); b = first mismatch
+           at or right of the minimizer's start. A k-mer at stored position t is present iff a <= t and t + k <= b. (A mismatch
+           inside the minimizer makes b < pm + m: what is still "present" then ends before the minimizer does, outside the run,
+           and the clip to the run's k-mers below drops it.) */
+        const uint64_t left = (1ULL << (2 * pm)) - 1;
+        const uint64_t l_lo = m_lo & left, g_lo = m_lo & ~left;
+        const int a = l_lo ? ((64 - __clzll((long long)l_lo)) >> 1) + 1 : 0;
         int b = 64;
         if (g_lo) b = (__ffsll((long long)g_lo) - 1) >> 1;
-        else if (g_hi) b = 32 + ((__ffsll((long long)g_hi) - 1) >> 1);
+        else if (m_hi) b = 32 + ((__ffsll((long long)m_hi) - 1) >> 1);
         const int t_lo = max(a, j_min), t_hi = min(min(b, j_max) - k, win - 1);
         if (t_lo > t_hi) return 0;
         const int lo = max(forward ? t_lo + d : e - t_hi, int(i_first)), hi = min(forward ? t_hi + d : e - t_lo, int(i_last));

@@ -21,11 +21,13 @@ cap() { # name regex key reads bench-args...
 if [ -z "$SKIP_CAPS" ]; then
 cap prof_s10_fi k_pseudoalign_small "k_pseudoalign_small@salmonella_10.fur" 2000000
 cap prof_big_fi_k1 k_fetch_color_sets "k_fetch_color_sets@$BIG.fur" 200000 --index $BIG.fur
+if [ -z "$ONLY_K1_CAPS" ]; then
 cap prof_big_fi_k2 k_color_sets_table "k_color_sets_table@$BIG.fur" 200000 --index $BIG.fur
 cap prof_big_fi_emit k_emit_bits "k_emit_bits@$BIG.fur" 200000 --index $BIG.fur
 cap prof_big_tu_k2 k_color_sets_table "k_color_sets_table[tu]@$BIG.fur" 200000 --index $BIG.fur --algo tu
+fi
 cap prof_big_mfur_tu_mixed_k1 k_fetch_color_sets "k_fetch_color_sets@$BIG.mfur" 200000 --index $BIG.mfur --algo tu --min-len 75 --max-len 300
-cap prof_big_mfur_tu_mixed_k2 k_color_sets_table "k_color_sets_table@$BIG.mfur" 200000 --index $BIG.mfur --algo tu --min-len 75 --max-len 300
+[ -z "$ONLY_K1_CAPS" ] && cap prof_big_mfur_tu_mixed_k2 k_color_sets_table "k_color_sets_table@$BIG.mfur" 200000 --index $BIG.mfur --algo tu --min-len 75 --max-len 300
 cp profiles/kernels.json gpurun_out/kernels.json
 fi
 if [ -z "$SKIP_TESTS" ]; then timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4; fi
