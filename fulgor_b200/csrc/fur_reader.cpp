@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -636,7 +637,10 @@ std::vector<uint8_t> build_image(const uint8_t* file, uint64_t size, int type) {
        of the unitig that contains it (buckets.hpp:13-40 + u2c), and the position of the canonical minimizer */
     std::vector<uint64_t> sk_records(H.num_super_kmers);
     std::vector<uint32_t> sk_cid;
-    const bool wide_cids = H.num_color_sets > (uint64_t(FGI_SK_CID_MASK) + 1);
+    /* color-set ids beyond the record's 21 bits go to a side array (sk_cid). FULGOR_GPU_FORCE_WIDE_CIDS=1 takes that layout for any
+       index: no index in the test tiers has 2^21 color sets, the tests use the switch to run the kernels' side-array branch */
+    const char* force_wide = std::getenv("FULGOR_GPU_FORCE_WIDE_CIDS");
+    const bool wide_cids = H.num_color_sets > (uint64_t(FGI_SK_CID_MASK) + 1) || (force_wide && force_wide[0] == '1');
     if (wide_cids) sk_cid.resize(H.num_super_kmers);
     const uint64_t max_window = H.k - H.m + 1;
     const uint64_t kmask = (1ULL << (2 * H.k)) - 1;

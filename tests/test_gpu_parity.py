@@ -75,6 +75,33 @@ def test_edge_cases(pair, algo, thr):
     assert _same(gpu.fetch_color_set_ids(reads), o.fetch_color_set_ids(reads))
 
 
+@pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_200.mfur", "synth_skew.fur"])
+def test_color_set_ids_in_the_side_array(index, built_lib, monkeypatch):
+    """the layout of indexes with more than 2^21 color sets (ids in the sk_cid side array, none in the records), forced on small
+    indexes by FULGOR_GPU_FORCE_WIDE_CIDS=1: every kernel that maps a super-k-mer to its color set must read the side array"""
+    import fulgor_b200 as fg
+
+    path = ck.index_path(index)
+    monkeypatch.setenv("FULGOR_GPU_FORCE_WIDE_CIDS", "1")
+    gpu = fg.Index.open(path, 0)
+    monkeypatch.delenv("FULGOR_GPU_FORCE_WIDE_CIDS")
+    o = ck.Oracle(path)
+    genomes = index.split(".")[0]
+    try:
+        for reads in (ck.gen_reads(_sized(gpu, 6000), 75, 300, seed=77, genomes=genomes), edge_reads(genomes)):
+            got = gpu.fetch_color_set_ids(reads, want_positive=True)
+            exp = o.fetch_color_set_ids(reads, want_positive=True)
+            assert _same(got, exp) and np.array_equal(got[2], exp[2])
+            for algo, thr in ((0, 1.0), (1, 0.8)):
+                assert _same(gpu.pseudoalign(reads, algo, thr), o.pseudoalign(reads, algo, thr))
+            got_off, got_tr = gpu.kmer_conservation(reads)
+            exp_off, exp_tr = o.kmer_conservation(reads)
+            assert np.array_equal(got_off, exp_off) and np.array_equal(got_tr, exp_tr)
+    finally:
+        gpu.close()
+        o.close()
+
+
 def test_empty_batch(pair):
     gpu, o = pair
     reads = ck.reads_from_list([])

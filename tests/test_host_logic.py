@@ -425,6 +425,45 @@ def test_emulated_kernels_on_packed_reads(index, packed_emul, built_lib):
     o.close()
 
 
+@pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_200.mfur", "synth_skew.fur"])
+def test_emulated_kernels_with_color_set_ids_in_the_side_array(index, emul, built_lib, monkeypatch):
+    """Indexes with more than 2^21 color sets keep the super-k-mer -> color-set id map in a side array (sk_cid) instead of the
+    record's 21 bits (image.h). No index of the test tiers is that large: FULGOR_GPU_FORCE_WIDE_CIDS=1 makes the loader take
+    that layout (records carry no id at all then), and the kernels must give the oracle's answers through it: stage 1, full
+    intersection / threshold union, the per-k-mer view (seed-and-extend items AND the per-k-mer paths of synth_skew.fur)."""
+    import fulgor_b200 as fg
+    from fulgor_b200 import imageview as iv
+
+    path = ck.index_path(index)
+    plain = fg.build_image(path)
+    monkeypatch.setenv("FULGOR_GPU_FORCE_WIDE_CIDS", "1")
+    img = fg.build_image(path)
+    monkeypatch.delenv("FULGOR_GPU_FORCE_WIDE_CIDS")
+    h = iv.header(img)
+    assert iv.header(plain).off_sk_cid == 0 and h.off_sk_cid != 0
+    rec_hi = iv.section(img, h.off_sk_records, "<u4", 2 * h.num_super_kmers)[1::2]
+    assert not np.any(rec_hi & ((1 << 21) - 1)), "the records of a wide image carry no color-set id"
+    o = ck.Oracle(path)
+    genomes = index.split(".")[0]
+    for reads in (ck.gen_reads(150 if o.num_colors <= 32 else 60, 75, 300, seed=23, genomes=genomes), _nasty_reads(genomes)):
+        got = emul_fetch(emul, img, reads, grid=2)
+        exp = o.fetch_color_set_ids(reads, want_positive=True)
+        for a, b in zip(got, exp):
+            assert np.array_equal(a, b)
+        for algo, thr in ((0, 1.0), (1, 0.6)):
+            got = emul_pseudoalign(emul, img, reads, algo, thr, o.num_colors, table=1)
+            exp = o.pseudoalign(reads, algo, thr)
+            assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+        bases, off = reads
+        nr = len(off) - 1
+        cap = int(off[nr]) + 1
+        toff, tr = np.zeros(nr + 1, dtype=np.uint64), np.zeros(3 * cap, dtype=np.uint32)
+        assert emul.emul_kmer_tool(img.ctypes.data, 0, bases.ctypes.data, off.ctypes.data, nr, toff.ctypes.data, tr.ctypes.data, cap, None, 2, 0) == 0
+        exp_off, exp_tr = o.kmer_conservation(reads)
+        assert np.array_equal(toff, exp_off) and np.array_equal(tr[: 3 * int(toff[nr])].reshape(-1, 3), exp_tr)
+    o.close()
+
+
 @pytest.mark.parametrize("index", ["salmonella_10.fur", "synth_skew.fur"])
 def test_emulated_kernels_with_weak_minimizer_keys(index, weak_key_emul, built_lib):
     """32-bit window minima: when the key bits cannot tell two m-mers of a window apart the kernel must notice and recompute the
