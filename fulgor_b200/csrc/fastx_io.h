@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cstdint>
 #include <cstdio>
@@ -163,6 +164,8 @@ public:
         if (fd_ >= 0) close(fd_);
     }
     /* threads = tokenising threads for memory-mapped input; span = bytes of file per batch */
+    /* tokenising threads of the next batch (the tool rebalances its parsing and formatting threads batch by batch) */
+    void set_threads(unsigned threads) { threads_ = std::max(1u, threads); }
     bool open(const char* path, unsigned threads, uint64_t span_bytes, uint64_t max_reads_serial, bool want_names = false) {
         want_names_ = want_names;
         if (const char* e = std::getenv("FULGOR_SLAB_KB")) slab_bytes_ = std::max<size_t>(64, std::strtoull(e, nullptr, 10)) << 10;
@@ -566,20 +569,28 @@ enum class out_format { ASCII, BINARY, COMPRESSED };
 class result_writer {
 public:
     bool open(const char* path, out_format fm, uint32_t num_colors, unsigned threads) {
-        f_ = std::fopen(path, "wb");
+        fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        pos_ = 0;
+        failed_ = false;
         fmt_ = fm;
         num_colors_ = num_colors;
-        threads_ = std::max(1u, threads);
-        pieces_.resize(threads_);
-        if (!f_) return false;
+        set_threads(threads);
+        if (fd_ < 0) return false;
         if (fmt_ == out_format::COMPRESSED) { /* psa_compressed_formatter::set_num_colors, src/ps_utils.cpp:160-166 */
             const uint64_t header = num_colors;
-            std::fwrite(&header, 8, 1, f_);
+            put(&header, 8, 0);
+            pos_ = 8;
             sparse_thr_ = uint32_t(0.25 * num_colors);
             dense_thr_ = uint32_t(0.75 * num_colors);
         }
         return true;
     }
+    /* formatting threads of the next write_batch (the tool rebalances its parsing and formatting threads batch by batch) */
+    void set_threads(unsigned threads) {
+        threads_ = std::max(1u, threads);
+        if (pieces_.size() < threads_) pieces_.resize(threads_);
+    }
+    bool ok() const { return !failed_; }
     /* records first_id .. first_id+n-1: colors[off[i] .. off[i+1]) each; with `rep` (deduplicated results: rep[i] = the read
        of this batch whose range holds read i's colors) record i carries colors[off[rep[i]] .. off[rep[i]+1]) -- every read id
        is written with its group's result, like the reference's preprocessed_query_reader path (tools/pseudoalign.cpp:39-44) */
@@ -607,13 +618,23 @@ public:
             cut[t] = lo;
         }
         cut[T] = n;
-        parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
-        for (unsigned t = 0; t < T; ++t)
-            if (!pieces_[t].empty()) std::fwrite(pieces_[t].data(), 1, pieces_[t].size(), f_);
+        /* every thread formats its records, then writes its piece at its own file position (the sizes of the pieces before it
+           are known after the formatting): no serial pass over the formatted bytes */
+        std::vector<uint64_t> at(T + 1, pos_);
+        if (T == 1) {
+            format(first_id, 0, n, off, colors, rep, vol[n] - vol[0], pieces_[0]);
+            put(pieces_[0].data(), pieces_[0].size(), pos_);
+            at[1] = pos_ + pieces_[0].size();
+        } else {
+            parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
+            for (unsigned t = 0; t < T; ++t) at[t + 1] = at[t] + pieces_[t].size();
+            parallel_for(T, [&](unsigned t) { put(pieces_[t].data(), pieces_[t].size(), at[t]); });
+        }
+        pos_ = at[T];
     }
     void close() {
-        if (f_) std::fclose(f_);
-        f_ = nullptr;
+        if (fd_ >= 0) ::close(fd_);
+        fd_ = -1;
     }
 
 private:
@@ -692,7 +713,23 @@ private:
         }
     }
 
-    FILE* f_ = nullptr;
+    void put(const void* data, size_t bytes, uint64_t at) {
+        const char* p = static_cast<const char*>(data);
+        while (bytes) {
+            const ssize_t w = ::pwrite(fd_, p, bytes, off_t(at));
+            if (w <= 0) {
+                failed_ = true;
+                return;
+            }
+            p += w;
+            at += uint64_t(w);
+            bytes -= size_t(w);
+        }
+    }
+
+    int fd_ = -1;
+    uint64_t pos_ = 0; /* file position of the next batch */
+    std::atomic<bool> failed_{false};
     out_format fmt_ = out_format::ASCII;
     uint32_t num_colors_ = 0, sparse_thr_ = 0, dense_thr_ = 0;
     unsigned threads_ = 1;

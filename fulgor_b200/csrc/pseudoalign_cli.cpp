@@ -17,6 +17,7 @@
  */
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +42,10 @@ struct args_t {
     double threshold = -1.0;
     bool has_threshold = false, verbose = false, deduplicate = false;
     int gpus = 1;
-    uint64_t batch_reads = 1u << 20;
+    uint64_t batch_reads = 1u << 17; /* reads per pipeline step: three batches are in flight, so a run costs (batches + 2) steps -- small
+                                        batches keep the fill and drain short (4 M reads, 8 host threads, GPU stage stubbed out:
+                                        382 ms at 2^20, 250 ms at 2^18, 230 ms at 2^17, 215 ms at 2^16 reads per batch) while one
+                                        batch still fills a GPU call (a chunk of the library's own pipeline holds 2^18 reads) */
     bool batch_given = false;
 };
 
@@ -302,15 +306,19 @@ int main(int argc, char** argv) {
     if (a.verbose) std::cout << "*** DONE: loading the index" << std::endl;
     if (a.verbose) std::cout << "performing queries from file '" << a.query << "'..." << std::endl;
 
-    /* host threads: half of -t parse, half format (the two stages overlap each other and the GPU call) */
-    const unsigned host_threads = unsigned(std::max<uint64_t>(1, a.threads / 2));
+    /* host threads: -t is shared by the parsing and the formatting stage (they overlap each other and the GPU call). Tokenising
+       150 bp FASTQ records costs more than formatting a handful of colors per read, formatting thousands of colors per read far
+       more than tokenising: the split starts at 5 : 3 and follows the measured work of the two stages batch by batch. */
+    const unsigned total_threads = unsigned(std::max<uint64_t>(2, a.threads));
+    unsigned parse_threads = std::max(1u, std::min(total_threads - 1, (total_threads * 5 + 4) / 8));
+    unsigned format_threads = total_threads - parse_threads;
     fgio::fastx_source reader;
-    if (!reader.open(a.query.c_str(), host_threads, std::min<uint64_t>(1ull << 30, a.batch_reads * 320), a.batch_reads)) {
+    if (!reader.open(a.query.c_str(), parse_threads, std::min<uint64_t>(1ull << 30, a.batch_reads * 320), a.batch_reads)) {
         std::cerr << "cannot open query file '" << a.query << "'" << std::endl;
         return 1;
     }
     fgio::result_writer out;
-    if (!out.open(a.output.c_str(), fmt, info.num_colors, host_threads)) {
+    if (!out.open(a.output.c_str(), fmt, info.num_colors, format_threads)) {
         std::cerr << "cannot open output file '" << a.output << "'" << std::endl;
         return 1;
     }
@@ -460,7 +468,9 @@ int main(int argc, char** argv) {
         }
         if (n) colors_per_read = std::max<uint64_t>(colors_per_read, hc[n] / n + 1);
     };
+    double parse_ms = 0, format_ms = 0; /* wall time of the last parsing / formatting stage */
     auto format_stage = [&](batch_ctx& c) {
+        const auto f0 = std::chrono::steady_clock::now();
         const uint32_t n = c.reads.n;
         uint64_t mapped = 0;
         for (uint32_t i = 0; i < n; ++i) {
@@ -469,6 +479,7 @@ int main(int argc, char** argv) {
         }
         num_mapped += mapped;
         out.write_batch(uint32_t(c.first_id), n, c.hc, c.hv, c.hr);
+        format_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - f0).count();
     };
 
     /* step i: parse batch i | GPU on batch i-1 | format batch i-2, each on its own thread */
@@ -484,7 +495,9 @@ int main(int argc, char** argv) {
         if (do_fmt) tf = std::thread(format_stage, std::ref(cf));
         cp.full = false;
         if (more) {
+            const auto p0 = std::chrono::steady_clock::now();
             more = reader.next_batch(cp.reads);
+            parse_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p0).count();
             if (more) {
                 cp.full = true;
                 cp.first_id = num_reads;
@@ -498,6 +511,19 @@ int main(int argc, char** argv) {
             cf.full = false;
             if (a.verbose) std::cout << "processed " << cf.first_id + cf.reads.n << " reads" << std::endl;
         }
+        if (more && do_fmt && parse_ms > 0 && format_ms > 0) {
+            /* both stages ran on full batches: a step lasts as long as its slower stage, so a thread moves to the stage that took
+               clearly longer (neither stage scales linearly with its threads: comparing thread-time would starve one of them) */
+            unsigned np = parse_threads;
+            if (parse_ms > 1.3 * format_ms && format_threads > 1) np += 1;
+            else if (format_ms > 1.3 * parse_ms && parse_threads > 1) np -= 1;
+            if (np != parse_threads) {
+                parse_threads = np;
+                format_threads = total_threads - parse_threads;
+                reader.set_threads(parse_threads);
+                out.set_threads(format_threads);
+            }
+        }
         if (do_gpu && cg.failed) return 1;
         if (too_many) {
             std::cerr << "more than 2^32 reads: read ids do not fit the output formats" << std::endl;
@@ -505,6 +531,10 @@ int main(int argc, char** argv) {
         }
     }
     out.close();
+    if (!out.ok()) {
+        std::cerr << "error in writing the output file '" << a.output << "'" << std::endl;
+        return 1;
+    }
     const auto t1 = std::chrono::high_resolution_clock::now();
     const double ms = double(std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
     if (a.verbose) std::cout << "*** DONE: pseudoalignment" << std::endl;

@@ -25,10 +25,12 @@ long long fxio_parse(const char* path, unsigned threads, unsigned long long span
         x.bases_cap = bb.size();
         x.reads_cap = bo.size();
     };
+    unsigned batch = 0;
     while (src.next_batch(b)) {
         const unsigned long long base = all.size();
         all.insert(all.end(), b.bases, b.bases + b.off[b.n]);
         for (uint32_t i = 1; i <= b.n; ++i) offs.push_back(base + b.off[i]);
+        src.set_threads(1 + (++batch * 3) % (threads + 2)); /* the tool changes the thread count between batches */
     }
     *was_mapped = *was_mapped && src.mapped();
     *bases = static_cast<char*>(std::malloc(all.size() + 1));
@@ -80,9 +82,10 @@ int fxio_format(const char* path, int fmt, unsigned num_colors, unsigned threads
         const unsigned lo = unsigned((unsigned long long)n * p / pieces), hi = unsigned((unsigned long long)n * (p + 1) / pieces);
         std::vector<uint64_t> o(off + lo, off + hi + 1);
         w.write_batch(lo, hi - lo, o.data(), reinterpret_cast<const uint32_t*>(colors));
+        w.set_threads(1 + ((p + 1) * 3) % (threads + 2)); /* the tool changes the thread count between batches */
     }
     w.close();
-    return 0;
+    return w.ok() ? 0 : -2;
 }
 
 /* the per-k-mer tools' lines for n reads named r<first+i>; which = 0: kmer-conservation (off = triple offsets, vals = triples),
