@@ -1047,9 +1047,6 @@ template <typename F>
 static inline void dispatch_table_kernel(int algo, uint32_t max_kmers, F&& f) {
     if (algo == FULGOR_GPU_FULL_INTERSECTION) f(std::true_type(), std::integral_constant<int, 1>(), std::integral_constant<int, 5>());
     else if (max_kmers < (1u << 7)) f(std::false_type(), std::integral_constant<int, 7>(), std::integral_constant<int, 5>());
-#ifdef FG_TU_NP9
-    else if (max_kmers < (1u << 9)) f(std::false_type(), std::integral_constant<int, 9>(), std::integral_constant<int, 5>());
-#endif
     else if (max_kmers < (1u << 10)) f(std::false_type(), std::integral_constant<int, 10>(), std::integral_constant<int, 5>());
     else if (max_kmers < (1u << 16)) f(std::false_type(), std::integral_constant<int, 16>(), std::integral_constant<int, 5>());
     else f(std::false_type(), std::integral_constant<int, 32>(), std::integral_constant<int, 1>());

@@ -4,7 +4,7 @@
 #   tools/cli_bench.sh [N_READS=10000000] [INDEX=data/salmonella_10.fur] [GPK=salmonella_10] [GPUS=1] [EXTRA_ARGS for both tools...]
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-N=${1:-10000000}; IDX=${2:-data/salmonella_10.fur}; GPK=${3:-salmonella_10}; GPUS=${4:-1}; shift 4 2>/dev/null; EXTRA="$*"
+N=${1:-10000000}; IDX=${2:-data/salmonella_10.fur}; GPK=${3:-salmonella_10}; GPUS=${4:-1}; if [ $# -ge 4 ]; then shift 4; else set --; fi; EXTRA="$*"
 T=$(nproc); W=/dev/shm/fg_cli_bench; mkdir -p $W gpurun_out build
 [ -f data/$GPK.gpk ] || [ -f fixtures_big/$GPK.gpk ] || xz -dkc data/$GPK.gpk.xz > $W/$GPK.gpk
 GP=$( [ -f data/$GPK.gpk ] && echo data/$GPK.gpk || ( [ -f fixtures_big/$GPK.gpk ] && echo fixtures_big/$GPK.gpk || echo $W/$GPK.gpk ) )
