@@ -28,7 +28,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -46,6 +48,71 @@ inline void parallel_for(unsigned n, const std::function<void(unsigned)>& f) {
     f(0);
     for (auto& t : th) t.join();
 }
+
+/* The same with PERSISTENT workers: the tool calls it a dozen times per batch (tokenising rounds, copies, formatting, writing), and
+   creating the threads anew each time cost as much as the work of a round (220-290 us per call of five threads on the build VM).
+   One team per stage object; run() is called by one thread at a time. */
+class thread_team {
+public:
+    thread_team() = default;
+    thread_team(const thread_team&) = delete;
+    thread_team& operator=(const thread_team&) = delete;
+    ~thread_team() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        work_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    /* runs f(0) .. f(n-1), f(0) on the caller's thread, and returns when all are done */
+    void run(unsigned n, const std::function<void(unsigned)>& f) {
+        if (n <= 1) {
+            if (n == 1) f(0);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            while (th_.size() + 1 < n) {
+                const unsigned id = unsigned(th_.size()) + 1;
+                th_.emplace_back([this, id] { worker(id); });
+            }
+            job_ = &f;
+            width_ = n;
+            pending_ = n - 1;
+            ++generation_;
+        }
+        work_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void worker(unsigned id) {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            work_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            if (id >= width_) continue; /* this call uses fewer workers */
+            const std::function<void(unsigned)>* job = job_;
+            lk.unlock();
+            (*job)(id);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable work_, done_;
+    std::vector<std::thread> th_;
+    const std::function<void(unsigned)>* job_ = nullptr;
+    unsigned width_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
 
 /* a batch of reads in the layout the C ABI takes: concatenated bases + CSR offsets. The buffers belong to the caller
    (pinned memory in the tool); grow() is called when a batch needs more room and must keep what the batch already holds. */
@@ -320,7 +387,7 @@ private:
                     o.ok = false;
                     return;
                 }
-                const size_t l3 = line_after(d, n, l2);
+                const size_t l3 = (l2 + 1 < n && d[l2 + 1] == '\n') ? l2 + 2 : line_after(d, n, l2); /* the separator line is almost always a bare '+' */
                 /* the quality line normally is exactly as long as the sequence: look for its newline there before scanning */
                 const size_t q_guess = l3 + (s_end - l1);
                 const size_t l4 = (q_guess < n && d[q_guess] == '\n') ? q_guess + 1 : (l3 < n ? line_after(d, n, l3) : n);
@@ -383,7 +450,7 @@ private:
             cut[0] = begin;
             for (unsigned t = 1; t <= T; ++t) cut[t] = std::max(cut[t - 1], find_record(begin + size_t((target - begin) * uint64_t(t) / T)));
             if (target == size_) cut[T] = size_;
-            parallel_for(T, [&](unsigned t) {
+            team_.run(T, [&](unsigned t) {
                 if (load_slab(cut[t], cut[t + 1], out[t])) tokenise(out[t].raw.data(), out[t].raw.size(), out[t]);
                 else out[t].ok = false;
             });
@@ -400,7 +467,7 @@ private:
             }
             if (read_at[T] > 0xffffffffull) return false;
             b.reserve(base_at[T] + 1, read_at[T] + 1);
-            parallel_for(T, [&](unsigned t) {
+            team_.run(T, [&](unsigned t) {
                 if (!out[t].bases.empty()) std::memcpy(b.bases + base_at[t], out[t].bases.data(), out[t].bases.size());
                 uint64_t o = base_at[t];
                 uint64_t* dst = b.off + read_at[t];
@@ -464,6 +531,7 @@ private:
     size_t size_ = 0, pos_ = 0;
     bool mapped_ = false, fastq_ = true, serial_open_ = false, want_names_ = false;
     unsigned threads_ = 1;
+    thread_team team_;
     uint64_t span_ = 1ull << 28, max_reads_serial_ = 1u << 22, reads_done_ = 0;
     size_t slab_bytes_ = 2u << 20;
     serial_fastx_reader serial_;
@@ -473,15 +541,45 @@ private:
 };
 
 /* ---------------------------------------------------------------- output formats (src/ps_utils.cpp:48-243) */
+/* decimal digits of v, two at a time from a table; color ids and list sizes are mostly below 10,000 */
+static const char fg_digit_pairs[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869"
+    "707172737475767778798081828384858687888990919293949596979899";
 inline char* put_u32(char* p, uint32_t v) {
+    if (v < 10) {
+        *p = char('0' + v);
+        return p + 1;
+    }
+    if (v < 100) {
+        std::memcpy(p, fg_digit_pairs + 2 * v, 2);
+        return p + 2;
+    }
+    if (v < 10000) {
+        const uint32_t q = v / 100, r = v % 100;
+        if (q < 10) *p++ = char('0' + q);
+        else {
+            std::memcpy(p, fg_digit_pairs + 2 * q, 2);
+            p += 2;
+        }
+        std::memcpy(p, fg_digit_pairs + 2 * r, 2);
+        return p + 2;
+    }
     char tmp[10];
     int n = 0;
-    do {
-        tmp[n++] = char('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
+    while (v >= 100) {
+        n += 2;
+        std::memcpy(tmp + 10 - n, fg_digit_pairs + 2 * (v % 100), 2);
+        v /= 100;
+    }
+    if (v >= 10) {
+        n += 2;
+        std::memcpy(tmp + 10 - n, fg_digit_pairs + 2 * v, 2);
+    } else {
+        n += 1;
+        tmp[10 - n] = char('0' + v);
+    }
+    std::memcpy(p, tmp + 10 - n, size_t(n));
+    return p + n;
 }
 
 struct bit_writer { /* LSB-first, like bits::bit_vector::builder */
@@ -626,9 +724,9 @@ public:
             put(pieces_[0].data(), pieces_[0].size(), pos_);
             at[1] = pos_ + pieces_[0].size();
         } else {
-            parallel_for(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
+            team_.run(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
             for (unsigned t = 0; t < T; ++t) at[t + 1] = at[t] + pieces_[t].size();
-            parallel_for(T, [&](unsigned t) { put(pieces_[t].data(), pieces_[t].size(), at[t]); });
+            team_.run(T, [&](unsigned t) { put(pieces_[t].data(), pieces_[t].size(), at[t]); });
         }
         pos_ = at[T];
     }
@@ -733,6 +831,7 @@ private:
     out_format fmt_ = out_format::ASCII;
     uint32_t num_colors_ = 0, sparse_thr_ = 0, dense_thr_ = 0;
     unsigned threads_ = 1;
+    thread_team team_;
     std::vector<std::vector<char>> pieces_;
 };
 
