@@ -41,6 +41,23 @@ long long fxio_parse(const char* path, unsigned threads, unsigned long long span
 }
 void fxio_free(void* p) { std::free(p); }
 
+/* fgio::thread_team: `calls` run() calls of varying width on one team; every f(t) must run exactly once per call and run() must
+   not return before all of them have. Returns 0 when every call saw exactly its own width of distinct indices. */
+int fxio_team_selftest(unsigned calls, unsigned max_width) {
+    fgio::thread_team team;
+    std::vector<unsigned> hits(max_width + 1);
+    unsigned long long state = 88172645463325252ull;
+    for (unsigned c = 0; c < calls; ++c) {
+        state ^= state << 13, state ^= state >> 7, state ^= state << 17;
+        const unsigned n = unsigned(state % (max_width + 1)); /* 0 .. max_width */
+        std::fill(hits.begin(), hits.end(), 0u);
+        team.run(n, [&](unsigned t) { hits[t] += 1 + c; });
+        for (unsigned t = 0; t <= max_width; ++t)
+            if (hits[t] != (t < n ? 1 + c : 0u)) return int(c) + 1;
+    }
+    return 0;
+}
+
 /* like fxio_parse with want_names: *names = the reads' names joined by '\n' (malloc'ed, NUL-terminated); returns the number of reads */
 long long fxio_parse_names(const char* path, unsigned threads, unsigned long long span, unsigned long long max_reads_serial, char** names) {
     fgio::fastx_source src;

@@ -280,3 +280,11 @@ def compressed_records_prefix(path, limit):
                 vals = [c for c in range(Cn) if c not in ms]
             recs[rid] = vals
     return Cn, recs
+
+
+def test_thread_team_runs_every_index_once(fx):
+    """fgio::thread_team (the persistent workers of the parsing and formatting stages): 20,000 calls of random width 0..9 on one
+    team -- each index of a call runs exactly once, and run() returns only after all of them did"""
+    fx.fxio_team_selftest.argtypes = [C.c_uint, C.c_uint]
+    assert fx.fxio_team_selftest(20000, 9) == 0
+
