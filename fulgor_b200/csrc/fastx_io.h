@@ -670,6 +670,7 @@ public:
         fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
         pos_ = 0;
         failed_ = false;
+        seekable_ = fd_ >= 0 && ::lseek(fd_, 0, SEEK_CUR) != off_t(-1); /* a pipe or a terminal takes the pieces in order instead */
         fmt_ = fm;
         num_colors_ = num_colors;
         set_threads(threads);
@@ -726,7 +727,9 @@ public:
         } else {
             team_.run(T, [&](unsigned t) { format(first_id, cut[t], cut[t + 1], off, colors, rep, vol[cut[t + 1]] - vol[cut[t]], pieces_[t]); });
             for (unsigned t = 0; t < T; ++t) at[t + 1] = at[t] + pieces_[t].size();
-            team_.run(T, [&](unsigned t) { put(pieces_[t].data(), pieces_[t].size(), at[t]); });
+            if (seekable_) team_.run(T, [&](unsigned t) { put(pieces_[t].data(), pieces_[t].size(), at[t]); });
+            else
+                for (unsigned t = 0; t < T; ++t) put(pieces_[t].data(), pieces_[t].size(), at[t]);
         }
         pos_ = at[T];
     }
@@ -814,7 +817,7 @@ private:
     void put(const void* data, size_t bytes, uint64_t at) {
         const char* p = static_cast<const char*>(data);
         while (bytes) {
-            const ssize_t w = ::pwrite(fd_, p, bytes, off_t(at));
+            const ssize_t w = seekable_ ? ::pwrite(fd_, p, bytes, off_t(at)) : ::write(fd_, p, bytes);
             if (w <= 0) {
                 failed_ = true;
                 return;
@@ -828,6 +831,7 @@ private:
     int fd_ = -1;
     uint64_t pos_ = 0; /* file position of the next batch */
     std::atomic<bool> failed_{false};
+    bool seekable_ = true;
     out_format fmt_ = out_format::ASCII;
     uint32_t num_colors_ = 0, sparse_thr_ = 0, dense_thr_ = 0;
     unsigned threads_ = 1;

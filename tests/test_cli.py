@@ -137,6 +137,22 @@ def csr_records(csr):
     return {i: vals[int(off[i]):int(off[i + 1])].tolist() for i in range(len(off) - 1)}
 
 
+def test_cli_writes_a_pipe_like_a_file(cli, tmp_path):
+    """the formatting threads place their pieces with positional writes; an output that cannot seek (a pipe: `-o /dev/stdout |`)
+    takes the pieces in order instead -- same bytes, with several threads and several batches, in every format"""
+    CLI, scale = cli
+    reads = ck.gen_reads(int(6000 * scale), 75, 300, seed=41, genomes="salmonella_10")
+    fq = str(tmp_path / "reads.fq")
+    write_fastq(fq, reads)
+    path = ck.index_path("salmonella_10.fur")
+    for fmt in ("ascii", "binary", "compressed"):
+        out = str(tmp_path / f"out.{fmt}")
+        args = [CLI, "-i", path, "-q", fq, "-t", "6", "--format", fmt, "--batch-reads", str(int(2500 * scale))]
+        subprocess.check_call(args + ["-o", out])
+        piped = subprocess.run(args + ["-o", "/dev/stdout"], stdout=subprocess.PIPE, check=True).stdout
+        assert piped == open(out, "rb").read() and len(piped) > 0
+
+
 @pytest.mark.parametrize("index,algo_args", [("salmonella_10.fur", []), ("salmonella_10.fur", ["-r", "0.8"]), ("salmonella_10.mfur", []),
                                              ("synth_200.fur", []), ("synth_200.mfur", ["-r", "0.6"]),
                                              ("salmonella_10.dfur", ["-r", "0.7"]), ("salmonella_10.mdfur", []),
